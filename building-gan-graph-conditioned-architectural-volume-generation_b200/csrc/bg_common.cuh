@@ -1,0 +1,138 @@
+// Shared device/host helpers for libbgb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "bg_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libbgb200 targets sm_100a (B200) only"
+#endif
+
+namespace bg {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define BG_REQUIRE(cond, code, ...)      \
+    do {                                 \
+        if (!(cond)) {                   \
+            bg::set_error(__VA_ARGS__);  \
+            return (code);               \
+        }                                \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Number of row-chunks a column reduction over N rows is split into.  Fixed function of N only,
+// so the reduction tree (and therefore the rounding) is reproducible run to run.
+static inline int reduce_splits(int64_t N, int rows_per_cta_iter) {
+    int64_t want = ceil_div(N, (int64_t)rows_per_cta_iter * 4);
+    if (want < 1) want = 1;
+    if (want > 2 * kSMs) want = 2 * kSMs;
+    return (int)want;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ void load(const float* p) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+// Butterfly sum over a group of LANES consecutive lanes (LANES power of two <= 32): every lane of
+// the group ends with the same, order-fixed result.
+template <int LANES>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+template <int LANES>
+__device__ __forceinline__ float group_max(float x) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// One group of LANES = C/VEC consecutive lanes owns one node row (VEC = min(4, C) channels per lane).
+template <int C>
+struct RowMap {
+    static constexpr int VEC = C >= 4 ? 4 : C;
+    static constexpr int LANES = C / VEC;
+    static constexpr int RPW = 32 / LANES;       // rows per warp
+    static constexpr int RPC = RPW * kWarps;     // rows per CTA
+};
+
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    if (LANES >= 32) return 0xffffffffu;
+    return ((1u << (LANES & 31)) - 1u) << ((lane / LANES) * LANES);
+}
+template <int LANES>
+__device__ __forceinline__ float gsum(float x, unsigned mask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
+    return x;
+}
+template <int LANES>
+__device__ __forceinline__ float gmax(float x, unsigned mask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(mask, x, o));
+    return x;
+}
+
+__device__ __forceinline__ float lrelu(float u, float slope) { return u > 0.f ? u : u * slope; }
+__device__ __forceinline__ float lrelu_grad(float u, float slope) { return u > 0.f ? 1.f : slope; }
+
+// "Last CTA finalises" ticket: every CTA publishes its partial, fences, takes a ticket; the CTA
+// that draws the last ticket returns true (and resets the counter so the buffer is reusable
+// without a memset).  The finaliser reads the partials in a FIXED order => deterministic.
+__device__ __forceinline__ bool last_cta_ticket(unsigned int* counter, unsigned int total) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == total - 1);
+        if (is_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+}  // namespace bg

@@ -1,0 +1,484 @@
+// Node-wise dense layers: y = act(LayerNorm(X W^T + b)) over a SEGMENTED input (the reference's
+// torch.cat at models.py:135-141,146,239 is never materialised), optional fused attention dots
+// s = y.a_src, d = y.a_dst (the `lin` of a GATConv), the split-N deterministic weight gradient
+// and the LayerNorm/activation backward.  fp32 FFMA: this is the rel-1e-5 parity mode.
+#include <algorithm>
+
+#include "bg_common.cuh"
+
+namespace bg {
+
+constexpr int BM = 64;  // rows per CTA
+constexpr int BK = 16;  // k-slab
+
+struct SegView {
+    int nseg;
+    int off[BG_MAX_SEG + 1];
+    BgSeg seg[BG_MAX_SEG];
+};
+
+__device__ __forceinline__ float seg_fetch(const SegView& sv, int64_t row, int k) {
+#pragma unroll
+    for (int q = 0; q < BG_MAX_SEG; ++q) {
+        if (q < sv.nseg && k < sv.off[q + 1]) {
+            const BgSeg& sg = sv.seg[q];
+            if (sg.ptr == nullptr) return 1.f;
+            const int64_t r = sg.gather ? (int64_t)__ldg(sg.gather + row) : row;
+            return __ldg(sg.ptr + r * sg.ld + (k - sv.off[q]));
+        }
+    }
+    return 0.f;
+}
+
+struct DenseParams {
+    int64_t N;
+    SegView x;
+    int K;
+    const float* W;
+    int64_t w_so, w_sk;
+    int Cout;
+    const float *bias, *gamma, *beta, *att_src, *att_dst;
+    int act;
+    float* out;
+    int64_t ld_out;
+    float *xhat, *rstd, *s, *d;
+};
+
+template <int BN, int TM, int TN>
+__global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p) {
+    constexpr int TX = BN / TN, TY = BM / TM;
+    static_assert(TX * TY == kThreads, "tile/thread mismatch");
+    __shared__ float Xs[BK][BM + 1];
+    __shared__ __align__(16) float Ws[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int col0 = blockIdx.y * BN;  // column tile (only without LayerNorm / attention dots)
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < BM * BK / kThreads; ++q) {
+            const int idx = tid + q * kThreads, r = idx / BK, kk = idx % BK;
+            const int64_t grow = row0 + r;
+            Xs[kk][r] = (grow < p.N && k0 + kk < p.K) ? seg_fetch(p.x, grow, k0 + kk) : 0.f;
+        }
+        for (int idx = tid; idx < BN * BK; idx += kThreads) {
+            int c, kk;
+            if (p.w_sk == 1) { c = idx / BK; kk = idx % BK; } else { kk = idx / BN; c = idx % BN; }
+            const int gc = col0 + c, gk = k0 + kk;
+            Ws[kk][c] = (gc < p.Cout && gk < p.K) ? __ldg(p.W + gc * p.w_so + gk * p.w_sk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float xr[TM], wr[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) xr[i] = Xs[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) wr[j] = Ws[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias, LayerNorm, activation, attention dots
+    float bj[TN], gj[TN], tj[TN], asj[TN], adj[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int c = col0 + tx * TN + j;
+        const bool ok = c < p.Cout;
+        bj[j] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+        gj[j] = (ok && p.gamma) ? __ldg(p.gamma + c) : 1.f;
+        tj[j] = (ok && p.beta) ? __ldg(p.beta + c) : 0.f;
+        asj[j] = (ok && p.att_src) ? __ldg(p.att_src + c) : 0.f;
+        adj[j] = (ok && p.att_dst) ? __ldg(p.att_dst + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t grow = row0 + ty * TM + i;
+        float y[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) y[j] = acc[i][j] + bj[j];
+        if (p.gamma) {  // LayerNorm over the BN (== Cout) columns of this row, eps = 1e-5
+            float sm = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) sm += y[j];
+            sm = group_sum<TX>(sm);
+            const float mean = sm / (float)BN;
+            float vs = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const float dlt = y[j] - mean;
+                vs = fmaf(dlt, dlt, vs);
+            }
+            vs = group_sum<TX>(vs);
+            const float rs = 1.f / sqrtf(vs / (float)BN + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const float xh = (y[j] - mean) * rs;
+                if (p.xhat && grow < p.N) p.xhat[grow * p.Cout + tx * TN + j] = xh;
+                y[j] = fmaf(xh, gj[j], tj[j]);
+            }
+            if (p.rstd && tx == 0 && grow < p.N) p.rstd[grow] = rs;
+        }
+        if (p.act == BG_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
+        } else if (p.act == BG_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) y[j] = y[j] > 0.f ? y[j] : 0.2f * y[j];
+        }
+        if (p.att_src) {
+            float ss = 0.f, dd = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                ss = fmaf(y[j], asj[j], ss);
+                dd = fmaf(y[j], adj[j], dd);
+            }
+            ss = group_sum<TX>(ss);
+            dd = group_sum<TX>(dd);
+            if (tx == 0 && grow < p.N) {
+                p.s[grow] = ss;
+                p.d[grow] = dd;
+            }
+        }
+        if (grow < p.N) {
+            float* orow = p.out + grow * p.ld_out + col0 + tx * TN;
+            if (TN % 4 == 0 && (p.ld_out & 3) == 0 && col0 + tx * TN + TN <= p.Cout &&
+                ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < TN; j += 4)
+                    *reinterpret_cast<float4*>(orow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (col0 + tx * TN + j < p.Cout) orow[j] = y[j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: dW[o,k] = sum_n gz[n,o] X[n,k] ; 64x64 tile, rows split over blockIdx.z
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+    int64_t N;
+    const float* gz;
+    int64_t ld_gz;
+    int Cout, K;
+    SegView x;
+    int64_t rows_per_split;
+    float* partial;  // [nsplit][Cout][K]
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
+    constexpr int T = 64, RB = 16;
+    __shared__ float Gs[RB][T + 4];
+    __shared__ float Xs[RB][T + 4];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int k0 = blockIdx.x * T, o0 = blockIdx.y * T;
+    const int64_t rbeg = (int64_t)blockIdx.z * p.rows_per_split, rend = min(p.N, rbeg + p.rows_per_split);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
+#pragma unroll
+        for (int q = 0; q < RB * T / kThreads; ++q) {
+            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
+            const int64_t r = r0 + rr;
+            const bool rok = r < rend;
+            Gs[rr][cc] = (rok && o0 + cc < p.Cout) ? __ldg(p.gz + r * p.ld_gz + o0 + cc) : 0.f;
+            Xs[rr][cc] = (rok && k0 + cc < p.K) ? seg_fetch(p.x, r, k0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) {
+            float g[4], x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] = Gs[rr][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = Xs[rr][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], x[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* base = p.partial + (int64_t)blockIdx.z * p.Cout * p.K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + ty * 4 + i, k = k0 + tx * 4 + j;
+            if (o < p.Cout && k < p.K) base[(int64_t)o * p.K + k] = acc[i][j];
+        }
+}
+
+__global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const float* __restrict__ partial, int nsplit, int Cout, int K,
+                                                              float* __restrict__ dW, int64_t ld_dw, int accumulate) {
+    const int64_t total = (int64_t)Cout * K;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        float t = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) t += partial[(int64_t)sp * total + i];
+        const int o = (int)(i / K), k = (int)(i % K);
+        float* dst = dW + (int64_t)o * ld_dw + k;
+        *dst = accumulate ? *dst + t : t;
+    }
+}
+
+static inline int wgrad_splits(int64_t N, int Cout, int K) {
+    const int64_t tiles = ceil_div(K, 64) * ceil_div(Cout, 64);
+    int64_t ns = ceil_div(2 * kSMs, tiles);
+    const int64_t maxs = ceil_div(N, 64);
+    if (ns > maxs) ns = maxs;
+    if (ns > 64) ns = 64;
+    if (ns < 1) ns = 1;
+    return (int)ns;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm + activation backward (row-wise) with deterministic column sums for dgamma/dbeta
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreads) ln_act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                                              const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, int64_t N, int G, int act,
+                                                              float* __restrict__ gz, float* dgamma, float* dbeta,
+                                                              int accumulate, unsigned int* counter, float* partials) {
+    using M = RowMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, RPC = M::RPC;
+    __shared__ float red[kThreads * 2 * VEC];
+    __shared__ float sums[2 * C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LANES, slot = warp * M::RPW + lane / LANES;
+    const unsigned gm = group_mask<LANES>(lane);
+    const int64_t chunk = ceil_div(N, G);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    float gam[VEC], dg[VEC], db[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        gam[v] = __ldg(gamma + sub * VEC + v);
+        dg[v] = 0.f;
+        db[v] = 0.f;
+    }
+    for (int64_t r = r0 + slot; r < r1; r += RPC) {
+        Vec<VEC> g, o, xh;
+        const int64_t off = r * C + sub * VEC;
+        g.load(gout + off);
+        o.load(out + off);
+        xh.load(xhat + off);
+        const float rs = __ldg(rstd + r);
+        float gx[VEC], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float gy = g.v[v];
+            if (act == BG_ACT_LRELU) gy = o.v[v] > 0.f ? gy : 0.2f * gy;
+            else if (act == BG_ACT_RELU) gy = o.v[v] > 0.f ? gy : 0.f;
+            dg[v] = fmaf(gy, xh.v[v], dg[v]);
+            db[v] += gy;
+            gx[v] = gy * gam[v];
+            s1 += gx[v];
+            s2 = fmaf(gx[v], xh.v[v], s2);
+        }
+        s1 = gsum<LANES>(s1, gm) / (float)C;
+        s2 = gsum<LANES>(s2, gm) / (float)C;
+        Vec<VEC> z;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) z.v[v] = rs * (gx[v] - s1 - xh.v[v] * s2);
+        z.store(gz + off);
+    }
+    // column sums over the CTA's row slots: fixed order
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        red[(slot * LANES + sub) * 2 * VEC + v] = dg[v];
+        red[(slot * LANES + sub) * 2 * VEC + VEC + v] = db[v];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
+        const int which = i / C, c = i % C, sb = c / VEC, v = c % VEC;
+        float t = 0.f;
+        for (int sl = 0; sl < RPC; ++sl) t += red[(sl * LANES + sb) * 2 * VEC + which * VEC + v];
+        partials[(int64_t)blockIdx.x * 2 * C + i] = t;
+    }
+    if (!last_cta_ticket(counter, gridDim.x)) return;
+    for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
+        float t = 0.f;
+        for (int g = 0; g < G; ++g) t += partials[(int64_t)g * 2 * C + i];
+        sums[i] = t;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+        if (accumulate) {
+            dgamma[c] += sums[c];
+            dbeta[c] += sums[C + c];
+        } else {
+            dgamma[c] = sums[c];
+            dbeta[c] = sums[C + c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                                           int64_t total, int act, float* __restrict__ gz) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const float o = out[i], g = gout[i];
+        gz[i] = act == BG_ACT_RELU ? (o > 0.f ? g : 0.f) : act == BG_ACT_LRELU ? (o > 0.f ? g : 0.2f * g) : g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        y[i] = fmaf(a, x[i], y[i]);
+}
+__global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ y, float v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) y[i] = v;
+}
+
+static inline int flat_grid(int64_t total) {
+    int64_t g = ceil_div(total, (int64_t)kThreads * 4);
+    if (g < 1) g = 1;
+    if (g > 8 * kSMs) g = 8 * kSMs;
+    return (int)g;
+}
+
+static int fill_segview(SegView& sv, int nseg, const BgSeg* seg, int* K) {
+    BG_REQUIRE(nseg >= 1 && nseg <= BG_MAX_SEG, BG_EINVAL, "segment count %d out of range [1,%d]", nseg, BG_MAX_SEG);
+    sv.nseg = nseg;
+    sv.off[0] = 0;
+    for (int q = 0; q < BG_MAX_SEG; ++q) {
+        if (q < nseg) {
+            BG_REQUIRE(seg[q].width > 0, BG_EINVAL, "segment %d has width %d", q, seg[q].width);
+            sv.seg[q] = seg[q];
+            sv.off[q + 1] = sv.off[q] + seg[q].width;
+        } else {
+            sv.seg[q] = BgSeg{nullptr, nullptr, 0, 0};
+            sv.off[q + 1] = sv.off[q];
+        }
+    }
+    *K = sv.off[nseg];
+    return BG_OK;
+}
+
+}  // namespace bg
+
+using namespace bg;
+
+extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
+    BG_REQUIRE(a && a->W && a->out, BG_EINVAL, "bg_dense_fwd: null pointer");
+    BG_REQUIRE(a->N > 0 && a->Cout > 0, BG_EINVAL, "bg_dense_fwd: N and Cout must be positive");
+    DenseParams p;
+    p.N = a->N;
+    if (int rc = fill_segview(p.x, a->nseg, a->seg, &p.K)) return rc;
+    p.W = a->W; p.w_so = a->w_so; p.w_sk = a->w_sk; p.Cout = a->Cout;
+    p.bias = a->bias; p.gamma = a->ln_gamma; p.beta = a->ln_beta;
+    p.att_src = a->att_src; p.att_dst = a->att_dst; p.act = a->act;
+    p.out = a->out; p.ld_out = a->ld_out; p.xhat = a->xhat; p.rstd = a->rstd; p.s = a->s; p.d = a->d;
+    const bool rowwise = a->ln_gamma || a->att_src;
+    BG_REQUIRE(!a->ln_gamma || a->ln_beta, BG_EINVAL, "bg_dense_fwd: LayerNorm needs gamma and beta");
+    BG_REQUIRE(!a->att_src || (a->att_dst && a->s && a->d), BG_EINVAL, "bg_dense_fwd: attention dots need att_dst, s, d");
+    BG_REQUIRE(!rowwise || a->Cout <= 128, BG_EUNSUPPORTED, "bg_dense_fwd: row-wise epilogue needs Cout<=128 (got %d)", a->Cout);
+    int bn = 8;
+    while (bn < a->Cout && bn < 128) bn <<= 1;
+    BG_REQUIRE(!a->ln_gamma || bn == a->Cout, BG_EUNSUPPORTED,
+               "bg_dense_fwd: LayerNorm width must be one of 8,16,32,64,128 (got %d)", a->Cout);
+    dim3 grid((unsigned)ceil_div(a->N, BM), (unsigned)ceil_div(a->Cout, bn));
+    cudaStream_t st = as_stream(stream);
+    switch (bn) {
+        case 8: dense_fwd_kernel<8, 2, 1><<<grid, kThreads, 0, st>>>(p); break;
+        case 16: dense_fwd_kernel<16, 2, 2><<<grid, kThreads, 0, st>>>(p); break;
+        case 32: dense_fwd_kernel<32, 2, 4><<<grid, kThreads, 0, st>>>(p); break;
+        case 64: dense_fwd_kernel<64, 4, 4><<<grid, kThreads, 0, st>>>(p); break;
+        default: dense_fwd_kernel<128, 4, 8><<<grid, kThreads, 0, st>>>(p); break;
+    }
+    return check_launch("bg_dense_fwd");
+}
+
+extern "C" size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K) {
+    return (size_t)wgrad_splits(N, Cout, K) * (size_t)Cout * (size_t)K * sizeof(float);
+}
+
+extern "C" int bg_dense_wgrad(const BgWgrad* a, void* stream) {
+    BG_REQUIRE(a && a->gz && a->dW && a->workspace, BG_EINVAL, "bg_dense_wgrad: null pointer");
+    WgradParams p;
+    p.N = a->N; p.gz = a->gz; p.ld_gz = a->ld_gz; p.Cout = a->Cout;
+    if (int rc = fill_segview(p.x, a->nseg, a->seg, &p.K)) return rc;
+    BG_REQUIRE(a->ws_bytes >= bg_dense_wgrad_ws(a->N, a->Cout, p.K), BG_EINVAL, "bg_dense_wgrad: workspace too small");
+    const int ns = wgrad_splits(a->N, a->Cout, p.K);
+    int64_t rps = ceil_div(a->N, ns);
+    rps = ceil_div(rps, 16) * 16;
+    p.rows_per_split = rps;
+    p.partial = a->workspace;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((unsigned)ceil_div(p.K, 64), (unsigned)ceil_div(a->Cout, 64), (unsigned)ns);
+    wgrad_kernel<<<grid, kThreads, 0, st>>>(p);
+    const int64_t total = (int64_t)a->Cout * p.K;
+    wgrad_fold_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, kThreads), 4 * kSMs), kThreads, 0, st>>>(
+        a->workspace, ns, a->Cout, p.K, a->dW, a->ld_dw, a->accumulate);
+    return check_launch("bg_dense_wgrad");
+}
+
+extern "C" size_t bg_ln_act_bwd_ws(int64_t N, int32_t C) {
+    (void)N;
+    return 256 + (size_t)(2 * kSMs) * 2 * (size_t)C * sizeof(float);
+}
+
+extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* xhat, const float* rstd, const float* gamma,
+                             int64_t N, int32_t C, int32_t act, float* gz, float* dgamma, float* dbeta, int32_t accumulate,
+                             float* workspace, size_t ws_bytes, void* stream) {
+    BG_REQUIRE(gout && out && gz, BG_EINVAL, "bg_ln_act_bwd: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (!xhat) {
+        const int64_t total = N * C;
+        act_bwd_kernel<<<flat_grid(total), kThreads, 0, st>>>(gout, out, total, act, gz);
+        return check_launch("bg_ln_act_bwd(act)");
+    }
+    BG_REQUIRE(rstd && gamma && dgamma && dbeta && workspace, BG_EINVAL, "bg_ln_act_bwd: LayerNorm path needs rstd/gamma/dgamma/dbeta/workspace");
+    BG_REQUIRE(ws_bytes >= bg_ln_act_bwd_ws(N, C), BG_EINVAL, "bg_ln_act_bwd: workspace too small");
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    float* partials = workspace + 64;
+#define CALL(CC)                                                                                                   \
+    {                                                                                                              \
+        const int G = reduce_splits(N, RowMap<CC>::RPC);                                                           \
+        ln_act_bwd_kernel<CC><<<G, kThreads, 0, st>>>(gout, out, xhat, rstd, gamma, N, G, act, gz, dgamma, dbeta, \
+                                                      accumulate, counter, partials);                              \
+    }
+    switch (C) {
+        case 8: CALL(8); break;
+        case 16: CALL(16); break;
+        case 32: CALL(32); break;
+        case 64: CALL(64); break;
+        case 128: CALL(128); break;
+        default:
+            bg::set_error("bg_ln_act_bwd: unsupported LayerNorm width %d (8,16,32,64,128)", C);
+            return BG_EUNSUPPORTED;
+    }
+#undef CALL
+    return check_launch("bg_ln_act_bwd");
+}
+
+extern "C" int bg_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
+    BG_REQUIRE(y && x, BG_EINVAL, "bg_axpy: null pointer");
+    if (n <= 0) return BG_OK;
+    axpy_kernel<<<flat_grid(n), kThreads, 0, as_stream(stream)>>>(y, x, a, n);
+    return check_launch("bg_axpy");
+}
+
+extern "C" int bg_fill(float* y, float v, int64_t n, void* stream) {
+    BG_REQUIRE(y, BG_EINVAL, "bg_fill: null pointer");
+    if (n <= 0) return BG_OK;
+    fill_kernel<<<flat_grid(n), kThreads, 0, as_stream(stream)>>>(y, v, n);
+    return check_launch("bg_fill");
+}

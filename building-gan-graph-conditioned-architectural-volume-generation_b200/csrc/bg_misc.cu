@@ -1,0 +1,276 @@
+// Error plumbing, the host-side graph build (collation, H1), type-matched program features (H2),
+// Gumbel-softmax straight-through (H7) and the generic segment primitives.
+#include <algorithm>
+#include <vector>
+
+#include "bg_common.cuh"
+
+namespace bg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return BG_ECUDA;
+    }
+    return BG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// H2: type table.  One warp per (type, feature): lane-strided partial sums in a fixed order, then a
+// fixed butterfly.  M is small (tens of program nodes per building).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) type_table_kernel(const float* __restrict__ lx, const int64_t* __restrict__ ltype,
+                                                              int64_t M, int F, int K, float* __restrict__ table) {
+    const int w = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= K * F) return;
+    const int t = w / F, f = w % F;
+    float sum = 0.f, cnt = 0.f;
+    for (int64_t r = lane; r < M; r += 32) {
+        if (ltype[r] == (int64_t)t) {
+            sum += lx[r * F + f];
+            cnt += 1.f;
+        }
+    }
+    sum = group_sum<32>(sum);
+    cnt = group_sum<32>(cnt);
+    if (lane == 0) table[t * F + f] = cnt > 0.f ? sum / cnt : 0.f;
+}
+
+// Backward of the type gather: per-CTA partial [K][C] over a row chunk, last CTA folds.
+__global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __restrict__ g, int64_t ld, const int32_t* __restrict__ type,
+                                                                int64_t N, int C, int K, int G, float* out,
+                                                                unsigned int* counter, float* partials) {
+    extern __shared__ float acc[];  // [K*C]
+    const int64_t chunk = ceil_div(N, G);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    // thread c owns column c (C <= kThreads): rows are visited in order => fixed summation order
+    for (int i = threadIdx.x; i < K * C; i += kThreads) acc[i] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads)
+        for (int64_t r = r0; r < r1; ++r) acc[__ldg(type + r) * C + c] += __ldg(g + r * ld + c);
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * C; i += kThreads) partials[(int64_t)blockIdx.x * K * C + i] = acc[i];
+    if (!last_cta_ticket(counter, gridDim.x)) return;
+    for (int i = threadIdx.x; i < K * C; i += kThreads) {
+        float t = 0.f;
+        for (int q = 0; q < G; ++q) t += partials[(int64_t)q * K * C + i];
+        out[i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// H7: Gumbel-softmax + straight-through, one thread per row (K <= 16)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
+                                                              int64_t N, int K, float* __restrict__ soft, float* __restrict__ hard,
+                                                              int32_t* __restrict__ amax) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= N) return;
+    float v[16], mx = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        v[k] = (logits[r * K + k] + noise[r * K + k]) / 1.0f;
+        mx = fmaxf(mx, v[k]);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) {
+        v[k] = expf(v[k] - mx);
+        sum += v[k];
+    }
+    int best = 0;
+    float bv = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        v[k] = v[k] / sum;
+        if (v[k] > bv) {  // first maximum wins, as torch.argmax does
+            bv = v[k];
+            best = k;
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        soft[r * K + k] = v[k];
+        const float one = (k == best) ? 1.f : 0.f;
+        hard[r * K + k] = (one - v[k]) + v[k];  // label_hard - label_soft.detach() + label_soft
+    }
+    if (amax) amax[r] = best;
+}
+
+__global__ void __launch_bounds__(kThreads) gumbel_bwd_kernel(const float* __restrict__ g_hard, const float* __restrict__ g_soft,
+                                                              const float* __restrict__ soft, int64_t N, int K,
+                                                              float* __restrict__ g_logits) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= N) return;
+    float g[16], dot = 0.f;
+    for (int k = 0; k < K; ++k) {
+        g[k] = (g_hard ? g_hard[r * K + k] : 0.f) + (g_soft ? g_soft[r * K + k] : 0.f);
+        dot = fmaf(g[k], soft[r * K + k], dot);
+    }
+    for (int k = 0; k < K; ++k) g_logits[r * K + k] = soft[r * K + k] * (g[k] - dot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic segment primitives (one warp per segment)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) segment_softmax_kernel(const float* __restrict__ v, const int32_t* __restrict__ ptr,
+                                                                   int64_t S, float* __restrict__ out) {
+    const int64_t sgm = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (sgm >= S) return;
+    const int b = ptr[sgm], e = ptr[sgm + 1];
+    float mx = -INFINITY;
+    for (int i = b + lane; i < e; i += 32) mx = fmaxf(mx, v[i]);
+    mx = group_max<32>(mx);
+    float sum = 0.f;
+    for (int i = b + lane; i < e; i += 32) sum += expf(v[i] - mx);
+    sum = group_sum<32>(sum) + 1e-16f;
+    for (int i = b + lane; i < e; i += 32) out[i] = expf(v[i] - mx) / sum;
+}
+
+__global__ void __launch_bounds__(kThreads) segment_pool_kernel(const float* __restrict__ x, const int32_t* __restrict__ ptr,
+                                                                int64_t S, int C, int mode, float* __restrict__ out) {
+    // one CTA per segment; thread c owns column c and walks the rows in order
+    const int64_t sgm = blockIdx.x;
+    if (sgm >= S) return;
+    const int b = ptr[sgm], e = ptr[sgm + 1];
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+        float a = mode == 1 ? -INFINITY : 0.f;
+        for (int r = b; r < e; ++r) {
+            const float t = x[(int64_t)r * C + c];
+            a = mode == 1 ? fmaxf(a, t) : a + t;
+        }
+        if (mode == 0) a = a / (float)max(1, e - b);
+        if (mode == 1 && e == b) a = 0.f;
+        out[sgm * C + c] = a;
+    }
+}
+
+}  // namespace bg
+
+using namespace bg;
+
+extern "C" int bg_version(void) { return 100; }
+extern "C" const char* bg_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// H1: host CSR/CSC build.  Stable counting sort by destination keeps, per row, the COO order of the
+// input (the reference's CPU scatter order); the self loop goes last.  No CUDA calls.
+// ---------------------------------------------------------------------------------------------
+extern "C" int bg_csr_build_host(const int64_t* coo, int64_t E_in, int64_t N, int32_t* rowptr, int32_t* col,
+                                 int32_t* cscptr, int32_t* cscrow, int32_t* perm, int64_t* E_out, int32_t* max_deg) {
+    BG_REQUIRE(rowptr && col && cscptr && cscrow && perm && E_out && max_deg, BG_EINVAL, "bg_csr_build_host: null output");
+    BG_REQUIRE(N > 0 && E_in >= 0 && (coo || E_in == 0), BG_EINVAL, "bg_csr_build_host: bad sizes N=%lld E=%lld",
+               (long long)N, (long long)E_in);
+    BG_REQUIRE(N < (int64_t)1 << 31 && E_in + N < (int64_t)1 << 31, BG_ERANGE, "bg_csr_build_host: graph exceeds int32 indexing");
+    const int64_t* src = coo;
+    const int64_t* dst = coo + E_in;
+    std::vector<int32_t> indeg(N + 1, 0), outdeg(N + 1, 0);
+    for (int64_t e = 0; e < E_in; ++e) {
+        const int64_t s = src[e], t = dst[e];
+        if (s < 0 || s >= N || t < 0 || t >= N) {
+            set_error("bg_csr_build_host: edge %lld = (%lld -> %lld) out of range [0,%lld)", (long long)e, (long long)s,
+                      (long long)t, (long long)N);
+            return BG_ERANGE;
+        }
+        if (s == t) continue;  // remove_self_loops
+        ++indeg[t];
+        ++outdeg[s];
+    }
+    rowptr[0] = 0;
+    cscptr[0] = 0;
+    int32_t md = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        rowptr[i + 1] = rowptr[i] + indeg[i] + 1;  // +1: add_self_loops
+        cscptr[i + 1] = cscptr[i] + outdeg[i] + 1;
+        md = std::max(md, indeg[i] + 1);
+    }
+    std::vector<int32_t> rfill(rowptr, rowptr + N), cfill(cscptr, cscptr + N);
+    // CSR fill in COO order
+    for (int64_t e = 0; e < E_in; ++e) {
+        const int64_t s = src[e], t = dst[e];
+        if (s == t) continue;
+        col[rfill[t]++] = (int32_t)s;
+    }
+    for (int64_t i = 0; i < N; ++i) col[rfill[i]++] = (int32_t)i;  // self loop last
+    // CSC: walk the CSR in order so every source's out-edges are listed by ascending destination
+    for (int64_t i = 0; i < N; ++i)
+        for (int32_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int32_t s = col[e];
+            const int32_t k = cfill[s]++;
+            cscrow[k] = (int32_t)i;
+            perm[k] = e;
+        }
+    *E_out = rowptr[N];
+    *max_deg = md;
+    return BG_OK;
+}
+
+extern "C" int bg_type_table(const float* local_x, const int64_t* local_type, int64_t M, int32_t F, int32_t K, float* table,
+                             void* stream) {
+    BG_REQUIRE(local_x && local_type && table, BG_EINVAL, "bg_type_table: null pointer");
+    BG_REQUIRE(M >= 0 && F > 0 && K > 0, BG_EINVAL, "bg_type_table: bad sizes");
+    const int warps = K * F;
+    type_table_kernel<<<(unsigned)ceil_div(warps * 32, kThreads), kThreads, 0, as_stream(stream)>>>(local_x, local_type, M, F, K, table);
+    return check_launch("bg_type_table");
+}
+
+static inline int scatter_splits(int64_t N) {
+    int64_t g = ceil_div(N, 128);
+    if (g > kSMs) g = kSMs;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" size_t bg_type_scatter_sum_ws(int64_t N, int32_t C, int32_t K) {
+    return 256 + (size_t)scatter_splits(N) * (size_t)K * (size_t)C * sizeof(float);
+}
+
+extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* type, int64_t N, int32_t C, int32_t K, float* out,
+                                   float* workspace, size_t ws_bytes, void* stream) {
+    BG_REQUIRE(g && type && out && workspace, BG_EINVAL, "bg_type_scatter_sum: null pointer");
+    BG_REQUIRE(ws_bytes >= bg_type_scatter_sum_ws(N, C, K), BG_EINVAL, "bg_type_scatter_sum: workspace too small");
+    BG_REQUIRE((size_t)K * C * sizeof(float) <= 48 * 1024, BG_EUNSUPPORTED, "bg_type_scatter_sum: K*C too large");
+    const int G = scatter_splits(N);
+    type_scatter_kernel<<<G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream)>>>(
+        g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + 64);
+    return check_launch("bg_type_scatter_sum");
+}
+
+extern "C" int bg_gumbel_st_fwd(const float* logits, const float* noise, int64_t N, int32_t K, float* soft, float* hard,
+                                int32_t* argmax, void* stream) {
+    BG_REQUIRE(logits && noise && soft && hard, BG_EINVAL, "bg_gumbel_st_fwd: null pointer");
+    BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_gumbel_st_fwd: K=%d not in [1,16]", K);
+    gumbel_fwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(logits, noise, N, K, soft, hard, argmax);
+    return check_launch("bg_gumbel_st_fwd");
+}
+
+extern "C" int bg_gumbel_st_bwd(const float* g_hard, const float* g_soft, const float* soft, int64_t N, int32_t K,
+                                float* g_logits, void* stream) {
+    BG_REQUIRE(soft && g_logits && (g_hard || g_soft), BG_EINVAL, "bg_gumbel_st_bwd: null pointer");
+    BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_gumbel_st_bwd: K=%d not in [1,16]", K);
+    gumbel_bwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(g_hard, g_soft, soft, N, K, g_logits);
+    return check_launch("bg_gumbel_st_bwd");
+}
+
+extern "C" int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_t S, float* out, void* stream) {
+    BG_REQUIRE(v && seg_ptr && out, BG_EINVAL, "bg_segment_softmax: null pointer");
+    if (S <= 0) return BG_OK;
+    segment_softmax_kernel<<<(unsigned)ceil_div(S * 32, kThreads), kThreads, 0, as_stream(stream)>>>(v, seg_ptr, S, out);
+    return check_launch("bg_segment_softmax");
+}
+
+extern "C" int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S, int32_t C, int32_t mode, float* out,
+                               void* stream) {
+    BG_REQUIRE(x && seg_ptr && out, BG_EINVAL, "bg_segment_pool: null pointer");
+    BG_REQUIRE(mode >= 0 && mode <= 2, BG_EINVAL, "bg_segment_pool: mode must be 0 (mean), 1 (max) or 2 (sum)");
+    if (S <= 0) return BG_OK;
+    segment_pool_kernel<<<(unsigned)S, kThreads, 0, as_stream(stream)>>>(x, seg_ptr, S, C, mode, out);
+    return check_launch("bg_segment_pool");
+}

@@ -1,0 +1,490 @@
+"""ctypes binding of ``libbgb200.so`` (C ABI declared in ``include/bg_b200.h``).
+
+Host side of the drop-in boundary: torch owns every buffer (device memory, streams); this module
+passes raw pointers + the current CUDA stream to the library and raises ``RuntimeError`` with
+``bg_last_error()`` on any non-zero return.  There is NO fallback of any kind: if the shared
+library has not been built (``python -c "import __graft_entry__ as g; g.build()"``) every entry
+point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbgb200.so")
+MAX_SEG = 5
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+SUPPORTED_WIDTHS = (1, 2, 4, 8, 16, 32, 64, 128)
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+
+
+class BgGraph(C.Structure):
+    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("cscptr", C.c_void_p), ("cscrow", C.c_void_p),
+                ("perm", C.c_void_p), ("graph_ptr", C.c_void_p), ("N", C.c_int64), ("E", C.c_int64),
+                ("B", C.c_int32), ("max_deg", C.c_int32)]
+
+
+class BgSeg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("gather", C.c_void_p), ("width", C.c_int32), ("ld", C.c_int32)]
+
+
+class BgDense(C.Structure):
+    _fields_ = [("N", C.c_int64), ("nseg", C.c_int32), ("seg", BgSeg * MAX_SEG), ("W", C.c_void_p),
+                ("w_so", C.c_int64), ("w_sk", C.c_int64), ("Cout", C.c_int32), ("bias", C.c_void_p),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("act", C.c_int32), ("att_src", C.c_void_p),
+                ("att_dst", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64), ("xhat", C.c_void_p),
+                ("rstd", C.c_void_p), ("s", C.c_void_p), ("d", C.c_void_p)]
+
+
+class BgWgrad(C.Structure):
+    _fields_ = [("N", C.c_int64), ("gz", C.c_void_p), ("ld_gz", C.c_int64), ("Cout", C.c_int32), ("nseg", C.c_int32),
+                ("seg", BgSeg * MAX_SEG), ("dW", C.c_void_p), ("ld_dw", C.c_int64), ("accumulate", C.c_int32),
+                ("workspace", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+_P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+SIGNATURES = {
+    "bg_version": (C.c_int, []),
+    "bg_last_error": (C.c_char_p, []),
+    "bg_csr_build_host": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "bg_type_table": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "bg_type_scatter_sum": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
+    "bg_type_scatter_sum_ws": (_SZ, [_I64, _I32, _I32]),
+    "bg_dense_fwd": (C.c_int, [C.POINTER(BgDense), _P]),
+    "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
+    "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
+    "bg_ln_act_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "bg_ln_act_bwd_ws": (_SZ, [_I64, _I32]),
+    "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
+    "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
+    "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),
+    "bg_graphnorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I64, _I32, _F, _P, _P, _P, _SZ, _P]),
+    "bg_graphnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _I64, _I32, _P, _P, _I32, _P, _P, _SZ, _P]),
+    "bg_graphnorm_bwd2": (C.c_int, [_P] * 8 + [_F, _I64, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "bg_graphnorm_ws": (_SZ, [_I64, _I32]),
+    "bg_gumbel_st_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "bg_gumbel_st_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "bg_segment_softmax": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "bg_segment_pool": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "bg_axpy": (C.c_int, [_P, _P, _F, _I64, _P]),
+    "bg_fill": (C.c_int, [_P, _F, _I64, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libbgb200.so and bind every symbol of the header.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a kernel library has not been built. Run "
+                "`python -c \"import __graft_entry__ as g; g.build()\"` (or `make -C <pkg>/csrc`). "
+                "There is no CPU/torch fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().bg_last_error().decode()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libbgb200 error {rc}: {last_error()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: libbgb200 kernels need CUDA tensors (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    return t
+
+
+def _cf32(t: Tensor, name: str) -> Tensor:
+    _f32(t, name)
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace: one persistent zero-initialised buffer per (device, stream); the first 256 bytes hold
+# the self-resetting ticket counter of the "last CTA folds" reductions.
+# ------------------------------------------------------------------------------------------------
+_workspaces: Dict[Tuple[int, int], Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    need = (nbytes + 3) // 4
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.float32, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# H1: host graph build
+# ------------------------------------------------------------------------------------------------
+def csr_build_host(edge_index: Tensor, num_nodes: int):
+    lib = load()
+    assert edge_index.dtype == torch.int64 and edge_index.device.type == "cpu" and edge_index.dim() == 2
+    ei = edge_index.contiguous()
+    e_in = int(ei.shape[1])
+    cap = e_in + num_nodes
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32)
+    cscptr = torch.empty(num_nodes + 1, dtype=torch.int32)
+    col = torch.empty(cap, dtype=torch.int32)
+    cscrow = torch.empty(cap, dtype=torch.int32)
+    perm = torch.empty(cap, dtype=torch.int32)
+    e_out, max_deg = C.c_int64(0), C.c_int32(0)
+    _check(lib.bg_csr_build_host(ei.data_ptr(), e_in, num_nodes, rowptr.data_ptr(), col.data_ptr(), cscptr.data_ptr(),
+                                 cscrow.data_ptr(), perm.data_ptr(), C.byref(e_out), C.byref(max_deg)))
+    e = int(e_out.value)
+    arrays = dict(rowptr=rowptr, col=col[:e].clone() if e < cap else col, cscptr=cscptr,
+                  cscrow=cscrow[:e].clone() if e < cap else cscrow, perm=perm[:e].clone() if e < cap else perm)
+    return arrays, e, int(max_deg.value)
+
+
+def make_bg_graph(csr) -> BgGraph:
+    g = BgGraph()
+    g.rowptr, g.col = csr.rowptr.data_ptr(), csr.col.data_ptr()
+    g.cscptr, g.cscrow, g.perm = csr.cscptr.data_ptr(), csr.cscrow.data_ptr(), csr.perm.data_ptr()
+    g.graph_ptr = csr.graph_ptr.data_ptr()
+    g.N, g.E, g.B, g.max_deg = csr.num_nodes, csr.num_edges, csr.num_graphs, csr.max_deg
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# H2
+# ------------------------------------------------------------------------------------------------
+def type_table(local_x: Tensor, local_type: Tensor, num_types: int) -> Tensor:
+    lib = load()
+    x = _cf32(local_x, "local_x")
+    t = local_type.contiguous()
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    table = torch.empty(num_types, x.shape[1], dtype=torch.float32, device=x.device)
+    _check(lib.bg_type_table(x.data_ptr(), t.data_ptr(), x.shape[0], x.shape[1], num_types, table.data_ptr(), _stream()))
+    return table
+
+
+def type_scatter_sum(g: Tensor, type32: Tensor, num_types: int, width: Optional[int] = None) -> Tensor:
+    """out[t] = sum of rows of g[:, :width] whose type is t (backward of table[type])."""
+    lib = load()
+    _f32(g, "g")
+    assert g.stride(1) == 1 and type32.dtype == torch.int32
+    n, c = g.shape[0], (width or g.shape[1])
+    out = torch.empty(num_types, c, dtype=torch.float32, device=g.device)
+    nb = lib.bg_type_scatter_sum_ws(n, c, num_types)
+    ws = workspace(nb, g.device)
+    _check(lib.bg_type_scatter_sum(g.data_ptr(), g.stride(0), type32.data_ptr(), n, c, num_types, out.data_ptr(),
+                                   ws.data_ptr(), ws.numel() * 4, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------------
+Seg = Union[None, Tensor, Tuple[Tensor, Optional[Tensor]]]
+
+
+def _fill_segs(arr, segs: Sequence[Seg]) -> Tuple[int, int]:
+    if not 1 <= len(segs) <= MAX_SEG:
+        raise RuntimeError(f"dense input needs 1..{MAX_SEG} segments, got {len(segs)}")
+    n_rows, k = -1, 0
+    for i, sg in enumerate(segs):
+        if sg is None:  # column of ones
+            arr[i].ptr, arr[i].gather, arr[i].width, arr[i].ld = None, None, 1, 0
+            k += 1
+            continue
+        t, gather = sg if isinstance(sg, tuple) else (sg, None)
+        _f32(t, f"segment {i}")
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise RuntimeError(f"segment {i}: expected a 2-D tensor with unit column stride")
+        arr[i].ptr, arr[i].width, arr[i].ld = t.data_ptr(), t.shape[1], t.stride(0)
+        if gather is not None:
+            assert gather.dtype == torch.int32 and gather.is_contiguous()
+            arr[i].gather = gather.data_ptr()
+            rows = gather.shape[0]
+        else:
+            arr[i].gather = None
+            rows = t.shape[0]
+        if n_rows not in (-1, rows):
+            raise RuntimeError(f"segment {i}: row count {rows} != {n_rows}")
+        n_rows = rows
+        k += t.shape[1]
+    return n_rows, k
+
+
+def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln: Optional[Tuple[Tensor, Tensor]] = None,
+              act: int = ACT_NONE, att: Optional[Tuple[Tensor, Tensor]] = None, transposed: bool = False,
+              save_ln: bool = False, out: Optional[Tensor] = None, cols: Optional[Tuple[int, int]] = None):
+    """out = act(LN(X @ Wop^T + bias)).  ``transposed=False``: Wop = W ([Cout,K]).  ``transposed=True``:
+    Wop = W^T, i.e. out = X @ W (the backward-input product); ``cols=(a,b)`` then restricts the output to
+    columns a..b of W (only those input gradients are needed).  Returns a dict of the produced tensors."""
+    lib = load()
+    a = BgDense()
+    n, k = _fill_segs(a.seg, segs)
+    _cf32(W, "W")
+    if transposed:
+        lo, hi = cols if cols is not None else (0, W.shape[1])
+        if W.shape[0] != k:
+            raise RuntimeError(f"dense_fwd(transposed): X has {k} columns but W has {W.shape[0]} rows")
+        cout, wptr, w_so, w_sk = hi - lo, W.data_ptr() + 4 * lo, 1, W.stride(0)
+    else:
+        if W.shape[1] != k:
+            raise RuntimeError(f"dense_fwd: X has {k} columns but W expects {W.shape[1]}")
+        cout, wptr, w_so, w_sk = W.shape[0], W.data_ptr(), W.stride(0), 1
+    dev = W.device
+    if out is None:
+        out = torch.empty(n, cout, dtype=torch.float32, device=dev)
+    res = {"out": out}
+    a.N, a.nseg, a.W, a.w_so, a.w_sk, a.Cout = n, len(segs), wptr, w_so, w_sk, cout
+    a.bias = _p(bias)
+    a.act = act
+    if ln is not None:
+        a.ln_gamma, a.ln_beta = ln[0].data_ptr(), ln[1].data_ptr()
+        if save_ln:
+            res["xhat"] = torch.empty(n, cout, dtype=torch.float32, device=dev)
+            res["rstd"] = torch.empty(n, dtype=torch.float32, device=dev)
+            a.xhat, a.rstd = res["xhat"].data_ptr(), res["rstd"].data_ptr()
+    if att is not None:
+        a.att_src, a.att_dst = att[0].data_ptr(), att[1].data_ptr()
+        res["s"] = torch.empty(n, dtype=torch.float32, device=dev)
+        res["d"] = torch.empty(n, dtype=torch.float32, device=dev)
+        a.s, a.d = res["s"].data_ptr(), res["d"].data_ptr()
+    a.out, a.ld_out = out.data_ptr(), out.stride(0)
+    _check(lib.bg_dense_fwd(C.byref(a), _stream()))
+    return res
+
+
+def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """dW[o,k] = sum_n gz[n,o] X[n,k]; a ``None`` segment is a column of ones (=> bias gradient column)."""
+    lib = load()
+    a = BgWgrad()
+    _f32(gz, "gz")
+    assert gz.dim() == 2 and gz.stride(1) == 1
+    n, k = _fill_segs(a.seg, segs)
+    if n == -1:
+        n = gz.shape[0]
+    cout = gz.shape[1]
+    if dW is None:
+        dW = torch.empty(cout, k, dtype=torch.float32, device=gz.device)
+        accumulate = False
+    assert dW.stride(1) == 1 or dW.shape[1] == 1
+    nb = lib.bg_dense_wgrad_ws(n, cout, k)
+    ws = workspace(nb + 256, gz.device)
+    a.N, a.gz, a.ld_gz, a.Cout, a.nseg = n, gz.data_ptr(), gz.stride(0), cout, len(segs)
+    a.dW, a.ld_dw, a.accumulate = dW.data_ptr(), dW.stride(0), int(accumulate)
+    a.workspace, a.ws_bytes = ws.data_ptr() + 256, ws.numel() * 4 - 256
+    _check(lib.bg_dense_wgrad(C.byref(a), _stream()))
+    return dW
+
+
+def ln_act_bwd(gout: Tensor, out: Tensor, act: int, xhat: Optional[Tensor] = None, rstd: Optional[Tensor] = None,
+               gamma: Optional[Tensor] = None, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None,
+               accumulate: bool = False):
+    """Pre-activation gradient gz of [LayerNorm +] activation; LayerNorm path also returns dgamma, dbeta."""
+    lib = load()
+    _cf32(gout, "gout"), _cf32(out, "out")
+    n, c = out.shape
+    gz = torch.empty_like(out)
+    if xhat is None:
+        _check(lib.bg_ln_act_bwd(gout.data_ptr(), out.data_ptr(), None, None, None, n, c, act, gz.data_ptr(), None, None, 0,
+                                 None, 0, _stream()))
+        return gz, None, None
+    if dgamma is None:
+        dgamma = torch.empty(c, dtype=torch.float32, device=out.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=out.device)
+        accumulate = False
+    nb = lib.bg_ln_act_bwd_ws(n, c)
+    ws = workspace(nb, out.device)
+    _check(lib.bg_ln_act_bwd(gout.data_ptr(), out.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), n, c, act,
+                             gz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate), ws.data_ptr(),
+                             ws.numel() * 4, _stream()))
+    return gz, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------
+# GAT aggregation
+# ------------------------------------------------------------------------------------------------
+def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope: float = 0.2):
+    lib = load()
+    _cf32(h, "h")
+    n, c = h.shape
+    out = torch.empty_like(h)
+    m = torch.empty(n, dtype=torch.float32, device=h.device)
+    z = torch.empty(n, dtype=torch.float32, device=h.device)
+    _check(lib.bg_gat_fwd(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
+                          m.data_ptr(), z.data_ptr(), c, slope, _stream()))
+    return out, m, z
+
+
+def gat_bwd(csr, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Tensor, a_src: Tensor, a_dst: Tensor,
+            slope: float = 0.2):
+    """Returns gh_tot[N,C], gsd[N,2], and the per-edge scratch (P, DU)."""
+    lib = load()
+    _cf32(gout, "gout")
+    n, c = h.shape
+    dev = h.device
+    P = torch.empty(csr.num_edges, dtype=torch.float32, device=dev)
+    DU = torch.empty(csr.num_edges, dtype=torch.float32, device=dev)
+    gh = torch.empty_like(h)
+    gsd = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    _check(lib.bg_gat_bwd(C.byref(csr.c_struct()), gout.data_ptr(), h.data_ptr(), s.data_ptr(), d.data_ptr(), m.data_ptr(),
+                          z.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), P.data_ptr(), DU.data_ptr(), gh.data_ptr(),
+                          gsd.data_ptr(), c, slope, _stream()))
+    return gh, gsd, P, DU
+
+
+def gat_bwd2(csr, Ht: Tensor, St: Tensor, Dt: Tensor, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Tensor,
+             a_src: Tensor, a_dst: Tensor, slope: float = 0.2):
+    """Cotangents (Ht,St,Dt) on (gh,gs,gd) -> gt[N,C] (on gout), ht_tot[N,C] (on h, incl. s/d paths), sdt[N,2]."""
+    lib = load()
+    _cf32(Ht, "Ht")
+    n, c = h.shape
+    dev = h.device
+    scratch = torch.empty(4 * csr.num_edges, dtype=torch.float32, device=dev)
+    gt = torch.empty_like(h)
+    ht = torch.empty_like(h)
+    sdt = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    _check(lib.bg_gat_bwd2(C.byref(csr.c_struct()), Ht.data_ptr(), St.data_ptr(), Dt.data_ptr(), gout.data_ptr(), h.data_ptr(),
+                           s.data_ptr(), d.data_ptr(), m.data_ptr(), z.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
+                           scratch.data_ptr(), gt.data_ptr(), ht.data_ptr(), sdt.data_ptr(), c, slope, _stream()))
+    return gt, ht, sdt
+
+
+# ------------------------------------------------------------------------------------------------
+# GraphNorm + ReLU + dropout mask
+# ------------------------------------------------------------------------------------------------
+def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optional[Tensor], keep_scale: float,
+                  eps: float = 1e-5):
+    lib = load()
+    _cf32(o, "o")
+    n, c = o.shape
+    x1 = torch.empty_like(o)
+    stats = torch.empty(3 * c, dtype=torch.float32, device=o.device)
+    ws = workspace(lib.bg_graphnorm_ws(n, c), o.device)
+    if keep is not None:
+        assert keep.dtype == torch.uint8 and keep.is_contiguous() and keep.shape == o.shape
+    _check(lib.bg_graphnorm_fwd(o.data_ptr(), w.data_ptr(), beta.data_ptr(), alpha.data_ptr(), _p(keep), keep_scale, n, c, eps,
+                                x1.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream()))
+    return x1, stats
+
+
+def graphnorm_bwd(gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, alpha: Tensor, stats: Tensor, keep_scale: float,
+                  dparams: Optional[Tensor] = None, accumulate: bool = False):
+    """Returns go, dparams[3,C] = (dw, dbeta, dalpha), bstats[2C]."""
+    lib = load()
+    _cf32(gx1, "gx1")
+    n, c = o.shape
+    go = torch.empty_like(o)
+    if dparams is None:
+        dparams = torch.empty(3, c, dtype=torch.float32, device=o.device)
+        accumulate = False
+    bstats = torch.empty(2 * c, dtype=torch.float32, device=o.device)
+    ws = workspace(lib.bg_graphnorm_ws(n, c), o.device)
+    _check(lib.bg_graphnorm_bwd(gx1.data_ptr(), o.data_ptr(), x1.data_ptr(), w.data_ptr(), alpha.data_ptr(), stats.data_ptr(),
+                                keep_scale, n, c, go.data_ptr(), dparams.data_ptr(), int(accumulate), bstats.data_ptr(),
+                                ws.data_ptr(), ws.numel() * 4, _stream()))
+    return go, dparams, bstats
+
+
+def graphnorm_bwd2(Xt: Tensor, gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, alpha: Tensor, stats: Tensor, bstats: Tensor,
+                   keep_scale: float, dparams2: Optional[Tensor] = None, accumulate: bool = False):
+    """Cotangent Xt on go -> gx1t (on gx1), ot (on o), dparams2[3,C] (on w, beta, alpha)."""
+    lib = load()
+    _cf32(Xt, "Xt")
+    n, c = o.shape
+    gx1t = torch.empty_like(o)
+    ot = torch.empty_like(o)
+    if dparams2 is None:
+        dparams2 = torch.empty(3, c, dtype=torch.float32, device=o.device)
+        accumulate = False
+    ws = workspace(lib.bg_graphnorm_ws(n, c), o.device)
+    _check(lib.bg_graphnorm_bwd2(Xt.data_ptr(), gx1.data_ptr(), o.data_ptr(), x1.data_ptr(), w.data_ptr(), alpha.data_ptr(),
+                                 stats.data_ptr(), bstats.data_ptr(), keep_scale, n, c, gx1t.data_ptr(), ot.data_ptr(),
+                                 dparams2.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream()))
+    return gx1t, ot, dparams2
+
+
+# ------------------------------------------------------------------------------------------------
+# Gumbel straight-through, segment primitives, utilities
+# ------------------------------------------------------------------------------------------------
+def gumbel_st_fwd(logits: Tensor, noise: Tensor):
+    lib = load()
+    _cf32(logits, "logits"), _cf32(noise, "noise")
+    n, k = logits.shape
+    soft, hard = torch.empty_like(logits), torch.empty_like(logits)
+    amax = torch.empty(n, dtype=torch.int32, device=logits.device)
+    _check(lib.bg_gumbel_st_fwd(logits.data_ptr(), noise.data_ptr(), n, k, soft.data_ptr(), hard.data_ptr(), amax.data_ptr(),
+                                _stream()))
+    return soft, hard, amax
+
+
+def gumbel_st_bwd(g_hard: Optional[Tensor], g_soft: Optional[Tensor], soft: Tensor) -> Tensor:
+    lib = load()
+    n, k = soft.shape
+    gl = torch.empty_like(soft)
+    _check(lib.bg_gumbel_st_bwd(_p(g_hard), _p(g_soft), soft.data_ptr(), n, k, gl.data_ptr(), _stream()))
+    return gl
+
+
+def segment_softmax(v: Tensor, seg_ptr: Tensor) -> Tensor:
+    lib = load()
+    _cf32(v, "v")
+    assert seg_ptr.dtype == torch.int32
+    out = torch.empty_like(v)
+    _check(lib.bg_segment_softmax(v.data_ptr(), seg_ptr.data_ptr(), seg_ptr.numel() - 1, out.data_ptr(), _stream()))
+    return out
+
+
+def segment_pool(x: Tensor, seg_ptr: Tensor, mode: str = "mean") -> Tensor:
+    lib = load()
+    _cf32(x, "x")
+    assert seg_ptr.dtype == torch.int32
+    s = seg_ptr.numel() - 1
+    out = torch.empty(s, x.shape[1], dtype=torch.float32, device=x.device)
+    _check(lib.bg_segment_pool(x.data_ptr(), seg_ptr.data_ptr(), s, x.shape[1], {"mean": 0, "max": 1, "sum": 2}[mode],
+                               out.data_ptr(), _stream()))
+    return out
+
+
+def axpy_(y: Tensor, x: Tensor, a: float = 1.0) -> Tensor:
+    lib = load()
+    _cf32(y, "y"), _cf32(x, "x")
+    assert y.numel() == x.numel()
+    _check(lib.bg_axpy(y.data_ptr(), x.data_ptr(), a, y.numel(), _stream()))
+    return y
+
+
+def fill_(y: Tensor, v: float) -> Tensor:
+    lib = load()
+    _cf32(y, "y")
+    _check(lib.bg_fill(y.data_ptr(), v, y.numel(), _stream()))
+    return y

@@ -1,0 +1,199 @@
+/*
+ * bg_b200.h - C ABI of libbgb200.so: the B200 (sm_100a) kernels behind the Building-GAN
+ * voxel-graph message-passing hot path.
+ *
+ * Every entry point replaces work the reference does through torch / torch_geometric ops
+ * (the reference has no native code of its own); the interface each one stands in for is
+ * cited as reference file:line next to it.  Conventions:
+ *
+ *   - pure C, POD only; device pointers are raw `float*` / `int32_t*`, `stream` is a
+ *     `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - the library never allocates, frees or synchronises: inputs, outputs, saved tensors and
+ *     workspaces are caller-owned; every launch goes to the caller's stream, so a sequence of
+ *     calls is CUDA-graph capturable;
+ *   - return 0 on success, a negative BG_E* code otherwise; `bg_last_error()` returns a
+ *     thread-local human-readable message.  There is NO CPU fallback.
+ *   - all activations are row-major fp32 `[N, C]`; supported GNN channel widths are
+ *     C in {1,2,4,8,16,32,64,128} (the reference's hourglass, models.py:68-88,187-208).
+ */
+#ifndef BG_B200_H
+#define BG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_OK 0
+#define BG_EINVAL (-1)   /* bad argument                                  */
+#define BG_EUNSUPPORTED (-2) /* width / mode not compiled                 */
+#define BG_ECUDA (-3)    /* launch failure reported by cudaGetLastError() */
+#define BG_ERANGE (-4)   /* index out of range in host-side graph build   */
+
+/* Borrowed-pointer view of one collated voxel batch (built once per batch, H1).
+ * rowptr/col: in-edges of each destination node (source ids), input self loops removed and one
+ * self loop appended LAST (GATConv add_self_loops, reference models.py:72 -> PyG GATConv);
+ * per-row order = COO order = the reference's CPU scatter order.
+ * cscptr/cscrow/perm: out-edges of each source node, and for each the index of the same edge in
+ * the CSR arrays.  graph_ptr: node range of each building (Batch.ptr, data.py:160-161). */
+typedef struct BgGraph {
+    const int32_t* rowptr;    /* [N+1] */
+    const int32_t* col;       /* [E]   */
+    const int32_t* cscptr;    /* [N+1] */
+    const int32_t* cscrow;    /* [E]   */
+    const int32_t* perm;      /* [E]   */
+    const int32_t* graph_ptr; /* [B+1] */
+    int64_t N;
+    int64_t E; /* edges incl. the N self loops */
+    int32_t B;
+    int32_t max_deg;
+} BgGraph;
+
+int bg_version(void);
+const char* bg_last_error(void);
+
+/* ---- H1: collation (reference data.py:156-163 Batch.from_data_list; PyG GATConv's
+ * remove_self_loops + add_self_loops that the reference re-runs inside every conv call).
+ * Host function, no CUDA context touched (fork-safe for DataLoader workers, data.py:177-184).
+ * coo = int64 [2,E_in] (row 0 sources, row 1 targets).  col/cscrow/perm need E_in+N slots.
+ * Writes *E_out (= kept edges + N) and *max_deg. */
+int bg_csr_build_host(const int64_t* coo, int64_t E_in, int64_t N, int32_t* rowptr, int32_t* col,
+                      int32_t* cscptr, int32_t* cscrow, int32_t* perm, int64_t* E_out, int32_t* max_deg);
+
+/* ---- H2: type-matched program features (reference models.py:122-129, 230-237).
+ * table[t,:] = mean of local_x rows with local_type==t (0 if none), K types, F features.
+ * The per-voxel gather table[voxel.type] is fused into the consumers (BgSeg.gather). */
+int bg_type_table(const float* local_x, const int64_t* local_type, int64_t M, int32_t F, int32_t K,
+                  float* table, void* stream);
+/* Backward of the gather: out[t, 0:C] = sum over rows n with type[n]==t of g[n*ld + 0:C]. */
+int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* type, int64_t N, int32_t C, int32_t K,
+                        float* out, float* workspace, size_t ws_bytes, void* stream);
+size_t bg_type_scatter_sum_ws(int64_t N, int32_t C, int32_t K);
+
+/* ---- H3/H4/H6/H8/H10 and the `lin` of every conv: node-wise dense layers
+ * (reference nn.Linear / nn.LayerNorm / nn.LeakyReLU / nn.ReLU at models.py:33-66,92-113,
+ * 177-185,212-225 and torch.cat at models.py:135-141,146,239 - the concatenation is never
+ * materialised: the input is a list of column segments). */
+typedef struct BgSeg {
+    const float* ptr;      /* NULL => a column of ones (used to fold the bias into wgrad) */
+    const int32_t* gather; /* optional row index: row n reads ptr[gather[n]*ld ...]       */
+    int32_t width;
+    int32_t ld; /* row stride in floats */
+} BgSeg;
+#define BG_MAX_SEG 5
+#define BG_ACT_NONE 0
+#define BG_ACT_RELU 1
+#define BG_ACT_LRELU 2 /* LeakyReLU(0.2) */
+
+typedef struct BgDense {
+    int64_t N;
+    int32_t nseg;
+    BgSeg seg[BG_MAX_SEG]; /* K = sum of widths */
+    const float* W;        /* element (o,k) at W[o*w_so + k*w_sk]: [Cout,K] row-major => (K,1);
+                              a transposed use (backward-input) => (1, Cout_fwd)               */
+    int64_t w_so, w_sk;
+    int32_t Cout;
+    const float* bias;                   /* [Cout] or NULL */
+    const float* ln_gamma;               /* [Cout] or NULL => no LayerNorm (eps 1e-5) */
+    const float* ln_beta;
+    int32_t act;
+    const float* att_src;                /* [Cout] or NULL: also emit s = y.att_src, d = y.att_dst */
+    const float* att_dst;
+    float* out; int64_t ld_out;          /* [N,Cout] */
+    float* xhat;                         /* optional [N,Cout] LayerNorm normalised value (saved for backward) */
+    float* rstd;                         /* optional [N] */
+    float* s; float* d;                  /* optional [N] each */
+} BgDense;
+int bg_dense_fwd(const BgDense* a, void* stream);
+
+/* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
+ * yields the bias gradient as an extra column); deterministic split-N reduction.
+ * dW is written with leading dimension ld_dw; accumulate!=0 adds into dW. */
+typedef struct BgWgrad {
+    int64_t N;
+    const float* gz; int64_t ld_gz; int32_t Cout;
+    int32_t nseg;
+    BgSeg seg[BG_MAX_SEG];
+    float* dW; int64_t ld_dw;
+    int32_t accumulate;
+    float* workspace; size_t ws_bytes;
+} BgWgrad;
+size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K);
+int bg_dense_wgrad(const BgWgrad* a, void* stream);
+
+/* Backward of LayerNorm + LeakyReLU(0.2) (or of a bare activation when xhat==NULL):
+ * gz = d loss / d (x W^T + b) from gout, the layer output `out`, xhat, rstd, gamma.
+ * Also column sums dgamma = sum gy*xhat, dbeta = sum gy (deterministic). */
+int bg_ln_act_bwd(const float* gout, const float* out, const float* xhat, const float* rstd,
+                  const float* gamma, int64_t N, int32_t C, int32_t act, float* gz,
+                  float* dgamma, float* dbeta, int32_t accumulate, float* workspace, size_t ws_bytes, void* stream);
+size_t bg_ln_act_bwd_ws(int64_t N, int32_t C);
+
+/* ---- H5a/H9: GATConv attention aggregation (PyG 2.6.1 GATConv.edge_update + message +
+ * aggregate; reference call sites models.py:72,82,192,202).  h = x W^T, s = h.a_src,
+ * d = h.a_dst come from bg_dense_fwd.  out_i = sum_e softmax_i(LeakyReLU(s_j+d_i)) h_j + bias.
+ * Saves the per-row softmax max `m` and denominator `z` (incl. PyG's +1e-16). */
+int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
+               float* out, float* m, float* z, int32_t C, float slope, void* stream);
+/* First-order backward.  Inputs gout[N,C] (= d loss/d out), h, s, d, m, z, a_src, a_dst.
+ * Outputs: gh_tot[N,C] = d loss/d h including the s- and d-paths, gsd[N,2] = (d loss/d s,
+ * d loss/d d) for the attention-vector gradients, and the per-edge scratch P[E], DU[E]
+ * (softmax weights and d loss/d logit, CSR order) that bwd2 reuses. */
+int bg_gat_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
+               const float* m, const float* z, const float* a_src, const float* a_dst,
+               float* P, float* DU, float* gh_tot, float* gsd, int32_t C, float slope, void* stream);
+/* Second-order backward (WGAN-GP, reference trainer.py:306-312 create_graph=True): given the
+ * cotangents Ht[N,C], St[N], Dt[N] on (gh, gs, gd) of bg_gat_bwd, returns
+ * gt[N,C] (cotangent on gout), ht_tot[N,C] (cotangent on h incl. s/d paths) and sdt[N,2]
+ * (cotangents on s, d).  scratch: 4*E floats. */
+int bg_gat_bwd2(const BgGraph* g, const float* Ht, const float* St, const float* Dt, const float* gout,
+                const float* h, const float* s, const float* d, const float* m, const float* z,
+                const float* a_src, const float* a_dst, float* scratch, float* gt, float* ht_tot,
+                float* sdt, int32_t C, float slope, void* stream);
+
+/* ---- H5b/H5c/H9: GraphNorm (called with batch=None => ONE segment over all nodes, reference
+ * models.py:73,83,193,203) fused with ReLU(inplace) and Dropout(0.2) (models.py:74-75).
+ * y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep * keep_scale.
+ * stats[3*C] = (mu, rstd, var) is written by fwd and read by bwd/bwd2.  keep: optional uint8
+ * [N,C] Bernoulli mask drawn by the caller (torch RNG, reference draw order); NULL in eval.
+ * seg_ptr/nseg: segment pointer for per-graph statistics (nseg==1 reproduces the reference). */
+int bg_graphnorm_fwd(const float* o, const float* w, const float* beta, const float* alpha,
+                     const uint8_t* keep, float keep_scale, int64_t N, int32_t C, float eps,
+                     float* x1, float* stats, float* workspace, size_t ws_bytes, void* stream);
+/* gx1 -> go, plus parameter gradients dparams[3*C] = (dw, dbeta, dalpha) and bstats[2*C] =
+ * (G0, G1) saved for bwd2. */
+int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x1, const float* w, const float* alpha,
+                     const float* stats, float keep_scale, int64_t N, int32_t C, float* go, float* dparams,
+                     int32_t accumulate, float* bstats, float* workspace, size_t ws_bytes, void* stream);
+/* Xt = cotangent on go.  Outputs: gx1t (cotangent on gx1), ot (cotangent on o), dparams2[3*C]
+ * (cotangents on w, beta(=0), alpha; accumulated when accumulate!=0). */
+int bg_graphnorm_bwd2(const float* Xt, const float* gx1, const float* o, const float* x1, const float* w,
+                      const float* alpha, const float* stats, const float* bstats, float keep_scale,
+                      int64_t N, int32_t C, float* gx1t, float* ot, float* dparams2, int32_t accumulate,
+                      float* workspace, size_t ws_bytes, void* stream);
+size_t bg_graphnorm_ws(int64_t N, int32_t C);
+
+/* ---- H7: Gumbel-softmax (tau=1) + straight-through one-hot (reference models.py:150-153).
+ * noise = Gumbel(0,1) samples drawn by the caller.  hard = (onehot(argmax soft) - soft) + soft. */
+int bg_gumbel_st_fwd(const float* logits, const float* noise, int64_t N, int32_t K, float* soft,
+                     float* hard, int32_t* argmax, void* stream);
+int bg_gumbel_st_bwd(const float* g_hard, const float* g_soft, const float* soft, int64_t N, int32_t K,
+                     float* g_logits, void* stream);
+
+/* ---- generic segment primitives named by north_star (same machinery as the edge softmax and
+ * the GraphNorm statistics, exposed with an arbitrary segment pointer). */
+int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_t S, float* out, void* stream);
+/* mode 0 = mean, 1 = max, 2 = sum; x[N,C] -> out[S,C] */
+int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S, int32_t C, int32_t mode,
+                    float* out, void* stream);
+
+/* ---- small utilities used by the host-side executor */
+int bg_axpy(float* y, const float* x, float a, int64_t n, void* stream);          /* y += a*x */
+int bg_fill(float* y, float v, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BG_B200_H */

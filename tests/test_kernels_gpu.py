@@ -1,0 +1,275 @@
+"""Per-kernel parity: every C-ABI entry point of libbgb200.so against the oracle (oracle/pyg.py
+evaluated in fp64 on the CPU), on seeded synthetic buildings.  Tolerance: rel 1e-5 of the tensor's
+max magnitude for elementwise/short-sum outputs, 3e-5 for length-N column reductions in fp32
+(stated at each assert).  Integer outputs (argmax) are bit-exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pyg
+from util import assert_close, small_batch
+
+from building_gan_b200 import lib
+
+pytestmark = pytest.mark.gpu
+WIDTHS = [1, 2, 4, 8, 16, 32, 64, 128]
+DEV = "cuda"
+
+
+def _graph(shuffle=False):
+    _, vb = small_batch(shuffle=shuffle)
+    edges = pyg.gat_edges(vb.edge_index, vb.num_nodes)
+    return vb, edges, vb.bg_csr.to(DEV)
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(777 + seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# GAT aggregation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_gat_fwd(C, shuffle):
+    vb, edges, csr = _graph(shuffle)
+    n = vb.num_nodes
+    h, s, d, b = _rand(n, C, seed=1), _rand(n, seed=2), _rand(n, seed=3), _rand(C, seed=4)
+    ref = pyg.gat_core(h, s, d, edges) + b
+    out, m, z = lib.gat_fwd(csr, h.float().to(DEV), s.float().to(DEV), d.float().to(DEV), b.float().to(DEV))
+    assert_close(out, ref, 1e-5, f"gat_fwd C={C}")
+    logit = F.leaky_relu(s[edges[0]] + d[edges[1]], 0.2)
+    mref = pyg.scatter(logit, edges[1], n, "max")
+    assert_close(m, mref, 1e-6, "softmax max")
+    zref = pyg.scatter((logit - mref[edges[1]]).exp(), edges[1], n, "sum") + 1e-16
+    assert_close(z, zref, 1e-5, "softmax denominator")
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+def test_gat_bwd(C):
+    vb, edges, csr = _graph()
+    n = vb.num_nodes
+    h, s, d = (_rand(n, C, seed=1).requires_grad_(), _rand(n, seed=2).requires_grad_(), _rand(n, seed=3).requires_grad_())
+    a_s, a_d, gout = _rand(C, seed=5), _rand(C, seed=6), _rand(n, C, seed=7)
+    out = pyg.gat_core(h, s, d, edges)
+    gh, gs, gd = torch.autograd.grad(out, (h, s, d), gout)
+    gh_tot_ref = gh + gs[:, None] * a_s + gd[:, None] * a_d
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    _, m, z = lib.gat_fwd(csr, f(h), f(s), f(d), None)
+    gh_tot, gsd, P, DU = lib.gat_bwd(csr, f(gout), f(h), f(s), f(d), m, z, f(a_s), f(a_d))
+    assert_close(gh_tot, gh_tot_ref, 1e-5, f"gat_bwd gh_tot C={C}")
+    assert_close(gsd[:, 0], gs, 1e-5, "gat_bwd gs")
+    assert_close(gsd[:, 1], gd, 1e-5, "gat_bwd gd")
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+def test_gat_bwd2(C):
+    """Second-order: VJP of (gh, gs, gd) = bwd(gout, h, s, d) with cotangents (Ht, St, Dt)."""
+    vb, edges, csr = _graph()
+    n = vb.num_nodes
+    h, s, d, gout = (_rand(n, C, seed=1).requires_grad_(), _rand(n, seed=2).requires_grad_(),
+                     _rand(n, seed=3).requires_grad_(), _rand(n, C, seed=7).requires_grad_())
+    a_s, a_d = _rand(C, seed=5), _rand(C, seed=6)
+    Ht, St, Dt = _rand(n, C, seed=8), _rand(n, seed=9), _rand(n, seed=10)
+    out = pyg.gat_core(h, s, d, edges)
+    gh, gs, gd = torch.autograd.grad(out, (h, s, d), gout, create_graph=True)
+    gt, ht, st, dt = torch.autograd.grad((gh, gs, gd), (gout, h, s, d), (Ht, St, Dt))
+    ht_tot_ref = ht + st[:, None] * a_s + dt[:, None] * a_d
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    _, m, z = lib.gat_fwd(csr, f(h), f(s), f(d), None)
+    gt_k, ht_k, sdt = lib.gat_bwd2(csr, f(Ht), f(St), f(Dt), f(gout), f(h), f(s), f(d), m, z, f(a_s), f(a_d))
+    assert_close(gt_k, gt, 1e-5, f"gat_bwd2 gt C={C}")
+    assert_close(sdt[:, 0], st, 1e-5, "gat_bwd2 st")
+    assert_close(sdt[:, 1], dt, 1e-5, "gat_bwd2 dt")
+    assert_close(ht_k, ht_tot_ref, 1e-5, f"gat_bwd2 ht_tot C={C}")
+
+
+def test_gat_deterministic():
+    vb, edges, csr = _graph()
+    n, C = vb.num_nodes, 64
+    f = lambda t: t.float().to(DEV)
+    h, s, d = f(_rand(n, C, seed=1)), f(_rand(n, seed=2)), f(_rand(n, seed=3))
+    a = lib.gat_fwd(csr, h, s, d, None)[0]
+    for _ in range(3):
+        assert torch.equal(a, lib.gat_fwd(csr, h, s, d, None)[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# GraphNorm + ReLU + dropout mask
+# ------------------------------------------------------------------------------------------------
+def _gn_ref(o, w, beta, alpha, keep, scale):
+    mu = o.mean(0)
+    oh = o - alpha * mu
+    var = oh.pow(2).mean(0)
+    y = w * oh / (var + 1e-5).sqrt() + beta
+    x1 = torch.relu(y)
+    if keep is not None:
+        x1 = x1 * keep * scale
+    return x1, mu, var
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("train", [False, True])
+def test_graphnorm_fwd_bwd_bwd2(C, train):
+    n = 1777
+    o = (_rand(n, C, seed=1) * 1.5 + 0.7).requires_grad_()
+    w, beta, alpha = ((_rand(C, seed=2) * 0.3 + 1).requires_grad_(), (_rand(C, seed=3) * 0.3).requires_grad_(),
+                      (_rand(C, seed=4) * 0.3 + 1).requires_grad_())
+    keep = (torch.rand(n, C, generator=torch.Generator().manual_seed(5)) < 0.8) if train else None
+    scale = 1.25 if train else 1.0
+    gx1 = _rand(n, C, seed=6).requires_grad_()
+    Xt = _rand(n, C, seed=7)
+    x1, mu, var = _gn_ref(o, w, beta, alpha, None if keep is None else keep.double(), scale)
+    go, dw, db, da = torch.autograd.grad(x1, (o, w, beta, alpha), gx1, create_graph=True)
+    gx1t, ot, wt, at = torch.autograd.grad(go, (gx1, o, w, alpha), Xt, allow_unused=True)
+
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    kk = None if keep is None else keep.to(torch.uint8).to(DEV)
+    x1_k, stats = lib.graphnorm_fwd(f(o), f(w), f(beta), f(alpha), kk, scale)
+    assert_close(stats[:C], mu, 1e-5, "mu")
+    assert_close(stats[2 * C:], var, 1e-5, "var")
+    assert_close(x1_k, x1, 1e-5, f"graphnorm_fwd C={C}")
+    go_k, dp, bst = lib.graphnorm_bwd(f(gx1), f(o), x1_k, f(w), f(alpha), stats, scale)
+    assert_close(go_k, go, 1e-5, "graphnorm_bwd go")
+    assert_close(dp[0], dw, 3e-5, "graphnorm_bwd dw")
+    assert_close(dp[1], db, 3e-5, "graphnorm_bwd dbeta")
+    assert_close(dp[2], da, 3e-5, "graphnorm_bwd dalpha")
+    gx1t_k, ot_k, dp2 = lib.graphnorm_bwd2(f(Xt), f(gx1), f(o), x1_k, f(w), f(alpha), stats, bst, scale)
+    assert_close(gx1t_k, gx1t, 1e-5, "graphnorm_bwd2 gx1t")
+    assert_close(ot_k, ot, 2e-5, "graphnorm_bwd2 ot")
+    assert_close(dp2[0], wt, 3e-5, "graphnorm_bwd2 wt")
+    assert_close(dp2[2], at, 3e-5, "graphnorm_bwd2 alphat")
+    assert float(dp2[1].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,ln,act", [(17, 128, True, 2), (128, 128, True, 2), (268, 128, True, 2),
+                                             (524, 128, True, 2), (128, 64, True, 2), (64, 32, True, 2),
+                                             (32, 16, True, 2), (16, 7, False, 0), (36, 64, False, 1),
+                                             (64, 32, False, 1), (8, 1, False, 0), (2, 1, False, 0), (1, 2, False, 0)])
+def test_dense_fwd(cin, cout, ln, act):
+    n = 333
+    x, W, b = _rand(n, cin, seed=1), _rand(cout, cin, seed=2, scale=0.2), _rand(cout, seed=3)
+    gamma, beta = _rand(cout, seed=4) * 0.2 + 1, _rand(cout, seed=5) * 0.2
+    y = x @ W.t() + b
+    if ln:
+        y = F.layer_norm(y, (cout,), gamma, beta, 1e-5)
+    y = F.leaky_relu(y, 0.2) if act == 2 else torch.relu(y) if act == 1 else y
+    f = lambda t: t.float().to(DEV).contiguous()
+    res = lib.dense_fwd([f(x)], f(W), f(b), (f(gamma), f(beta)) if ln else None, act, save_ln=ln)
+    assert_close(res["out"], y, 1e-5, f"dense_fwd {cin}->{cout}")
+
+
+def test_dense_segments_gather_att():
+    """cat[table[type] | vx | z] @ W^T with attention dots, as the generator's encoder input and a conv `lin`."""
+    n = 500
+    table, typ = _rand(7, 128, seed=1), torch.randint(0, 7, (n,), generator=torch.Generator().manual_seed(2))
+    vx, z = _rand(n, 12, seed=3), _rand(n, 128, seed=4)
+    W, a_s, a_d = _rand(64, 268, seed=5, scale=0.1), _rand(64, seed=6), _rand(64, seed=7)
+    x = torch.cat([table[typ], vx, z], 1)
+    y = x @ W.t()
+    f = lambda t: t.float().to(DEV).contiguous()
+    res = lib.dense_fwd([(f(table), typ.to(torch.int32).to(DEV)), f(vx), f(z)], f(W), att=(f(a_s), f(a_d)))
+    assert_close(res["out"], y, 1e-5, "segmented dense")
+    assert_close(res["s"], y @ a_s, 1e-5, "s")
+    assert_close(res["d"], y @ a_d, 1e-5, "d")
+
+
+def test_dense_transposed_and_wgrad():
+    n, cin, cout = 1234, 268, 128
+    x, W, gz = _rand(n, cin, seed=1), _rand(cout, cin, seed=2, scale=0.1), _rand(n, cout, seed=3)
+    f = lambda t: t.float().to(DEV).contiguous()
+    gx = lib.dense_fwd([f(gz)], f(W), transposed=True)["out"]
+    assert_close(gx, gz @ W, 1e-5, "backward-input product")
+    gx_part = lib.dense_fwd([f(gz)], f(W), transposed=True, cols=(12, 140))["out"]
+    assert_close(gx_part, (gz @ W)[:, 12:140], 1e-5, "backward-input product, column window")
+    a, b = f(x[:, :100]), f(x[:, 100:])
+    dW = lib.dense_wgrad(f(gz), [a, b, None])
+    assert_close(dW[:, :cin], gz.t() @ x, 3e-5, "wgrad")
+    assert_close(dW[:, cin], gz.sum(0), 3e-5, "bias grad via ones segment")
+    dW2 = lib.dense_wgrad(f(gz), [a, b, None], dW=dW.clone(), accumulate=True)
+    assert_close(dW2, 2 * torch.cat([gz.t() @ x, gz.sum(0)[:, None]], 1), 3e-5, "wgrad accumulate")
+
+
+@pytest.mark.parametrize("C", [16, 32, 64, 128])
+def test_ln_act_bwd(C):
+    n = 777
+    zpre = _rand(n, C, seed=1).requires_grad_()
+    gamma, beta = (_rand(C, seed=2) * 0.2 + 1).requires_grad_(), (_rand(C, seed=3) * 0.2).requires_grad_()
+    gout = _rand(n, C, seed=4)
+    out = F.leaky_relu(F.layer_norm(zpre, (C,), gamma, beta, 1e-5), 0.2)
+    gz, dg, db = torch.autograd.grad(out, (zpre, gamma, beta), gout)
+    mean, var = zpre.mean(1, keepdim=True), zpre.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    xhat = (zpre - mean) * rstd
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    gz_k, dg_k, db_k = lib.ln_act_bwd(f(gout), f(out), 2, f(xhat), f(rstd.squeeze(1)), f(gamma))
+    assert_close(gz_k, gz, 1e-5, "ln_act_bwd gz")
+    assert_close(dg_k, dg, 3e-5, "dgamma")
+    assert_close(db_k, db, 3e-5, "dbeta")
+    o2 = torch.relu(zpre)
+    gz2 = lib.ln_act_bwd(f(gout), f(o2), 1)[0]
+    assert_close(gz2, gout * (zpre > 0), 1e-6, "relu backward")
+
+
+# ------------------------------------------------------------------------------------------------
+# type table, gumbel, segment primitives
+# ------------------------------------------------------------------------------------------------
+def test_type_table_and_scatter():
+    from oracle.models import type_matched_features
+    lb, vb = small_batch()
+    ref = type_matched_features(lb.x.double(), lb.type, vb.type)
+    table = lib.type_table(lb.x.to(DEV), lb.type.to(DEV), 7)
+    got = table[vb.type.to(DEV)]
+    assert_close(got, ref, 1e-6, "type-matched features")
+    g = _rand(vb.num_nodes, 140, seed=3)
+    want = torch.zeros(7, 128, dtype=torch.float64).index_add_(0, vb.type, g[:, :128])
+    out = lib.type_scatter_sum(g.float().to(DEV), vb.type.to(torch.int32).to(DEV), 7, width=128)
+    assert_close(out, want, 3e-5, "type scatter sum")
+
+
+def test_gumbel_st():
+    from oracle.models import gumbel_straight_through
+    n = 4097
+    logits = _rand(n, 7, seed=1).float().requires_grad_()
+    noise = -torch.empty(n, 7).exponential_(generator=torch.Generator().manual_seed(3)).log()
+    hard, soft = gumbel_straight_through(logits, noise)
+    gh, gs = _rand(n, 7, seed=4).float(), _rand(n, 7, seed=5).float()
+    (gl,) = torch.autograd.grad((hard, soft), logits, (gh, gs))
+    soft_k, hard_k, amax = lib.gumbel_st_fwd(logits.detach().to(DEV), noise.to(DEV))
+    assert_close(soft_k, soft.detach(), 1e-5, "label_soft")
+    # argmax labels: bit-exact except where the oracle's own top-2 gap is below 1e-6 (near ties)
+    top2 = soft.detach().topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-6
+    assert torch.equal(amax.cpu()[safe].long(), soft.detach().argmax(1)[safe])
+    assert int((~safe).sum()) <= 2
+    assert_close(hard_k, hard.detach(), 1e-6, "label_hard")
+    gl_k = lib.gumbel_st_bwd(gh.to(DEV), gs.to(DEV), soft_k)
+    assert_close(gl_k, gl, 1e-5, "gumbel backward")
+
+
+def test_segment_primitives():
+    lb, vb = small_batch()
+    ptr = vb.ptr.to(torch.int32).to(DEV)
+    n = vb.num_nodes
+    v = _rand(n, seed=1)
+    ref = pyg.segment_softmax(v, vb.batch, vb.num_graphs)
+    assert_close(lib.segment_softmax(v.float().to(DEV), ptr), ref, 1e-5, "segment softmax")
+    x = _rand(n, 64, seed=2)
+    assert_close(lib.segment_pool(x.float().to(DEV), ptr, "mean"), pyg.scatter(x, vb.batch, vb.num_graphs, "mean"), 1e-5, "pool mean")
+    assert_close(lib.segment_pool(x.float().to(DEV), ptr, "max"), pyg.scatter(x, vb.batch, vb.num_graphs, "max"), 1e-6, "pool max")
+    assert_close(lib.segment_pool(x.float().to(DEV), ptr, "sum"), pyg.scatter(x, vb.batch, vb.num_graphs, "sum"), 1e-5, "pool sum")
+
+
+def test_errors_are_loud():
+    vb, edges, csr = _graph()
+    n = vb.num_nodes
+    h = torch.zeros(n, 3, device=DEV)
+    s = torch.zeros(n, device=DEV)
+    with pytest.raises(RuntimeError, match="unsupported channel width"):
+        lib.gat_fwd(csr, h, s, s, None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lib.graphnorm_fwd(torch.zeros(4, 4), torch.ones(4), torch.zeros(4), torch.ones(4), None, 1.0)
