@@ -225,13 +225,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
 }
 
 __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const float* __restrict__ partial, int nsplit, int Cout, int K,
-                                                              float* __restrict__ dW, int64_t ld_dw, int accumulate) {
+                                                              float* __restrict__ dW, int64_t ld_dw, float* __restrict__ dbias,
+                                                              int accumulate) {
     const int64_t total = (int64_t)Cout * K;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
         float t = 0.f;
         for (int sp = 0; sp < nsplit; ++sp) t += partial[(int64_t)sp * total + i];
         const int o = (int)(i / K), k = (int)(i % K);
-        float* dst = dW + (int64_t)o * ld_dw + k;
+        float* dst = (dbias && k == K - 1) ? dbias + o : dW + (int64_t)o * ld_dw + k;
         *dst = accumulate ? *dst + t : t;
     }
 }
@@ -411,7 +412,7 @@ extern "C" size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K) {
 }
 
 extern "C" int bg_dense_wgrad(const BgWgrad* a, void* stream) {
-    BG_REQUIRE(a && a->gz && a->dW && a->workspace, BG_EINVAL, "bg_dense_wgrad: null pointer");
+    BG_REQUIRE(a && a->gz && (a->dW || a->dbias) && a->workspace, BG_EINVAL, "bg_dense_wgrad: null pointer");
     WgradParams p;
     p.N = a->N; p.gz = a->gz; p.ld_gz = a->ld_gz; p.Cout = a->Cout;
     if (int rc = fill_segview(p.x, a->nseg, a->seg, &p.K)) return rc;
@@ -426,7 +427,7 @@ extern "C" int bg_dense_wgrad(const BgWgrad* a, void* stream) {
     wgrad_kernel<<<grid, kThreads, 0, st>>>(p);
     const int64_t total = (int64_t)a->Cout * p.K;
     wgrad_fold_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, kThreads), 4 * kSMs), kThreads, 0, st>>>(
-        a->workspace, ns, a->Cout, p.K, a->dW, a->ld_dw, a->accumulate);
+        a->workspace, ns, a->Cout, p.K, a->dW, a->ld_dw, a->dbias, a->accumulate);
     return check_launch("bg_dense_wgrad");
 }
 

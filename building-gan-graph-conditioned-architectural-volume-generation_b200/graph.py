@@ -159,7 +159,7 @@ class Batch(Data):
         starts = object.__getattribute__(self, "_starts")
         one = Data()
         for key, v in self._fields.items():
-            if key in ("ptr", "batch", "bg_csr"):
+            if key in ("ptr", "batch", "bg_csr", "_bg_cache"):
                 continue
             if not isinstance(v, Tensor):
                 one._fields[key] = v[gi]
@@ -168,11 +168,6 @@ class Batch(Data):
             else:
                 one._fields[key] = v[cuts[key][gi]:cuts[key][gi + 1]]
         return one
-
-    def _moved(self, fn) -> None:
-        for k, v in self._fields.items():
-            if isinstance(v, Tensor):
-                self._fields[k] = fn(v)
 
     def to(self, device, non_blocking: bool = False):
         super().to(device, non_blocking=non_blocking)

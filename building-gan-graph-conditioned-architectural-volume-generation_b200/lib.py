@@ -17,7 +17,7 @@ from torch import Tensor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbgb200.so")
-MAX_SEG = 5
+MAX_SEG = 6
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 SUPPORTED_WIDTHS = (1, 2, 4, 8, 16, 32, 64, 128)
 
@@ -45,7 +45,8 @@ class BgDense(C.Structure):
 
 class BgWgrad(C.Structure):
     _fields_ = [("N", C.c_int64), ("gz", C.c_void_p), ("ld_gz", C.c_int64), ("Cout", C.c_int32), ("nseg", C.c_int32),
-                ("seg", BgSeg * MAX_SEG), ("dW", C.c_void_p), ("ld_dw", C.c_int64), ("accumulate", C.c_int32),
+                ("seg", BgSeg * MAX_SEG), ("dW", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),
+                ("accumulate", C.c_int32),
                 ("workspace", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
@@ -257,9 +258,10 @@ def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln:
             raise RuntimeError(f"dense_fwd(transposed): X has {k} columns but W has {W.shape[0]} rows")
         cout, wptr, w_so, w_sk = hi - lo, W.data_ptr() + 4 * lo, 1, W.stride(0)
     else:
-        if W.shape[1] != k:
-            raise RuntimeError(f"dense_fwd: X has {k} columns but W expects {W.shape[1]}")
-        cout, wptr, w_so, w_sk = W.shape[0], W.data_ptr(), W.stride(0), 1
+        lo, hi = cols if cols is not None else (0, W.shape[1])  # cols: use only input columns lo..hi of W
+        if hi - lo != k:
+            raise RuntimeError(f"dense_fwd: X has {k} columns but W expects {hi - lo}")
+        cout, wptr, w_so, w_sk = W.shape[0], W.data_ptr() + 4 * lo, W.stride(0), 1
     dev = W.device
     if out is None:
         out = torch.empty(n, cout, dtype=torch.float32, device=dev)
@@ -283,8 +285,10 @@ def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln:
     return res
 
 
-def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
-    """dW[o,k] = sum_n gz[n,o] X[n,k]; a ``None`` segment is a column of ones (=> bias gradient column)."""
+def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, accumulate: bool = False,
+                dbias: Optional[Tensor] = None) -> Tensor:
+    """dW[o,k] = sum_n gz[n,o] X[n,k]; a ``None`` segment is a column of ones (=> bias gradient column).
+    ``dbias`` routes the last column (put the ones segment last) to a separate [Cout] tensor."""
     lib = load()
     a = BgWgrad()
     _f32(gz, "gz")
@@ -294,13 +298,13 @@ def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, ac
         n = gz.shape[0]
     cout = gz.shape[1]
     if dW is None:
-        dW = torch.empty(cout, k, dtype=torch.float32, device=gz.device)
+        dW = torch.empty(cout, k - (1 if dbias is not None else 0), dtype=torch.float32, device=gz.device)
         accumulate = False
     assert dW.stride(1) == 1 or dW.shape[1] == 1
     nb = lib.bg_dense_wgrad_ws(n, cout, k)
     ws = workspace(nb + 256, gz.device)
     a.N, a.gz, a.ld_gz, a.Cout, a.nseg = n, gz.data_ptr(), gz.stride(0), cout, len(segs)
-    a.dW, a.ld_dw, a.accumulate = dW.data_ptr(), dW.stride(0), int(accumulate)
+    a.dW, a.ld_dw, a.accumulate, a.dbias = dW.data_ptr(), dW.stride(0), int(accumulate), _p(dbias)
     a.workspace, a.ws_bytes = ws.data_ptr() + 256, ws.numel() * 4 - 256
     _check(lib.bg_dense_wgrad(C.byref(a), _stream()))
     return dW

@@ -1,0 +1,431 @@
+"""Drop-in ``VoxelGNNGenerator`` / ``VoxelGNNDiscriminator`` (reference building_gan/src/models.py:14-245)
+on the libbgb200 kernels.
+
+Same constructor and ``forward`` signatures, same sub-module names / parameter shapes (state-dict
+interchange), same initialisation order, same train/eval semantics (dropout masks
+and Gumbel noise are drawn from torch's device generator, z / the GP mixing factor come from the
+caller), and full autograd support: first order for the generator, first AND second order for the
+discriminator (``torch.autograd.grad(..., create_graph=True)`` of WGAN-GP, trainer.py:306-312).
+Everything between the inputs and the outputs runs in hand-written sm_100a kernels; there is no
+torch / CPU fallback - on a machine without the built library or without CUDA ``forward`` raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import executor as ex
+from . import lib
+from .executor import ConvSpec, DenseSpec
+from .graph import csr_of
+from .lib import ACT_LRELU, ACT_NONE, ACT_RELU
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders with torch_geometric's names and initialisers (never called as modules)
+# ------------------------------------------------------------------------------------------------
+def _glorot(t: Tensor) -> None:
+    bound = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
+
+
+class _PygLinearParams(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        _glorot(self.weight)
+
+
+class GATConv(nn.Module):
+    """Parameters of tgnn.GATConv(in, out) (heads=1): att_src[1,1,C], att_dst[1,1,C], bias[C], lin.weight."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        if out_channels not in lib.SUPPORTED_WIDTHS or in_channels > 128:
+            raise ValueError(f"GATConv({in_channels}, {out_channels}): libbgb200 supports widths {lib.SUPPORTED_WIDTHS}")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _PygLinearParams(in_channels, out_channels)
+        self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        _glorot(self.lin.weight)  # PyG's reset_parameters() re-draws lin before the attention vectors
+        _glorot(self.att_src)
+        _glorot(self.att_dst)
+
+
+class GraphNorm(nn.Module):
+    def __init__(self, channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+        self.mean_scale = nn.Parameter(torch.ones(channels))
+
+
+class _GnnStack(nn.Module):
+    """Registers children as ``module_{i}`` exactly like tgnn.Sequential (models.py:90,210)."""
+
+    def __init__(self, widths: List[int]):
+        super().__init__()
+        self.specs: List[ConvSpec] = []
+        i = 0
+        for a, b in zip(widths[:-1], widths[1:]):
+            setattr(self, f"module_{i}", GATConv(a, b))
+            setattr(self, f"module_{i + 1}", GraphNorm(b))
+            setattr(self, f"module_{i + 2}", nn.ReLU(True))
+            setattr(self, f"module_{i + 3}", nn.Dropout(0.2))
+            self.specs.append(ConvSpec(f"module_{i}", f"module_{i + 1}", a, b))
+            i += 4
+
+
+def _ln_mlp(widths: List[int], final_plain: Optional[int] = None) -> nn.Sequential:
+    mods: List[nn.Module] = []
+    for a, b in zip(widths[:-1], widths[1:]):
+        mods += [nn.Linear(a, b), nn.LayerNorm(b), nn.LeakyReLU(0.2)]
+    if final_plain is not None:
+        mods.append(nn.Linear(widths[-1], final_plain))
+    return nn.Sequential(*mods)
+
+
+def _hourglass(hidden: int, repeat: int) -> List[int]:
+    down = [hidden // (2 ** k) for k in range(repeat + 1)]
+    return down + down[-2::-1]
+
+
+def _require_gat(kind: str) -> None:
+    if kind not in ("GCNCONV", "GRAPHCONV", "GATCONV", "GATV2CONV"):
+        raise ValueError(f"Invalid conv_type: {kind}")  # models.py:31,175
+    if kind != "GATCONV":
+        raise NotImplementedError(
+            f"conv_type {kind}: only GATCONV (the reference default, config.py:89,93) has sm_100a kernels so far; "
+            "there is no torch fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# per-batch cache of data-only quantities (hoisted out of every forward call)
+# ------------------------------------------------------------------------------------------------
+class _BatchCtx:
+    __slots__ = ("csr", "type32", "vx", "table", "local_id", "n", "real_onehot")
+
+
+def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
+    ctx = getattr(voxel_graph, "_bg_cache", None) if not hasattr(voxel_graph, "_fields") else voxel_graph._fields.get("_bg_cache")
+    dev = voxel_graph.x.device
+    if dev.type != "cuda":
+        raise RuntimeError("building_gan_b200 models run on CUDA only (no CPU fallback): move the batch with .to('cuda')")
+    if ctx is None or ctx.local_id != id(local_graph) or ctx.vx.device != dev:
+        ctx = _BatchCtx()
+        ctx.csr = csr_of(voxel_graph)
+        ctx.type32 = voxel_graph.type.to(torch.int32).contiguous()
+        ctx.vx = voxel_graph.x.to(torch.float32).contiguous()
+        ctx.table = lib.type_table(local_graph.x.to(torch.float32).contiguous(), local_graph.type, num_types)
+        ctx.local_id = id(local_graph)
+        ctx.n = int(ctx.vx.shape[0])
+        ctx.real_onehot = None
+        try:
+            voxel_graph._bg_cache = ctx
+        except Exception:
+            pass
+    return ctx
+
+
+def _draw_keeps(n: int, specs: List[ConvSpec], training: bool, device) -> List[Optional[Tensor]]:
+    """Dropout keep-masks, one per block, drawn with torch's own dropout kernel in layer order so the
+    device RNG stream is consumed exactly as the reference consumes it."""
+    if not training:
+        return [None] * len(specs)
+    cmax = max(s.cout for s in specs)
+    ones = torch.ones(n * cmax, device=device)
+    return [torch.native_dropout(ones[: n * s.cout].view(n, s.cout), 0.2, True)[1].view(torch.uint8) for s in specs]
+
+
+# ------------------------------------------------------------------------------------------------
+# generator
+# ------------------------------------------------------------------------------------------------
+class VoxelGNNGenerator(nn.Module):
+    def __init__(self, configuration, local_graph_dim: int, voxel_graph_dim: int):
+        super().__init__()
+        c = configuration
+        self.configuration = c
+        self.local_graph_dim, self.voxel_graph_dim = local_graph_dim, voxel_graph_dim
+        _require_gat(c.GENERATOR_CONV_TYPE)
+        le, gh = c.LOCAL_ENCODER_HIDDEN_DIM, c.GENERATOR_HIDDEN_DIM
+        self.matched_features_encoder = _ln_mlp([local_graph_dim] + [le] * (c.LOCAL_GRAPH_ENCODER_REPEAT + 1))
+        self.mlp_encoder = _ln_mlp([le + voxel_graph_dim + c.Z_DIM] + [gh] * (c.GENERATOR_MLP_ENCODER_REPEAT + 1))
+        widths = _hourglass(gh, c.GENERATOR_ENCODER_REPEAT)
+        self.encoder = _GnnStack(widths)
+        self.decoder = _ln_mlp([le + voxel_graph_dim + c.Z_DIM + widths[-1] + gh, gh, gh // 2, gh // 4, gh // 8],
+                               final_plain=c.NUM_CLASSES)
+        self._le, self._gh, self._enc_out = le, gh, widths[-1]
+        self._menc = [DenseSpec(f"matched_features_encoder.{3 * i}", f"matched_features_encoder.{3 * i + 1}", ACT_LRELU)
+                      for i in range(c.LOCAL_GRAPH_ENCODER_REPEAT + 1)]
+        self._mlp = [DenseSpec(f"mlp_encoder.{3 * i}", f"mlp_encoder.{3 * i + 1}", ACT_LRELU)
+                     for i in range(c.GENERATOR_MLP_ENCODER_REPEAT + 1)]
+        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout) for s in self.encoder.specs]
+        self._dec = [DenseSpec(f"decoder.{3 * i}", f"decoder.{3 * i + 1}", ACT_LRELU) for i in range(4)]
+        self._dec.append(DenseSpec("decoder.12", None, ACT_NONE))
+        self._names = [n for n, _ in self.named_parameters()]
+        self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
+        self.to(c.DEVICE)
+
+    def forward(self, local_graph, voxel_graph, z, gumbel_noise: Optional[Tensor] = None, keeps=None):
+        lib.load()
+        bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
+        zz = z.squeeze(0).to(bc.vx.device, torch.float32).contiguous()
+        if keeps is None:
+            keeps = _draw_keeps(bc.n, self._convs, self.training, bc.vx.device)
+        if gumbel_noise is None:
+            gumbel_noise = -torch.empty(bc.n, self.configuration.NUM_CLASSES, device=bc.vx.device).exponential_().log()
+        params = [p for _, p in self.named_parameters()]
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        logits, hard, soft = _GenFn.apply(self, bc, zz, gumbel_noise.contiguous(), keeps, need, *params)
+        return logits, hard, soft
+
+    # -- passes -----------------------------------------------------------------------------------
+    def _forward_pass(self, P: Dict[str, Tensor], bc: _BatchCtx, zz: Tensor, noise: Tensor, keeps, save: bool):
+        sv = {"menc": [], "mlp": [], "conv": [], "dec": []}
+        e = bc.table
+        for spec in self._menc:                                     # 7-row encoder: row-wise ops commute with the gather
+            r = ex.dense_forward(P, spec, [e], save)
+            sv["menc"].append(r)
+            e = r["out"]
+        enc_seg = (e, bc.type32)
+        segs = [enc_seg, bc.vx, zz]
+        for spec in self._mlp:
+            r = ex.dense_forward(P, spec, segs, save)
+            sv["mlp"].append(r)
+            segs = [r["out"]]
+        x = segs[0]
+        h = x
+        for spec, keep in zip(self._convs, keeps):
+            h, s = ex.conv_forward(P, spec, bc.csr, h, keep, save)
+            sv["conv"].append(s)
+        segs = [h, x, enc_seg, bc.vx, zz]
+        for spec in self._dec:
+            r = ex.dense_forward(P, spec, segs, save)
+            sv["dec"].append(r)
+            segs = [r["out"]]
+        logits = segs[0]
+        soft, hard, amax = lib.gumbel_st_fwd(logits, noise)
+        sv["soft"] = soft
+        return logits, hard, soft, sv
+
+    def _backward_pass(self, P, bc: _BatchCtx, sv, g_logits, g_hard, g_soft) -> Tensor:
+        flat = torch.empty(self._layout.total, dtype=torch.float32, device=bc.vx.device)
+        G = ex.grad_views(self._layout, flat, self._convs)
+        le, gh, eo = self._le, self._gh, self._enc_out
+        if g_hard is not None or g_soft is not None:
+            gl = lib.gumbel_st_bwd(g_hard, g_soft, sv["soft"])
+            if g_logits is not None:
+                lib.axpy_(gl, g_logits)
+        else:
+            gl = g_logits
+        g = gl
+        for spec, saved in zip(self._dec[:0:-1], sv["dec"][:0:-1]):
+            _, (g,) = ex.dense_backward(P, G, spec, saved, g, [(0, saved["segs"][0].shape[1])], False)
+        _, (g_enc_out, g_x_skip, g_e1) = ex.dense_backward(P, G, self._dec[0], sv["dec"][0], g,
+                                                           [(0, eo), (eo, eo + gh), (eo + gh, eo + gh + le)], False)
+        g = g_enc_out
+        for spec, saved in zip(self._convs[::-1], sv["conv"][::-1]):
+            g = ex.conv_backward(P, G, spec, bc.csr, saved, g, False)
+        lib.axpy_(g, g_x_skip)
+        for spec, saved in zip(self._mlp[:0:-1], sv["mlp"][:0:-1]):
+            _, (g,) = ex.dense_backward(P, G, spec, saved, g, [(0, gh)], False)
+        _, (g_e2,) = ex.dense_backward(P, G, self._mlp[0], sv["mlp"][0], g, [(0, le)], False)
+        k = self.configuration.NUM_CLASSES
+        ge = lib.type_scatter_sum(g_e1, bc.type32, k)
+        lib.axpy_(ge, lib.type_scatter_sum(g_e2, bc.type32, k))
+        for i in range(len(self._menc) - 1, -1, -1):
+            spec, saved = self._menc[i], sv["menc"][i]
+            _, gins = ex.dense_backward(P, G, spec, saved, ge, [(0, saved["segs"][0].shape[1])] if i > 0 else None, False)
+            if i > 0:
+                ge = gins[0]
+        return flat
+
+
+class _GenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, *params):
+        P = dict(zip(model._names, params))
+        logits, hard, soft, sv = model._forward_pass(P, bc, zz, noise, keeps, save=need)
+        if getattr(model, "debug_keep_saved", False):
+            model.debug_saved = sv  # test hook: the activation patterns of the last forward
+        ctx.model, ctx.bc, ctx.sv, ctx.P = model, bc, sv if need else None, P if need else None
+        return logits, hard, soft
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_logits, g_hard, g_soft):
+        if ctx.sv is None:
+            raise RuntimeError("generator backward called but the forward ran without grad")
+        cont = lambda t: None if t is None else t.contiguous()
+        flat = ctx.model._backward_pass(ctx.P, ctx.bc, ctx.sv, cont(g_logits), cont(g_hard), cont(g_soft))
+        lay = ctx.model._layout
+        return (None, None, None, None, None, None) + tuple(lay.view(flat, n) for n in ctx.model._names)
+
+
+# ------------------------------------------------------------------------------------------------
+# discriminator
+# ------------------------------------------------------------------------------------------------
+class VoxelGNNDiscriminator(nn.Module):
+    def __init__(self, configuration, local_graph_dim: int, voxel_graph_dim: int):
+        super().__init__()
+        c = configuration
+        self.configuration = c
+        self.local_graph_dim, self.voxel_graph_dim = local_graph_dim, voxel_graph_dim
+        _require_gat(c.DISCRIMINATOR_CONV_TYPE)
+        dh = c.DISCRIMINATOR_HIDDEN_DIM
+        self.mlp_encoder = nn.Sequential(nn.Linear(local_graph_dim + voxel_graph_dim + c.NUM_CLASSES, dh), nn.ReLU(True),
+                                         nn.Linear(dh, dh), nn.ReLU(True))
+        self.encoder = _GnnStack(_hourglass(dh, c.DISCRIMINATOR_ENCODER_REPEAT))
+        tail: List[nn.Module] = [nn.Linear(dh, dh // 2), nn.ReLU(True), nn.Linear(dh // 2, dh // 4), nn.ReLU(True),
+                                 nn.Linear(dh // 4, dh // 8), nn.ReLU(True), nn.Linear(dh // 8, 1)]
+        if not c.USE_WGANGP:
+            raise NotImplementedError("USE_WGANGP=False (sigmoid + BCE critic) has no sm_100a kernel yet; "
+                                      "the reference default is WGAN-GP (config.py:106)")
+        self.decoder = nn.Sequential(*tail)
+        self._pre = [DenseSpec("mlp_encoder.0", None, ACT_RELU), DenseSpec("mlp_encoder.2", None, ACT_RELU)]
+        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout) for s in self.encoder.specs]
+        self._dec = [DenseSpec("decoder.0", None, ACT_RELU), DenseSpec("decoder.2", None, ACT_RELU),
+                     DenseSpec("decoder.4", None, ACT_RELU), DenseSpec("decoder.6", None, ACT_NONE)]
+        self._names = [n for n, _ in self.named_parameters()]
+        self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
+        self._label_lo = local_graph_dim + voxel_graph_dim
+        self.to(c.DEVICE)
+
+    def forward(self, local_graph, voxel_graph, label_hard, keeps=None):
+        lib.load()
+        bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
+        label = label_hard.squeeze(0)
+        if label.dtype != torch.float32:  # the real sample is an int64 one-hot (trainer.py:319); torch.cat promotes it
+            label = label.to(torch.float32)
+        label = label.to(bc.vx.device).contiguous()
+        if keeps is None:
+            keeps = _draw_keeps(bc.n, self._convs, self.training, bc.vx.device)
+        params = [p for _, p in self.named_parameters()]
+        need = torch.is_grad_enabled() and (label.requires_grad or any(p.requires_grad for p in params))
+        return _DiscFn.apply(self, bc, keeps, need, label, *params)
+
+    # -- passes -----------------------------------------------------------------------------------
+    def _forward_pass(self, P, bc: _BatchCtx, label: Tensor, keeps, save: bool):
+        sv = {"pre": [], "conv": [], "dec": []}
+        segs = [(bc.table, bc.type32), bc.vx, label]
+        for spec in self._pre:
+            r = ex.dense_forward(P, spec, segs, save)
+            sv["pre"].append(r)
+            segs = [r["out"]]
+        h = segs[0]
+        for spec, keep in zip(self._convs, keeps):
+            h, s = ex.conv_forward(P, spec, bc.csr, h, keep, save)
+            sv["conv"].append(s)
+        segs = [h]
+        for spec in self._dec:
+            r = ex.dense_forward(P, spec, segs, save)
+            sv["dec"].append(r)
+            segs = [r["out"]]
+        return segs[0], sv
+
+    def _backward_pass(self, P, bc, sv, g_score: Optional[Tensor], flat: Optional[Tensor], accumulate: bool,
+                       inject=None, for_bwd2: bool = False) -> Tensor:
+        """First-order backward.  ``flat`` = grad bucket (None: skip parameter gradients).  ``inject`` = per-block
+        (ot, ht) cotangents of the second-order sweep; then g_score is None (nothing flows in from the top)."""
+        G = None if flat is None else ex.grad_views(self._layout, flat, self._convs)
+        g = g_score
+        if g is not None:
+            for i in range(len(self._dec) - 1, -1, -1):
+                spec, saved = self._dec[i], sv["dec"][i]
+                gz, (g,) = ex.dense_backward(P, G, spec, saved, g, [(0, saved["segs"][0].shape[1])], accumulate)
+                if for_bwd2:
+                    saved["b_gz"] = gz
+        for i in range(len(self._convs) - 1, -1, -1):
+            g = ex.conv_backward(P, G, self._convs[i], bc.csr, sv["conv"][i], g, accumulate,
+                                 None if inject is None else inject[i], for_bwd2)
+        gz, (g,) = ex.dense_backward(P, G, self._pre[1], sv["pre"][1], g, [(0, sv["pre"][1]["segs"][0].shape[1])], accumulate)
+        if for_bwd2:
+            sv["pre"][1]["b_gz"] = gz
+        lo = self._label_lo
+        gz, (g_label,) = ex.dense_backward(P, G, self._pre[0], sv["pre"][0], g, [(lo, lo + self.configuration.NUM_CLASSES)],
+                                           accumulate)
+        if for_bwd2:
+            sv["pre"][0]["b_gz"] = gz
+        return g_label
+
+    def _backward2_pass(self, P, bc, sv, Lt: Tensor, flat2: Tensor, want_g_score: bool) -> Optional[Tensor]:
+        """Second-order sweep: Lt = cotangent on g_label.  Accumulates the direct parameter cotangents into flat2,
+        then runs the injected first-order sweep (also into flat2).  Returns the cotangent on g_score."""
+        G2 = ex.grad_views(self._layout, flat2, self._convs)
+        lo, k = self._label_lo, self.configuration.NUM_CLASSES
+        W0 = P["mlp_encoder.0.weight"]
+        # layer pre[0] backward was: gz0 = g_a * [x_a>0] ; g_label = gz0 @ W0[:, lo:lo+k]
+        s0, s1 = sv["pre"][0], sv["pre"][1]
+        lib.dense_wgrad(s0["b_gz"], [Lt], dW=G2["mlp_encoder.0.weight"][:, lo:lo + k], accumulate=True)
+        t = lib.dense_fwd([Lt], W0, cols=(lo, lo + k))["out"]                   # cot(gz0) = Lt @ W0w^T
+        t = lib.ln_act_bwd(t, s0["out"], ACT_RELU)[0]                            # cot(g_a) = cot(gz0) * mask_a
+        # layer pre[1] backward was: gz1 = g_b * [x_b>0] ; g_a = gz1 @ W1
+        lib.dense_wgrad(s1["b_gz"], [t], dW=G2["mlp_encoder.2.weight"], accumulate=True)
+        t = lib.dense_fwd([t], P["mlp_encoder.2.weight"])["out"]                # cot(gz1) = cot(g_a) @ W1^T
+        t = lib.ln_act_bwd(t, s1["out"], ACT_RELU)[0]                            # cot(g_b)
+        inject = []
+        for spec, saved in zip(self._convs, sv["conv"]):
+            t, inj = ex.conv_backward2(P, G2, spec, bc.csr, saved, t)
+            inject.append(inj)
+        gt = None
+        for spec, saved in zip(self._dec, sv["dec"]):
+            # backward was: gz = g_y * act'(y) ; g_in = gz @ W     (t = cot(g_in))
+            lib.dense_wgrad(saved["b_gz"], [t], dW=G2[spec.lin + ".weight"], accumulate=True)
+            t = lib.dense_fwd([t], P[spec.lin + ".weight"])["out"]               # cot(gz)
+            if spec.act != ACT_NONE:
+                t = lib.ln_act_bwd(t, saved["out"], spec.act)[0]                 # cot(g_y)
+        gt = t if want_g_score else None
+        self._backward_pass(P, bc, sv, None, flat2, True, inject=inject)
+        return gt
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, keeps, need, label, *params):
+        P = dict(zip(model._names, params))
+        score, sv = model._forward_pass(P, bc, label, keeps, save=need)
+        if getattr(model, "debug_keep_saved", False):
+            model.debug_saved = sv
+        ctx.model, ctx.bc, ctx.sv, ctx.nparams = model, bc, sv if need else None, len(params)
+        ctx.save_for_backward(label, *params)
+        return score
+
+    @staticmethod
+    def backward(ctx, g_score):
+        if ctx.sv is None:
+            raise RuntimeError("discriminator backward called but the forward ran without grad")
+        label, *params = ctx.saved_tensors
+        outs = _DiscBwdFn.apply(ctx.model, ctx.bc, ctx.sv, torch.is_grad_enabled(), g_score.contiguous(), label, *params)
+        return (None, None, None, None) + tuple(outs)
+
+
+class _DiscBwdFn(torch.autograd.Function):
+    """The discriminator's first-order backward as a differentiable op: (g_score, label, params) ->
+    (g_label, param grads).  Its own backward is the second-order sweep; parameter gradients are not
+    differentiable a second time (the reference never asks for that: only_inputs=True, trainer.py:311)."""
+
+    @staticmethod
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, sv, second_order: bool, g_score, label, *params):
+        P = dict(zip(model._names, params))
+        flat = torch.empty(model._layout.total, dtype=torch.float32, device=g_score.device)
+        g_label = model._backward_pass(P, bc, sv, g_score, flat, False, for_bwd2=second_order)
+        ctx.model, ctx.bc, ctx.sv, ctx.P = model, bc, sv, P
+        grads = tuple(model._layout.view(flat, n) for n in model._names)
+        ctx.mark_non_differentiable(*grads)
+        return (g_label,) + grads
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, Lt, *unused):
+        model = ctx.model
+        flat2 = torch.zeros(model._layout.total, dtype=torch.float32, device=Lt.device)
+        gt = model._backward2_pass(ctx.P, ctx.bc, ctx.sv, Lt.contiguous(), flat2, ctx.needs_input_grad[4])
+        # the cotangent on `label` (third-order coupling into the generator) is not needed by WGAN-GP: the
+        # interpolate is built from detached samples (trainer.py:298-301)
+        return (None, None, None, None, gt, None) + tuple(model._layout.view(flat2, n) for n in model._names)

@@ -82,7 +82,7 @@ typedef struct BgSeg {
     int32_t width;
     int32_t ld; /* row stride in floats */
 } BgSeg;
-#define BG_MAX_SEG 5
+#define BG_MAX_SEG 6
 #define BG_ACT_NONE 0
 #define BG_ACT_RELU 1
 #define BG_ACT_LRELU 2 /* LeakyReLU(0.2) */
@@ -110,13 +110,16 @@ int bg_dense_fwd(const BgDense* a, void* stream);
 
 /* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
  * yields the bias gradient as an extra column); deterministic split-N reduction.
- * dW is written with leading dimension ld_dw; accumulate!=0 adds into dW. */
+ * dW is written with leading dimension ld_dw; accumulate!=0 adds into dW (and dbias).
+ * dbias != NULL routes the LAST column of X (put the ones segment there) to dbias[o] and dW
+ * receives the first K-1 columns. */
 typedef struct BgWgrad {
     int64_t N;
     const float* gz; int64_t ld_gz; int32_t Cout;
     int32_t nseg;
     BgSeg seg[BG_MAX_SEG];
     float* dW; int64_t ld_dw;
+    float* dbias;
     int32_t accumulate;
     float* workspace; size_t ws_bytes;
 } BgWgrad;
