@@ -81,6 +81,51 @@ SIGNATURES = {
 
 _lib = None
 
+# ---- launch accounting (bench.py reports `gpu_launches`) and optional per-op CUDA-event timing ----
+LAUNCHES = 0                      # kernels of libbgb200 launched so far by this process
+_prof: Optional[list] = None      # when a list: (op name, tensor shapes, start event, end event) per call
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_end() -> Dict[str, Dict[str, float]]:
+    """Per-op totals {name: {calls, ms}} from CUDA events recorded on the launching stream."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out: Dict[str, Dict[str, float]] = {}
+    for name, shapes, e0, e1 in rec:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "by_shape": {}})
+        ms = e0.elapsed_time(e1)
+        d["calls"] += 1
+        d["ms"] += ms
+        b = d["by_shape"].setdefault(shapes, [0, 0.0])
+        b[0] += 1
+        b[1] += ms
+    return out
+
+
+def _op(name: str, launches: int):
+    def deco(fn):
+        def wrapped(*a, **k):
+            global LAUNCHES
+            LAUNCHES += launches
+            if _prof is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            shapes = tuple(tuple(t.shape) for t in a if isinstance(t, Tensor))
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            _prof.append((name, shapes, e0, e1))
+            return r
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
 
 def load() -> C.CDLL:
     """Load libbgb200.so and bind every symbol of the header.  Raises if it is not built."""
@@ -183,6 +228,7 @@ def make_bg_graph(csr) -> BgGraph:
 # ------------------------------------------------------------------------------------------------
 # H2
 # ------------------------------------------------------------------------------------------------
+@_op("type_table", 1)
 def type_table(local_x: Tensor, local_type: Tensor, num_types: int) -> Tensor:
     lib = load()
     x = _cf32(local_x, "local_x")
@@ -194,6 +240,7 @@ def type_table(local_x: Tensor, local_type: Tensor, num_types: int) -> Tensor:
     return table
 
 
+@_op("type_scatter_sum", 1)
 def type_scatter_sum(g: Tensor, type32: Tensor, num_types: int, width: Optional[int] = None) -> Tensor:
     """out[t] = sum of rows of g[:, :width] whose type is t (backward of table[type])."""
     lib = load()
@@ -242,6 +289,7 @@ def _fill_segs(arr, segs: Sequence[Seg]) -> Tuple[int, int]:
     return n_rows, k
 
 
+@_op("dense_fwd", 1)
 def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln: Optional[Tuple[Tensor, Tensor]] = None,
               act: int = ACT_NONE, att: Optional[Tuple[Tensor, Tensor]] = None, transposed: bool = False,
               save_ln: bool = False, out: Optional[Tensor] = None, cols: Optional[Tuple[int, int]] = None):
@@ -285,6 +333,7 @@ def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln:
     return res
 
 
+@_op("dense_wgrad", 2)
 def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, accumulate: bool = False,
                 dbias: Optional[Tensor] = None) -> Tensor:
     """dW[o,k] = sum_n gz[n,o] X[n,k]; a ``None`` segment is a column of ones (=> bias gradient column).
@@ -310,6 +359,7 @@ def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, ac
     return dW
 
 
+@_op("ln_act_bwd", 1)
 def ln_act_bwd(gout: Tensor, out: Tensor, act: int, xhat: Optional[Tensor] = None, rstd: Optional[Tensor] = None,
                gamma: Optional[Tensor] = None, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None,
                accumulate: bool = False):
@@ -337,6 +387,7 @@ def ln_act_bwd(gout: Tensor, out: Tensor, act: int, xhat: Optional[Tensor] = Non
 # ------------------------------------------------------------------------------------------------
 # GAT aggregation
 # ------------------------------------------------------------------------------------------------
+@_op("gat_fwd", 1)
 def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope: float = 0.2):
     lib = load()
     _cf32(h, "h")
@@ -349,6 +400,7 @@ def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope:
     return out, m, z
 
 
+@_op("gat_bwd", 2)
 def gat_bwd(csr, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Tensor, a_src: Tensor, a_dst: Tensor,
             slope: float = 0.2):
     """Returns gh_tot[N,C], gsd[N,2], and the per-edge scratch (P, DU)."""
@@ -366,6 +418,7 @@ def gat_bwd(csr, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Te
     return gh, gsd, P, DU
 
 
+@_op("gat_bwd2", 2)
 def gat_bwd2(csr, Ht: Tensor, St: Tensor, Dt: Tensor, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Tensor,
              a_src: Tensor, a_dst: Tensor, slope: float = 0.2):
     """Cotangents (Ht,St,Dt) on (gh,gs,gd) -> gt[N,C] (on gout), ht_tot[N,C] (on h, incl. s/d paths), sdt[N,2]."""
@@ -386,6 +439,7 @@ def gat_bwd2(csr, Ht: Tensor, St: Tensor, Dt: Tensor, gout: Tensor, h: Tensor, s
 # ------------------------------------------------------------------------------------------------
 # GraphNorm + ReLU + dropout mask
 # ------------------------------------------------------------------------------------------------
+@_op("graphnorm_fwd", 2)
 def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optional[Tensor], keep_scale: float,
                   eps: float = 1e-5):
     lib = load()
@@ -401,6 +455,7 @@ def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optio
     return x1, stats
 
 
+@_op("graphnorm_bwd", 2)
 def graphnorm_bwd(gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, alpha: Tensor, stats: Tensor, keep_scale: float,
                   dparams: Optional[Tensor] = None, accumulate: bool = False):
     """Returns go, dparams[3,C] = (dw, dbeta, dalpha), bstats[2C]."""
@@ -419,6 +474,7 @@ def graphnorm_bwd(gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, alpha: Tensor, 
     return go, dparams, bstats
 
 
+@_op("graphnorm_bwd2", 2)
 def graphnorm_bwd2(Xt: Tensor, gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, alpha: Tensor, stats: Tensor, bstats: Tensor,
                    keep_scale: float, dparams2: Optional[Tensor] = None, accumulate: bool = False):
     """Cotangent Xt on go -> gx1t (on gx1), ot (on o), dparams2[3,C] (on w, beta, alpha)."""
@@ -440,6 +496,7 @@ def graphnorm_bwd2(Xt: Tensor, gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, al
 # ------------------------------------------------------------------------------------------------
 # Gumbel straight-through, segment primitives, utilities
 # ------------------------------------------------------------------------------------------------
+@_op("gumbel_st_fwd", 1)
 def gumbel_st_fwd(logits: Tensor, noise: Tensor):
     lib = load()
     _cf32(logits, "logits"), _cf32(noise, "noise")
@@ -451,6 +508,7 @@ def gumbel_st_fwd(logits: Tensor, noise: Tensor):
     return soft, hard, amax
 
 
+@_op("gumbel_st_bwd", 1)
 def gumbel_st_bwd(g_hard: Optional[Tensor], g_soft: Optional[Tensor], soft: Tensor) -> Tensor:
     lib = load()
     n, k = soft.shape
@@ -459,6 +517,7 @@ def gumbel_st_bwd(g_hard: Optional[Tensor], g_soft: Optional[Tensor], soft: Tens
     return gl
 
 
+@_op("segment_softmax", 1)
 def segment_softmax(v: Tensor, seg_ptr: Tensor) -> Tensor:
     lib = load()
     _cf32(v, "v")
@@ -468,6 +527,7 @@ def segment_softmax(v: Tensor, seg_ptr: Tensor) -> Tensor:
     return out
 
 
+@_op("segment_pool", 1)
 def segment_pool(x: Tensor, seg_ptr: Tensor, mode: str = "mean") -> Tensor:
     lib = load()
     _cf32(x, "x")
@@ -479,6 +539,7 @@ def segment_pool(x: Tensor, seg_ptr: Tensor, mode: str = "mean") -> Tensor:
     return out
 
 
+@_op("axpy", 1)
 def axpy_(y: Tensor, x: Tensor, a: float = 1.0) -> Tensor:
     lib = load()
     _cf32(y, "y"), _cf32(x, "x")
@@ -487,6 +548,7 @@ def axpy_(y: Tensor, x: Tensor, a: float = 1.0) -> Tensor:
     return y
 
 
+@_op("fill", 1)
 def fill_(y: Tensor, v: float) -> Tensor:
     lib = load()
     _cf32(y, "y")

@@ -1,0 +1,121 @@
+"""One optimisation step of the reference trainer on the B200 path.
+
+Mirrors ``TrainerHelper`` (reference building_gan/src/trainer.py): ``gradient_penalty`` (:291-316),
+``discriminator_loss`` (:318-332), ``generator_loss`` (:334-385) and the body of
+``_train_each_epoch`` (:467-495, N_CRITIC critic updates + one generator update).  The reference's
+own ``trainer.py`` can drive the drop-in models unchanged; this module exists because (a)
+/root/reference is not importable at run time and (b) the reference's per-graph Python FAR loop
+(``voxel_graph[gi]`` B times with D2H syncs, trainer.py:362-380) is replaced by a sync-free
+per-graph segment sum that returns the same number.
+
+``rng="cpu"`` draws z and the GP mixing factor on the CPU generator exactly like the reference
+(trainer.py:298,470,484: bit-identical stream, one H2D per draw); ``rng="device"`` draws them on the
+GPU (same distributions, no host round trip) - the fast default of the benchmark.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import lib
+
+
+def _rand(shape, device, rng: str, normal: bool) -> Tensor:
+    if rng == "cpu":
+        t = torch.randn(*shape) if normal else torch.rand(*shape)
+        return t.to(device, non_blocking=True)
+    return torch.randn(*shape, device=device) if normal else torch.rand(*shape, device=device)
+
+
+def gradient_penalty(discriminator, local_graph, voxel_graph, label_soft: Tensor, cfg, rng: str = "cpu") -> Tensor:
+    n = voxel_graph.types_onehot.shape[0]
+    e = _rand((n, 1), label_soft.device, rng, normal=False)
+    mixed = (e * voxel_graph.types_onehot + (1 - e) * label_soft.squeeze(0)).requires_grad_(True)
+    score = discriminator(local_graph, voxel_graph, mixed.unsqueeze(0))
+    (grad,) = torch.autograd.grad(score, mixed, torch.ones_like(score), create_graph=True, only_inputs=True)
+    return ((grad.norm(dim=1) - 1) ** 2).mean() * cfg.LAMBDA_GP
+
+
+def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tensor, label_soft: Tensor, cfg,
+                       rng: str = "cpu") -> Tensor:
+    d_real = discriminator(local_graph, voxel_graph, voxel_graph.types_onehot.unsqueeze(0))
+    d_fake = discriminator(local_graph, voxel_graph, label_hard)
+    if not cfg.USE_WGANGP:
+        raise NotImplementedError("USE_WGANGP=False is not on the B200 path")
+    return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng)
+
+
+def far_loss(voxel_graph, label_hard: Tensor, cfg) -> Tensor:
+    """trainer.py:357-381 without the per-graph Python loop: generated floor area per building by a segment
+    sum over ``Batch.ptr`` (bg_segment_pool), then MSE against the recorded FAR.  Detached, like the
+    reference's ``torch.tensor(list)`` construction."""
+    with torch.no_grad():
+        lab = label_hard.squeeze(0)
+        x = voxel_graph.x
+        solid = (lab.argmax(dim=1) != cfg.VOID).to(torch.float32)
+        dims = x[:, 3:6] * cfg.NORMALIZATION_FACTOR_DIMENSION
+        area = (dims[:, 1] * dims[:, 2] * solid).unsqueeze(1).contiguous()
+        ptr = voxel_graph.ptr
+        ptr32 = ptr.to(torch.int32) if ptr.dtype != torch.int32 else ptr
+        gfa = lib.segment_pool(area, ptr32.contiguous(), "sum").squeeze(1)
+        first = ptr[:-1]
+        got = gfa / voxel_graph.site_area[first]
+        want = x[first, 9]
+        return F.mse_loss(got, want) * cfg.LAMBDA_FAR
+
+
+def generator_loss(discriminator, local_graph, voxel_graph, logits: Tensor, label_hard: Tensor, cfg) -> Tensor:
+    d_fake = discriminator(local_graph, voxel_graph, label_hard)
+    adv = -d_fake.mean() * cfg.LAMBDA_ADV
+    ce = F.cross_entropy(logits, voxel_graph.type) * cfg.LAMBDA_LABEL
+    n = voxel_graph.num_nodes
+    ratio_g = label_hard.squeeze(0).sum(dim=0) / n
+    ratio = voxel_graph.types_onehot.sum(dim=0) / n
+    r_main = F.mse_loss(ratio_g[:-2], ratio[:-2]) * cfg.LAMBDA_RATIO
+    r_void = F.mse_loss(ratio_g[-2:], ratio[-2:]) * cfg.LAMBDA_RATIO_VOID
+    return adv + r_main + ce + r_void + far_loss(voxel_graph, label_hard, cfg)
+
+
+def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng: str = "cpu",
+               grad_sync=None, sync_losses: bool = True):
+    """trainer.py:467-495 for one device-resident batch.  ``grad_sync(model)`` (optional) is called after each
+    backward, before the optimiser step - the data-parallel gradient all-reduce hooks in here.
+    Returns (critic losses, generator loss, label_hard[1,N,7]); losses are floats when ``sync_losses`` (the
+    reference's ``.item()``, one D2H each) else 0-dim device tensors."""
+    dev = voxel_graph.x.device
+    n = voxel_graph.num_nodes
+    d_losses = []
+    for _ in range(cfg.N_CRITIC):
+        with torch.no_grad():
+            z = _rand((1, n, cfg.Z_DIM), dev, rng, normal=True)
+            _, hard, soft = generator(local_graph, voxel_graph, z)
+            hard, soft = hard.unsqueeze(0), soft.unsqueeze(0)
+        opt_d.zero_grad()
+        d_loss = discriminator_loss(discriminator, local_graph, voxel_graph, hard, soft, cfg, rng)
+        d_loss.backward()
+        if grad_sync is not None:
+            grad_sync(discriminator)
+        d_losses.append(d_loss.item() if sync_losses else d_loss.detach())
+        opt_d.step()
+    z = _rand((1, n, cfg.Z_DIM), dev, rng, normal=True)
+    logits, hard, soft = generator(local_graph, voxel_graph, z)
+    hard = hard.unsqueeze(0)
+    opt_g.zero_grad()
+    g_loss = generator_loss(discriminator, local_graph, voxel_graph, logits, hard, cfg)
+    g_loss.backward()
+    if grad_sync is not None:
+        grad_sync(generator)
+    g_val = g_loss.item() if sync_losses else g_loss.detach()
+    opt_g.step()
+    return d_losses, g_val, hard.detach()
+
+
+@torch.no_grad()
+def sample(generator, local_graph, voxel_graph, cfg, rng: str = "device") -> Tensor:
+    """Generator-only sampling pass (trainer.py:769-770 + :73): voxel -> program labels [N] (int64)."""
+    z = _rand((1, voxel_graph.num_nodes, cfg.Z_DIM), voxel_graph.x.device, rng, normal=True)
+    _, hard, _ = generator(local_graph, voxel_graph, z)
+    return hard.argmax(dim=1)

@@ -123,35 +123,54 @@ def raw_building(building_id: int, **grid_kw) -> Tuple[dict, dict, dict]:
             for i in range(loc.shape[0])
         ]
     }
+    glob = _global_record(g)
+    return glob, {"node": _local_nodes(g)}, voxel
+
+
+def _global_record(g: Dict[str, np.ndarray]) -> dict:
+    typ = g["type"]
     site_area = int(min(1600, max(324, int(g["plan"][0]) * int(g["plan"][1]))))
     solid = typ >= 0
-    gfa = float((g["dimension"][solid, 1] * g["dimension"][solid, 2]).sum())
-    area_by_type = np.array([(g["dimension"][typ == t, 1] * g["dimension"][typ == t, 2]).sum() for t in range(6)])
+    area = g["dimension"][:, 1] * g["dimension"][:, 2]
+    gfa = float(area[solid].sum())
+    area_by_type = np.array([area[typ == t].sum() for t in range(6)])
     prop = area_by_type / max(area_by_type.sum(), 1.0)
-    glob = {
+    return {
         "far": gfa / site_area,
         "site_area": site_area,
         "global_node": [{"type": t, "proportion": float(prop[t])} for t in range(6) if prop[t] > 0],
     }
-    # program graph: one node per (floor, type); same-floor nodes are chained, same-type nodes of
-    # consecutive floors are linked.  models.py never reads local edges (only trainer.py:106 plots them).
+
+
+def _local_nodes(g: Dict[str, np.ndarray]) -> List[dict]:
+    """Program graph: one node per (floor, type); same-floor nodes are chained, same-type nodes of consecutive
+    floors are linked.  models.py never reads local edges (only trainer.py:106 plots them)."""
+    F = int(g["F"])
+    loc, typ = g["location"], g["type"]
+    mid = g["coordinate"] + g["dimension"] / 2
     nodes, index = [], {}
     for f in range(F):
+        on_floor = loc[:, 0] == f
         for t in range(6):
-            sel = (loc[:, 0] == f) & (typ == t)
+            sel = on_floor & (typ == t)
             if sel.any():
-                ctr = (g["coordinate"][sel] + g["dimension"][sel] / 2).mean(0)
                 index[(f, t, 0)] = len(nodes)
-                nodes.append({"floor": f, "type": t, "type_id": 0, "center": ctr.tolist(), "neighbors": []})
+                nodes.append({"floor": f, "type": t, "type_id": 0, "center": mid[sel].mean(0).tolist(), "neighbors": []})
     keys = list(index.keys())
-    for a, ka in enumerate(keys):
-        for kb in keys[a + 1:]:
-            same_floor_chain = ka[0] == kb[0] and kb[1] == min(k[1] for k in keys if k[0] == ka[0] and k[1] > ka[1])
-            stacked = ka[1] == kb[1] and kb[0] == ka[0] + 1
-            if same_floor_chain or stacked:
-                nodes[index[ka]]["neighbors"].append(list(kb))
-                nodes[index[kb]]["neighbors"].append(list(ka))
-    return glob, {"node": nodes}, voxel
+    by_floor: Dict[int, List[int]] = {}
+    for k in keys:
+        by_floor.setdefault(k[0], []).append(k[1])
+    for ka in keys:
+        nxt = [t for t in by_floor[ka[0]] if t > ka[1]]
+        links = []
+        if nxt:
+            links.append((ka[0], min(nxt), 0))
+        if (ka[0] + 1, ka[1], 0) in index:
+            links.append((ka[0] + 1, ka[1], 0))
+        for kb in links:
+            nodes[index[ka]]["neighbors"].append(list(kb))
+            nodes[index[kb]]["neighbors"].append(list(ka))
+    return nodes
 
 
 def process_raw(glob: dict, local: dict, voxel: dict, cfg=Configuration, data_number: str = "000000"):
@@ -219,19 +238,26 @@ def building_pair(building_id: int, cfg=Configuration, **grid_kw) -> Tuple[Data,
     return Data(**lf), Data(**vf)
 
 
-def large_grid_pair(building_id: int, floors: int = 10, ny: int = 100, nx: int = 100, cfg=Configuration) -> Tuple[Data, Data]:
-    """BASELINE config 4: one F x Y x X irregular grid (default 1e5 voxels, 576 000 directed edges)
-    built straight from arrays - the JSON detour of ``raw_building`` is O(N) Python objects."""
-    g = grid_arrays(building_id, floors=floors, ny=ny, nx=nx)
+def building_pair_fast(building_id: int, cfg=Configuration, **grid_kw) -> Tuple[Data, Data]:
+    """Same (local Data, voxel Data) as ``building_pair`` - bit for bit, tests/test_collate.py - but built straight
+    from arrays: the JSON detour of ``raw_building`` costs O(N) Python objects (0.1-0.2 s per building)."""
+    g = grid_arrays(building_id, **grid_kw)
     F, Y, X = int(g["F"]), int(g["Y"]), int(g["X"])
     K = cfg.NUM_CLASSES
+    number = f"{building_id:06d}"
+    glob = _global_record(g)
+    far = torch.tensor([glob["far"]])
+    site = torch.tensor([glob["site_area"]])
+    site_n = site / cfg.NORMALIZATION_FACTOR_SITE
+    ratio = [0] * K
+    for gn in glob["global_node"]:
+        ratio[gn["type"]] = gn["proportion"]
+    ratio = torch.tensor(ratio)
+
     src, dst = _neighbour_pairs(g["location"], F, Y, X)
     n = g["location"].shape[0]
     typ = torch.from_numpy(np.where(g["type"] < 0, cfg.VOID, g["type"]))
     onehot = torch.nn.functional.one_hot(typ, num_classes=K)
-    site = torch.tensor([1600])
-    solid = g["type"] >= 0
-    far = torch.tensor([float((g["dimension"][solid, 1] * g["dimension"][solid, 2]).sum()) / 1600.0])
     loc = torch.from_numpy(g["location"])
     feats = torch.from_numpy(np.concatenate(
         [g["coordinate"] / cfg.NORMALIZATION_FACTOR_COORDINATE, g["dimension"] / cfg.NORMALIZATION_FACTOR_DIMENSION,
@@ -239,25 +265,30 @@ def large_grid_pair(building_id: int, floors: int = 10, ny: int = 100, nx: int =
     floor = loc[:, 0].clone()
     counts = torch.bincount(typ, minlength=K) / n
     vx = torch.cat([feats, torch.zeros(n, 1) + far, (floor / cfg.NORMALIZATION_FACTOR_FLOOR_LEVEL).unsqueeze(1),
-                    (site / cfg.NORMALIZATION_FACTOR_SITE).repeat(n).unsqueeze(1)], 1)
+                    site_n.repeat(n).unsqueeze(1)], 1)
     voxel = Data(
         x=vx, edge_index=torch.from_numpy(np.stack([src, dst])), voxel_level=floor, type=typ, types_onehot=onehot,
         coordinate=torch.from_numpy(g["coordinate"]).float(), dimension=torch.from_numpy(g["dimension"]).float(),
-        location=loc, node_ratio=(onehot * counts).max(dim=1)[0].unsqueeze(1),
-        data_number=[f"{building_id:06d}"] * n, site_area=site.repeat(n))
-    # program graph: one node per (floor, type) present
-    rows = sorted({(int(f), int(t)) for f, t in zip(g["location"][:, 0], g["type"]) if t >= 0})
-    m = len(rows)
-    l_floor = torch.tensor([r[0] for r in rows])
-    l_type = torch.tensor([r[1] for r in rows])
+        location=loc, node_ratio=(onehot * counts).max(dim=1)[0].unsqueeze(1), data_number=[number] * n,
+        site_area=site.repeat(n))
+
+    ln = _local_nodes(g)
+    m = len(ln)
+    l_floor = torch.tensor([v["floor"] for v in ln])
+    l_type = torch.tensor([v["type"] for v in ln])
     l_onehot = torch.nn.functional.one_hot(l_type, num_classes=K)
-    ratio = torch.bincount(typ[typ != cfg.VOID], minlength=K).float()
-    ratio = ratio / ratio.sum().clamp(min=1)
-    lx = torch.cat([l_onehot, l_onehot * ratio, torch.zeros(m, 1) + far,
-                    (l_floor / cfg.NORMALIZATION_FACTOR_FLOOR_LEVEL).unsqueeze(1),
-                    (site / cfg.NORMALIZATION_FACTOR_SITE).repeat(m).unsqueeze(1)], 1)
+    l_ratio = l_onehot * ratio
+    lookup = {(v["floor"], v["type"], v["type_id"]): i for i, v in enumerate(ln)}
+    pairs = sorted({(lookup[(v["floor"], v["type"], v["type_id"])], lookup[tuple(nb)]) for v in ln for nb in v["neighbors"]})
+    lx = torch.cat([l_onehot, l_ratio, torch.zeros(m, 1) + far, (l_floor / cfg.NORMALIZATION_FACTOR_FLOOR_LEVEL).unsqueeze(1),
+                    site_n.repeat(m).unsqueeze(1)], 1)
     local = Data(
-        x=lx, edge_index=torch.zeros(2, 0, dtype=torch.long), node_cluster=l_type.clone(), node_ratio=l_onehot * ratio,
-        types_onehot=l_onehot, center=torch.zeros(m, 3), type=l_type, type_id=torch.zeros(m, dtype=torch.long),
-        floor=l_floor, data_number=[f"{building_id:06d}"] * m, site_area=site.repeat(m))
+        x=lx, edge_index=torch.tensor(pairs, dtype=torch.long).reshape(-1, 2).t().contiguous(), node_cluster=l_type.clone(),
+        node_ratio=l_ratio, types_onehot=l_onehot, center=torch.tensor([v["center"] for v in ln]), type=l_type,
+        type_id=torch.tensor([v["type_id"] for v in ln]), floor=l_floor, data_number=[number] * m, site_area=site.repeat(m))
     return local, voxel
+
+
+def large_grid_pair(building_id: int, floors: int = 10, ny: int = 100, nx: int = 100, cfg=Configuration) -> Tuple[Data, Data]:
+    """BASELINE config 4: one F x Y x X irregular grid (default 1e5 voxels, 576 000 directed edges)."""
+    return building_pair_fast(building_id, cfg=cfg, floors=floors, ny=ny, nx=nx)

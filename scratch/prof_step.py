@@ -1,0 +1,23 @@
+"""One training step under cudaProfilerStart/Stop for ncu (--profile-from-start off)."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import torch
+import bench
+from building_gan_b200 import Configuration, lib, step
+from building_gan_b200.models import VoxelGNNDiscriminator, VoxelGNNGenerator
+dev = torch.device("cuda", 0)
+cfg = Configuration()
+torch.manual_seed(777)
+G, D = VoxelGNNGenerator(cfg, 17, 12).to(dev), VoxelGNNDiscriminator(cfg, 17, 12).to(dev)
+og = torch.optim.Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS)
+od = torch.optim.Adam(D.parameters(), lr=2e-4, betas=cfg.BETAS)
+host = bench._make_batches(0, 1, 32, pin=False)
+lb, vb = bench._clone_to(*host[0], dev)
+for _ in range(2):
+    step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("N", vb.num_nodes, "E'", vb.bg_csr.num_edges)
