@@ -16,6 +16,7 @@ namespace bg {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kSMs = 148;  // B200
+constexpr int kCounterBytes = 4096;  // head of every reduction workspace: self-resetting ticket counters
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
@@ -114,6 +115,25 @@ __device__ __forceinline__ float gmax(float x, unsigned mask) {
     for (int o = LANES / 2; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(mask, x, o));
     return x;
 }
+
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11): 4 uniform 32-bit words per (counter, key).
+// Used for the fused dropout masks and Gumbel noise: element i of call `offset` reads word i%4 of
+// philox(counter = (i/4, offset), key = seed) - stateless, reproducible, CUDA-graph safe.
+__device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t seed) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// 32 random bits -> uniform in (0, 1]
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
 
 __device__ __forceinline__ float lrelu(float u, float slope) { return u > 0.f ? u : u * slope; }
 __device__ __forceinline__ float lrelu_grad(float u, float slope) { return u > 0.f ? 1.f : slope; }

@@ -166,25 +166,44 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
 }
 
 // ------------------------------------------------------------------------------------------
-// weight gradient: dW[o,k] = sum_n gz[n,o] X[n,k] ; 64x64 tile, rows split over blockIdx.z
+// weight gradients: dW[o,k] = sum_n gz[n,o] X[n,k].  Up to BG_MAX_WGRAD independent problems per launch
+// (a conv block's lin.weight, [att_src;att_dst] and bias reductions share one launch).  grid =
+// (64x64 output tiles of all problems, S row splits).  Every CTA reduces its row range for its tile and
+// publishes a partial; the CTA that draws the tile's last ticket folds the S partials in split order
+// (deterministic) and writes / accumulates the result.  No separate fold launch, no float atomics.
 // ------------------------------------------------------------------------------------------
-struct WgradParams {
-    int64_t N;
+struct WgProblem {
     const float* gz;
     int64_t ld_gz;
     int Cout, K;
     SegView x;
-    int64_t rows_per_split;
-    float* partial;  // [nsplit][Cout][K]
+    float* dW;
+    int64_t ld_dw;
+    float* dbias;
+    int tiles_k, tile_base, ntiles;
+};
+struct WgBatch {
+    int64_t N, rows_per_split;
+    int nprob, S, accumulate;
+    float* partial;          // [total_tiles][S][64*64]
+    unsigned int* counters;  // [total_tiles], zero on entry, zero on exit
+    WgProblem p[BG_MAX_WGRAD];
 };
 
-__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
-    constexpr int T = 64, RB = 16;
+__global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) {
+    constexpr int T = 64, RB = 32;
     __shared__ float Gs[RB][T + 4];
     __shared__ float Xs[RB][T + 4];
+    __shared__ bool is_last;
+    int pi = 0;
+#pragma unroll
+    for (int q = 1; q < BG_MAX_WGRAD; ++q)
+        if (q < b.nprob && (int)blockIdx.x >= b.p[q].tile_base) pi = q;
+    const WgProblem& p = b.p[pi];
+    const int lt = blockIdx.x - p.tile_base;
+    const int k0 = (lt % p.tiles_k) * T, o0 = (lt / p.tiles_k) * T;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-    const int k0 = blockIdx.x * T, o0 = blockIdx.y * T;
-    const int64_t rbeg = (int64_t)blockIdx.z * p.rows_per_split, rend = min(p.N, rbeg + p.rows_per_split);
+    const int64_t rbeg = (int64_t)blockIdx.y * b.rows_per_split, rend = min(b.N, rbeg + b.rows_per_split);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -214,32 +233,46 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
         }
         __syncthreads();
     }
-    float* base = p.partial + (int64_t)blockIdx.z * p.Cout * p.K;
+    float* tile_part = b.partial + ((int64_t)blockIdx.x * b.S) * (T * T);
+    float* mine = tile_part + (int64_t)blockIdx.y * (T * T);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(mine + (ty * 4 + i) * T + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(b.counters + blockIdx.x, 1u);
+        is_last = (t == (unsigned)b.S - 1);
+        if (is_last) b.counters[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = o0 + ty * 4 + i, k = k0 + tx * 4 + j;
-            if (o < p.Cout && k < p.K) base[(int64_t)o * p.K + k] = acc[i][j];
+    for (int i = 0; i < 4; ++i) {
+        const int off = (ty * 4 + i) * T + tx * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < b.S; ++sp) {
+            const float4 v = *reinterpret_cast<const float4*>(tile_part + (int64_t)sp * (T * T) + off);
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-}
-
-__global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const float* __restrict__ partial, int nsplit, int Cout, int K,
-                                                              float* __restrict__ dW, int64_t ld_dw, float* __restrict__ dbias,
-                                                              int accumulate) {
-    const int64_t total = (int64_t)Cout * K;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
-        float t = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) t += partial[(int64_t)sp * total + i];
-        const int o = (int)(i / K), k = (int)(i % K);
-        float* dst = (dbias && k == K - 1) ? dbias + o : dW + (int64_t)o * ld_dw + k;
-        *dst = accumulate ? *dst + t : t;
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+        const int o = o0 + ty * 4 + i;
+        if (o < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + tx * 4 + j;
+                if (k < p.K) {
+                    float* dst = (p.dbias && k == p.K - 1) ? p.dbias + o : p.dW + (int64_t)o * p.ld_dw + k;
+                    *dst = b.accumulate ? *dst + tv[j] : tv[j];
+                }
+            }
+        }
     }
 }
 
-static inline int wgrad_splits(int64_t N, int Cout, int K) {
-    const int64_t tiles = ceil_div(K, 64) * ceil_div(Cout, 64);
-    int64_t ns = ceil_div(2 * kSMs, tiles);
+static inline int wgrad_splits(int64_t N, int total_tiles) {
+    int64_t ns = ceil_div(2 * kSMs, total_tiles);
     const int64_t maxs = ceil_div(N, 64);
     if (ns > maxs) ns = maxs;
     if (ns > 64) ns = 64;
@@ -407,33 +440,59 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     return check_launch("bg_dense_fwd");
 }
 
-extern "C" size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K) {
-    return (size_t)wgrad_splits(N, Cout, K) * (size_t)Cout * (size_t)K * sizeof(float);
+static int wgrad_tiles(int Cout, int K) { return (int)(ceil_div(K, 64) * ceil_div(Cout, 64)); }
+
+extern "C" size_t bg_wgrad_multi_ws(int64_t N, int32_t nprob, const int32_t* Cout, const int32_t* K) {
+    int tiles = 0;
+    for (int i = 0; i < nprob; ++i) tiles += wgrad_tiles(Cout[i], K[i]);
+    return (size_t)kCounterBytes + (size_t)tiles * (size_t)wgrad_splits(N, tiles) * 64 * 64 * sizeof(float);
 }
 
+extern "C" int bg_wgrad_multi(const BgWgrad* probs, int32_t nprob, float* workspace, size_t ws_bytes, void* stream) {
+    BG_REQUIRE(probs && workspace, BG_EINVAL, "bg_wgrad_multi: null pointer");
+    BG_REQUIRE(nprob >= 1 && nprob <= BG_MAX_WGRAD, BG_EINVAL, "bg_wgrad_multi: nprob %d out of range [1,%d]", nprob, BG_MAX_WGRAD);
+    WgBatch b;
+    b.N = probs[0].N;
+    b.nprob = nprob;
+    b.accumulate = probs[0].accumulate;
+    int tiles = 0;
+    int32_t couts[BG_MAX_WGRAD], ks[BG_MAX_WGRAD];
+    for (int i = 0; i < nprob; ++i) {
+        const BgWgrad& a = probs[i];
+        BG_REQUIRE(a.gz && (a.dW || a.dbias), BG_EINVAL, "bg_wgrad_multi: problem %d has null pointers", i);
+        BG_REQUIRE(a.N == b.N && a.accumulate == b.accumulate, BG_EINVAL, "bg_wgrad_multi: problems must share N and accumulate");
+        WgProblem& p = b.p[i];
+        p.gz = a.gz; p.ld_gz = a.ld_gz; p.Cout = a.Cout;
+        if (int rc = fill_segview(p.x, a.nseg, a.seg, &p.K)) return rc;
+        p.dW = a.dW; p.ld_dw = a.ld_dw; p.dbias = a.dbias;
+        p.tiles_k = (int)ceil_div(p.K, 64);
+        p.tile_base = tiles;
+        p.ntiles = wgrad_tiles(p.Cout, p.K);
+        tiles += p.ntiles;
+        couts[i] = p.Cout; ks[i] = p.K;
+    }
+    BG_REQUIRE((size_t)tiles * sizeof(unsigned int) <= (size_t)kCounterBytes, BG_EUNSUPPORTED, "bg_wgrad_multi: too many output tiles (%d)", tiles);
+    BG_REQUIRE(ws_bytes >= bg_wgrad_multi_ws(b.N, nprob, couts, ks), BG_EINVAL, "bg_wgrad_multi: workspace too small");
+    b.S = wgrad_splits(b.N, tiles);
+    int64_t rps = ceil_div(b.N, b.S);
+    b.rows_per_split = ceil_div(rps, 32) * 32;
+    b.counters = reinterpret_cast<unsigned int*>(workspace);
+    b.partial = workspace + kCounterBytes / sizeof(float);
+    dim3 grid((unsigned)tiles, (unsigned)b.S);
+    wgrad_multi_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(b);
+    return check_launch("bg_wgrad_multi");
+}
+
+extern "C" size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K) { return bg_wgrad_multi_ws(N, 1, &Cout, &K); }
+
 extern "C" int bg_dense_wgrad(const BgWgrad* a, void* stream) {
-    BG_REQUIRE(a && a->gz && (a->dW || a->dbias) && a->workspace, BG_EINVAL, "bg_dense_wgrad: null pointer");
-    WgradParams p;
-    p.N = a->N; p.gz = a->gz; p.ld_gz = a->ld_gz; p.Cout = a->Cout;
-    if (int rc = fill_segview(p.x, a->nseg, a->seg, &p.K)) return rc;
-    BG_REQUIRE(a->ws_bytes >= bg_dense_wgrad_ws(a->N, a->Cout, p.K), BG_EINVAL, "bg_dense_wgrad: workspace too small");
-    const int ns = wgrad_splits(a->N, a->Cout, p.K);
-    int64_t rps = ceil_div(a->N, ns);
-    rps = ceil_div(rps, 16) * 16;
-    p.rows_per_split = rps;
-    p.partial = a->workspace;
-    cudaStream_t st = as_stream(stream);
-    dim3 grid((unsigned)ceil_div(p.K, 64), (unsigned)ceil_div(a->Cout, 64), (unsigned)ns);
-    wgrad_kernel<<<grid, kThreads, 0, st>>>(p);
-    const int64_t total = (int64_t)a->Cout * p.K;
-    wgrad_fold_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, kThreads), 4 * kSMs), kThreads, 0, st>>>(
-        a->workspace, ns, a->Cout, p.K, a->dW, a->ld_dw, a->dbias, a->accumulate);
-    return check_launch("bg_dense_wgrad");
+    BG_REQUIRE(a && a->workspace, BG_EINVAL, "bg_dense_wgrad: null pointer");
+    return bg_wgrad_multi(a, 1, a->workspace, a->ws_bytes, stream);
 }
 
 extern "C" size_t bg_ln_act_bwd_ws(int64_t N, int32_t C) {
     (void)N;
-    return 256 + (size_t)(2 * kSMs) * 2 * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)(2 * kSMs) * 2 * (size_t)C * sizeof(float);
 }
 
 extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* xhat, const float* rstd, const float* gamma,
@@ -449,7 +508,7 @@ extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* x
     BG_REQUIRE(rstd && gamma && dgamma && dbeta && workspace, BG_EINVAL, "bg_ln_act_bwd: LayerNorm path needs rstd/gamma/dgamma/dbeta/workspace");
     BG_REQUIRE(ws_bytes >= bg_ln_act_bwd_ws(N, C), BG_EINVAL, "bg_ln_act_bwd: workspace too small");
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
-    float* partials = workspace + 64;
+    float* partials = workspace + kCounterBytes / sizeof(float);
 #define CALL(CC)                                                                                                   \
     {                                                                                                              \
         const int G = reduce_splits(N, RowMap<CC>::RPC);                                                           \

@@ -72,13 +72,23 @@ __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __r
 // H7: Gumbel-softmax + straight-through, one thread per row (K <= 16)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
-                                                              int64_t N, int K, float* __restrict__ soft, float* __restrict__ hard,
+                                                              uint64_t seed, uint64_t offset, int64_t N, int K,
+                                                              float* __restrict__ soft, float* __restrict__ hard,
                                                               int32_t* __restrict__ amax) {
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (r >= N) return;
     float v[16], mx = -INFINITY;
     for (int k = 0; k < K; ++k) {
-        v[k] = (logits[r * K + k] + noise[r * K + k]) / 1.0f;
+        float g;
+        if (noise) g = noise[r * K + k];
+        else {  // Gumbel(0,1) = -log(Exp(1)), Exp(1) = -log(U): what F.gumbel_softmax draws, from Philox
+            if ((k & 3) == 0) {
+                const uint4 rnd = philox4x32((uint64_t)r * 4 + (k >> 2), offset, seed);
+                v[12] = u01(rnd.x); v[13] = u01(rnd.y); v[14] = u01(rnd.z); v[15] = u01(rnd.w);
+            }
+            g = -logf(-logf(v[12 + (k & 3)]) + 1e-20f);
+        }
+        v[k] = (logits[r * K + k] + g) / 1.0f;
         mx = fmaxf(mx, v[k]);
     }
     float sum = 0.f;
@@ -229,7 +239,7 @@ static inline int scatter_splits(int64_t N) {
 }
 
 extern "C" size_t bg_type_scatter_sum_ws(int64_t N, int32_t C, int32_t K) {
-    return 256 + (size_t)scatter_splits(N) * (size_t)K * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)scatter_splits(N) * (size_t)K * (size_t)C * sizeof(float);
 }
 
 extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* type, int64_t N, int32_t C, int32_t K, float* out,
@@ -239,15 +249,16 @@ extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* ty
     BG_REQUIRE((size_t)K * C * sizeof(float) <= 48 * 1024, BG_EUNSUPPORTED, "bg_type_scatter_sum: K*C too large");
     const int G = scatter_splits(N);
     type_scatter_kernel<<<G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream)>>>(
-        g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + 64);
+        g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
     return check_launch("bg_type_scatter_sum");
 }
 
-extern "C" int bg_gumbel_st_fwd(const float* logits, const float* noise, int64_t N, int32_t K, float* soft, float* hard,
-                                int32_t* argmax, void* stream) {
-    BG_REQUIRE(logits && noise && soft && hard, BG_EINVAL, "bg_gumbel_st_fwd: null pointer");
-    BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_gumbel_st_fwd: K=%d not in [1,16]", K);
-    gumbel_fwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(logits, noise, N, K, soft, hard, argmax);
+extern "C" int bg_gumbel_st_fwd(const float* logits, const float* noise, uint64_t seed, uint64_t offset, int64_t N, int32_t K,
+                                float* soft, float* hard, int32_t* argmax, void* stream) {
+    BG_REQUIRE(logits && soft && hard, BG_EINVAL, "bg_gumbel_st_fwd: null pointer");
+    BG_REQUIRE(K >= 1 && K <= 12, BG_EUNSUPPORTED, "bg_gumbel_st_fwd: K=%d not in [1,12]", K);
+    gumbel_fwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(logits, noise, seed, offset, N, K, soft,
+                                                                                          hard, argmax);
     return check_launch("bg_gumbel_st_fwd");
 }
 

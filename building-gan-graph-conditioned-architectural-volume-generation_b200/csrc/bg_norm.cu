@@ -169,11 +169,13 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
     }
 }
 
-// y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep * keep_scale      (flat elementwise)
+// y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep / keep_prob      (flat elementwise)
+// keep: explicit uint8 mask, or (keep == NULL && keep_prob < 1) a Philox Bernoulli(keep_prob) mask.
 __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restrict__ o, const float* __restrict__ w,
                                                             const float* __restrict__ beta, const float* __restrict__ alpha,
                                                             const float* __restrict__ stats, const uint8_t* __restrict__ keep,
-                                                            float keep_scale, int64_t total, int C, float* __restrict__ x1) {
+                                                            float keep_prob, uint64_t seed, uint64_t offset, int64_t total, int C,
+                                                            float* __restrict__ x1) {
     __shared__ float sc[128], sh[128];  // y = o*sc + sh
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const float mu = stats[c], r = stats[C + c];
@@ -181,19 +183,30 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
         sh[c] = beta[c] - w[c] * r * alpha[c] * mu;
     }
     __syncthreads();
+    const bool fused = (keep == nullptr) && keep_prob < 1.f;
+    const float keep_scale = (keep != nullptr || fused) ? 1.f / keep_prob : 1.f;
     const int64_t n4 = total / 4;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(o) + i);
         const int c0 = (int)((i * 4) % C);
         float xv[4] = {x.x, x.y, x.z, x.w}, y[4];
-        uint32_t kp = 0x01010101u;
-        if (keep) kp = __ldg(reinterpret_cast<const uint32_t*>(keep) + i);
+        bool kp[4] = {true, true, true, true};
+        if (keep) {
+            const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(keep) + i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kp[k] = ((m >> (8 * k)) & 0xffu) != 0;
+        } else if (fused) {
+            const uint4 rnd = philox4x32((uint64_t)i, offset, seed);
+            const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kp[k] = u01(rv[k]) <= keep_prob;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = (c0 + k) % C;
             float t = fmaf(xv[k], sc[c], sh[c]);
             t = t > 0.f ? t : 0.f;
-            y[k] = ((kp >> (8 * k)) & 0xffu) ? t * keep_scale : 0.f;
+            y[k] = kp[k] ? t * keep_scale : 0.f;
         }
         reinterpret_cast<float4*>(x1)[i] = make_float4(y[0], y[1], y[2], y[3]);
     }
@@ -202,7 +215,14 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
         const int c = (int)(i % C);
         float t = fmaf(o[i], sc[c], sh[c]);
         t = t > 0.f ? t : 0.f;
-        x1[i] = (!keep || keep[i]) ? t * keep_scale : 0.f;
+        bool kp = true;
+        if (keep) kp = keep[i] != 0;
+        else if (fused) {
+            const uint4 rnd = philox4x32((uint64_t)n4, offset, seed);
+            const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+            kp = u01(rv[threadIdx.x]) <= keep_prob;
+        }
+        x1[i] = kp ? t * keep_scale : 0.f;
     }
 }
 
@@ -427,7 +447,7 @@ using namespace bg;
 
 extern "C" size_t bg_graphnorm_ws(int64_t N, int32_t C) {
     (void)N;
-    return 256 + (size_t)(4 * kSMs) * 3 * (size_t)C * sizeof(float) + 4 * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)(4 * kSMs) * 3 * (size_t)C * sizeof(float) + 4 * (size_t)C * sizeof(float);
 }
 
 #define BG_GN_DISPATCH(C, CALL)                                                                    \
@@ -446,14 +466,15 @@ extern "C" size_t bg_graphnorm_ws(int64_t N, int32_t C) {
     }
 
 extern "C" int bg_graphnorm_fwd(const float* o, const float* w, const float* beta, const float* alpha,
-                                const uint8_t* keep, float keep_scale, int64_t N, int32_t C, float eps, float* x1,
-                                float* stats, float* workspace, size_t ws_bytes, void* stream) {
+                                const uint8_t* keep, float keep_prob, uint64_t seed, uint64_t offset, int64_t N, int32_t C,
+                                float eps, float* x1, float* stats, float* workspace, size_t ws_bytes, void* stream) {
     BG_REQUIRE(o && w && beta && alpha && x1 && stats && workspace, BG_EINVAL, "bg_graphnorm_fwd: null pointer");
     BG_REQUIRE(N > 0, BG_EINVAL, "bg_graphnorm_fwd: N must be > 0");
+    BG_REQUIRE(keep_prob > 0.f && keep_prob <= 1.f, BG_EINVAL, "bg_graphnorm_fwd: keep_prob must be in (0,1]");
     BG_REQUIRE(ws_bytes >= bg_graphnorm_ws(N, C), BG_EINVAL, "bg_graphnorm_fwd: workspace too small");
     cudaStream_t st = as_stream(stream);
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
-    float* partials = workspace + 64;
+    float* partials = workspace + kCounterBytes / sizeof(float);
 #define CALL(CC)                                                                                            \
     {                                                                                                       \
         const int G = gn_splits<CC>(N);                                                                     \
@@ -462,7 +483,7 @@ extern "C" int bg_graphnorm_fwd(const float* o, const float* w, const float* bet
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
     const int64_t total = N * C;
-    gn_apply_kernel<<<flat_grid(total), kThreads, 0, st>>>(o, w, beta, alpha, stats, keep, keep_scale, total, C, x1);
+    gn_apply_kernel<<<flat_grid(total), kThreads, 0, st>>>(o, w, beta, alpha, stats, keep, keep_prob, seed, offset, total, C, x1);
     return check_launch("bg_graphnorm_fwd");
 }
 
@@ -474,7 +495,7 @@ extern "C" int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x
     BG_REQUIRE(ws_bytes >= bg_graphnorm_ws(N, C), BG_EINVAL, "bg_graphnorm_bwd: workspace too small");
     cudaStream_t st = as_stream(stream);
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
-    float* partials = workspace + 64;
+    float* partials = workspace + kCounterBytes / sizeof(float);
     BwdMoments p{gx1, o, x1, alpha, stats, keep_scale};
 #define CALL(CC)                                                                                                     \
     {                                                                                                                \
@@ -497,7 +518,7 @@ extern "C" int bg_graphnorm_bwd2(const float* Xt, const float* gx1, const float*
     BG_REQUIRE(ws_bytes >= bg_graphnorm_ws(N, C), BG_EINVAL, "bg_graphnorm_bwd2: workspace too small");
     cudaStream_t st = as_stream(stream);
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
-    float* b2 = workspace + 64;           // 4*C floats
+    float* b2 = workspace + kCounterBytes / sizeof(float);  // 4*C floats
     float* partials = b2 + 4 * (size_t)C;
     Bwd2Moments p{Xt, gx1, o, x1, alpha, stats, keep_scale};
 #define CALL(CC)                                                                                                        \

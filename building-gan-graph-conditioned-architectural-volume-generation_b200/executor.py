@@ -109,12 +109,18 @@ def _wgrad_with_bias(gz: Tensor, segs, dW: Tensor, db: Tensor, accumulate: bool)
     lib.dense_wgrad(gz, list(segs) + [None], dW=dW, accumulate=accumulate, dbias=db)
 
 
-def conv_forward(P, spec: ConvSpec, csr, x: Tensor, keep: Optional[Tensor], save: bool):
+def conv_forward(P, spec: ConvSpec, csr, x: Tensor, keep, save: bool):
+    """keep: None (eval), an explicit uint8 mask, or ("philox", seed, offset) for in-kernel masks."""
     a_s, a_d = P[spec.conv + ".att_src"].view(-1), P[spec.conv + ".att_dst"].view(-1)
     lin = lib.dense_fwd([x], P[spec.conv + ".lin.weight"], att=(a_s, a_d))
     o, m, z = lib.gat_fwd(csr, lin["out"], lin["s"], lin["d"], P[spec.conv + ".bias"])
-    x1, stats = lib.graphnorm_fwd(o, P[spec.norm + ".weight"], P[spec.norm + ".bias"], P[spec.norm + ".mean_scale"], keep,
-                                  KEEP_SCALE if keep is not None else 1.0)
+    gnp = (P[spec.norm + ".weight"], P[spec.norm + ".bias"], P[spec.norm + ".mean_scale"])
+    if keep is None:
+        x1, stats = lib.graphnorm_fwd(o, *gnp, None, 1.0)
+    elif isinstance(keep, tuple):
+        x1, stats = lib.graphnorm_fwd(o, *gnp, None, KEEP_P, keep[1], keep[2])
+    else:
+        x1, stats = lib.graphnorm_fwd(o, *gnp, keep, KEEP_P)
     sv = None
     if save:
         sv = dict(x=x, h=lin["out"], s=lin["s"], d=lin["d"], o=o, m=m, z=z, x1=x1, stats=stats,

@@ -43,6 +43,15 @@ class BgDense(C.Structure):
                 ("rstd", C.c_void_p), ("s", C.c_void_p), ("d", C.c_void_p)]
 
 
+class BgModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("local_dim", "voxel_dim", "num_classes", "z_dim", "le_dim", "le_layers", "g_hidden",
+                                         "g_mlp_layers", "g_repeat", "d_hidden", "d_repeat")]
+
+
+class BgBatchIn(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("type32", C.c_void_p), ("vx", C.c_void_p)]
+
+
 class BgWgrad(C.Structure):
     _fields_ = [("N", C.c_int64), ("gz", C.c_void_p), ("ld_gz", C.c_int64), ("Cout", C.c_int32), ("nseg", C.c_int32),
                 ("seg", BgSeg * MAX_SEG), ("dW", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),
@@ -51,7 +60,8 @@ class BgWgrad(C.Structure):
 
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
-_P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+_P, _I64, _I32, _F, _SZ, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_uint64
+_MD, _BI, _GR = C.POINTER(BgModelDesc), C.POINTER(BgBatchIn), C.POINTER(BgGraph)
 SIGNATURES = {
     "bg_version": (C.c_int, []),
     "bg_last_error": (C.c_char_p, []),
@@ -62,19 +72,35 @@ SIGNATURES = {
     "bg_dense_fwd": (C.c_int, [C.POINTER(BgDense), _P]),
     "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
+    "bg_wgrad_multi_ws": (_SZ, [_I64, _I32, _P, _P]),
+    "bg_wgrad_multi": (C.c_int, [C.POINTER(BgWgrad), _I32, _P, _SZ, _P]),
     "bg_ln_act_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
     "bg_ln_act_bwd_ws": (_SZ, [_I64, _I32]),
     "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),
-    "bg_graphnorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I64, _I32, _F, _P, _P, _P, _SZ, _P]),
+    "bg_graphnorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _U64, _U64, _I64, _I32, _F, _P, _P, _P, _SZ, _P]),
     "bg_graphnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _I64, _I32, _P, _P, _I32, _P, _P, _SZ, _P]),
     "bg_graphnorm_bwd2": (C.c_int, [_P] * 8 + [_F, _I64, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
     "bg_graphnorm_ws": (_SZ, [_I64, _I32]),
-    "bg_gumbel_st_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "bg_gumbel_st_fwd": (C.c_int, [_P, _P, _U64, _U64, _I64, _I32, _P, _P, _P, _P]),
     "bg_gumbel_st_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "bg_segment_softmax": (C.c_int, [_P, _P, _I64, _P, _P]),
     "bg_segment_pool": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "bg_gen_num_params": (C.c_int32, [_MD]),
+    "bg_disc_num_params": (C.c_int32, [_MD]),
+    "bg_gen_fwd_ws": (_SZ, [_MD, _I64, _I64]),
+    "bg_gen_bwd_ws": (_SZ, [_MD, _I64, _I64]),
+    "bg_gen_forward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _I32, _U64, _U64, _P, _SZ, _P, _SZ, _P, _P, _P, _P]),
+    "bg_gen_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    "bg_disc_fwd_ws": (_SZ, [_MD, _I64, _I64]),
+    "bg_disc_bwd_saved_ws": (_SZ, [_MD, _I64, _I64]),
+    "bg_disc_tmp_ws": (_SZ, [_MD, _I64, _I64]),
+    "bg_disc_forward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _I32, _U64, _U64, _P, _SZ, _P, _SZ, _P, _P]),
+    "bg_disc_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P, _SZ, _P, _P]),
+    "bg_disc_backward2": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P, _P]),
+    "bg_gen_ws_offsets": (C.c_int32, [_MD, _I64, _P, _I32]),
+    "bg_disc_ws_offsets": (C.c_int32, [_MD, _I64, _P, _I32]),
     "bg_axpy": (C.c_int, [_P, _P, _F, _I64, _P]),
     "bg_fill": (C.c_int, [_P, _F, _I64, _P]),
 }
@@ -177,8 +203,8 @@ def _cf32(t: Tensor, name: str) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
-# workspace: one persistent zero-initialised buffer per (device, stream); the first 256 bytes hold
-# the self-resetting ticket counter of the "last CTA folds" reductions.
+# workspace: one persistent zero-initialised buffer per (device, stream); the first 4096 bytes hold
+# the self-resetting ticket counters of the "last CTA folds" reductions.
 # ------------------------------------------------------------------------------------------------
 _workspaces: Dict[Tuple[int, int], Tensor] = {}
 
@@ -188,7 +214,7 @@ def workspace(nbytes: int, device: torch.device) -> Tensor:
     ws = _workspaces.get(key)
     need = (nbytes + 3) // 4
     if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 1 << 20), dtype=torch.float32, device=device)
+        ws = torch.zeros(max(need, 4 << 20), dtype=torch.float32, device=device)
         _workspaces[key] = ws
     return ws
 
@@ -351,10 +377,10 @@ def dense_wgrad(gz: Tensor, segs: Sequence[Seg], dW: Optional[Tensor] = None, ac
         accumulate = False
     assert dW.stride(1) == 1 or dW.shape[1] == 1
     nb = lib.bg_dense_wgrad_ws(n, cout, k)
-    ws = workspace(nb + 256, gz.device)
+    ws = workspace(nb, gz.device)
     a.N, a.gz, a.ld_gz, a.Cout, a.nseg = n, gz.data_ptr(), gz.stride(0), cout, len(segs)
     a.dW, a.ld_dw, a.accumulate, a.dbias = dW.data_ptr(), dW.stride(0), int(accumulate), _p(dbias)
-    a.workspace, a.ws_bytes = ws.data_ptr() + 256, ws.numel() * 4 - 256
+    a.workspace, a.ws_bytes = ws.data_ptr(), ws.numel() * 4
     _check(lib.bg_dense_wgrad(C.byref(a), _stream()))
     return dW
 
@@ -440,8 +466,10 @@ def gat_bwd2(csr, Ht: Tensor, St: Tensor, Dt: Tensor, gout: Tensor, h: Tensor, s
 # GraphNorm + ReLU + dropout mask
 # ------------------------------------------------------------------------------------------------
 @_op("graphnorm_fwd", 2)
-def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optional[Tensor], keep_scale: float,
-                  eps: float = 1e-5):
+def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optional[Tensor], keep_prob: float = 1.0,
+                  seed: int = 0, offset: int = 0, eps: float = 1e-5):
+    """GraphNorm + ReLU + dropout.  keep: explicit uint8 mask (then keep_prob = its Bernoulli parameter);
+    keep None and keep_prob < 1: Philox mask from (seed, offset); keep None and keep_prob == 1: eval."""
     lib = load()
     _cf32(o, "o")
     n, c = o.shape
@@ -450,8 +478,8 @@ def graphnorm_fwd(o: Tensor, w: Tensor, beta: Tensor, alpha: Tensor, keep: Optio
     ws = workspace(lib.bg_graphnorm_ws(n, c), o.device)
     if keep is not None:
         assert keep.dtype == torch.uint8 and keep.is_contiguous() and keep.shape == o.shape
-    _check(lib.bg_graphnorm_fwd(o.data_ptr(), w.data_ptr(), beta.data_ptr(), alpha.data_ptr(), _p(keep), keep_scale, n, c, eps,
-                                x1.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream()))
+    _check(lib.bg_graphnorm_fwd(o.data_ptr(), w.data_ptr(), beta.data_ptr(), alpha.data_ptr(), _p(keep), keep_prob, seed, offset,
+                                n, c, eps, x1.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream()))
     return x1, stats
 
 
@@ -497,14 +525,16 @@ def graphnorm_bwd2(Xt: Tensor, gx1: Tensor, o: Tensor, x1: Tensor, w: Tensor, al
 # Gumbel straight-through, segment primitives, utilities
 # ------------------------------------------------------------------------------------------------
 @_op("gumbel_st_fwd", 1)
-def gumbel_st_fwd(logits: Tensor, noise: Tensor):
+def gumbel_st_fwd(logits: Tensor, noise: Optional[Tensor], seed: int = 0, offset: int = 0):
     lib = load()
-    _cf32(logits, "logits"), _cf32(noise, "noise")
+    _cf32(logits, "logits")
+    if noise is not None:
+        _cf32(noise, "noise")
     n, k = logits.shape
     soft, hard = torch.empty_like(logits), torch.empty_like(logits)
     amax = torch.empty(n, dtype=torch.int32, device=logits.device)
-    _check(lib.bg_gumbel_st_fwd(logits.data_ptr(), noise.data_ptr(), n, k, soft.data_ptr(), hard.data_ptr(), amax.data_ptr(),
-                                _stream()))
+    _check(lib.bg_gumbel_st_fwd(logits.data_ptr(), _p(noise), seed, offset, n, k, soft.data_ptr(), hard.data_ptr(),
+                                amax.data_ptr(), _stream()))
     return soft, hard, amax
 
 
@@ -554,3 +584,23 @@ def fill_(y: Tensor, v: float) -> Tensor:
     _cf32(y, "y")
     _check(lib.bg_fill(y.data_ptr(), v, y.numel(), _stream()))
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-pass executors (csrc/bg_passes.cu): one C call per generator / discriminator pass
+# ------------------------------------------------------------------------------------------------
+RED_BYTES = 32 << 20
+
+
+def pass_launches(n: int) -> None:
+    """Launch accounting for the native passes (they bypass the per-op wrappers)."""
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def ptr_array(tensors) -> "C.Array":
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def u8_buffer(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

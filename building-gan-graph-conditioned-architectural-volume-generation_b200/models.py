@@ -11,7 +11,9 @@ torch / CPU fallback - on a machine without the built library or without CUDA ``
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -105,11 +107,63 @@ def _require_gat(kind: str) -> None:
             "there is no torch fallback")
 
 
+# "native" (default): one C call per pass (csrc/bg_passes.cu).  "python": the same passes composed op by op in
+# executor.py (kept as the readable specification of the pass structure and for debugging).
+EXECUTOR = os.environ.get("BG_EXECUTOR", "native")
+# "philox" (default): dropout masks / Gumbel noise generated inside the kernels (Philox4x32-10, seeded from
+# torch.cuda.initial_seed()).  "torch": drawn with torch's device generator in the reference's draw order
+#  - bit-identical RNG stream to the reference running on the same GPU, ~200 extra launches
+# per training step.
+RNG_MODE = os.environ.get("BG_RNG", "philox")
+_philox_calls = 0
+
+
+def _philox_ticket():
+    """(seed, offset) for one model call: offsets are disjoint per call (a call uses offset .. offset+1000)."""
+    global _philox_calls
+    _philox_calls += 1
+    return torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF, _philox_calls * 2048
+
+
+def _model_desc(c, local_dim: int, voxel_dim: int) -> "lib.BgModelDesc":
+    md = lib.BgModelDesc()
+    md.local_dim, md.voxel_dim, md.num_classes, md.z_dim = local_dim, voxel_dim, c.NUM_CLASSES, c.Z_DIM
+    md.le_dim, md.le_layers = c.LOCAL_ENCODER_HIDDEN_DIM, c.LOCAL_GRAPH_ENCODER_REPEAT + 1
+    md.g_hidden, md.g_mlp_layers, md.g_repeat = c.GENERATOR_HIDDEN_DIM, c.GENERATOR_MLP_ENCODER_REPEAT + 1, c.GENERATOR_ENCODER_REPEAT
+    md.d_hidden, md.d_repeat = c.DISCRIMINATOR_HIDDEN_DIM, c.DISCRIMINATOR_ENCODER_REPEAT
+    return md
+
+
+class _NativeState:
+    """Per-model host-side constants of the native executor: model descriptor, grad-bucket offsets, cached
+    parameter-pointer table (invalidated by nn.Module._apply, i.e. .to()/.cuda()/.float())."""
+
+    def __init__(self, model, md, layout):
+        self.md, self.layout = md, layout
+        self.goff = (C.c_int64 * len(layout.names))(*[layout.offsets[n] for n in layout.names])
+        self._ptrs, self._key = None, None
+
+    def ptrs(self, params):
+        key = (params[0].data_ptr(), params[-1].data_ptr(), len(params))
+        if self._key != key:
+            self._ptrs, self._key = lib.ptr_array(params), key
+        return self._ptrs
+
+
+def _batch_in(bc) -> "lib.BgBatchIn":
+    b = getattr(bc, "c_in", None)
+    if b is None:
+        b = lib.BgBatchIn()
+        b.table, b.type32, b.vx = bc.table.data_ptr(), bc.type32.data_ptr(), bc.vx.data_ptr()
+        bc.c_in = b
+    return b
+
+
 # ------------------------------------------------------------------------------------------------
 # per-batch cache of data-only quantities (hoisted out of every forward call, SURVEY H1/H2)
 # ------------------------------------------------------------------------------------------------
 class _BatchCtx:
-    __slots__ = ("csr", "type32", "vx", "table", "local_id", "n", "real_onehot")
+    __slots__ = ("csr", "type32", "vx", "table", "local_id", "n", "real_onehot", "c_in")
 
 
 def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
@@ -126,6 +180,7 @@ def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
         ctx.local_id = id(local_graph)
         ctx.n = int(ctx.vx.shape[0])
         ctx.real_onehot = None
+        ctx.c_in = None
         try:
             voxel_graph._bg_cache = ctx
         except Exception:
@@ -170,19 +225,30 @@ class VoxelGNNGenerator(nn.Module):
         self._dec.append(DenseSpec("decoder.12", None, ACT_NONE))
         self._names = [n for n, _ in self.named_parameters()]
         self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
+        self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
+        assert lib.load().bg_gen_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
     def forward(self, local_graph, voxel_graph, z, gumbel_noise: Optional[Tensor] = None, keeps=None):
+        """(logits, label_hard, label_soft), reference models.py:119-155.  ``gumbel_noise`` [N,7] / ``keeps`` (one
+        uint8 [N,C] keep-mask per conv block) inject the random draws explicitly (parity tests); by default they
+        are drawn according to RNG_MODE."""
         lib.load()
         bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
         zz = z.squeeze(0).to(bc.vx.device, torch.float32).contiguous()
-        if keeps is None:
-            keeps = _draw_keeps(bc.n, self._convs, self.training, bc.vx.device)
-        if gumbel_noise is None:
+        seed, offset = _philox_ticket()
+        if keeps is None and self.training and (RNG_MODE == "torch" or EXECUTOR == "python"):
+            keeps = _draw_keeps(bc.n, self._convs, True, bc.vx.device)
+        if gumbel_noise is None and (RNG_MODE == "torch" or EXECUTOR == "python"):
             gumbel_noise = -torch.empty(bc.n, self.configuration.NUM_CLASSES, device=bc.vx.device).exponential_().log()
-        params = [p for _, p in self.named_parameters()]
+        if gumbel_noise is not None:
+            gumbel_noise = gumbel_noise.to(torch.float32).contiguous()
+        params = list(self.parameters())
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        logits, hard, soft = _GenFn.apply(self, bc, zz, gumbel_noise.contiguous(), keeps, need, *params)
+        fn = _GenFn if EXECUTOR == "python" else _GenNativeFn
+        if EXECUTOR == "python" and keeps is None:
+            keeps = [None] * len(self._convs)
+        logits, hard, soft = fn.apply(self, bc, zz, gumbel_noise, keeps, need, (seed, offset), *params)
         return logits, hard, soft
 
     # -- passes -----------------------------------------------------------------------------------
@@ -249,7 +315,7 @@ class VoxelGNNGenerator(nn.Module):
 
 class _GenFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, *params):
+    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, ticket, *params):
         P = dict(zip(model._names, params))
         logits, hard, soft, sv = model._forward_pass(P, bc, zz, noise, keeps, save=need)
         if getattr(model, "debug_keep_saved", False):
@@ -265,7 +331,87 @@ class _GenFn(torch.autograd.Function):
         cont = lambda t: None if t is None else t.contiguous()
         flat = ctx.model._backward_pass(ctx.P, ctx.bc, ctx.sv, cont(g_logits), cont(g_hard), cont(g_soft))
         lay = ctx.model._layout
-        return (None, None, None, None, None, None) + tuple(lay.view(flat, n) for n in ctx.model._names)
+        return (None, None, None, None, None, None, None) + tuple(lay.view(flat, n) for n in ctx.model._names)
+
+
+def _saved_views(model, ws: Tensor, n: int, last: Tensor, is_gen: bool):
+    """Test hook: the post-activation tensors of the last native forward as views into its workspace, in the
+    dict shape the python executor produces ({"menc"/"mlp"/"pre", "conv", "dec"} -> [{"out"| "x1": tensor}])."""
+    L, st = lib.load(), model._native
+    off = (C.c_int64 * 64)()
+    cnt = (L.bg_gen_ws_offsets if is_gen else L.bg_disc_ws_offsets)(C.byref(st.md), n, off, 64)
+    offs = list(off[:cnt])
+    wsf = ws.view(torch.float32)
+
+    def take(rows, width):
+        o = offs.pop(0) // 4
+        return wsf[o: o + rows * width].view(rows, width)
+
+    k = model.configuration.NUM_CLASSES
+    sv = {}
+    if is_gen:
+        sv["menc"] = [{"out": take(k, model._le)} for _ in model._menc]
+        sv["mlp"] = [{"out": take(n, model._gh)} for _ in model._mlp]
+    else:
+        dh = model.configuration.DISCRIMINATOR_HIDDEN_DIM
+        sv["pre"] = [{"out": take(n, dh)} for _ in model._pre]
+    sv["conv"] = [{"x1": take(n, c.cout)} for c in model._convs]
+    widths = ([model._gh, model._gh // 2, model._gh // 4, model._gh // 8, k] if is_gen else
+              [dh // 2, dh // 4, dh // 8, 1])
+    sv["dec"] = [{"out": take(n, w)} for w in widths]
+    sv["dec"][-1]["out"] = last
+    return sv
+
+
+def _launches_gen_fwd(model) -> int:
+    return len(model._menc) + len(model._mlp) + 4 * len(model._convs) + len(model._dec) + 1
+
+
+class _GenNativeFn(torch.autograd.Function):
+    """Generator forward/backward as two C calls (bg_gen_forward / bg_gen_backward)."""
+
+    @staticmethod
+    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, ticket, *params):
+        L, st = lib.load(), model._native
+        dev, n, e, k = zz.device, bc.n, bc.csr.num_edges, model.configuration.NUM_CLASSES
+        ws = lib.u8_buffer(L.bg_gen_fwd_ws(C.byref(st.md), n, e), dev)
+        red = lib.workspace(lib.RED_BYTES, dev)
+        logits = torch.empty(n, k, dtype=torch.float32, device=dev)
+        hard, soft = torch.empty_like(logits), torch.empty_like(logits)
+        kp = None if not keeps or keeps[0] is None else lib.ptr_array(keeps)
+        lib._check(L.bg_gen_forward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
+                                    zz.data_ptr(), lib._p(noise), kp, int(model.training), ticket[0], ticket[1], ws.data_ptr(),
+                                    ws.numel(), red.data_ptr(), red.numel() * 4, logits.data_ptr(), hard.data_ptr(),
+                                    soft.data_ptr(), lib._stream()))
+        lib.pass_launches(_launches_gen_fwd(model))
+        if getattr(model, "debug_keep_saved", False):
+            model.debug_saved = _saved_views(model, ws, n, logits, True)
+        if need:
+            ctx.model, ctx.bc, ctx.ws, ctx.zz, ctx.training = model, bc, ws, zz, model.training
+            ctx.save_for_backward(logits, soft, *params)
+        ctx.need = need
+        return logits, hard, soft
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_logits, g_hard, g_soft):
+        if not ctx.need:
+            raise RuntimeError("generator backward called but the forward ran without grad")
+        L, model, bc = lib.load(), ctx.model, ctx.bc
+        st = model._native
+        logits, soft, *params = ctx.saved_tensors
+        dev, n, e = logits.device, bc.n, bc.csr.num_edges
+        flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
+        tmp = lib.u8_buffer(L.bg_gen_bwd_ws(C.byref(st.md), n, e), dev)
+        red = lib.workspace(lib.RED_BYTES, dev)
+        cont = lambda t: None if t is None else t.contiguous()
+        g_logits, g_hard, g_soft = cont(g_logits), cont(g_hard), cont(g_soft)
+        lib._check(L.bg_gen_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
+                                     ctx.zz.data_ptr(), ctx.ws.data_ptr(), logits.data_ptr(), soft.data_ptr(), lib._p(g_logits),
+                                     lib._p(g_hard), lib._p(g_soft), int(ctx.training), flat.data_ptr(), st.goff, tmp.data_ptr(),
+                                     tmp.numel(), red.data_ptr(), red.numel() * 4, lib._stream()))
+        lib.pass_launches(2 + 3 * (len(model._menc) + len(model._mlp) + len(model._dec)) + 7 * len(model._convs) + 8)
+        return (None,) * 7 + tuple(st.layout.view(flat, nm) for nm in model._names)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,20 +441,28 @@ class VoxelGNNDiscriminator(nn.Module):
         self._names = [n for n, _ in self.named_parameters()]
         self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
         self._label_lo = local_graph_dim + voxel_graph_dim
+        self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
+        assert lib.load().bg_disc_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
     def forward(self, local_graph, voxel_graph, label_hard, keeps=None):
+        """Per-voxel critic score [N,1], reference models.py:229-245.  ``keeps`` injects explicit dropout masks."""
         lib.load()
         bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
         label = label_hard.squeeze(0)
         if label.dtype != torch.float32:  # the real sample is an int64 one-hot (trainer.py:319); torch.cat promotes it
-            label = label.to(torch.float32)
+            if bc.real_onehot is None or bc.real_onehot[0] != label.data_ptr():
+                bc.real_onehot = (label.data_ptr(), label.to(bc.vx.device, torch.float32).contiguous())
+            label = bc.real_onehot[1]
         label = label.to(bc.vx.device).contiguous()
-        if keeps is None:
-            keeps = _draw_keeps(bc.n, self._convs, self.training, bc.vx.device)
-        params = [p for _, p in self.named_parameters()]
+        seed, offset = _philox_ticket()
+        if keeps is None and self.training and (RNG_MODE == "torch" or EXECUTOR == "python"):
+            keeps = _draw_keeps(bc.n, self._convs, True, bc.vx.device)
+        params = list(self.parameters())
         need = torch.is_grad_enabled() and (label.requires_grad or any(p.requires_grad for p in params))
-        return _DiscFn.apply(self, bc, keeps, need, label, *params)
+        if EXECUTOR == "python":
+            return _DiscFn.apply(self, bc, keeps if keeps is not None else [None] * len(self._convs), need, label, *params)
+        return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset), label, *params)
 
     # -- passes -----------------------------------------------------------------------------------
     def _forward_pass(self, P, bc: _BatchCtx, label: Tensor, keeps, save: bool):
@@ -429,3 +583,85 @@ class _DiscBwdFn(torch.autograd.Function):
         # the cotangent on `label` (third-order coupling into the generator) is not needed by WGAN-GP: the
         # interpolate is built from detached samples (trainer.py:298-301)
         return (None, None, None, None, gt, None) + tuple(model._layout.view(flat2, n) for n in model._names)
+
+
+# ------------------------------------------------------------------------------------------------
+# native discriminator passes: bg_disc_forward / bg_disc_backward / bg_disc_backward2
+# ------------------------------------------------------------------------------------------------
+class _DiscNativeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, keeps, need, ticket, label, *params):
+        L, st = lib.load(), model._native
+        dev, n, e = label.device, bc.n, bc.csr.num_edges
+        ws = lib.u8_buffer(L.bg_disc_fwd_ws(C.byref(st.md), n, e), dev)
+        red = lib.workspace(lib.RED_BYTES, dev)
+        score = torch.empty(n, 1, dtype=torch.float32, device=dev)
+        kp = None if not keeps or keeps[0] is None else lib.ptr_array(keeps)
+        lib._check(L.bg_disc_forward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
+                                     label.data_ptr(), kp, int(model.training), ticket[0], ticket[1], ws.data_ptr(), ws.numel(),
+                                     red.data_ptr(), red.numel() * 4, score.data_ptr(), lib._stream()))
+        lib.pass_launches(2 + 4 * len(model._convs) + 4)
+        if getattr(model, "debug_keep_saved", False):
+            model.debug_saved = _saved_views(model, ws, n, score, False)
+        ctx.need = need
+        if need:
+            ctx.model, ctx.bc, ctx.ws, ctx.training = model, bc, ws, model.training
+            ctx.save_for_backward(label, score, *params)
+        return score
+
+    @staticmethod
+    def backward(ctx, g_score):
+        if not ctx.need:
+            raise RuntimeError("discriminator backward called but the forward ran without grad")
+        label, score, *params = ctx.saved_tensors
+        outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training, torch.is_grad_enabled(), score,
+                                      g_score.contiguous(), label, *params)
+        return (None, None, None, None, None) + tuple(outs)
+
+
+class _DiscNativeBwdFn(torch.autograd.Function):
+    """First-order backward of the discriminator as a differentiable op (its backward = the second-order sweep)."""
+
+    @staticmethod
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, second_order, score, g_score, label, *params):
+        L, st = lib.load(), model._native
+        dev, n, e = label.device, bc.n, bc.csr.num_edges
+        flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
+        saved = lib.u8_buffer(L.bg_disc_bwd_saved_ws(C.byref(st.md), n, e), dev) if second_order else None
+        tmp = lib.u8_buffer(L.bg_disc_tmp_ws(C.byref(st.md), n, e), dev)
+        red = lib.workspace(lib.RED_BYTES, dev)
+        g_label = torch.empty_like(label)
+        lib._check(L.bg_disc_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
+                                      label.data_ptr(), ws.data_ptr(), score.data_ptr(), g_score.data_ptr(), int(training),
+                                      flat.data_ptr(), st.goff, lib._p(saved), 0 if saved is None else saved.numel(),
+                                      tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4, g_label.data_ptr(),
+                                      lib._stream()))
+        lib.pass_launches(3 * 4 + 7 * len(model._convs) + 3 * 2)
+        ctx.model, ctx.bc, ctx.ws, ctx.saved, ctx.training = model, bc, ws, saved, training
+        ctx.save_for_backward(label, score, *params)
+        grads = tuple(st.layout.view(flat, nm) for nm in model._names)
+        ctx.mark_non_differentiable(*grads)
+        return (g_label,) + grads
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, Lt, *unused):
+        if ctx.saved is None:
+            raise RuntimeError("second-order backward requested but the first backward ran without create_graph=True")
+        L, model, bc = lib.load(), ctx.model, ctx.bc
+        st = model._native
+        label, score, *params = ctx.saved_tensors
+        dev, n, e = label.device, bc.n, bc.csr.num_edges
+        flat2 = torch.zeros(st.layout.total, dtype=torch.float32, device=dev)
+        tmp = lib.u8_buffer(2 * L.bg_disc_tmp_ws(C.byref(st.md), n, e), dev)
+        red = lib.workspace(lib.RED_BYTES, dev)
+        want_gt = ctx.needs_input_grad[6]
+        gt = torch.empty_like(score) if want_gt else None
+        lib._check(L.bg_disc_backward2(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
+                                       label.data_ptr(), ctx.ws.data_ptr(), score.data_ptr(), ctx.saved.data_ptr(),
+                                       Lt.contiguous().data_ptr(), int(ctx.training), flat2.data_ptr(), st.goff, tmp.data_ptr(),
+                                       tmp.numel(), red.data_ptr(), red.numel() * 4, lib._p(gt), lib._stream()))
+        lib.pass_launches(6 + 9 * len(model._convs) + 8 + 7 * len(model._convs) + 6)
+        # the cotangent on `label` (third-order coupling into the generator) is not needed by WGAN-GP: the interpolate is
+        # built from detached samples (trainer.py:298-301)
+        return (None, None, None, None, None, None, gt, None) + tuple(st.layout.view(flat2, nm) for nm in model._names)

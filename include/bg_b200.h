@@ -83,6 +83,7 @@ typedef struct BgSeg {
     int32_t ld; /* row stride in floats */
 } BgSeg;
 #define BG_MAX_SEG 6
+#define BG_MAX_WGRAD 4
 #define BG_ACT_NONE 0
 #define BG_ACT_RELU 1
 #define BG_ACT_LRELU 2 /* LeakyReLU(0.2) */
@@ -125,6 +126,11 @@ typedef struct BgWgrad {
 } BgWgrad;
 size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K);
 int bg_dense_wgrad(const BgWgrad* a, void* stream);
+/* Up to BG_MAX_WGRAD weight-gradient problems over the same N rows in ONE launch (the workspace / ws_bytes
+ * fields of the individual problems are ignored; all must share N and accumulate).  The first 4096 bytes of
+ * every reduction workspace hold self-resetting ticket counters: zero them once, never again. */
+size_t bg_wgrad_multi_ws(int64_t N, int32_t nprob, const int32_t* Cout, const int32_t* K);
+int bg_wgrad_multi(const BgWgrad* probs, int32_t nprob, float* workspace, size_t ws_bytes, void* stream);
 
 /* Backward of LayerNorm + LeakyReLU(0.2) (or of a bare activation when xhat==NULL):
  * gz = d loss / d (x W^T + b) from gout, the layer output `out`, xhat, rstd, gamma.
@@ -158,13 +164,15 @@ int bg_gat_bwd2(const BgGraph* g, const float* Ht, const float* St, const float*
 
 /* ---- H5b/H5c/H9: GraphNorm (called with batch=None => ONE segment over all nodes, reference
  * models.py:73,83,193,203) fused with ReLU(inplace) and Dropout(0.2) (models.py:74-75).
- * y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep * keep_scale.
- * stats[3*C] = (mu, rstd, var) is written by fwd and read by bwd/bwd2.  keep: optional uint8
- * [N,C] Bernoulli mask drawn by the caller (torch RNG, reference draw order); NULL in eval.
- * seg_ptr/nseg: segment pointer for per-graph statistics (nseg==1 reproduces the reference). */
+ * y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep / keep_prob.
+ * stats[3*C] = (mu, rstd, var) is written by fwd and read by bwd/bwd2.  Dropout mask, three modes:
+ * keep != NULL: explicit uint8 [N,C] Bernoulli mask drawn by the caller (torch RNG, reference draw
+ * order); keep == NULL && keep_prob < 1: Philox4x32-10 mask from (seed, offset) generated in the
+ * kernel; keep == NULL && keep_prob == 1: eval (no dropout).  The backward kernels take
+ * keep_scale = 1/keep_prob (1 in eval) and recover the mask from x1 > 0. */
 int bg_graphnorm_fwd(const float* o, const float* w, const float* beta, const float* alpha,
-                     const uint8_t* keep, float keep_scale, int64_t N, int32_t C, float eps,
-                     float* x1, float* stats, float* workspace, size_t ws_bytes, void* stream);
+                     const uint8_t* keep, float keep_prob, uint64_t seed, uint64_t offset, int64_t N, int32_t C,
+                     float eps, float* x1, float* stats, float* workspace, size_t ws_bytes, void* stream);
 /* gx1 -> go, plus parameter gradients dparams[3*C] = (dw, dbeta, dalpha) and bstats[2*C] =
  * (G0, G1) saved for bwd2. */
 int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x1, const float* w, const float* alpha,
@@ -179,9 +187,10 @@ int bg_graphnorm_bwd2(const float* Xt, const float* gx1, const float* o, const f
 size_t bg_graphnorm_ws(int64_t N, int32_t C);
 
 /* ---- H7: Gumbel-softmax (tau=1) + straight-through one-hot (reference models.py:150-153).
- * noise = Gumbel(0,1) samples drawn by the caller.  hard = (onehot(argmax soft) - soft) + soft. */
-int bg_gumbel_st_fwd(const float* logits, const float* noise, int64_t N, int32_t K, float* soft,
-                     float* hard, int32_t* argmax, void* stream);
+ * noise = Gumbel(0,1) samples drawn by the caller, or NULL: drawn in the kernel from Philox(seed, offset).
+ * hard = (onehot(argmax soft) - soft) + soft. */
+int bg_gumbel_st_fwd(const float* logits, const float* noise, uint64_t seed, uint64_t offset, int64_t N,
+                     int32_t K, float* soft, float* hard, int32_t* argmax, void* stream);
 int bg_gumbel_st_bwd(const float* g_hard, const float* g_soft, const float* soft, int64_t N, int32_t K,
                      float* g_logits, void* stream);
 
@@ -191,6 +200,62 @@ int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_t S, float*
 /* mode 0 = mean, 1 = max, 2 = sum; x[N,C] -> out[S,C] */
 int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S, int32_t C, int32_t mode,
                     float* out, void* stream);
+
+/* ---- whole-pass executors: ONE call = one forward / backward / second-order-backward pass of the reference's
+ * VoxelGNNGenerator (models.py:119-155) or VoxelGNNDiscriminator (models.py:229-245) as a fixed sequence of
+ * launches on `stream`.  `params` = device pointers in torch's named_parameters() order of the reference
+ * modules; `grad_off[i]` = offset (floats) of parameter i's gradient inside `grad_flat` (GraphNorm's
+ * weight/bias/mean_scale and GATConv's att_src/att_dst must be back to back).  `ws` holds the activations the
+ * backward needs (size from *_fwd_ws, caller-owned, must stay alive until the backward ran); `red` is a
+ * reduction workspace whose first 4096 bytes are zero on first use (>= 8 MiB); `tmp` is scratch.
+ * Dropout: training!=0 with keeps==NULL draws Philox masks from (seed, offset + block index); keeps[k] != NULL
+ * supplies explicit uint8 [N,C_k] masks (reference RNG order); training==0 disables dropout.
+ * Gumbel noise: `noise` [N,K] explicit, or NULL => Philox(seed, offset + 1000). */
+typedef struct BgModelDesc {
+    int32_t local_dim, voxel_dim, num_classes, z_dim;
+    int32_t le_dim, le_layers;              /* LOCAL_ENCODER_HIDDEN_DIM, LOCAL_GRAPH_ENCODER_REPEAT + 1 */
+    int32_t g_hidden, g_mlp_layers, g_repeat; /* GENERATOR_HIDDEN_DIM, GENERATOR_MLP_ENCODER_REPEAT + 1, GENERATOR_ENCODER_REPEAT */
+    int32_t d_hidden, d_repeat;
+} BgModelDesc;
+typedef struct BgBatchIn {
+    const float* table;    /* [num_classes, local_dim] type table (bg_type_table) */
+    const int32_t* type32; /* [N] voxel type */
+    const float* vx;       /* [N, voxel_dim] voxel features */
+} BgBatchIn;
+int32_t bg_gen_num_params(const BgModelDesc* md);
+int32_t bg_disc_num_params(const BgModelDesc* md);
+size_t bg_gen_fwd_ws(const BgModelDesc* md, int64_t N, int64_t E);
+size_t bg_gen_bwd_ws(const BgModelDesc* md, int64_t N, int64_t E);
+int bg_gen_forward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
+                   const float* z, const float* noise, const uint8_t* const* keeps, int32_t training, uint64_t seed,
+                   uint64_t offset, void* ws, size_t ws_bytes, float* red, size_t red_bytes, float* logits, float* hard,
+                   float* soft, void* stream);
+int bg_gen_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
+                    const float* z, const void* ws_fwd, const float* logits, const float* soft, const float* g_logits,
+                    const float* g_hard, const float* g_soft, int32_t training, float* grad_flat, const int64_t* grad_off,
+                    void* tmp, size_t tmp_bytes, float* red, size_t red_bytes, void* stream);
+size_t bg_disc_fwd_ws(const BgModelDesc* md, int64_t N, int64_t E);
+size_t bg_disc_bwd_saved_ws(const BgModelDesc* md, int64_t N, int64_t E);
+size_t bg_disc_tmp_ws(const BgModelDesc* md, int64_t N, int64_t E);
+int bg_disc_forward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
+                    const float* label, const uint8_t* const* keeps, int32_t training, uint64_t seed, uint64_t offset,
+                    void* ws, size_t ws_bytes, float* red, size_t red_bytes, float* score, void* stream);
+/* grad_flat may be NULL (input gradient only); saved != NULL keeps the intermediates bg_disc_backward2 needs. */
+int bg_disc_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
+                     const float* label, const void* ws_fwd, const float* score, const float* g_score, int32_t training,
+                     float* grad_flat, const int64_t* grad_off, void* saved, size_t saved_bytes, void* tmp, size_t tmp_bytes,
+                     float* red, size_t red_bytes, float* g_label, void* stream);
+/* WGAN-GP (reference trainer.py:306-312): Lt = cotangent on g_label; grad_flat must be zero on entry and receives
+ * the parameter cotangents (second-order sweep + forward-graph sweep with injections); tmp >= 2*bg_disc_tmp_ws. */
+int bg_disc_backward2(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
+                      const float* label, const void* ws_fwd, const float* score, const void* saved, const float* Lt,
+                      int32_t training, float* grad_flat, const int64_t* grad_off, void* tmp, size_t tmp_bytes, float* red,
+                      size_t red_bytes, float* gt_score, void* stream);
+
+/* Test hooks: byte offsets of the saved post-activation tensors inside a forward workspace, layer order
+ * (generator: menc, mlp, conv x1, dec; discriminator: pre, conv x1, dec).  Returns the count. */
+int32_t bg_gen_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
+int32_t bg_disc_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
 
 /* ---- small utilities used by the host-side executor */
 int bg_axpy(float* y, const float* x, float a, int64_t n, void* stream);          /* y += a*x */

@@ -126,7 +126,7 @@ def test_graphnorm_fwd_bwd_bwd2(C, train):
 
     f = lambda t: t.detach().float().to(DEV).contiguous()
     kk = None if keep is None else keep.to(torch.uint8).to(DEV)
-    x1_k, stats = lib.graphnorm_fwd(f(o), f(w), f(beta), f(alpha), kk, scale)
+    x1_k, stats = lib.graphnorm_fwd(f(o), f(w), f(beta), f(alpha), kk, 0.8 if train else 1.0)
     assert_close(stats[:C], mu, 1e-5, "mu")
     assert_close(stats[2 * C:], var, 1e-5, "var")
     assert_close(x1_k, x1, 1e-5, f"graphnorm_fwd C={C}")
@@ -251,6 +251,32 @@ def test_gumbel_st():
     assert_close(gl_k, gl, 1e-5, "gumbel backward")
 
 
+def test_philox_dropout_and_gumbel_statistics():
+    """Fused RNG mode: Bernoulli(0.8) keep-masks and Gumbel(0,1) noise generated in the kernels from Philox4x32-10
+    (the reference draws them with torch's generator; only the distribution is part of the contract)."""
+    n, C = 20000, 64
+    o = _rand(n, C, seed=1).float().to(DEV)
+    one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    x_eval, _ = lib.graphnorm_fwd(o, one, zero, one, None, 1.0)
+    x_a, _ = lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1234, 7)
+    x_b, _ = lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1234, 7)
+    x_c, _ = lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1234, 8)
+    assert torch.equal(x_a, x_b) and not torch.equal(x_a, x_c)          # counter-based: reproducible, offset-dependent
+    pos = x_eval > 0
+    kept = (x_a > 0)[pos].float().mean().item()
+    assert abs(kept - 0.8) < 0.005, kept
+    assert torch.allclose(x_a[x_a > 0], x_eval[x_a > 0] * 1.25, rtol=1e-6)
+    # column-wise keep rates are uniform (no stripe artefacts from the 4-wide counter layout)
+    col = ((x_a > 0).float().sum(0) / pos.float().sum(0).clamp_min(1)).cpu()
+    assert float((col - 0.8).abs().max()) < 0.03
+    logits = torch.zeros(200000, 7, device=DEV)
+    soft, hard, amax = lib.gumbel_st_fwd(logits, None, 99, 3)
+    freq = torch.bincount(amax.long(), minlength=7).float() / amax.numel()    # argmax of iid Gumbel is uniform
+    assert float((freq - 1 / 7).abs().max()) < 0.005, freq
+    g = torch.log(soft) - torch.log(soft).mean(1, keepdim=True)                # = noise - rowmean(noise)
+    assert abs(float(g.var()) * 7 / 6 - 3.14159 ** 2 / 6) < 0.05              # Var[Gumbel] = pi^2/6
+
+
 def test_segment_primitives():
     lb, vb = small_batch()
     ptr = vb.ptr.to(torch.int32).to(DEV)
@@ -272,4 +298,4 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError, match="unsupported channel width"):
         lib.gat_fwd(csr, h, s, s, None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        lib.graphnorm_fwd(torch.zeros(4, 4), torch.ones(4), torch.zeros(4), torch.ones(4), None, 1.0)
+        lib.graphnorm_fwd(torch.zeros(4, 4), torch.ones(4), torch.zeros(4), torch.ones(4), None)
