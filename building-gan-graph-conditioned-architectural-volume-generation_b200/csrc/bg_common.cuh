@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <vector>
+
 #include "bg_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -20,6 +22,28 @@ constexpr int kCounterBytes = 4096;  // head of every reduction workspace: self-
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+
+// ---- deferred weight-gradient folds (bg_dense.cu): partial sums are queued and folded once per pass
+struct FoldEntry {
+    const float* partial;  // [S][Cout*K]
+    float* dW;
+    float* dbias;          // last column of K routed here when non-null
+    int64_t ld_dw;
+    int S, Cout, K, accumulate, block_base;
+};
+struct FoldBatch {
+    static constexpr int kMax = 56;
+    int n;
+    FoldEntry e[kMax];
+};
+struct WgradQueue {
+    static constexpr int kPhases = 4;
+    std::vector<FoldEntry> phase[kPhases];
+    float* buf = nullptr;
+    size_t cap = 0, used = 0;  // floats
+};
+int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st);
+int wgrad_flush(WgradQueue& q, cudaStream_t st);
 
 #define BG_REQUIRE(cond, code, ...)      \
     do {                                 \
@@ -153,6 +177,68 @@ __device__ __forceinline__ bool last_cta_ticket(unsigned int* counter, unsigned 
     __syncthreads();
     if (is_last) __threadfence();
     return is_last;
+}
+
+// "Last CTA" ticket on an arbitrary counter (self-resetting).
+__device__ __forceinline__ bool ticket_last(unsigned int* counter, unsigned int total) {
+    __shared__ bool is_last_t;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        is_last_t = (t == total - 1);
+        if (is_last_t) *counter = 0u;
+    }
+    __syncthreads();
+    const bool r = is_last_t;
+    if (r) __threadfence();
+    __syncthreads();
+    return r;
+}
+
+// Fixed-order fold of `G` partial vectors of length L (partials[g*L + i]) by the last CTA.
+// Uses S = kThreads / Lp slices (Lp = L rounded up to a power of two, capped at kThreads).
+__device__ __forceinline__ void fold_partials(const float* partials, int G, int L, float* red /*>= kThreads*/,
+                                              float* result /*shared, >= L*/) {
+    for (int base = 0; base < L; base += kThreads) {
+        const int Lt = min(L - base, kThreads);
+        int Lp = 1;
+        while (Lp < Lt) Lp <<= 1;
+        const int S = kThreads / Lp;
+        const int i = threadIdx.x % Lp, sl = threadIdx.x / Lp;
+        float t = 0.f;
+        if (i < Lt)
+#pragma unroll 8
+            for (int g = sl; g < G; g += S) t += partials[(int64_t)g * L + base + i];
+        red[threadIdx.x] = t;
+        __syncthreads();
+        if (threadIdx.x < Lt) {
+            float a = 0.f;
+            for (int q = 0; q < S; ++q) a += red[q * Lp + threadIdx.x];
+            result[base + threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+}
+
+
+// Two-level deterministic fold of G per-CTA partial vectors (length L): the last CTA of every group of
+// kFoldGroup folds its group, the last group folds the group results.  Both folds are <= ~20 deep, so the
+// critical path stays short even with ~300 CTAs.  counters[0] = global ticket, counters[1+g] = group g.
+// Returns true in exactly one CTA, whose `result` (shared, >= L floats) then holds the column sums.
+constexpr int kFoldGroup = 16;
+__device__ __forceinline__ bool hier_fold(float* partials, float* gpartials, int L, unsigned int* counters, float* red,
+                                          float* result) {
+    const int G = gridDim.x;
+    const int group = blockIdx.x / kFoldGroup, ngroups = (G + kFoldGroup - 1) / kFoldGroup;
+    const int gsize = min(kFoldGroup, G - group * kFoldGroup);
+    if (!ticket_last(counters + 1 + group, gsize)) return false;
+    fold_partials(partials + (int64_t)group * kFoldGroup * L, gsize, L, red, result);
+    if (ngroups == 1) return true;
+    for (int i = threadIdx.x; i < L; i += kThreads) gpartials[(int64_t)group * L + i] = result[i];
+    if (!ticket_last(counters, ngroups)) return false;
+    fold_partials(gpartials, ngroups, L, red, result);
+    return true;
 }
 
 }  // namespace bg

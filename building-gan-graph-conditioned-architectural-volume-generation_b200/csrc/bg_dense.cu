@@ -3,6 +3,7 @@
 // s = y.a_src, d = y.a_dst (the `lin` of a GATConv), the split-N deterministic weight gradient
 // and the LayerNorm/activation backward.  fp32 FFMA: this is the rel-1e-5 parity mode.
 #include <algorithm>
+#include <vector>
 
 #include "bg_common.cuh"
 
@@ -29,6 +30,8 @@ __device__ __forceinline__ float seg_fetch(const SegView& sv, int64_t row, int k
     }
     return 0.f;
 }
+
+static int fill_segview(SegView& sv, int nseg, const BgSeg* seg, int* K);
 
 struct DenseParams {
     int64_t N;
@@ -60,17 +63,35 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     for (int k0 = 0; k0 < p.K; k0 += BK) {
+        constexpr int XPER = BM * BK / kThreads, WPER = (BN * BK + kThreads - 1) / kThreads;
+        float xv[XPER], wv[WPER];
 #pragma unroll
-        for (int q = 0; q < BM * BK / kThreads; ++q) {
+        for (int q = 0; q < XPER; ++q) {  // all global loads of the slab first, shared-memory fill afterwards
             const int idx = tid + q * kThreads, r = idx / BK, kk = idx % BK;
             const int64_t grow = row0 + r;
-            Xs[kk][r] = (grow < p.N && k0 + kk < p.K) ? seg_fetch(p.x, grow, k0 + kk) : 0.f;
+            xv[q] = (grow < p.N && k0 + kk < p.K) ? seg_fetch(p.x, grow, k0 + kk) : 0.f;
         }
-        for (int idx = tid; idx < BN * BK; idx += kThreads) {
+#pragma unroll
+        for (int q = 0; q < WPER; ++q) {
+            const int idx = tid + q * kThreads;
             int c, kk;
             if (p.w_sk == 1) { c = idx / BK; kk = idx % BK; } else { kk = idx / BN; c = idx % BN; }
             const int gc = col0 + c, gk = k0 + kk;
-            Ws[kk][c] = (gc < p.Cout && gk < p.K) ? __ldg(p.W + gc * p.w_so + gk * p.w_sk) : 0.f;
+            wv[q] = (idx < BN * BK && gc < p.Cout && gk < p.K) ? __ldg(p.W + gc * p.w_so + gk * p.w_sk) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < XPER; ++q) {
+            const int idx = tid + q * kThreads;
+            Xs[idx % BK][idx / BK] = xv[q];
+        }
+#pragma unroll
+        for (int q = 0; q < WPER; ++q) {
+            const int idx = tid + q * kThreads;
+            if (idx < BN * BK) {
+                int c, kk;
+                if (p.w_sk == 1) { c = idx / BK; kk = idx % BK; } else { kk = idx / BN; c = idx % BN; }
+                Ws[kk][c] = wv[q];
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -169,24 +190,21 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
 // weight gradients: dW[o,k] = sum_n gz[n,o] X[n,k].  Up to BG_MAX_WGRAD independent problems per launch
 // (a conv block's lin.weight, [att_src;att_dst] and bias reductions share one launch).  grid =
 // (64x64 output tiles of all problems, S row splits).  Every CTA reduces its row range for its tile and
-// publishes a partial; the CTA that draws the tile's last ticket folds the S partials in split order
-// (deterministic) and writes / accumulates the result.  No separate fold launch, no float atomics.
+// writes a compact partial [S][Cout*K]; a fold kernel sums the S partials of every queued problem in split
+// order (deterministic, no float atomics).  The whole-pass executors queue the folds and run ONE fold
+// launch per pass (bg_passes.cu); the stand-alone entry point folds immediately.
 // ------------------------------------------------------------------------------------------
 struct WgProblem {
     const float* gz;
     int64_t ld_gz;
     int Cout, K;
     SegView x;
-    float* dW;
-    int64_t ld_dw;
-    float* dbias;
+    float* partial;  // [S][Cout*K]
     int tiles_k, tile_base, ntiles;
 };
 struct WgBatch {
     int64_t N, rows_per_split;
-    int nprob, S, accumulate;
-    float* partial;          // [total_tiles][S][64*64]
-    unsigned int* counters;  // [total_tiles], zero on entry, zero on exit
+    int nprob, S;
     WgProblem p[BG_MAX_WGRAD];
 };
 
@@ -194,7 +212,6 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     constexpr int T = 64, RB = 32;
     __shared__ float Gs[RB][T + 4];
     __shared__ float Xs[RB][T + 4];
-    __shared__ bool is_last;
     int pi = 0;
 #pragma unroll
     for (int q = 1; q < BG_MAX_WGRAD; ++q)
@@ -204,71 +221,85 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     const int k0 = (lt % p.tiles_k) * T, o0 = (lt / p.tiles_k) * T;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int64_t rbeg = (int64_t)blockIdx.y * b.rows_per_split, rend = min(b.N, rbeg + b.rows_per_split);
+    const int no = min(T, p.Cout - o0), nk = min(T, p.K - k0);  // valid extent of this tile
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
+        // issue every global load of this slab first (independent, all in flight), then fill shared memory
+        constexpr int PER = RB * T / kThreads;
+        float gv[PER], xv[PER];
 #pragma unroll
-        for (int q = 0; q < RB * T / kThreads; ++q) {
+        for (int q = 0; q < PER; ++q) {
             const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
             const int64_t r = r0 + rr;
             const bool rok = r < rend;
-            Gs[rr][cc] = (rok && o0 + cc < p.Cout) ? __ldg(p.gz + r * p.ld_gz + o0 + cc) : 0.f;
-            Xs[rr][cc] = (rok && k0 + cc < p.K) ? seg_fetch(p.x, r, k0 + cc) : 0.f;
+            gv[q] = (rok && cc < no) ? __ldg(p.gz + r * p.ld_gz + o0 + cc) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
+            const int64_t r = r0 + rr;
+            xv[q] = (r < rend && cc < nk) ? seg_fetch(p.x, r, k0 + cc) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
+            Gs[rr][cc] = gv[q];
+            Xs[rr][cc] = xv[q];
         }
         __syncthreads();
+        if (ty * 4 < no && tx * 4 < nk) {
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) {
-            float g[4], x[4];
+            for (int rr = 0; rr < RB; ++rr) {
+                float g[4], x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) g[i] = Gs[rr][ty * 4 + i];
+                for (int i = 0; i < 4; ++i) g[i] = Gs[rr][ty * 4 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = Xs[rr][tx * 4 + j];
+                for (int j = 0; j < 4; ++j) x[j] = Xs[rr][tx * 4 + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], x[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float* tile_part = b.partial + ((int64_t)blockIdx.x * b.S) * (T * T);
-    float* mine = tile_part + (int64_t)blockIdx.y * (T * T);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(mine + (ty * 4 + i) * T + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int t = atomicAdd(b.counters + blockIdx.x, 1u);
-        is_last = (t == (unsigned)b.S - 1);
-        if (is_last) b.counters[blockIdx.x] = 0u;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int off = (ty * 4 + i) * T + tx * 4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < b.S; ++sp) {
-            const float4 v = *reinterpret_cast<const float4*>(tile_part + (int64_t)sp * (T * T) + off);
-            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-        }
-        const float tv[4] = {t.x, t.y, t.z, t.w};
-        const int o = o0 + ty * 4 + i;
-        if (o < p.Cout) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + tx * 4 + j;
-                if (k < p.K) {
-                    float* dst = (p.dbias && k == p.K - 1) ? p.dbias + o : p.dW + (int64_t)o * p.ld_dw + k;
-                    *dst = b.accumulate ? *dst + tv[j] : tv[j];
-                }
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], x[j], acc[i][j]);
             }
         }
+        __syncthreads();
     }
+    float* mine = p.partial + (int64_t)blockIdx.y * p.Cout * p.K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + ty * 4 + i, k = k0 + tx * 4 + j;
+            if (o < p.Cout && k < p.K) mine[(int64_t)o * p.K + k] = acc[i][j];
+        }
+}
+
+__global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb) {
+    int e = 0;
+#pragma unroll 1
+    for (int q = 1; q < fb.n; ++q)
+        if ((int)blockIdx.x >= fb.e[q].block_base) e = q;
+    const FoldEntry& f = fb.e[e];
+    const int count = f.Cout * f.K;
+    const int i = ((int)blockIdx.x - f.block_base) * kThreads + threadIdx.x;
+    if (i >= count) return;
+    float t = 0.f;
+    const float* src = f.partial + i;
+    int sp = 0;
+    for (; sp + 8 <= f.S; sp += 8) {  // 8 independent loads in flight, summed in split order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (int64_t)(sp + u) * count);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; sp < f.S; ++sp) t += __ldg(src + (int64_t)sp * count);
+    const int o = i / f.K, k = i % f.K;
+    float* dst = (f.dbias && k == f.K - 1) ? f.dbias + o : f.dW + (int64_t)o * f.ld_dw + k;
+    *dst = f.accumulate ? *dst + t : t;
 }
 
 static inline int wgrad_splits(int64_t N, int total_tiles) {
@@ -278,6 +309,80 @@ static inline int wgrad_splits(int64_t N, int total_tiles) {
     if (ns > 64) ns = 64;
     if (ns < 1) ns = 1;
     return (int)ns;
+}
+static int wgrad_tiles(int Cout, int K) { return (int)(ceil_div(K, 64) * ceil_div(Cout, 64)); }
+
+// Launch the partial-sum kernel for `nprob` problems and queue their folds.
+int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st) {
+    BG_REQUIRE(nprob >= 1 && nprob <= BG_MAX_WGRAD, BG_EINVAL, "wgrad: nprob %d out of range [1,%d]", nprob, BG_MAX_WGRAD);
+    WgBatch b;
+    b.N = probs[0].N;
+    b.nprob = nprob;
+    int tiles = 0;
+    for (int i = 0; i < nprob; ++i) {
+        const BgWgrad& a = probs[i];
+        BG_REQUIRE(a.gz && (a.dW || a.dbias), BG_EINVAL, "wgrad: problem %d has null pointers", i);
+        BG_REQUIRE(a.N == b.N, BG_EINVAL, "wgrad: problems of one launch must share N");
+        WgProblem& p = b.p[i];
+        p.gz = a.gz; p.ld_gz = a.ld_gz; p.Cout = a.Cout;
+        if (int rc = fill_segview(p.x, a.nseg, a.seg, &p.K)) return rc;
+        p.tiles_k = (int)ceil_div(p.K, 64);
+        p.tile_base = tiles;
+        p.ntiles = wgrad_tiles(p.Cout, p.K);
+        tiles += p.ntiles;
+    }
+    b.S = wgrad_splits(b.N, tiles);
+    b.rows_per_split = ceil_div(ceil_div(b.N, b.S), 32) * 32;
+    for (int i = 0; i < nprob; ++i) {
+        WgProblem& p = b.p[i];
+        const size_t need = (size_t)b.S * p.Cout * p.K;
+        BG_REQUIRE(q.used + need <= q.cap, BG_EINVAL, "wgrad: partial-sum workspace too small (%zu + %zu > %zu floats)", q.used,
+                   need, q.cap);
+        p.partial = q.buf + q.used;
+        q.used += (need + 63) / 64 * 64;
+        FoldEntry f{p.partial, probs[i].dW, probs[i].dbias, probs[i].ld_dw, b.S, p.Cout, p.K, probs[i].accumulate, 0};
+        // a contribution whose destination overlaps an already queued one goes to a later fold launch (the folds of
+        // one launch run concurrently: no two may read-modify-write the same addresses)
+        auto overlaps = [](const FoldEntry& a, const FoldEntry& b) {
+            auto hit = [](const float* p0, size_t n0, const float* p1, size_t n1) {
+                return p0 && p1 && p0 < p1 + n1 && p1 < p0 + n0;
+            };
+            const size_t aw = a.dW ? (size_t)(a.Cout - 1) * a.ld_dw + a.K : 0, bw = b.dW ? (size_t)(b.Cout - 1) * b.ld_dw + b.K : 0;
+            return hit(a.dW, aw, b.dW, bw) || hit(a.dW, aw, b.dbias, b.Cout) || hit(a.dbias, a.Cout, b.dW, bw) ||
+                   hit(a.dbias, a.Cout, b.dbias, b.Cout);
+        };
+        int phase = 0;
+        for (int ph = 0; ph < WgradQueue::kPhases; ++ph)
+            for (const FoldEntry& g : q.phase[ph])
+                if (ph >= phase && overlaps(f, g)) phase = ph + 1;
+        BG_REQUIRE(phase < WgradQueue::kPhases, BG_EUNSUPPORTED, "wgrad: too many contributions to one destination");
+        if (phase > 0) f.accumulate = 1;
+        q.phase[phase].push_back(f);
+    }
+    dim3 grid((unsigned)tiles, (unsigned)b.S);
+    wgrad_multi_kernel<<<grid, kThreads, 0, st>>>(b);
+    return check_launch("wgrad");
+}
+
+// Fold every queued problem: one launch per phase (and per kMaxFold entries).
+int wgrad_flush(WgradQueue& q, cudaStream_t st) {
+    for (int ph = 0; ph < WgradQueue::kPhases; ++ph) {
+        std::vector<FoldEntry>& v = q.phase[ph];
+        for (size_t base = 0; base < v.size(); base += FoldBatch::kMax) {
+            FoldBatch fb;
+            fb.n = (int)std::min<size_t>(FoldBatch::kMax, v.size() - base);
+            int blocks = 0;
+            for (int i = 0; i < fb.n; ++i) {
+                fb.e[i] = v[base + i];
+                fb.e[i].block_base = blocks;
+                blocks += (int)ceil_div((int64_t)fb.e[i].Cout * fb.e[i].K, kThreads);
+            }
+            wgrad_fold_kernel<<<blocks, kThreads, 0, st>>>(fb);
+        }
+        v.clear();
+    }
+    q.used = 0;
+    return check_launch("wgrad fold");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -344,13 +449,8 @@ __global__ void __launch_bounds__(kThreads) ln_act_bwd_kernel(const float* __res
         for (int sl = 0; sl < RPC; ++sl) t += red[(sl * LANES + sb) * 2 * VEC + which * VEC + v];
         partials[(int64_t)blockIdx.x * 2 * C + i] = t;
     }
-    if (!last_cta_ticket(counter, gridDim.x)) return;
-    for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
-        float t = 0.f;
-        for (int g = 0; g < G; ++g) t += partials[(int64_t)g * 2 * C + i];
-        sums[i] = t;
-    }
     __syncthreads();
+    if (!hier_fold(partials, partials + (int64_t)G * 2 * C, 2 * C, counter, red, sums)) return;
     for (int c = threadIdx.x; c < C; c += kThreads) {
         if (accumulate) {
             dgamma[c] += sums[c];
@@ -440,47 +540,25 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     return check_launch("bg_dense_fwd");
 }
 
-static int wgrad_tiles(int Cout, int K) { return (int)(ceil_div(K, 64) * ceil_div(Cout, 64)); }
-
 extern "C" size_t bg_wgrad_multi_ws(int64_t N, int32_t nprob, const int32_t* Cout, const int32_t* K) {
     int tiles = 0;
-    for (int i = 0; i < nprob; ++i) tiles += wgrad_tiles(Cout[i], K[i]);
-    return (size_t)kCounterBytes + (size_t)tiles * (size_t)wgrad_splits(N, tiles) * 64 * 64 * sizeof(float);
+    size_t elems = 0;
+    for (int i = 0; i < nprob; ++i) {
+        tiles += wgrad_tiles(Cout[i], K[i]);
+        elems += ((size_t)Cout[i] * K[i] + 63) / 64 * 64;
+    }
+    return (size_t)kCounterBytes + elems * (size_t)wgrad_splits(N, tiles) * sizeof(float) + 4096;
 }
 
 extern "C" int bg_wgrad_multi(const BgWgrad* probs, int32_t nprob, float* workspace, size_t ws_bytes, void* stream) {
     BG_REQUIRE(probs && workspace, BG_EINVAL, "bg_wgrad_multi: null pointer");
-    BG_REQUIRE(nprob >= 1 && nprob <= BG_MAX_WGRAD, BG_EINVAL, "bg_wgrad_multi: nprob %d out of range [1,%d]", nprob, BG_MAX_WGRAD);
-    WgBatch b;
-    b.N = probs[0].N;
-    b.nprob = nprob;
-    b.accumulate = probs[0].accumulate;
-    int tiles = 0;
-    int32_t couts[BG_MAX_WGRAD], ks[BG_MAX_WGRAD];
-    for (int i = 0; i < nprob; ++i) {
-        const BgWgrad& a = probs[i];
-        BG_REQUIRE(a.gz && (a.dW || a.dbias), BG_EINVAL, "bg_wgrad_multi: problem %d has null pointers", i);
-        BG_REQUIRE(a.N == b.N && a.accumulate == b.accumulate, BG_EINVAL, "bg_wgrad_multi: problems must share N and accumulate");
-        WgProblem& p = b.p[i];
-        p.gz = a.gz; p.ld_gz = a.ld_gz; p.Cout = a.Cout;
-        if (int rc = fill_segview(p.x, a.nseg, a.seg, &p.K)) return rc;
-        p.dW = a.dW; p.ld_dw = a.ld_dw; p.dbias = a.dbias;
-        p.tiles_k = (int)ceil_div(p.K, 64);
-        p.tile_base = tiles;
-        p.ntiles = wgrad_tiles(p.Cout, p.K);
-        tiles += p.ntiles;
-        couts[i] = p.Cout; ks[i] = p.K;
-    }
-    BG_REQUIRE((size_t)tiles * sizeof(unsigned int) <= (size_t)kCounterBytes, BG_EUNSUPPORTED, "bg_wgrad_multi: too many output tiles (%d)", tiles);
-    BG_REQUIRE(ws_bytes >= bg_wgrad_multi_ws(b.N, nprob, couts, ks), BG_EINVAL, "bg_wgrad_multi: workspace too small");
-    b.S = wgrad_splits(b.N, tiles);
-    int64_t rps = ceil_div(b.N, b.S);
-    b.rows_per_split = ceil_div(rps, 32) * 32;
-    b.counters = reinterpret_cast<unsigned int*>(workspace);
-    b.partial = workspace + kCounterBytes / sizeof(float);
-    dim3 grid((unsigned)tiles, (unsigned)b.S);
-    wgrad_multi_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(b);
-    return check_launch("bg_wgrad_multi");
+    BG_REQUIRE(ws_bytes > (size_t)kCounterBytes, BG_EINVAL, "bg_wgrad_multi: workspace too small");
+    WgradQueue q;
+    q.buf = workspace + kCounterBytes / sizeof(float);
+    q.cap = (ws_bytes - kCounterBytes) / sizeof(float);
+    q.used = 0;
+    if (int rc = wgrad_launch(probs, nprob, q, as_stream(stream))) return rc;
+    return wgrad_flush(q, as_stream(stream));
 }
 
 extern "C" size_t bg_dense_wgrad_ws(int64_t N, int32_t Cout, int32_t K) { return bg_wgrad_multi_ws(N, 1, &Cout, &K); }
@@ -492,7 +570,7 @@ extern "C" int bg_dense_wgrad(const BgWgrad* a, void* stream) {
 
 extern "C" size_t bg_ln_act_bwd_ws(int64_t N, int32_t C) {
     (void)N;
-    return (size_t)kCounterBytes + (size_t)(2 * kSMs) * 2 * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)(2 * kSMs + 2 * kSMs / kFoldGroup + 2) * 2 * (size_t)C * sizeof(float);
 }
 
 extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* xhat, const float* rstd, const float* gamma,

@@ -60,12 +60,10 @@ __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __r
         for (int64_t r = r0; r < r1; ++r) acc[__ldg(type + r) * C + c] += __ldg(g + r * ld + c);
     __syncthreads();
     for (int i = threadIdx.x; i < K * C; i += kThreads) partials[(int64_t)blockIdx.x * K * C + i] = acc[i];
-    if (!last_cta_ticket(counter, gridDim.x)) return;
-    for (int i = threadIdx.x; i < K * C; i += kThreads) {
-        float t = 0.f;
-        for (int q = 0; q < G; ++q) t += partials[(int64_t)q * K * C + i];
-        out[i] = t;
-    }
+    __shared__ float red[kThreads];
+    __syncthreads();
+    if (!hier_fold(partials, partials + (int64_t)G * K * C, K * C, counter, red, acc)) return;
+    for (int i = threadIdx.x; i < K * C; i += kThreads) out[i] = acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,7 +237,7 @@ static inline int scatter_splits(int64_t N) {
 }
 
 extern "C" size_t bg_type_scatter_sum_ws(int64_t N, int32_t C, int32_t K) {
-    return (size_t)kCounterBytes + (size_t)scatter_splits(N) * (size_t)K * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)(scatter_splits(N) + scatter_splits(N) / kFoldGroup + 2) * (size_t)K * (size_t)C * sizeof(float);
 }
 
 extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* type, int64_t N, int32_t C, int32_t K, float* out,

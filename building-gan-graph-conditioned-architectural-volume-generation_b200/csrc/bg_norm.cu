@@ -50,125 +50,6 @@ __device__ __forceinline__ void cta_colsum(float (&val)[K * ColMap<C>::VEC], flo
     __syncthreads();
 }
 
-// Fixed-order fold of `G` partial vectors of length L (partials[g*L + i]) by the last CTA.
-// Uses S = kThreads / Lp slices (Lp = L rounded up to a power of two, capped at kThreads).
-__device__ __forceinline__ void fold_partials(const float* partials, int G, int L, float* red /*>= kThreads*/,
-                                              float* result /*shared, >= L*/) {
-    for (int base = 0; base < L; base += kThreads) {
-        const int Lt = min(L - base, kThreads);
-        int Lp = 1;
-        while (Lp < Lt) Lp <<= 1;
-        const int S = kThreads / Lp;
-        const int i = threadIdx.x % Lp, sl = threadIdx.x / Lp;
-        float t = 0.f;
-        if (i < Lt)
-            for (int g = sl; g < G; g += S) t += partials[(int64_t)g * L + base + i];
-        red[threadIdx.x] = t;
-        __syncthreads();
-        if (threadIdx.x < Lt) {
-            float a = 0.f;
-            for (int q = 0; q < S; ++q) a += red[q * Lp + threadIdx.x];
-            result[base + threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// forward statistics: mu, rstd, var  (Chan combination of per-chunk mean / M2)
-// workspace: [0,64) ticket counter | partials G * (2*C) floats (mean_b, M2_b) ; chunk sizes are
-// implied by (N, G).
-// ------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ o, const float* __restrict__ alpha,
-                                                            int64_t N, int G, float eps, float* __restrict__ stats,
-                                                            unsigned int* counter, float* partials) {
-    using M = ColMap<C>;
-    constexpr int VEC = M::VEC, TPR = M::TPR, RPI = M::RPI;
-    __shared__ float red[kWarps * 2 * C > kThreads ? kWarps * 2 * C : kThreads];
-    __shared__ float mean_s[C];
-    const int cv = threadIdx.x % TPR, rs = threadIdx.x / TPR;
-    const int64_t chunk = ceil_div(N, G);
-    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
-    const float nb = (float)max((int64_t)0, r1 - r0);
-
-    float sum[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
-    for (int64_t r = r0 + rs; r < r1; r += RPI) {
-        Vec<VEC> x;
-        x.load(o + r * C + cv * VEC);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) sum[v] += x.v[v];
-    }
-    cta_colsum<C, 1>(sum, red);
-    if (threadIdx.x < C) mean_s[threadIdx.x] = nb > 0.f ? red[threadIdx.x] / nb : 0.f;
-    __syncthreads();
-    float m2[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) m2[v] = 0.f;
-    for (int64_t r = r0 + rs; r < r1; r += RPI) {
-        Vec<VEC> x;
-        x.load(o + r * C + cv * VEC);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float dlt = x.v[v] - mean_s[cv * VEC + v];
-            m2[v] = fmaf(dlt, dlt, m2[v]);
-        }
-    }
-    cta_colsum<C, 1>(m2, red);
-    if (threadIdx.x < C) {
-        partials[(int64_t)blockIdx.x * 2 * C + threadIdx.x] = mean_s[threadIdx.x];
-        partials[(int64_t)blockIdx.x * 2 * C + C + threadIdx.x] = red[threadIdx.x];
-    }
-    if (!last_cta_ticket(counter, gridDim.x)) return;
-    // Chan fold: S slices fold interleaved chunks (fixed order), then one thread per column merges
-    // the S slice results (fixed order).
-    constexpr int S = (kThreads / C) < 8 ? (kThreads / C) : 8;
-    __shared__ float cn[S][C], cm[S][C], cM[S][C];
-    {
-        const int c = threadIdx.x % C, sl = threadIdx.x / C;
-        if (sl < S) {
-            float n = 0.f, mean = 0.f, M2 = 0.f;
-#pragma unroll 4
-            for (int g = sl; g < G; g += S) {
-                const int64_t a0 = (int64_t)g * chunk;
-                const float nbk = (float)max((int64_t)0, min(N, a0 + chunk) - a0);
-                const float mb = partials[(int64_t)g * 2 * C + c], Mb = partials[(int64_t)g * 2 * C + C + c];
-                if (nbk > 0.f) {
-                    const float tot = n + nbk, dlt = mb - mean;
-                    mean += dlt * (nbk / tot);
-                    M2 += Mb + dlt * dlt * (n * nbk / tot);
-                    n = tot;
-                }
-            }
-            cn[sl][c] = n;
-            cm[sl][c] = mean;
-            cM[sl][c] = M2;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < C) {
-        const int c = threadIdx.x;
-        float n = 0.f, mean = 0.f, M2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < S; ++q) {
-            const float nbk = cn[q][c];
-            if (nbk > 0.f) {
-                const float tot = n + nbk, dlt = cm[q][c] - mean;
-                mean += dlt * (nbk / tot);
-                M2 += cM[q][c] + dlt * dlt * (n * nbk / tot);
-                n = tot;
-            }
-        }
-        const float shift = mean * (1.f - __ldg(alpha + c));  // mean of (o - alpha*mu)
-        const float var = (M2 + n * shift * shift) / n;
-        stats[c] = mean;
-        stats[C + c] = 1.f / sqrtf(var + eps);
-        stats[2 * C + c] = var;
-    }
-}
-
 // y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep / keep_prob      (flat elementwise)
 // keep: explicit uint8 mask, or (keep == NULL && keep_prob < 1) a Philox Bernoulli(keep_prob) mask.
 __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restrict__ o, const float* __restrict__ w,
@@ -239,7 +120,7 @@ struct Bwd2Moments {  // K=3: sum Xt, sum Xt*gy, sum Xt*ohat
 };
 
 template <int C, int K, class F>
-__device__ __forceinline__ void moments_body(const F& f, int64_t N, int G, unsigned int* counter, float* partials,
+__device__ __forceinline__ void moments_body(const F& f, int64_t N, int G, unsigned int* counters, float* partials,
                                              float* sums_out /*shared result, K*C*/, bool& is_last) {
     using M = ColMap<C>;
     constexpr int VEC = M::VEC, TPR = M::TPR, RPI = M::RPI;
@@ -253,9 +134,52 @@ __device__ __forceinline__ void moments_body(const F& f, int64_t N, int G, unsig
     for (int64_t r = r0 + rs; r < r1; r += RPI) f.template accumulate<C>(r, cv, acc);
     cta_colsum<C, K>(acc, red);
     for (int i = threadIdx.x; i < K * C; i += kThreads) partials[(int64_t)blockIdx.x * K * C + i] = red[i];
-    is_last = last_cta_ticket(counter, gridDim.x);
+    is_last = hier_fold(partials, partials + (int64_t)G * K * C, K * C, counters, red, sums_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward statistics: mu, rstd, var in ONE pass: sums of d = x - shift and d^2 with shift = row 0 of the
+// column (a sample of the distribution, so |mean(d)| is a few sigma at most and the variance
+// S2/n - (S1/n)^2 does not suffer the E[x^2]-E[x]^2 cancellation of unshifted sums).
+// ------------------------------------------------------------------------------------------
+struct StatsAcc {
+    const float* o;
+    template <int CC>
+    __device__ __forceinline__ void accumulate(int64_t r, int cv, float* acc) const {
+        constexpr int VEC = ColMap<CC>::VEC;
+        Vec<VEC> x, sh;
+        x.load(o + r * CC + cv * VEC);
+        sh.load(o + cv * VEC);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float d = x.v[v] - sh.v[v];
+            acc[v] += d;
+            acc[VEC + v] = fmaf(d, d, acc[VEC + v]);
+        }
+    }
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ o, const float* __restrict__ alpha,
+                                                            int64_t N, int G, float eps, float* __restrict__ stats,
+                                                            unsigned int* counters, float* partials) {
+    __shared__ float sums[2 * C];
+    bool is_last;
+    StatsAcc f{o};
+    moments_body<C, 2>(f, N, G, counters, partials, sums, is_last);
     if (!is_last) return;
-    fold_partials(partials, G, K * C, red, sums_out);
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        const float n = (float)N;
+        const float md = sums[c] / n;
+        const float mean = o[c] + md;
+        const float M2 = fmaxf(sums[C + c] - sums[c] * md, 0.f);
+        const float shift = mean * (1.f - __ldg(alpha + c));  // mean of (o - alpha*mu)
+        const float var = (M2 + n * shift * shift) / n;
+        stats[c] = mean;
+        stats[C + c] = 1.f / sqrtf(var + eps);
+        stats[2 * C + c] = var;
+    }
 }
 
 template <int C>
@@ -447,7 +371,7 @@ using namespace bg;
 
 extern "C" size_t bg_graphnorm_ws(int64_t N, int32_t C) {
     (void)N;
-    return (size_t)kCounterBytes + (size_t)(4 * kSMs) * 3 * (size_t)C * sizeof(float) + 4 * (size_t)C * sizeof(float);
+    return (size_t)kCounterBytes + (size_t)(2 * kSMs + 2 * kSMs / kFoldGroup + 2) * 3 * (size_t)C * sizeof(float) + 4 * (size_t)C * sizeof(float);
 }
 
 #define BG_GN_DISPATCH(C, CALL)                                                                    \

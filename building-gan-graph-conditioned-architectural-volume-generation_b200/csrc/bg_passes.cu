@@ -16,6 +16,7 @@ namespace bg {
 
 constexpr int kMaxLayers = 8;
 constexpr int kMaxConvs = 16;
+constexpr size_t kWgradOffsetBytes = 4u << 20;  // reduction workspace: [0,4 MiB) tickets + small partials, rest = wgrad partials
 constexpr float kKeepProb = 0.8f;  // nn.Dropout(0.2), hard-coded in the reference (models.py:75,85,195,205)
 
 struct Arena {
@@ -173,8 +174,18 @@ struct Ctx {
     size_t red_bytes;
     void* st;
     int accumulate;
+    WgradQueue* q;           // deferred weight-gradient folds of this pass
     float* g(int pidx) const { return (G && pidx >= 0) ? G + goff[pidx] : nullptr; }
 };
+
+static int init_queue(WgradQueue& q, float* red, size_t red_bytes) {
+    BG_REQUIRE(red_bytes >= 2 * kWgradOffsetBytes, BG_EINVAL, "reduction workspace too small (%zu bytes, need >= %zu)", red_bytes,
+               2 * kWgradOffsetBytes);
+    q.buf = red + kWgradOffsetBytes / sizeof(float);
+    q.cap = (red_bytes - kWgradOffsetBytes) / sizeof(float);
+    q.used = 0;
+    return BG_OK;
+}
 
 static inline BgSeg seg(const float* p, int width, int ld, const int32_t* gather = nullptr) { return BgSeg{p, gather, width, ld}; }
 
@@ -253,17 +264,18 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
         go = const_cast<float*>(inj_o);
     }
     BG_TRY(bg_gat_bwd(c.graph, go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, gh, gsd, C, 0.2f, c.st));
-    if (c.G) {  // bias, [att_src; att_dst] (before the injection at h: those cotangents belong to the h-path only)
-        BgSeg ones = seg(nullptr, 1, 0), hseg = seg(L.h, C, C);
+    BgSeg ones = seg(nullptr, 1, 0), hseg = seg(L.h, C, C), xseg = seg(x_in, L.cin, L.cin);
+    if (c.G && inj_h) {  // bias, [att_src; att_dst] see gh BEFORE the injection at h (those cotangents are h-path only)
         BgWgrad pr[2] = {wg(c.N, go, C, C, &ones, 1, c.g(L.p_bias), 1, nullptr, c.accumulate),
                          wg(c.N, gsd, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, c.accumulate)};
-        BG_TRY(bg_wgrad_multi(pr, 2, c.red, c.red_bytes, c.st));
+        BG_TRY(wgrad_launch(pr, 2, *c.q, as_stream(c.st)));
     }
     if (inj_h) BG_TRY(bg_axpy(gh, inj_h, 1.f, c.N * C, c.st));
     if (c.G) {
-        BgSeg xseg = seg(x_in, L.cin, L.cin);
-        BgWgrad pr = wg(c.N, gh, C, C, &xseg, 1, c.g(L.p_W), L.cin, nullptr, c.accumulate);
-        BG_TRY(bg_wgrad_multi(&pr, 1, c.red, c.red_bytes, c.st));
+        BgWgrad pr[3] = {wg(c.N, gh, C, C, &xseg, 1, c.g(L.p_W), L.cin, nullptr, c.accumulate),
+                         wg(c.N, go, C, C, &ones, 1, c.g(L.p_bias), 1, nullptr, c.accumulate),
+                         wg(c.N, gsd, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, c.accumulate)};
+        BG_TRY(wgrad_launch(pr, inj_h ? 1 : 3, *c.q, as_stream(c.st)));
     }
     if (gx_out) BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out));
     if (keep && gx1) BG_TRY(cudaMemcpyAsync(L.b_gx1, gx1, (size_t)c.N * C * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) ==
@@ -292,9 +304,7 @@ static int conv_backward2(const Ctx& c, const ConvL& L, const float* Xt, float k
         BgWgrad pr[3] = {wg(c.N, L.b_gh, C, C, &xt, 1, c.g(L.p_W), L.cin, nullptr, 1),
                          wg(c.N, L.b_gsd, 2, 2, &hts, 1, c.g(L.p_as), C, nullptr, 1),
                          wg(c.N, sdt, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, 1)};
-        // problems 1 and 2 both accumulate into [att_src; att_dst]: two launches keep the order fixed
-        BG_TRY(bg_wgrad_multi(pr, 2, c.red, c.red_bytes, c.st));
-        BG_TRY(bg_wgrad_multi(pr + 2, 1, c.red, c.red_bytes, c.st));
+        BG_TRY(wgrad_launch(pr, 3, *c.q, as_stream(c.st)));  // the two [att_src; att_dst] contributions fold in separate phases
     }
     return bg_graphnorm_bwd2(gt, L.b_gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, L.b_bstats, keep_scale, c.N, C, gx1t, ot,
                              c.g(L.p_gw), 1, c.red, c.red_bytes, c.st);
@@ -308,8 +318,6 @@ static int dense_backward(const Ctx& c, const DenseL& l, int64_t rows, const BgS
     if (l.pg >= 0) {
         float* dgam = c.G ? c.g(l.pg) : nullptr;
         float* dbet = c.G ? c.g(l.pbeta) : nullptr;
-        float dummy_needed = 0.f;
-        (void)dummy_needed;
         BG_REQUIRE(c.G, BG_EINVAL, "LayerNorm backward needs a grad bucket");
         BG_TRY(bg_ln_act_bwd(gout, l.out, l.xhat, l.rstd, c.P[l.pg], rows, l.cout, l.act, gz_buf, dgam, dbet, c.accumulate, c.red,
                              c.red_bytes, c.st));
@@ -323,7 +331,7 @@ static int dense_backward(const Ctx& c, const DenseL& l, int64_t rows, const BgS
         for (int i = 0; i < nseg; ++i) all[i] = segs[i];
         all[nseg] = seg(nullptr, 1, 0);
         BgWgrad pr = wg(rows, gz, l.cout, l.cout, all, nseg + 1, c.g(l.pW), l.cin, c.g(l.pb), c.accumulate);
-        BG_TRY(bg_wgrad_multi(&pr, 1, c.red, c.red_bytes, c.st));
+        BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(c.st)));
     }
     for (int i = 0; i < nwin; ++i) BG_TRY(matmul_nn(c, gz, rows, l.cout, c.P[l.pW], l.cin, win[i][0], win[i][1], gin[i]));
     if (gz_out) *gz_out = gz;
@@ -368,7 +376,7 @@ extern "C" int bg_gen_forward(const BgModelDesc* md, const float* const* params,
     BG_REQUIRE(ws_bytes >= bg_gen_fwd_ws(md, N, graph->E), BG_EINVAL, "bg_gen_forward: workspace too small");
     Arena A{static_cast<char*>(ws), 0};
     layout_gen(*md, g, N, A);
-    Ctx c{params, nullptr, nullptr, graph, N, red, red_bytes, stream, 0};
+    Ctx c{params, nullptr, nullptr, graph, N, red, red_bytes, stream, 0, nullptr};
     const int K = md->num_classes;
     // type-matched encoder on the K table rows (row-wise ops commute with the per-voxel gather)
     const float* e = in->table;
@@ -431,7 +439,9 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     layout_gen(*md, net, N, A);
     net.dec[net.n_dec - 1].out = const_cast<float*>(logits);
     BG_REQUIRE(tmp_bytes >= bg_gen_bwd_ws(md, N, graph->E), BG_EINVAL, "bg_gen_backward: scratch too small");
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0};
+    WgradQueue queue;
+    BG_TRY(init_queue(queue, red, red_bytes));
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0, &queue};
     const int K = md->num_classes, le = md->le_dim, gh = md->g_hidden;
     Arena T{static_cast<char*>(tmp), 0};
     const size_t wide = (size_t)N * (gh > le ? gh : le);
@@ -514,7 +524,7 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
         BG_TRY(dense_backward(c, net.menc[i], K, &s, 1, gcur, small_gz, win, gin, i > 0 ? 1 : 0, nullptr));
         gcur = dst;
     }
-    return BG_OK;
+    return wgrad_flush(queue, as_stream(stream));
 }
 
 // =====================================================================================================
@@ -539,7 +549,7 @@ extern "C" int bg_disc_forward(const BgModelDesc* md, const float* const* params
     BG_REQUIRE(ws_bytes >= bg_disc_fwd_ws(md, N, graph->E), BG_EINVAL, "bg_disc_forward: workspace too small");
     Arena A{static_cast<char*>(ws), 0};
     layout_disc(d, N, A);
-    Ctx c{params, nullptr, nullptr, graph, N, red, red_bytes, stream, 0};
+    Ctx c{params, nullptr, nullptr, graph, N, red, red_bytes, stream, 0, nullptr};
     BgSeg s3[3] = {seg(in->table, md->local_dim, md->local_dim, in->type32), seg(in->vx, md->voxel_dim, md->voxel_dim),
                    seg(label, md->num_classes, md->num_classes)};
     BG_TRY(dense_fwd_call(c, d.pre[0], N, s3, 3, false));
@@ -651,10 +661,13 @@ extern "C" int bg_disc_backward(const BgModelDesc* md, const float* const* param
         layout_disc_bwd_saved(d, N, S);
     }
     BG_REQUIRE(tmp_bytes >= bg_disc_tmp_ws(md, N, graph->E), BG_EINVAL, "bg_disc_backward: scratch too small");
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0};
+    WgradQueue queue;
+    BG_TRY(init_queue(queue, red, red_bytes));
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0, &queue};
     Arena T{static_cast<char*>(tmp), 0};
-    return disc_backward_impl(md, d, c, in, label, score, g_score, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr, saved != nullptr,
-                              T, g_label);
+    BG_TRY(disc_backward_impl(md, d, c, in, label, score, g_score, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr,
+                              saved != nullptr, T, g_label));
+    return wgrad_flush(queue, as_stream(stream));
 }
 
 // Second-order sweep (WGAN-GP).  Lt = cotangent on g_label.  grad_flat (zero-initialised by the caller) receives the
@@ -673,7 +686,9 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
     Arena S{static_cast<char*>(const_cast<void*>(saved)), 0};
     layout_disc_bwd_saved(d, N, S);
     BG_REQUIRE(tmp_bytes >= 2 * bg_disc_tmp_ws(md, N, graph->E), BG_EINVAL, "bg_disc_backward2: scratch too small");
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 1};
+    WgradQueue queue;
+    BG_TRY(init_queue(queue, red, red_bytes));
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 1, &queue};
     const float keep_scale = training ? 1.f / kKeepProb : 1.f;
     const int dh = md->d_hidden, K = md->num_classes, lo = md->local_dim + md->voxel_dim;
     Arena T{static_cast<char*>(tmp), 0};
@@ -690,7 +705,7 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
     {
         BgSeg lt = seg(Lt, K, K);
         BgWgrad pr = wg(N, d.pre[0].b_gz, dh, dh, &lt, 1, c.g(d.pre[0].pW) + lo, d.pre[0].cin, nullptr, 1);
-        BG_TRY(bg_wgrad_multi(&pr, 1, red, red_bytes, stream));
+        BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
         BG_TRY(matmul_nt(c, Lt, N, params[d.pre[0].pW], dh, d.pre[0].cin, lo, lo + K, ta));          // cot(gz0)
         BG_TRY(bg_ln_act_bwd(ta, d.pre[0].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
     }
@@ -698,7 +713,7 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
     {
         BgSeg ts = seg(tb, dh, dh);
         BgWgrad pr = wg(N, d.pre[1].b_gz, dh, dh, &ts, 1, c.g(d.pre[1].pW), dh, nullptr, 1);
-        BG_TRY(bg_wgrad_multi(&pr, 1, red, red_bytes, stream));
+        BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
         BG_TRY(matmul_nt(c, tb, N, params[d.pre[1].pW], dh, dh, 0, dh, ta));                         // cot(gz1)
         BG_TRY(bg_ln_act_bwd(ta, d.pre[1].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
     }
@@ -714,7 +729,7 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         const DenseL& l = d.dec[i];
         BgSeg ts = seg(t, l.cin, l.cin);
         BgWgrad pr = wg(N, l.b_gz, l.cout, l.cout, &ts, 1, c.g(l.pW), l.cin, nullptr, 1);
-        BG_TRY(bg_wgrad_multi(&pr, 1, red, red_bytes, stream));
+        BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
         if (i == 3 && !gt_score) break;
         BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, other));                  // cot(gz)
         if (l.act != BG_ACT_NONE) {
@@ -730,7 +745,8 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
     // forward-graph sweep with the injected cotangents (nothing flows in from the top: the score itself is
     // not part of the second-order loss)
     T.off = t_mark;
-    return disc_backward_impl(md, d, c, in, label, score, nullptr, keep_scale, inj_o, inj_h, false, T, nullptr);
+    BG_TRY(disc_backward_impl(md, d, c, in, label, score, nullptr, keep_scale, inj_o, inj_h, false, T, nullptr));
+    return wgrad_flush(queue, as_stream(stream));
 }
 
 // ---- debug / test hooks: byte offsets of the saved post-activation tensors inside the forward workspace, in

@@ -589,7 +589,7 @@ def fill_(y: Tensor, v: float) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # whole-pass executors (csrc/bg_passes.cu): one C call per generator / discriminator pass
 # ------------------------------------------------------------------------------------------------
-RED_BYTES = 32 << 20
+RED_BYTES = 72 << 20
 
 
 def pass_launches(n: int) -> None:
