@@ -33,6 +33,35 @@ __device__ __forceinline__ float seg_fetch(const SegView& sv, int64_t row, int k
 
 static int fill_segview(SegView& sv, int nseg, const BgSeg* seg, int* K);
 
+// Column k of the segmented input resolved once (the column a thread fetches is loop-invariant): afterwards a
+// fetch is one (or, with a gather index, two dependent) loads without any segment search.
+struct SegCol {
+    const float* base;      // segment pointer + column offset; nullptr with ones => constant 1, without => constant 0
+    const int32_t* gather;
+    int ld;
+    bool ones;
+};
+__device__ __forceinline__ SegCol seg_resolve(const SegView& sv, int k, int K) {
+    SegCol c{nullptr, nullptr, 0, false};
+    if (k >= K) return c;
+#pragma unroll
+    for (int q = 0; q < BG_MAX_SEG; ++q) {
+        if (q < sv.nseg && k >= sv.off[q] && k < sv.off[q + 1]) {
+            const BgSeg& sg = sv.seg[q];
+            c.ones = (sg.ptr == nullptr);
+            c.base = sg.ptr ? sg.ptr + (k - sv.off[q]) : nullptr;
+            c.gather = sg.gather;
+            c.ld = sg.ld;
+        }
+    }
+    return c;
+}
+__device__ __forceinline__ float seg_load(const SegCol& c, int64_t row) {
+    if (c.base == nullptr) return c.ones ? 1.f : 0.f;
+    const int64_t r = c.gather ? (int64_t)__ldg(c.gather + row) : row;
+    return __ldg(c.base + r * c.ld);
+}
+
 struct DenseParams {
     int64_t N;
     SegView x;
@@ -65,11 +94,12 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
     for (int k0 = 0; k0 < p.K; k0 += BK) {
         constexpr int XPER = BM * BK / kThreads, WPER = (BN * BK + kThreads - 1) / kThreads;
         float xv[XPER], wv[WPER];
+        const SegCol xcol = seg_resolve(p.x, k0 + tid % BK, p.K);  // this thread's column of the slab (256 % BK == 0)
 #pragma unroll
         for (int q = 0; q < XPER; ++q) {  // all global loads of the slab first, shared-memory fill afterwards
-            const int idx = tid + q * kThreads, r = idx / BK, kk = idx % BK;
+            const int idx = tid + q * kThreads, r = idx / BK;
             const int64_t grow = row0 + r;
-            xv[q] = (grow < p.N && k0 + kk < p.K) ? seg_fetch(p.x, grow, k0 + kk) : 0.f;
+            xv[q] = (grow < p.N) ? seg_load(xcol, grow) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < WPER; ++q) {
@@ -227,6 +257,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // every thread always fetches column tid % 64 of both operands (256 % 64 == 0): resolve it once
+    const int mycol = tid % T;
+    const SegCol xcol = seg_resolve(p.x, k0 + mycol, mycol < nk ? p.K : 0);
+    const float* gcol = mycol < no ? p.gz + o0 + mycol : nullptr;
     for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
         // issue every global load of this slab first (independent, all in flight), then fill shared memory
         constexpr int PER = RB * T / kThreads;
@@ -236,13 +270,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
             const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
             const int64_t r = r0 + rr;
             const bool rok = r < rend;
-            gv[q] = (rok && cc < no) ? __ldg(p.gz + r * p.ld_gz + o0 + cc) : 0.f;
+            (void)cc;
+            gv[q] = (rok && gcol) ? __ldg(gcol + r * p.ld_gz) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
             const int64_t r = r0 + rr;
-            xv[q] = (r < rend && cc < nk) ? seg_fetch(p.x, r, k0 + cc) : 0.f;
+            (void)cc;
+            xv[q] = (r < rend) ? seg_load(xcol, r) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < PER; ++q) {

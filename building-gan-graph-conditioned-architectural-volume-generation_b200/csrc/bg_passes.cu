@@ -428,7 +428,7 @@ extern "C" size_t bg_gen_bwd_ws(const BgModelDesc* md, int64_t N, int64_t E) {
 extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
                                const float* z, const void* ws_fwd, const float* logits, const float* soft, const float* g_logits,
                                const float* g_hard, const float* g_soft, int32_t training, float* grad_flat, const int64_t* grad_off,
-                               void* tmp, size_t tmp_bytes, float* red, size_t red_bytes, void* stream) {
+                               int32_t accumulate, void* tmp, size_t tmp_bytes, float* red, size_t red_bytes, void* stream) {
     BG_REQUIRE(md && params && graph && in && z && ws_fwd && soft && grad_flat && grad_off && tmp && red, BG_EINVAL,
                "bg_gen_backward: null pointer");
     BG_REQUIRE(g_logits || g_hard || g_soft, BG_EINVAL, "bg_gen_backward: no incoming gradient");
@@ -441,7 +441,7 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     BG_REQUIRE(tmp_bytes >= bg_gen_bwd_ws(md, N, graph->E), BG_EINVAL, "bg_gen_backward: scratch too small");
     WgradQueue queue;
     BG_TRY(init_queue(queue, red, red_bytes));
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0, &queue};
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, accumulate ? 1 : 0, &queue};
     const int K = md->num_classes, le = md->le_dim, gh = md->g_hidden;
     Arena T{static_cast<char*>(tmp), 0};
     const size_t wide = (size_t)N * (gh > le ? gh : le);
@@ -646,8 +646,8 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
 
 extern "C" int bg_disc_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
                                 const float* label, const void* ws_fwd, const float* score, const float* g_score, int32_t training,
-                                float* grad_flat, const int64_t* grad_off, void* saved, size_t saved_bytes, void* tmp, size_t tmp_bytes,
-                                float* red, size_t red_bytes, float* g_label, void* stream) {
+                                float* grad_flat, const int64_t* grad_off, int32_t accumulate, void* saved, size_t saved_bytes, void* tmp,
+                                size_t tmp_bytes, float* red, size_t red_bytes, float* g_label, void* stream) {
     BG_REQUIRE(md && params && graph && in && label && ws_fwd && score && g_score && tmp && red, BG_EINVAL,
                "bg_disc_backward: null pointer");
     DiscNet d;
@@ -663,7 +663,7 @@ extern "C" int bg_disc_backward(const BgModelDesc* md, const float* const* param
     BG_REQUIRE(tmp_bytes >= bg_disc_tmp_ws(md, N, graph->E), BG_EINVAL, "bg_disc_backward: scratch too small");
     WgradQueue queue;
     BG_TRY(init_queue(queue, red, red_bytes));
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 0, &queue};
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, accumulate ? 1 : 0, &queue};
     Arena T{static_cast<char*>(tmp), 0};
     BG_TRY(disc_backward_impl(md, d, c, in, label, score, g_score, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr,
                               saved != nullptr, T, g_label));

@@ -92,12 +92,12 @@ SIGNATURES = {
     "bg_gen_fwd_ws": (_SZ, [_MD, _I64, _I64]),
     "bg_gen_bwd_ws": (_SZ, [_MD, _I64, _I64]),
     "bg_gen_forward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _I32, _U64, _U64, _P, _SZ, _P, _SZ, _P, _P, _P, _P]),
-    "bg_gen_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    "bg_gen_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _I32, _P, _SZ, _P, _SZ, _P]),
     "bg_disc_fwd_ws": (_SZ, [_MD, _I64, _I64]),
     "bg_disc_bwd_saved_ws": (_SZ, [_MD, _I64, _I64]),
     "bg_disc_tmp_ws": (_SZ, [_MD, _I64, _I64]),
     "bg_disc_forward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _I32, _U64, _U64, _P, _SZ, _P, _SZ, _P, _P]),
-    "bg_disc_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P, _SZ, _P, _P]),
+    "bg_disc_backward": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _I32, _P, _P, _I32, _P, _SZ, _P, _SZ, _P, _SZ, _P, _P]),
     "bg_disc_backward2": (C.c_int, [_MD, _P, _GR, _BI, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _SZ, _P, _P]),
     "bg_gen_ws_offsets": (C.c_int32, [_MD, _I64, _P, _I32]),
     "bg_disc_ws_offsets": (C.c_int32, [_MD, _I64, _P, _I32]),

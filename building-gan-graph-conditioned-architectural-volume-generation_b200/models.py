@@ -115,6 +115,14 @@ EXECUTOR = os.environ.get("BG_EXECUTOR", "native")
 #  - bit-identical RNG stream to the reference running on the same GPU, ~200 extra launches
 # per training step.
 RNG_MODE = os.environ.get("BG_RNG", "philox")
+# "bucket" (default): the backward passes accumulate parameter gradients IN THE KERNELS, straight into ``p.grad`` - every
+# ``p.grad`` of a model is a view of one flat fp32 bucket (also the NCCL all-reduce payload).  This is what ``loss.backward()``
+# + ``optimizer.step()`` (the only pattern trainer.py uses) needs, and it removes ~900 tiny torch add kernels per training
+# step.  A backward that runs under ``create_graph=True`` (the WGAN-GP ``torch.autograd.grad(..., inputs=interpolated)``,
+# trainer.py:306-312) computes input gradients only, exactly like autograd's ``only_inputs``.  NOT supported in this mode:
+# ``torch.autograd.grad`` w.r.t. parameters and ``backward(create_graph=True)``.
+# "autograd": parameter gradients are returned to autograd like any op (fully general, slower).
+GRAD_MODE = os.environ.get("BG_GRADS", "bucket")
 _philox_calls = 0
 
 
@@ -142,6 +150,38 @@ class _NativeState:
         self.md, self.layout = md, layout
         self.goff = (C.c_int64 * len(layout.names))(*[layout.offsets[n] for n in layout.names])
         self._ptrs, self._key = None, None
+        self.bucket, self.views, self.anchor = None, None, None
+
+    def get_anchor(self, device) -> Tensor:
+        """1-element leaf that carries the autograd edge of a bucket-mode pass (parameters are not autograd inputs)."""
+        if self.anchor is None or self.anchor.device != device:
+            self.anchor = torch.zeros(1, device=device, requires_grad=True)
+        return self.anchor
+
+    def bind_grads(self, params) -> Tensor:
+        """Make every ``p.grad`` a view of the flat bucket (zeroing what ``zero_grad(set_to_none=True)`` dropped)."""
+        dev = params[0].device
+        if self.bucket is None or self.bucket.device != dev:
+            self.bucket = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+            self.views = [self.layout.view(self.bucket, n) for n in self.layout.names]
+            for p, v in zip(params, self.views):
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+            return self.bucket
+        missing = [p.grad is None for p in params]
+        if all(missing):
+            self.bucket.zero_()
+            for p, v in zip(params, self.views):
+                p.grad = v
+        elif any(missing) or params[0].grad.data_ptr() != self.views[0].data_ptr():
+            for p, v, m in zip(params, self.views, missing):
+                if m:
+                    v.zero_()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                p.grad = v
+        return self.bucket
 
     def ptrs(self, params):
         key = (params[0].data_ptr(), params[-1].data_ptr(), len(params))
@@ -248,7 +288,11 @@ class VoxelGNNGenerator(nn.Module):
         fn = _GenFn if EXECUTOR == "python" else _GenNativeFn
         if EXECUTOR == "python" and keeps is None:
             keeps = [None] * len(self._convs)
-        logits, hard, soft = fn.apply(self, bc, zz, gumbel_noise, keeps, need, (seed, offset), *params)
+        if EXECUTOR != "python" and GRAD_MODE == "bucket":
+            logits, hard, soft = fn.apply(self, bc, zz, gumbel_noise, keeps, need, (seed, offset, True),
+                                          self._native.get_anchor(zz.device))
+        else:
+            logits, hard, soft = fn.apply(self, bc, zz, gumbel_noise, keeps, need, (seed, offset, False), *params)
         return logits, hard, soft
 
     # -- passes -----------------------------------------------------------------------------------
@@ -368,11 +412,13 @@ def _launches_gen_fwd(model) -> int:
 
 
 class _GenNativeFn(torch.autograd.Function):
-    """Generator forward/backward as two C calls (bg_gen_forward / bg_gen_backward)."""
+    """Generator forward/backward as two C calls (bg_gen_forward / bg_gen_backward).  ``tensors`` = the parameters
+    (GRAD_MODE "autograd") or the 1-element anchor (GRAD_MODE "bucket")."""
 
     @staticmethod
-    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, ticket, *params):
+    def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, ticket, *tensors):
         L, st = lib.load(), model._native
+        params = list(model.parameters())
         dev, n, e, k = zz.device, bc.n, bc.csr.num_edges, model.configuration.NUM_CLASSES
         ws = lib.u8_buffer(L.bg_gen_fwd_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
@@ -386,10 +432,10 @@ class _GenNativeFn(torch.autograd.Function):
         lib.pass_launches(_launches_gen_fwd(model))
         if getattr(model, "debug_keep_saved", False):
             model.debug_saved = _saved_views(model, ws, n, logits, True)
+        ctx.need, ctx.bucket_mode = need, ticket[2]
         if need:
             ctx.model, ctx.bc, ctx.ws, ctx.zz, ctx.training = model, bc, ws, zz, model.training
-            ctx.save_for_backward(logits, soft, *params)
-        ctx.need = need
+            ctx.save_for_backward(logits, soft)
         return logits, hard, soft
 
     @staticmethod
@@ -399,18 +445,22 @@ class _GenNativeFn(torch.autograd.Function):
             raise RuntimeError("generator backward called but the forward ran without grad")
         L, model, bc = lib.load(), ctx.model, ctx.bc
         st = model._native
-        logits, soft, *params = ctx.saved_tensors
+        params = list(model.parameters())
+        logits, soft = ctx.saved_tensors
         dev, n, e = logits.device, bc.n, bc.csr.num_edges
-        flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
+        flat = st.bind_grads(params) if ctx.bucket_mode else torch.empty(st.layout.total, dtype=torch.float32, device=dev)
         tmp = lib.u8_buffer(L.bg_gen_bwd_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
         cont = lambda t: None if t is None else t.contiguous()
         g_logits, g_hard, g_soft = cont(g_logits), cont(g_hard), cont(g_soft)
         lib._check(L.bg_gen_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
                                      ctx.zz.data_ptr(), ctx.ws.data_ptr(), logits.data_ptr(), soft.data_ptr(), lib._p(g_logits),
-                                     lib._p(g_hard), lib._p(g_soft), int(ctx.training), flat.data_ptr(), st.goff, tmp.data_ptr(),
-                                     tmp.numel(), red.data_ptr(), red.numel() * 4, lib._stream()))
-        lib.pass_launches(2 + 3 * (len(model._menc) + len(model._mlp) + len(model._dec)) + 7 * len(model._convs) + 8)
+                                     lib._p(g_hard), lib._p(g_soft), int(ctx.training), flat.data_ptr(), st.goff,
+                                     int(ctx.bucket_mode), tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4,
+                                     lib._stream()))
+        lib.pass_launches(2 + 3 * (len(model._menc) + len(model._mlp) + len(model._dec)) + 6 * len(model._convs) + 8)
+        if ctx.bucket_mode:
+            return (None,) * 8
         return (None,) * 7 + tuple(st.layout.view(flat, nm) for nm in model._names)
 
 
@@ -462,7 +512,9 @@ class VoxelGNNDiscriminator(nn.Module):
         need = torch.is_grad_enabled() and (label.requires_grad or any(p.requires_grad for p in params))
         if EXECUTOR == "python":
             return _DiscFn.apply(self, bc, keeps if keeps is not None else [None] * len(self._convs), need, label, *params)
-        return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset), label, *params)
+        if GRAD_MODE == "bucket":
+            return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, True), label, self._native.get_anchor(label.device))
+        return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, False), label, *params)
 
     # -- passes -----------------------------------------------------------------------------------
     def _forward_pass(self, P, bc: _BatchCtx, label: Tensor, keeps, save: bool):
@@ -590,8 +642,9 @@ class _DiscBwdFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class _DiscNativeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: VoxelGNNDiscriminator, bc, keeps, need, ticket, label, *params):
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, keeps, need, ticket, label, *tensors):
         L, st = lib.load(), model._native
+        params = list(model.parameters())
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         ws = lib.u8_buffer(L.bg_disc_fwd_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
@@ -603,19 +656,19 @@ class _DiscNativeFn(torch.autograd.Function):
         lib.pass_launches(2 + 4 * len(model._convs) + 4)
         if getattr(model, "debug_keep_saved", False):
             model.debug_saved = _saved_views(model, ws, n, score, False)
-        ctx.need = need
+        ctx.need, ctx.bucket_mode = need, ticket[2]
         if need:
             ctx.model, ctx.bc, ctx.ws, ctx.training = model, bc, ws, model.training
-            ctx.save_for_backward(label, score, *params)
+            ctx.save_for_backward(label, score, *tensors)
         return score
 
     @staticmethod
     def backward(ctx, g_score):
         if not ctx.need:
             raise RuntimeError("discriminator backward called but the forward ran without grad")
-        label, score, *params = ctx.saved_tensors
-        outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training, torch.is_grad_enabled(), score,
-                                      g_score.contiguous(), label, *params)
+        label, score, *tensors = ctx.saved_tensors
+        outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training, (torch.is_grad_enabled(), ctx.bucket_mode), score,
+                                      g_score.contiguous(), label, *tensors)
         return (None, None, None, None, None) + tuple(outs)
 
 
@@ -623,22 +676,29 @@ class _DiscNativeBwdFn(torch.autograd.Function):
     """First-order backward of the discriminator as a differentiable op (its backward = the second-order sweep)."""
 
     @staticmethod
-    def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, second_order, score, g_score, label, *params):
+    def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, flags, score, g_score, label, *tensors):
         L, st = lib.load(), model._native
+        params = list(model.parameters())
+        second_order, bucket_mode = flags
         dev, n, e = label.device, bc.n, bc.csr.num_edges
-        flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
+        if bucket_mode:  # under create_graph only the input gradient is wanted (autograd.grad(..., only_inputs=True))
+            flat = None if second_order else st.bind_grads(params)
+        else:
+            flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
         saved = lib.u8_buffer(L.bg_disc_bwd_saved_ws(C.byref(st.md), n, e), dev) if second_order else None
         tmp = lib.u8_buffer(L.bg_disc_tmp_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
         g_label = torch.empty_like(label)
         lib._check(L.bg_disc_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
                                       label.data_ptr(), ws.data_ptr(), score.data_ptr(), g_score.data_ptr(), int(training),
-                                      flat.data_ptr(), st.goff, lib._p(saved), 0 if saved is None else saved.numel(),
+                                      lib._p(flat), st.goff, int(bucket_mode), lib._p(saved), 0 if saved is None else saved.numel(),
                                       tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4, g_label.data_ptr(),
                                       lib._stream()))
-        lib.pass_launches(3 * 4 + 7 * len(model._convs) + 3 * 2)
-        ctx.model, ctx.bc, ctx.ws, ctx.saved, ctx.training = model, bc, ws, saved, training
-        ctx.save_for_backward(label, score, *params)
+        lib.pass_launches((3 * 4 + 6 * len(model._convs) + 3 * 2) if flat is not None else (2 * 4 + 5 * len(model._convs) + 4))
+        ctx.model, ctx.bc, ctx.ws, ctx.saved, ctx.training, ctx.bucket_mode = model, bc, ws, saved, training, bucket_mode
+        ctx.save_for_backward(label, score)
+        if bucket_mode:
+            return (g_label, None)
         grads = tuple(st.layout.view(flat, nm) for nm in model._names)
         ctx.mark_non_differentiable(*grads)
         return (g_label,) + grads
@@ -650,9 +710,10 @@ class _DiscNativeBwdFn(torch.autograd.Function):
             raise RuntimeError("second-order backward requested but the first backward ran without create_graph=True")
         L, model, bc = lib.load(), ctx.model, ctx.bc
         st = model._native
-        label, score, *params = ctx.saved_tensors
+        params = list(model.parameters())
+        label, score = ctx.saved_tensors
         dev, n, e = label.device, bc.n, bc.csr.num_edges
-        flat2 = torch.zeros(st.layout.total, dtype=torch.float32, device=dev)
+        flat2 = st.bind_grads(params) if ctx.bucket_mode else torch.zeros(st.layout.total, dtype=torch.float32, device=dev)
         tmp = lib.u8_buffer(2 * L.bg_disc_tmp_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
         want_gt = ctx.needs_input_grad[6]
@@ -661,7 +722,9 @@ class _DiscNativeBwdFn(torch.autograd.Function):
                                        label.data_ptr(), ctx.ws.data_ptr(), score.data_ptr(), ctx.saved.data_ptr(),
                                        Lt.contiguous().data_ptr(), int(ctx.training), flat2.data_ptr(), st.goff, tmp.data_ptr(),
                                        tmp.numel(), red.data_ptr(), red.numel() * 4, lib._p(gt), lib._stream()))
-        lib.pass_launches(6 + 9 * len(model._convs) + 8 + 7 * len(model._convs) + 6)
+        lib.pass_launches(6 + 8 * len(model._convs) + 8 + 6 * len(model._convs) + 6)
         # the cotangent on `label` (third-order coupling into the generator) is not needed by WGAN-GP: the interpolate is
         # built from detached samples (trainer.py:298-301)
+        if ctx.bucket_mode:
+            return (None, None, None, None, None, None, gt, None, None)
         return (None, None, None, None, None, None, gt, None) + tuple(st.layout.view(flat2, nm) for nm in model._names)

@@ -233,18 +233,19 @@ int bg_gen_forward(const BgModelDesc* md, const float* const* params, const BgGr
 int bg_gen_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
                     const float* z, const void* ws_fwd, const float* logits, const float* soft, const float* g_logits,
                     const float* g_hard, const float* g_soft, int32_t training, float* grad_flat, const int64_t* grad_off,
-                    void* tmp, size_t tmp_bytes, float* red, size_t red_bytes, void* stream);
+                    int32_t accumulate, void* tmp, size_t tmp_bytes, float* red, size_t red_bytes, void* stream);
 size_t bg_disc_fwd_ws(const BgModelDesc* md, int64_t N, int64_t E);
 size_t bg_disc_bwd_saved_ws(const BgModelDesc* md, int64_t N, int64_t E);
 size_t bg_disc_tmp_ws(const BgModelDesc* md, int64_t N, int64_t E);
 int bg_disc_forward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
                     const float* label, const uint8_t* const* keeps, int32_t training, uint64_t seed, uint64_t offset,
                     void* ws, size_t ws_bytes, float* red, size_t red_bytes, float* score, void* stream);
-/* grad_flat may be NULL (input gradient only); saved != NULL keeps the intermediates bg_disc_backward2 needs. */
+/* grad_flat may be NULL (input gradient only); accumulate != 0 adds the parameter gradients into grad_flat instead of
+ * overwriting it; saved != NULL keeps the intermediates bg_disc_backward2 needs. */
 int bg_disc_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
                      const float* label, const void* ws_fwd, const float* score, const float* g_score, int32_t training,
-                     float* grad_flat, const int64_t* grad_off, void* saved, size_t saved_bytes, void* tmp, size_t tmp_bytes,
-                     float* red, size_t red_bytes, float* g_label, void* stream);
+                     float* grad_flat, const int64_t* grad_off, int32_t accumulate, void* saved, size_t saved_bytes, void* tmp,
+                     size_t tmp_bytes, float* red, size_t red_bytes, float* g_label, void* stream);
 /* WGAN-GP (reference trainer.py:306-312): Lt = cotangent on g_label; grad_flat must be zero on entry and receives
  * the parameter cotangents (second-order sweep + forward-graph sweep with injections); tmp >= 2*bg_disc_tmp_ws. */
 int bg_disc_backward2(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,

@@ -25,10 +25,13 @@ print("wall ms/step", (time.perf_counter() - t0) / 5 * 1e3)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
     torch.cuda.synchronize()
-ev = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"] if hasattr(prof.key_averages()[0], "device_type") else prof.key_averages()
-rows = sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)
-tot = sum(e.self_device_time_total for e in rows)
-print("total device us", tot)
-for e in rows[:32]:
-    if e.self_device_time_total <= 0: continue
-    print(f"{e.key[:80]:80s} {e.count:6d} {e.self_device_time_total:10.0f} us {e.self_device_time_total/max(e.count,1):8.2f} {100*e.self_device_time_total/tot:5.1f}%")
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if str(e.device_type).endswith("CUDA"):
+        agg[e.name][0] += 1; agg[e.name][1] += e.device_time
+tot = sum(v[1] for v in agg.values())
+ours = sum(v[1] for k, v in agg.items() if "bg::" in k)
+print(f"GPU kernel time total {tot/1e3:.2f} ms, launches {sum(v[0] for v in agg.values())}; libbgb200: {ours/1e3:.2f} ms in {sum(v[0] for k, v in agg.items() if 'bg::' in k)} launches")
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{k[:90]:90s} {c:5d} {t:9.0f} us {t/c:8.2f} {100*t/tot:5.1f}%")

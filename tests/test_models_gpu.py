@@ -298,3 +298,38 @@ def test_no_cpu_fallback():
     cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
     with pytest.raises(RuntimeError, match="CUDA only"):
         G(lb.to("cpu"), vb.to("cpu"), torch.zeros(1, vb.num_nodes, 128))
+
+
+@pytest.mark.parametrize("mode", ["bucket", "autograd"])
+def test_grad_modes_agree_on_a_critic_and_generator_update(mode, monkeypatch):
+    """The two gradient-delivery modes (kernels accumulate into p.grad views of one flat bucket / autograd receives every
+    parameter gradient) give the same p.grad after the reference's loss.backward() sequence, bit for bit on the forward
+    and to fp32 re-association on the sums (the bucket adds passes in-kernel, autograd adds them with torch.add)."""
+    from building_gan_b200 import models, step
+    results = {}
+    for m in ("autograd", mode):
+        monkeypatch.setattr(models, "GRAD_MODE", m)
+        cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
+        G.eval(), D.eval()
+        torch.manual_seed(11)
+        z = torch.randn(1, vb.num_nodes, cfg.Z_DIM).to(DEV)
+        noise = -torch.empty(vb.num_nodes, 7).exponential_().log().to(DEV)
+        with torch.no_grad():
+            _, hard, soft = G(lb, vb, z, noise)
+        loss = step.discriminator_loss(D, lb, vb, hard.unsqueeze(0), soft.unsqueeze(0), cfg, rng="cpu")
+        loss.backward()
+        logits, hard, soft = G(lb, vb, z, noise)
+        gl = step.generator_loss(D, lb, vb, logits, hard.unsqueeze(0), cfg)
+        gl.backward()
+        results[m] = (float(loss), float(gl), {k: p.grad.clone() for k, p in D.named_parameters()},
+                      {k: p.grad.clone() for k, p in G.named_parameters()})
+    a, b = results["autograd"], results[mode]
+    assert a[0] == b[0] and a[1] == b[1]
+    for ga, gb in ((a[2], b[2]), (a[3], b[3])):
+        gmax = max(float(v.abs().max()) for v in ga.values())
+        for k in ga:
+            err = float((ga[k] - gb[k]).abs().max())
+            assert err <= 1e-5 * float(ga[k].abs().max()) or err <= 1e-6 * gmax, (k, err)
+    if mode == "bucket":  # every p.grad is a view of the one flat bucket
+        base = D._native.bucket.data_ptr()
+        assert all(base <= p.grad.data_ptr() < base + D._native.bucket.numel() * 4 for p in D.parameters())
