@@ -159,6 +159,10 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, ui
 // 32 random bits -> uniform in (0, 1]
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
 
+// Fire-and-forget L2 prefetch of the 128-byte line holding p: unlike a load it holds no register, so the bytes in
+// flight are not bounded by the register file.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float lrelu(float u, float slope) { return u > 0.f ? u : u * slope; }
 __device__ __forceinline__ float lrelu_grad(float u, float slope) { return u > 0.f ? 1.f : slope; }
 

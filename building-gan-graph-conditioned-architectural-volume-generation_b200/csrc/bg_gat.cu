@@ -7,6 +7,8 @@
 // per-row reductions are butterflies inside the group with a FIXED edge order (CSR order = the
 // reference's COO order, self loop last) - no atomics, bitwise reproducible.
 // Roofline: HBM.  Algorithmic bytes per launch are stated in DESIGN.md section "Kernels".
+#include <stdlib.h>
+
 #include "bg_common.cuh"
 
 namespace bg {
@@ -18,7 +20,7 @@ template <int C>
 __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ h,
     const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
-    float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int64_t N, float slope) {
+    float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int64_t N, float slope, int pf_rows) {
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -26,6 +28,19 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(
     const unsigned gm = group_mask<LANES>(lane);
     const int64_t row = (int64_t)blockIdx.x * M::RPC + warp * M::RPW + lane / LANES;
     if (row >= N) return;  // whole groups leave together; group masks keep the rest legal
+    // Large graphs are latency-bound on the dependent chain rowptr -> col -> s -> h (every array cold in L2): pull the
+    // lines a block ~2 waves ahead will need into L2 now.  Prefetches hold no registers, so they decouple the bytes in
+    // flight from the register file; the block that later owns those rows finds its whole chain L2-resident.
+    const int64_t prow = row + pf_rows;
+    int pbeg = -1;
+    if (pf_rows > 0 && prow < N) {
+        if (sub == 0) {
+            pbeg = __ldg(rowptr + prow);  // consumed only at the end of the kernel (no stall here)
+            prefetch_l2(d + prow);
+            prefetch_l2(s + prow);
+        }
+        if (((sub * VEC * 4) & 127) == 0) prefetch_l2(h + prow * C + sub * VEC);
+    }
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const float di = __ldg(d + row);
 
@@ -72,6 +87,10 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(
     if (sub == 0) {
         m_out[row] = mx;
         z_out[row] = zs;
+        if (pbeg >= 0) {
+            prefetch_l2(col + pbeg);
+            prefetch_l2(col + pbeg + 8);
+        }
     }
 }
 
@@ -281,11 +300,21 @@ __global__ void __launch_bounds__(kThreads) gat_bwd2_dst_kernel(
     if (sub == 0) sdt[2 * row + 1] = dt;
 }
 
+// Prefetch distance in rows: ~2 waves of resident CTAs ahead; 0 (off) for graphs whose working set is L2-resident anyway.
+template <int C>
+static int prefetch_rows(int64_t N) {
+    static const int env = getenv("BG_GAT_PF") ? atoi(getenv("BG_GAT_PF")) : -1;
+    if (env >= 0) return env * RowMap<C>::RPC;
+    if (N * C * 4 < (int64_t)(24 << 20)) return 0;
+    return 2 * kSMs * 5 * RowMap<C>::RPC;
+}
+
 template <int C>
 static int launch_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                       float* out, float* m, float* z, float slope, cudaStream_t st) {
     const int64_t grid = ceil_div(g->N, RowMap<C>::RPC);
-    gat_fwd_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, h, s, d, bias, out, m, z, g->N, slope);
+    gat_fwd_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, h, s, d, bias, out, m, z, g->N, slope,
+                                                          prefetch_rows<C>(g->N));
     return check_launch("bg_gat_fwd");
 }
 template <int C>

@@ -1,19 +1,20 @@
-"""Data-parallel plumbing: one process per GPU, graphs of the global batch sharded across ranks,
-gradients averaged with ONE NCCL all-reduce per backward over a flat fp32 bucket (SURVEY section 8e,
-"default" semantics = what DistributedDataParallel around the reference would compute: GraphNorm /
-type-table statistics stay rank-local).  The payload is tiny (G 1.10 MB, D 63 KB) => latency-bound:
-a single bucket per model, launched on the compute stream right after the last backward kernel.
+"""Data-parallel plumbing: one process per GPU, graphs of the global batch sharded across ranks, gradients averaged
+with ONE all-reduce per backward over a flat fp32 bucket ("default" semantics = what
+DistributedDataParallel around the reference would compute: GraphNorm / type-table statistics and the batch-mean
+losses stay rank-local).  The payload is tiny (G 1.10 MB, D 63 KB) => latency-bound: a single bucket per model, issued
+on the compute stream right after the last backward kernel.  In BG_GRADS=bucket mode the bucket IS where the kernels
+accumulated the gradients (every ``p.grad`` is a view of it), so there is no flatten / unflatten copy at all.
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Sequence
 
 import torch
 import torch.distributed as dist
 
 
 class GradSync:
-    """``sync(model)`` averages ``p.grad`` of every parameter over the ranks with a single all-reduce."""
+    """``sync(model)`` averages the parameter gradients of ``model`` over the ranks with a single all-reduce."""
 
     def __init__(self, world_size: int):
         self.world = world_size
@@ -22,12 +23,18 @@ class GradSync:
     def __call__(self, model: torch.nn.Module) -> None:
         if self.world <= 1:
             return
+        native = getattr(model, "_native", None)
+        bucket = getattr(native, "bucket", None)
         params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.grad is not None]
         if not params:
             return
+        if bucket is not None and params[0].grad.data_ptr() == native.views[0].data_ptr():
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)  # grads already live in one flat bucket
+            bucket.mul_(1.0 / self.world)
+            return
         total = sum(p.numel() for p in params)
         flat = self._buckets.get(id(model))
-        if flat is None or flat.numel() != total:
+        if flat is None or flat.numel() != total or flat.device != params[0].device:
             flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
             self._buckets[id(model)] = flat
         views, off = [], 0
@@ -40,9 +47,24 @@ class GradSync:
         torch._foreach_copy_([p.grad for p in params], views)
 
 
-def shard_ids(ids: List[int], rank: int, world: int) -> List[int]:
-    """Contiguous shard of the global batch's graph list for this rank (balanced to +-1 graph)."""
+def shard_ids(ids: Sequence[int], rank: int, world: int) -> List[int]:
+    """Contiguous shard of the global batch's graph list for this rank (sizes differ by at most one graph)."""
     n = len(ids)
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
-    return ids[lo:hi]
+    return list(ids[(n * rank) // world: (n * (rank + 1)) // world])
+
+
+def shard_by_nodes(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Contiguous partition of a batch's graphs into ``world`` shards balanced by voxel count (greedy prefix split):
+    returns the graph indices of every shard."""
+    total, out, acc, cur, r = sum(sizes), [], 0, [], 0
+    for i, s in enumerate(sizes):
+        cur.append(i)
+        acc += s
+        remaining_graphs = len(sizes) - i - 1
+        if r < world - 1 and (acc >= total * (r + 1) / world or remaining_graphs == world - r - 1):
+            out.append(cur)
+            cur, r = [], r + 1
+    out.append(cur)
+    while len(out) < world:
+        out.append([])
+    return out
