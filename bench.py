@@ -238,7 +238,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     roofline, ops = None, None
     if rank == 0:
         roofline = _gat_roofline(resident[0][1], G, D, flush)
-        ops = _kernel_shares(lambda: step_resident(0))
+        # local step (no gradient all-reduce: the other ranks do not take part in this extra step)
+        ops = _kernel_shares(lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=None,
+                                                     sync_losses=False))
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = _cpu_baseline(host)
