@@ -261,25 +261,24 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     const int mycol = tid % T;
     const SegCol xcol = seg_resolve(p.x, k0 + mycol, mycol < nk ? p.K : 0);
     const float* gcol = mycol < no ? p.gz + o0 + mycol : nullptr;
-    for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
-        // issue every global load of this slab first (independent, all in flight), then fill shared memory
-        constexpr int PER = RB * T / kThreads;
-        float gv[PER], xv[PER];
+    // software pipeline: the global loads of slab i+1 are issued (into registers) before slab i is multiplied, so the
+    // load latency overlaps the FMAs / the barrier instead of adding to every iteration
+    constexpr int PER = RB * T / kThreads;
+    float gv[PER], xv[PER];
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
-            const int64_t r = r0 + rr;
-            const bool rok = r < rend;
-            (void)cc;
-            gv[q] = (rok && gcol) ? __ldg(gcol + r * p.ld_gz) : 0.f;
+            const int64_t r = r0 + (tid + q * kThreads) / T;
+            gv[q] = (r < rend && gcol) ? __ldg(gcol + r * p.ld_gz) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
-            const int64_t r = r0 + rr;
-            (void)cc;
+            const int64_t r = r0 + (tid + q * kThreads) / T;
             xv[q] = (r < rend) ? seg_load(xcol, r) : 0.f;
         }
+    };
+    if (rbeg < rend) fetch(rbeg);
+    for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
@@ -287,6 +286,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
             Xs[rr][cc] = xv[q];
         }
         __syncthreads();
+        if (r0 + RB < rend) fetch(r0 + RB);
         if (ty * 4 < no && tx * 4 < nk) {
 #pragma unroll
             for (int rr = 0; rr < RB; ++rr) {
@@ -339,10 +339,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb
 }
 
 static inline int wgrad_splits(int64_t N, int total_tiles) {
-    int64_t ns = ceil_div(2 * kSMs, total_tiles);
+    // small outputs (a handful of tiles) are pure latency: use many short row ranges (the folds of a whole pass run as
+    // one parallel launch, so more partials are cheap); large outputs keep the partial traffic bounded
+    int64_t ns = ceil_div(total_tiles <= 4 ? 4 * kSMs : 2 * kSMs, total_tiles);
     const int64_t maxs = ceil_div(N, 64);
+    const int64_t cap = total_tiles <= 4 ? 128 : 64;
     if (ns > maxs) ns = maxs;
-    if (ns > 64) ns = 64;
+    if (ns > cap) ns = cap;
     if (ns < 1) ns = 1;
     return (int)ns;
 }
