@@ -45,6 +45,9 @@ struct WgradQueue {
 int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st);
 int wgrad_flush(WgradQueue& q, cudaStream_t st);
 
+// tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
+int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
+
 #define BG_REQUIRE(cond, code, ...)      \
     do {                                 \
         if (!(cond)) {                   \

@@ -563,6 +563,10 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     BG_REQUIRE(!a->ln_gamma || a->ln_beta, BG_EINVAL, "bg_dense_fwd: LayerNorm needs gamma and beta");
     BG_REQUIRE(!a->att_src || (a->att_dst && a->s && a->d), BG_EINVAL, "bg_dense_fwd: attention dots need att_dst, s, d");
     BG_REQUIRE(!rowwise || a->Cout <= 128, BG_EUNSUPPORTED, "bg_dense_fwd: row-wise epilogue needs Cout<=128 (got %d)", a->Cout);
+    {  // 128/64-wide layers with plain row-major weights go to the tensor cores (tcgen05, 3xTF32 split: fp32-accurate)
+        const int rc = dense_tc_try(a, p.K, as_stream(stream));
+        if (rc <= 0) return rc;
+    }
     int bn = 8;
     while (bn < a->Cout && bn < 128) bn <<= 1;
     BG_REQUIRE(!a->ln_gamma || bn == a->Cout, BG_EUNSUPPORTED,

@@ -1,0 +1,368 @@
+// Dense layers on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via the 3xTF32 split.
+//
+// y[128 rows, BN] = epilogue(X[128, K] W[BN, K]^T): the 128/64-wide Linear(+LayerNorm+LeakyReLU/ReLU)(+attention dots)
+// layers of the generator / discriminator (reference models.py:49-66,92-113 and the conv `lin`s).
+//
+// TF32 keeps 10 mantissa bits, a single TF32 product is ~1e-3 accurate - not enough for the rel-1e-5 parity mode.  Every
+// fp32 operand is therefore split into hi = a with its low 13 mantissa bits cleared (exactly a TF32 number) and
+// lo = a - hi (exact in fp32, <= 13 significant bits), and the accumulator receives hi*hi + lo*hi + hi*lo (the dropped
+// lo*lo term is ~2^-22 relative).  Operands are staged in shared memory K-major in the canonical SWIZZLE_128B layout
+// (one 128-byte row = 32 fp32 = 4 UMMA k-steps), accumulators live in TMEM (128 lanes x BN columns fp32), the epilogue
+// reads them back with tcgen05.ld, one thread per row (bias, LayerNorm, activation, attention dots, store).
+//
+// Pipeline per CTA: 2 shared-memory stages.  All 256 threads load / split / store the next stage while the tensor core
+// consumes the previous one; one thread issues the 12 MMAs of a stage and a tcgen05.commit that frees it.
+#include <stdlib.h>
+
+#include "bg_common.cuh"
+
+namespace bg {
+
+constexpr int TC_M = 128;        // rows per CTA = UMMA M
+constexpr int TC_K = 32;         // fp32 per 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+
+struct SegViewTc {
+    int nseg;
+    int off[BG_MAX_SEG + 1];
+    BgSeg seg[BG_MAX_SEG];
+};
+struct SegColTc {
+    const float* base;
+    const int32_t* gather;
+    int ld;
+    bool ones;
+};
+__device__ __forceinline__ SegColTc seg_resolve_tc(const SegViewTc& sv, int k, int K) {
+    SegColTc c{nullptr, nullptr, 0, false};
+    if (k >= K) return c;
+#pragma unroll
+    for (int q = 0; q < BG_MAX_SEG; ++q) {
+        if (q < sv.nseg && k >= sv.off[q] && k < sv.off[q + 1]) {
+            const BgSeg& sg = sv.seg[q];
+            c.ones = (sg.ptr == nullptr);
+            c.base = sg.ptr ? sg.ptr + (k - sv.off[q]) : nullptr;
+            c.gather = sg.gather;
+            c.ld = sg.ld;
+        }
+    }
+    return c;
+}
+__device__ __forceinline__ float seg_load_tc(const SegColTc& c, int64_t row) {
+    if (c.base == nullptr) return c.ones ? 1.f : 0.f;
+    const int64_t r = c.gather ? (int64_t)__ldg(c.gather + row) : row;
+    return __ldg(c.base + r * c.ld);
+}
+
+struct DenseTcParams {
+    int64_t N;
+    SegViewTc x;
+    int K;
+    const float* W;  // [BN, K] row-major
+    const float *bias, *gamma, *beta, *att_src, *att_dst;
+    int act;
+    float* out;
+    int64_t ld_out;
+    float *xhat, *rstd, *s, *d;
+};
+
+// ---- raw PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for one swizzle atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+    return d;
+}
+// byte offset of element (row, k) inside a [rows][32 fp32] SWIZZLE_128B tile (Swizzle<3,4,3>: 16-byte chunk ^= row & 7)
+__device__ __forceinline__ int swz(int row, int k) { return row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int A_BYTES = TC_M * 128, B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);  // [TC_STAGES]
+    uint64_t* accum_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TC_M;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(empty_bar + s, 1);
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    const int nkb = (p.K + TC_K - 1) / TC_K;
+    // Loader mapping: a thread owns one 16-byte chunk (4 consecutive k) of the 128-byte row, rows tid/8 + 32 i: 128-bit global
+    // loads (coalesced: 8 threads = one row), 128-bit swizzled shared stores (8 distinct chunks per row: conflict-free).
+    // Needs every segment width / row stride / pointer to be a multiple of 4 floats (checked on the host).
+    const int chunk = tid & 7;
+    const int rbase = tid >> 3;  // 0..31
+    struct Regs {
+        float4 a[TC_M / 32], b[BN / 32];
+    };
+    auto fetch = [&](int kb, Regs& R) {  // global -> registers for k-block kb, issued TWO iterations ahead of its use
+        const int kg = kb * TC_K + chunk * 4;
+        const SegColTc xc = seg_resolve_tc(p.x, kg, p.K);
+#pragma unroll
+        for (int i = 0; i < TC_M / 32; ++i) {
+            const int64_t r = row0 + rbase + 32 * i;
+            R.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < p.N && xc.base) {
+                const int64_t rr = xc.gather ? (int64_t)__ldg(xc.gather + r) : r;
+                R.a[i] = __ldg(reinterpret_cast<const float4*>(xc.base + rr * xc.ld));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i)
+            R.b[i] = kg < p.K ? __ldg(reinterpret_cast<const float4*>(p.W + (int64_t)(rbase + 32 * i) * p.K + kg))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto split_store = [&](const float4& v, uint8_t* hi_tile, uint8_t* lo_tile, int row) {
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // round-to-nearest TF32 split: hi + lo == a up to 2^-22 |a|, both unbiased
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[u]));
+            hi[u] = __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(in[u] - hi[u]));
+            lo[u] = __uint_as_float(lb);
+        }
+        const int o = row * 128 + ((chunk ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(hi_tile + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(lo_tile + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    };
+    auto process = [&](int kb, Regs& R) {
+        const int s = kb % TC_STAGES;
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (kb >= TC_STAGES) mbar_wait(empty_bar + s, ((kb / TC_STAGES) - 1) & 1);  // MMAs that read this stage retired
+#pragma unroll
+        for (int i = 0; i < TC_M / 32; ++i) split_store(R.a[i], st, st + A_BYTES, rbase + 32 * i);
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) split_store(R.b[i], st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, rbase + 32 * i);
+        if (kb + 2 < nkb) fetch(kb + 2, R);  // refill this register set: in flight for two full iterations
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < TC_K / 8; ++ks) {  // UMMA K = 8 tf32 = 32 bytes
+                const uint32_t adv = ks * 32;
+                tc_mma_tf32(tmem_base, make_desc(a_hi + adv), make_desc(b_hi + adv), IDESC, (kb | ks) != 0);
+                tc_mma_tf32(tmem_base, make_desc(a_lo + adv), make_desc(b_hi + adv), IDESC, 1);
+                tc_mma_tf32(tmem_base, make_desc(a_hi + adv), make_desc(b_lo + adv), IDESC, 1);
+            }
+            tc_commit(empty_bar + s);               // frees the stage when these MMAs have read it
+            if (kb == nkb - 1) tc_commit(accum_bar);  // accumulator complete
+        }
+    };
+    Regs R0, R1;
+    fetch(0, R0);
+    if (nkb > 1) fetch(1, R1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+        process(kb, R0);
+        if (kb + 1 < nkb) process(kb + 1, R1);
+    }
+
+    // ---- epilogue: warps 0..3, one thread per row (TMEM lane = row), columns in chunks of 32
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    if (warp < 4) {
+        const int r_local = warp * 32 + lane;
+        const int64_t grow = row0 + r_local;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float mean = 0.f, rs = 1.f;
+        if (p.gamma) {
+            float sm = 0.f;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+                    "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sm += __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+            }
+            mean = sm / (float)BN;
+            float vs = 0.f;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+                    "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float dlt = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - mean;
+                    vs = fmaf(dlt, dlt, vs);
+                }
+            }
+            rs = 1.f / sqrtf(vs / (float)BN + 1e-5f);
+            if (p.rstd && grow < p.N) p.rstd[grow] = rs;
+        }
+        float ss = 0.f, dd = 0.f;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+                "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float y[32];
+            if (p.gamma && p.xhat && grow < p.N) {  // normalised value saved for the backward, 128-bit stores
+                float4* x4 = reinterpret_cast<float4*>(p.xhat + grow * BN + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) q[u] = (__uint_as_float(v[j + u]) + (p.bias ? __ldg(p.bias + c0 + j + u) : 0.f) - mean) * rs;
+                    x4[j >> 2] = make_float4(q[0], q[1], q[2], q[3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                if (p.gamma) {
+                    const float xh = (t - mean) * rs;
+                    t = fmaf(xh, __ldg(p.gamma + c), __ldg(p.beta + c));
+                }
+                if (p.act == BG_ACT_RELU) t = t > 0.f ? t : 0.f;
+                else if (p.act == BG_ACT_LRELU) t = t > 0.f ? t : 0.2f * t;
+                if (p.att_src) {
+                    ss = fmaf(t, __ldg(p.att_src + c), ss);
+                    dd = fmaf(t, __ldg(p.att_dst + c), dd);
+                }
+                y[j] = t;
+            }
+            if (grow < p.N) {
+                float4* o4 = reinterpret_cast<float4*>(p.out + grow * p.ld_out + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) o4[j >> 2] = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+        }
+        if (p.att_src && grow < p.N) {
+            p.s[grow] = ss;
+            p.d[grow] = dd;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+}
+
+static int g_dense_tc = -1;  // -1: read BG_DENSE_TC on first use (default on)
+
+// Returns BG_OK if the layer was launched on the tensor-core path, 1 if the shape is not eligible (caller falls back to
+// the FFMA kernel), negative on error.
+int dense_tc_try(const BgDense* a, int K, cudaStream_t st) {
+    if (g_dense_tc < 0) g_dense_tc = getenv("BG_DENSE_TC") ? atoi(getenv("BG_DENSE_TC")) : 1;
+    if (!g_dense_tc) return 1;
+    if (a->w_sk != 1 || a->w_so != K) return 1;                 // plain [Cout, K] row-major weights only
+    // measured crossover against the FFMA kernel: 128-wide layers from K=128, 64-wide layers from K=256
+    if (!((a->Cout == 128 && K >= 128) || (a->Cout == 64 && K >= 256)) || a->N < 128) return 1;
+    if (K % 4) return 1;
+    for (int q = 0; q < a->nseg; ++q) {  // 128-bit loads: widths, row strides and pointers in units of 4 floats; no ones-segment
+        const BgSeg& sg = a->seg[q];
+        if (!sg.ptr || (sg.width & 3) || (sg.ld & 3) || (reinterpret_cast<uintptr_t>(sg.ptr) & 15)) return 1;
+    }
+    if (reinterpret_cast<uintptr_t>(a->W) & 15) return 1;
+    if ((a->ld_out & 3) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return 1;
+    DenseTcParams p;
+    p.N = a->N;
+    p.x.nseg = a->nseg;
+    p.x.off[0] = 0;
+    for (int q = 0; q < BG_MAX_SEG; ++q) {
+        p.x.seg[q] = q < a->nseg ? a->seg[q] : BgSeg{nullptr, nullptr, 0, 0};
+        p.x.off[q + 1] = p.x.off[q] + (q < a->nseg ? a->seg[q].width : 0);
+    }
+    p.K = K;
+    p.W = a->W; p.bias = a->bias; p.gamma = a->ln_gamma; p.beta = a->ln_beta;
+    p.att_src = a->att_src; p.att_dst = a->att_dst; p.act = a->act;
+    p.out = a->out; p.ld_out = a->ld_out; p.xhat = a->xhat; p.rstd = a->rstd; p.s = a->s; p.d = a->d;
+    const unsigned grid = (unsigned)ceil_div(a->N, TC_M);
+    if (a->Cout == 128) {
+        constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 128 * 128) + 1024 + 64;
+        static bool once = (cudaFuncSetAttribute(dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
+        (void)once;
+        dense_tc_kernel<128><<<grid, kThreads, smem, st>>>(p);
+    } else {
+        constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 64 * 128) + 1024 + 64;
+        static bool once = (cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
+        (void)once;
+        dense_tc_kernel<64><<<grid, kThreads, smem, st>>>(p);
+    }
+    return check_launch("bg_dense_fwd(tcgen05)");
+}
+
+}  // namespace bg
+
+extern "C" int bg_set_dense_tc(int32_t on) {
+    const int prev = bg::g_dense_tc;
+    bg::g_dense_tc = on ? 1 : 0;
+    return prev;
+}

@@ -70,6 +70,7 @@ SIGNATURES = {
     "bg_type_scatter_sum": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "bg_type_scatter_sum_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_fwd": (C.c_int, [C.POINTER(BgDense), _P]),
+    "bg_set_dense_tc": (C.c_int, [_I32]),
     "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
     "bg_wgrad_multi_ws": (_SZ, [_I64, _I32, _P, _P]),
@@ -168,6 +169,11 @@ def load() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
+
+
+def set_dense_tc(on: bool) -> int:
+    """Switch the tcgen05 3xTF32 dense path on/off at run time (default on; BG_DENSE_TC=0 in the environment disables it)."""
+    return load().bg_set_dense_tc(int(bool(on)))
 
 
 def last_error() -> str:

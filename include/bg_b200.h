@@ -108,6 +108,12 @@ typedef struct BgDense {
     float* s; float* d;                  /* optional [N] each */
 } BgDense;
 int bg_dense_fwd(const BgDense* a, void* stream);
+/* 128-wide (K >= 128) and 64-wide (K >= 256) layers with plain row-major weights run on the tensor cores: tcgen05.mma
+ * kind::tf32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo), accumulators in TMEM (csrc/bg_dense_tc.cu).  Per-layer error
+ * <= 1e-5 of max|y| (the tensor core accumulates with round-toward-zero: ~4e-6 at K=524 against ~1.4e-6 for the FFMA
+ * kernel).  bg_set_dense_tc(0) (or BG_DENSE_TC=0) forces the FP32 FFMA kernel everywhere; returns the previous setting
+ * (-1 = not yet initialised from the environment). */
+int bg_set_dense_tc(int32_t on);
 
 /* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
  * yields the bias gradient as an extra column); deterministic split-N reduction.

@@ -150,8 +150,21 @@ def _grads_close(model, omodel, tol, what, omodel32=None):
     assert not bad, f"{what}: " + "; ".join(bad)
 
 
+@pytest.mark.parametrize("dense", ["ffma", "tcgen05"])
 @pytest.mark.parametrize("train", [False, True])
-def test_generator_forward_backward(train):
+def test_generator_forward_backward(train, dense):
+    """dense="ffma": every Linear in FP32 FFMA (strict parity mode, BG_DENSE_TC=0): end-to-end logits as accurate as the
+    reference's own fp32 arithmetic.  dense="tcgen05" (default): the 128-wide layers on the tensor cores with the 3xTF32
+    split - stated tolerance 1e-4 of max|logit| through 33 layers (tensor-core accumulation rounds toward zero)."""
+    from building_gan_b200 import lib
+    lib.set_dense_tc(dense == "tcgen05")
+    try:
+        _generator_forward_backward(train, 1e-4 if dense == "tcgen05" else 1e-5)
+    finally:
+        lib.set_dense_tc(True)
+
+
+def _generator_forward_backward(train, fwd_tol):
     cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
     n = vb.num_nodes
     z = torch.randn(1, n, cfg.Z_DIM, generator=torch.Generator().manual_seed(5))
@@ -165,12 +178,12 @@ def test_generator_forward_backward(train):
     kk = [None if k is None else k.to(torch.uint8).to(DEV) for k in keeps]
     G.debug_keep_saved = True
     logits, hard, soft = G(lb, vb, z.to(DEV), noise.to(DEV), keeps=kk)
-    print("generator logits rel err (ours, fp32 oracle):", _act_close(logits, ologits, l32.detach(), 1e-5, "logits"))
-    _act_close(soft, osoft, s32.detach(), 1e-5, "label_soft")
+    print("generator logits rel err (ours, fp32 oracle):", _act_close(logits, ologits, l32.detach(), fwd_tol, "logits"))
+    _act_close(soft, osoft, s32.detach(), fwd_tol, "label_soft")
     top2 = osoft.topk(2, dim=1).values
-    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    safe = (top2[:, 0] - top2[:, 1]) > 10 * fwd_tol
     assert torch.equal(hard.argmax(1).cpu()[safe], ohard.argmax(1)[safe]), "voxel->program argmax labels"
-    assert int((~safe).sum()) <= 2
+    assert int((~safe).sum()) <= 3
     w1, w2, w3 = (torch.randn(n, 7, generator=torch.Generator().manual_seed(s), dtype=torch.float64) for s in (8, 9, 10))
     _sync_patterns(oG, G.debug_saved, ovb.type)  # gradients are compared on the SAME activation pattern
     plogits, phard, psoft = oG(olb, ovb, z.double(), noise.double())
