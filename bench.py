@@ -74,6 +74,7 @@ def _clone_to(lb, vb, device):
         object.__setattr__(nb, "_fields", dict(b._fields))
         object.__setattr__(nb, "_cuts", object.__getattribute__(b, "_cuts"))
         object.__setattr__(nb, "_starts", object.__getattribute__(b, "_starts"))
+        object.__setattr__(nb, "_pack", b.__dict__.get("_pack"))
         nb._fields.pop("_bg_cache", None)
         out.append(nb.to(device, non_blocking=True))
     return out
@@ -217,8 +218,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
 
     def step_e2e(i):
         lb, vb = _clone_to(*host[i % len(host)], dev)  # pinned host -> device, every step
-        d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses=True)
-        result_sink.append((d_losses, g_loss))  # 6 floats read back per step (trainer.py:479,493)
+        d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step")
+        result_sink.append((d_losses, g_loss))  # the step's 6 losses (trainer.py:479,493) read back as floats, one D2H
 
     for i in range(args.warmup):
         step_resident(i)

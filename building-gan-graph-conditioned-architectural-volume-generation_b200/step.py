@@ -80,13 +80,16 @@ def generator_loss(discriminator, local_graph, voxel_graph, logits: Tensor, labe
 
 
 def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng: str = "cpu",
-               grad_sync=None, sync_losses: bool = True):
+               grad_sync=None, sync_losses="each"):
     """trainer.py:467-495 for one device-resident batch.  ``grad_sync(model)`` (optional) is called after each
     backward, before the optimiser step - the data-parallel gradient all-reduce hooks in here.
-    Returns (critic losses, generator loss, label_hard[1,N,7]); losses are floats when ``sync_losses`` (the
-    reference's ``.item()``, one D2H each) else 0-dim device tensors."""
+    Returns (critic losses, generator loss, label_hard[1,N,7]).  ``sync_losses``: "each" = ``.item()`` right after every
+    backward exactly like the reference (6 host syncs per step, trainer.py:479,493); "step" = the same 6 floats read
+    back with ONE device->host copy at the end of the step (the host keeps running ahead of the GPU inside the step);
+    False = 0-dim device tensors, no sync."""
     dev = voxel_graph.x.device
     n = voxel_graph.num_nodes
+    each = sync_losses in (True, "each")
     d_losses = []
     for _ in range(cfg.N_CRITIC):
         with torch.no_grad():
@@ -98,7 +101,7 @@ def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph,
         d_loss.backward()
         if grad_sync is not None:
             grad_sync(discriminator)
-        d_losses.append(d_loss.item() if sync_losses else d_loss.detach())
+        d_losses.append(d_loss.item() if each else d_loss.detach())
         opt_d.step()
     z = _rand((1, n, cfg.Z_DIM), dev, rng, normal=True)
     logits, hard, soft = generator(local_graph, voxel_graph, z)
@@ -108,8 +111,11 @@ def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph,
     g_loss.backward()
     if grad_sync is not None:
         grad_sync(generator)
-    g_val = g_loss.item() if sync_losses else g_loss.detach()
+    g_val = g_loss.item() if each else g_loss.detach()
     opt_g.step()
+    if sync_losses == "step":
+        vals = torch.stack(d_losses + [g_val]).tolist()  # one D2H copy + one sync for the whole step
+        d_losses, g_val = vals[:-1], vals[-1]
     return d_losses, g_val, hard.detach()
 
 
