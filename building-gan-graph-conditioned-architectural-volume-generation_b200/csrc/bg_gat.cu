@@ -9,87 +9,275 @@
 // Roofline: HBM.  Algorithmic bytes per launch are stated in DESIGN.md section "Kernels".
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "bg_common.cuh"
 
 namespace bg {
 
 // ------------------------------------------------------------------------------------------
+// Row-block mapping shared by the forward and first-order backward kernels.
+//
+// A CTA owns a CONTIGUOUS chunk of node rows and sweeps it front to back (on large graphs the grid is SMs x resident
+// CTAs, so every SM walks a few contiguous windows): voxel grids are numbered floor-major, so a row's x/y neighbours
+// and the row itself are touched by the same CTA within a short window and stay L1-resident; only the first touch of
+// a row and the floor +-1 neighbours go to L2 / HBM.
+//
+// The per-edge scalar work (col index, s_j, leaky-relu, exp, softmax weight) is done ONCE per edge: edge slot t of a
+// row (t < CAP = 8) lives in lane t % LANES of the row's lane group (register k = t / LANES) and is broadcast with one
+// SHFL when the gather loop reaches it.  (r01b, before: every lane recomputed exp()/div per edge, 464 instructions per
+// warp, issue-bound at 61% SM throughput.)  The gather runs as two blocks of four independent 128-bit loads; its trip
+// count is warp-uniform (padding slots carry weight 0 and point at the row itself - an L1 hit), so all 32 lanes stay
+// convergent and every shuffle uses the full mask.  Warps that hold a row with more than CAP edges take the generic
+// per-row path.
+//
+// Graphs larger than L2 use the software-pipelined variants: a warp's dependent chain rowptr -> col -> s[j] -> h[j]
+// is spread over four consecutive sweep iterations,
+//   A (it+3): rowptr     B (it+2): col, d     C (it+1): s[j], L2 prefetch of far gather rows     D (it): math + gather,
+// so every load was issued one iteration before it is consumed, and the DRAM misses of the gather (first touch of the
+// row itself - prefetched as a sequential stream a few iterations ahead - and the floor +-1 neighbours) are taken by
+// register-free prefetches.  Stages that refer to an iteration < 0 redo iteration 0 with degree 0.
+// ------------------------------------------------------------------------------------------
+constexpr int kGatMaxThreads = 1024;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNearRows = 512;  // neighbours closer than this are L1/L2-resident through the sweep itself
+
+template <int C>
+struct GatMap : RowMap<C> {
+    static constexpr int LANES_ = RowMap<C>::LANES;
+    static constexpr int EPL = LANES_ >= 8 ? 1 : 8 / LANES_;  // edge slots per lane
+    static constexpr int CAP = 8;                              // edge slots per row
+    static constexpr int LINES = (C * 4 + 127) / 128;          // 128-byte lines per feature row
+};
+
+__device__ __forceinline__ float rcp_fast(float x) {  // x >= 1 here (softmax denominators): MUFU.RCP, <= 1 ulp
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// value of edge slot t (compile-time constant after unrolling), broadcast inside the row's lane group
+template <int LANES, int EPL, typename T>
+__device__ __forceinline__ T slot_get(const T (&a)[EPL], int t) {
+    if constexpr (LANES == 1) {
+        return a[t];
+    } else {
+        return __shfl_sync(kFull, a[t / LANES], t % LANES, LANES);
+    }
+}
+
+// acc += sum_{q < 4} w[t0+q] * X[idx[t0+q], :]   (4 independent 128-bit gathers in flight)
+template <int C, int EPL>
+__device__ __forceinline__ void gather_fma4(const float* __restrict__ xb, const int (&idx)[EPL], const float (&w)[EPL],
+                                            int t0, float (&acc)[RowMap<C>::VEC]) {
+    constexpr int VEC = RowMap<C>::VEC, LANES = RowMap<C>::LANES;
+    int jj[4];
+    float pp[4];
+    Vec<VEC> xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) jj[q] = slot_get<LANES, EPL>(idx, t0 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q].load(xb + (int64_t)jj[q] * C);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pp[q] = slot_get<LANES, EPL>(w, t0 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(pp[q], xv[q].v[v], acc[v]);
+}
+
+// L2 prefetch of the feature row `j` by the slot's owner lane when the row is far from the sweep position
+template <int C>
+__device__ __forceinline__ void prefetch_far_row(const float* __restrict__ x, int j, int row, bool ok) {
+    const int dist = j - row;
+    if (ok && (dist >= kNearRows || dist <= -kNearRows)) {
+#pragma unroll
+        for (int l = 0; l < GatMap<C>::LINES; ++l) prefetch_l2(x + (int64_t)j * C + l * 32);
+    }
+}
+// sequential prefetch stream of the rows a warp will own `ahead` iterations later (first touch of the row itself)
+template <int C>
+__device__ __forceinline__ void prefetch_stream(const float* __restrict__ x, int row_ahead, int r1, int sub) {
+    if (row_ahead < r1 && ((sub * RowMap<C>::VEC * 4) & 127) == 0) prefetch_l2(x + (int64_t)row_ahead * C + sub * RowMap<C>::VEC);
+}
+
+// ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(kThreads) gat_fwd_kernel(
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ h,
-    const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
-    float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int64_t N, float slope, int pf_rows) {
+__device__ __noinline__ void gat_fwd_row_generic(int row, int sub, unsigned gm, const int32_t* __restrict__ rowptr,
+                                                 const int32_t* __restrict__ col, const float* __restrict__ h,
+                                                 const float* __restrict__ s, const float* __restrict__ d,
+                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                 float* __restrict__ m_out, float* __restrict__ z_out, float slope) {
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % LANES;
-    const unsigned gm = group_mask<LANES>(lane);
-    const int64_t row = (int64_t)blockIdx.x * M::RPC + warp * M::RPW + lane / LANES;
-    if (row >= N) return;  // whole groups leave together; group masks keep the rest legal
-    // Large graphs are latency-bound on the dependent chain rowptr -> col -> s -> h (every array cold in L2): pull the
-    // lines a block ~2 waves ahead will need into L2 now.  Prefetches hold no registers, so they decouple the bytes in
-    // flight from the register file; the block that later owns those rows finds its whole chain L2-resident.
-    const int64_t prow = row + pf_rows;
-    int pbeg = -1;
-    if (pf_rows > 0 && prow < N) {
-        if (sub == 0) {
-            pbeg = __ldg(rowptr + prow);  // consumed only at the end of the kernel (no stall here)
-            prefetch_l2(d + prow);
-            prefetch_l2(s + prow);
-        }
-        if (((sub * VEC * 4) & 127) == 0) prefetch_l2(h + prow * C + sub * VEC);
-    }
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const float di = __ldg(d + row);
-
-    // softmax statistics, edges spread over the group's lanes
     float mx = -INFINITY;
     for (int e = beg + sub; e < end; e += LANES) mx = fmaxf(mx, lrelu(__ldg(s + __ldg(col + e)) + di, slope));
     mx = gmax<LANES>(mx, gm);
     float zs = 0.f;
     for (int e = beg + sub; e < end; e += LANES) zs += expf(lrelu(__ldg(s + __ldg(col + e)) + di, slope) - mx);
     zs = gsum<LANES>(zs, gm) + 1e-16f;
-
+    const float inv = rcp_fast(zs);
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     const float* hb = h + sub * VEC;
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {  // 4 independent gathers in flight
-        int j[4];
-        float p[4];
-        Vec<VEC> hv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) j[k] = __ldg(col + e + k);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hv[k].load(hb + (int64_t)j[k] * C);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = expf(lrelu(__ldg(s + j[k]) + di, slope) - mx) / zs;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p[k], hv[k].v[v], acc[v]);
-    }
-    for (; e < end; ++e) {
+    for (int e = beg; e < end; ++e) {
         const int j = __ldg(col + e);
         Vec<VEC> hv;
         hv.load(hb + (int64_t)j * C);
-        const float p = expf(lrelu(__ldg(s + j) + di, slope) - mx) / zs;
+        const float p = expf(lrelu(__ldg(s + j) + di, slope) - mx) * inv;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p, hv.v[v], acc[v]);
     }
     Vec<VEC> o;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) o.v[v] = acc[v] + (bias ? __ldg(bias + sub * VEC + v) : 0.f);
-    o.store(out + row * C + sub * VEC);
+    o.store(out + (int64_t)row * C + sub * VEC);
     if (sub == 0) {
         m_out[row] = mx;
         z_out[row] = zs;
-        if (pbeg >= 0) {
-            prefetch_l2(col + pbeg);
-            prefetch_l2(col + pbeg + 8);
+    }
+}
+
+// fast path: softmax over the register-resident slots (u = leaky-relu'd logits, -inf in padding slots) + gather
+template <int C>
+__device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg, int sub,
+                                                 const int (&j)[GatMap<C>::EPL], const float (&u)[GatMap<C>::EPL],
+                                                 const float* __restrict__ hb, const float* __restrict__ bias,
+                                                 float* __restrict__ out, float* __restrict__ m_out,
+                                                 float* __restrict__ z_out) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
+    float p[EPL];
+    float mx = u[0];
+#pragma unroll
+    for (int k = 1; k < EPL; ++k) mx = fmaxf(mx, u[k]);
+    mx = group_max<LANES>(mx);
+    float zs = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        p[k] = expf(u[k] - mx);  // exp(-inf) == 0 in the padding slots
+        zs += p[k];
+    }
+    zs = group_sum<LANES>(zs) + 1e-16f;
+    const float inv = rcp_fast(zs);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) p[k] *= inv;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    gather_fma4<C, EPL>(hb, j, p, 0, acc);
+    if (maxdeg > 4) gather_fma4<C, EPL>(hb, j, p, 4, acc);
+    if (valid) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o.v[v] = acc[v] + (bias ? __ldg(bias + sub * VEC + v) : 0.f);
+        o.store(out + (int64_t)row * C + sub * VEC);
+        if (sub == 0) {
+            m_out[row] = mx;
+            z_out[row] = zs;
+        }
+    }
+}
+
+template <int C, bool PIPE>
+__global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ h,
+    const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
+    float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int N, float slope,
+    int rows_per_cta, int ahead) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int sub = lane % LANES, grow = lane / LANES;
+    const unsigned gm = group_mask<LANES>(lane);
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    const int stride = nwarp * RPW;
+    const int base = r0 + warp * RPW;
+    const float* hb = h + sub * VEC;
+    if constexpr (!PIPE) {
+        for (int b = base; b < r1; b += stride) {
+            const int row = b + grow;
+            const bool valid = row < r1;
+            const int rr = valid ? row : r1 - 1;
+            const int beg = __ldg(rowptr + rr);
+            const int deg = __ldg(rowptr + rr + 1) - beg;
+            const int maxdeg = __reduce_max_sync(kFull, deg);
+            if (maxdeg > CAP) {
+                if (valid) gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                continue;
+            }
+            const float di = __ldg(d + rr);
+            int j[EPL];
+            float u[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const bool ok = sub + k * LANES < deg;
+                j[k] = ok ? __ldg(col + beg + sub + k * LANES) : rr;
+                u[k] = ok ? lrelu(__ldg(s + j[k]) + di, slope) : -INFINITY;
+            }
+            gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j, u, hb, bias, out, m_out, z_out);
+        }
+    } else {
+        if (base >= r1) return;
+        auto row_at = [&](int it) -> int {  // this lane's (clamped) row in sweep iteration max(it, 0)
+            const int r = base + (it > 0 ? it : 0) * stride + grow;
+            return r < r1 ? r : r1 - 1;
+        };
+        int beg2 = 0, deg2 = 0, deg1 = 0, deg0 = 0;
+        int j1[EPL], j0[EPL];
+        float s0[EPL], d1 = 0.f, d0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            j1[k] = j0[k] = row_at(0);
+            s0[k] = 0.f;
+        }
+        const int niter = (r1 - base + stride - 1) / stride;
+        for (int it = -3; it < niter; ++it) {
+            // A: rowptr of iteration it+3
+            const int r3 = row_at(it + 3);
+            const int beg3 = __ldg(rowptr + r3);
+            const int deg3 = __ldg(rowptr + r3 + 1) - beg3;
+            // B: col / d of iteration it+2
+            const int r2 = row_at(it + 2);
+            int j2[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) j2[k] = sub + k * LANES < deg2 ? __ldg(col + beg2 + sub + k * LANES) : r2;
+            const float d2 = __ldg(d + r2);
+            // C: s[j] of iteration it+1, prefetch of its far gather rows and of the row stream `ahead` iterations on
+            const int rc = row_at(it + 1);
+            float s1[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const bool ok = sub + k * LANES < deg1;
+                s1[k] = __ldg(s + j1[k]);
+                prefetch_far_row<C>(h, j1[k], rc, ok);
+            }
+            prefetch_stream<C>(h, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            // D: softmax + aggregation of iteration it
+            if (it >= 0) {
+                const int row = base + it * stride + grow;
+                const bool valid = row < r1;
+                const int maxdeg = __reduce_max_sync(kFull, deg0);
+                if (maxdeg > CAP) {
+                    if (valid) gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                } else {
+                    float u[EPL];
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k) u[k] = sub + k * LANES < deg0 ? lrelu(s0[k] + d0, slope) : -INFINITY;
+                    gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j0, u, hb, bias, out, m_out, z_out);
+                }
+            }
+            // rotate the pipeline registers
+            deg0 = deg1, d0 = d1;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) j0[k] = j1[k], s0[k] = s1[k], j1[k] = j2[k];
+            deg1 = deg2, d1 = d2;
+            beg2 = beg3, deg2 = deg3;
         }
     }
 }
@@ -99,22 +287,18 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(
 // d pre-activation logit u_e = s_j + d_i) and gsd[2i+1] = d loss / d d_i.
 // ------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ gout,
-    const float* __restrict__ h, const float* __restrict__ s, const float* __restrict__ d,
-    const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
-    float* __restrict__ DU, float* __restrict__ gsd, int64_t N, float slope) {
+__device__ __noinline__ void gat_bwd_dst_row_generic(int row, int sub, unsigned gm, const int32_t* __restrict__ rowptr,
+                                                     const int32_t* __restrict__ col, const float* __restrict__ gout,
+                                                     const float* __restrict__ h, const float* __restrict__ s,
+                                                     const float* __restrict__ d, const float* __restrict__ m_in,
+                                                     const float* __restrict__ z_in, float* __restrict__ P,
+                                                     float* __restrict__ DU, float* __restrict__ gsd, float slope) {
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % LANES;
-    const unsigned gm = group_mask<LANES>(lane);
-    const int64_t row = (int64_t)blockIdx.x * M::RPC + warp * M::RPW + lane / LANES;
-    if (row >= N) return;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const float di = __ldg(d + row), mi = __ldg(m_in + row), zi = __ldg(z_in + row);
+    const float di = __ldg(d + row), mi = __ldg(m_in + row), inv = rcp_fast(__ldg(z_in + row));
     Vec<VEC> gi;
-    gi.load(gout + row * C + sub * VEC);
+    gi.load(gout + (int64_t)row * C + sub * VEC);
     const float* hb = h + sub * VEC;
     float r = 0.f;
     for (int e = beg; e < end; ++e) {
@@ -125,7 +309,7 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
 #pragma unroll
         for (int v = 0; v < VEC; ++v) c = fmaf(gi.v[v], hv.v[v], c);
         c = gsum<LANES>(c, gm);
-        const float p = expf(lrelu(__ldg(s + j) + di, slope) - mi) / zi;
+        const float p = expf(lrelu(__ldg(s + j) + di, slope) - mi) * inv;
         r = fmaf(p, c, r);
         if (sub == 0) {
             P[e] = p;
@@ -141,7 +325,166 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
         gd += du;
     }
     gd = gsum<LANES>(gd, gm);
-    if (sub == 0) gsd[2 * row + 1] = gd;
+    if (sub == 0) gsd[2 * (int64_t)row + 1] = gd;
+}
+
+// c[slot] = g_i . h_j for 4 slots: gather, partial dots, butterfly, the slot's owner lane keeps the result
+template <int C, int EPL>
+__device__ __forceinline__ void gather_dot4(const float* __restrict__ hb, const int (&j)[EPL],
+                                            const Vec<RowMap<C>::VEC>& gi, int t0, int sub, float (&c)[EPL]) {
+    constexpr int VEC = RowMap<C>::VEC, LANES = RowMap<C>::LANES;
+    int jj[4];
+    Vec<VEC> hv[4];
+    float cc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) jj[q] = slot_get<LANES, EPL>(j, t0 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) hv[q].load(hb + (int64_t)jj[q] * C);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cc[q] = 0.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) cc[q] = fmaf(gi.v[v], hv[q].v[v], cc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cc[q] = group_sum<LANES>(cc[q]);
+        const int t = t0 + q;
+        if (sub == t % LANES) c[t / LANES] = cc[q];
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void gat_bwd_dst_row_fast(int row, bool valid, int beg, int deg, int maxdeg, int sub,
+                                                     const int (&j)[GatMap<C>::EPL], const float (&sj)[GatMap<C>::EPL],
+                                                     float di, float mi, float zi, const float* __restrict__ gout,
+                                                     const float* __restrict__ hb, float* __restrict__ P,
+                                                     float* __restrict__ DU, float* __restrict__ gsd, float slope,
+                                                     int rr) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
+    Vec<VEC> gi;
+    gi.load(gout + (int64_t)rr * C + sub * VEC);
+    const float inv = rcp_fast(zi);
+    float p[EPL], lg[EPL], c[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const bool ok = sub + k * LANES < deg;
+        const float u = sj[k] + di;
+        p[k] = ok ? expf(lrelu(u, slope) - mi) * inv : 0.f;
+        lg[k] = lrelu_grad(u, slope);
+        c[k] = 0.f;
+    }
+    gather_dot4<C, EPL>(hb, j, gi, 0, sub, c);
+    if (maxdeg > 4) gather_dot4<C, EPL>(hb, j, gi, 4, sub, c);
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) r = fmaf(p[k], c[k], r);
+    r = group_sum<LANES>(r);
+    float gd = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const float du = lg[k] * p[k] * (c[k] - r);
+        if (valid && sub + k * LANES < deg) {
+            P[beg + sub + k * LANES] = p[k];
+            DU[beg + sub + k * LANES] = du;
+        }
+        gd += du;
+    }
+    gd = group_sum<LANES>(gd);
+    if (valid && sub == 0) gsd[2 * (int64_t)row + 1] = gd;
+}
+
+template <int C, bool PIPE>
+__global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ gout,
+    const float* __restrict__ h, const float* __restrict__ s, const float* __restrict__ d,
+    const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
+    float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int rows_per_cta, int ahead) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int sub = lane % LANES, grow = lane / LANES;
+    const unsigned gm = group_mask<LANES>(lane);
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    const int stride = nwarp * RPW;
+    const int base = r0 + warp * RPW;
+    const float* hb = h + sub * VEC;
+    if constexpr (!PIPE) {
+        for (int b = base; b < r1; b += stride) {
+            const int row = b + grow;
+            const bool valid = row < r1;
+            const int rr = valid ? row : r1 - 1;
+            const int beg = __ldg(rowptr + rr);
+            const int deg = __ldg(rowptr + rr + 1) - beg;
+            const int maxdeg = __reduce_max_sync(kFull, deg);
+            if (maxdeg > CAP) {
+                if (valid) gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
+                continue;
+            }
+            int j[EPL];
+            float sj[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                j[k] = sub + k * LANES < deg ? __ldg(col + beg + sub + k * LANES) : rr;
+                sj[k] = __ldg(s + j[k]);
+            }
+            gat_bwd_dst_row_fast<C>(row, valid, beg, deg, maxdeg, sub, j, sj, __ldg(d + rr), __ldg(m_in + rr),
+                                    __ldg(z_in + rr), gout, hb, P, DU, gsd, slope, rr);
+        }
+    } else {
+        if (base >= r1) return;
+        auto row_at = [&](int it) -> int {
+            const int r = base + (it > 0 ? it : 0) * stride + grow;
+            return r < r1 ? r : r1 - 1;
+        };
+        int beg2 = 0, deg2 = 0, beg1 = 0, deg1 = 0, beg0 = 0, deg0 = 0;
+        int j1[EPL], j0[EPL];
+        float s0[EPL], d1 = 0.f, d0 = 0.f, m0 = 0.f, z0 = 1.f;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            j1[k] = j0[k] = row_at(0);
+            s0[k] = 0.f;
+        }
+        const int niter = (r1 - base + stride - 1) / stride;
+        for (int it = -3; it < niter; ++it) {
+            const int r3 = row_at(it + 3);
+            const int beg3 = __ldg(rowptr + r3);
+            const int deg3 = __ldg(rowptr + r3 + 1) - beg3;
+            const int r2 = row_at(it + 2);
+            int j2[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) j2[k] = sub + k * LANES < deg2 ? __ldg(col + beg2 + sub + k * LANES) : r2;
+            const float d2 = __ldg(d + r2);
+            const int rc = row_at(it + 1);
+            float s1[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                s1[k] = __ldg(s + j1[k]);
+                prefetch_far_row<C>(h, j1[k], rc, sub + k * LANES < deg1);
+            }
+            const float m1 = __ldg(m_in + rc), z1 = __ldg(z_in + rc);
+            prefetch_stream<C>(h, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            prefetch_stream<C>(gout, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            if (it >= 0) {
+                const int row = base + it * stride + grow;
+                const bool valid = row < r1;
+                const int maxdeg = __reduce_max_sync(kFull, deg0);
+                if (maxdeg > CAP) {
+                    if (valid)
+                        gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
+                } else {
+                    gat_bwd_dst_row_fast<C>(row, valid, beg0, deg0, maxdeg, sub, j0, s0, d0, m0, z0, gout, hb, P, DU, gsd,
+                                            slope, valid ? row : r1 - 1);
+                }
+            }
+            beg0 = beg1, deg0 = deg1, d0 = d1, m0 = m1, z0 = z1;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) j0[k] = j1[k], s0[k] = s1[k], j1[k] = j2[k];
+            beg1 = beg2, deg1 = deg2, d1 = d2;
+            beg2 = beg3, deg2 = deg3;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -150,48 +493,21 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
 // Shared by the first- and second-order backward (different P/DU/G).
 // ------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
-    const int32_t* __restrict__ cscptr, const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
-    const float* __restrict__ P, const float* __restrict__ DU, const float* __restrict__ G,
-    const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out_tot,
-    float* __restrict__ gsd, int64_t N) {
+__device__ __noinline__ void gat_bwd_src_row_generic(int row, int sub, const int32_t* __restrict__ cscptr,
+                                                     const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
+                                                     const float* __restrict__ P, const float* __restrict__ DU,
+                                                     const float* __restrict__ G, const float* __restrict__ a_src,
+                                                     const float* __restrict__ a_dst, float* __restrict__ out_tot,
+                                                     float* __restrict__ gsd) {
     using M = RowMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % LANES;
-    const int64_t row = (int64_t)blockIdx.x * M::RPC + warp * M::RPW + lane / LANES;
-    if (row >= N) return;
+    constexpr int VEC = M::VEC;
     const int beg = __ldg(cscptr + row), end = __ldg(cscptr + row + 1);
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     float gs = 0.f;
     const float* gb = G + sub * VEC;
-    int k = beg;
-    for (; k + 4 <= end; k += 4) {
-        int i[4], e[4];
-        float p[4], du[4];
-        Vec<VEC> gv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            i[q] = __ldg(cscrow + k + q);
-            e[q] = __ldg(perm + k + q);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) gv[q].load(gb + (int64_t)i[q] * C);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            p[q] = P[e[q]];
-            du[q] = DU[e[q]];
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            gs += du[q];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p[q], gv[q].v[v], acc[v]);
-        }
-    }
-    for (; k < end; ++k) {
+    for (int k = beg; k < end; ++k) {
         const int i = __ldg(cscrow + k), e = __ldg(perm + k);
         Vec<VEC> gv;
         gv.load(gb + (int64_t)i * C);
@@ -200,13 +516,137 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p, gv.v[v], acc[v]);
     }
-    const float gd = gsd[2 * row + 1];
+    const float gd = gsd[2 * (int64_t)row + 1];
     Vec<VEC> o;
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
         o.v[v] = acc[v] + gs * __ldg(a_src + sub * VEC + v) + gd * __ldg(a_dst + sub * VEC + v);
-    o.store(out_tot + row * C + sub * VEC);
-    if (sub == 0) gsd[2 * row] = gs;
+    o.store(out_tot + (int64_t)row * C + sub * VEC);
+    if (sub == 0) gsd[2 * (int64_t)row] = gs;
+}
+
+template <int C>
+__device__ __forceinline__ void gat_bwd_src_row_fast(int row, bool valid, int maxdeg, int sub,
+                                                     const int (&i)[GatMap<C>::EPL], const float (&p)[GatMap<C>::EPL],
+                                                     const float (&du)[GatMap<C>::EPL], float gd,
+                                                     const float* __restrict__ gb, const float* __restrict__ a_src,
+                                                     const float* __restrict__ a_dst, float* __restrict__ out_tot,
+                                                     float* __restrict__ gsd) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
+    float gs = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) gs += du[k];
+    gs = group_sum<LANES>(gs);
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    gather_fma4<C, EPL>(gb, i, p, 0, acc);
+    if (maxdeg > 4) gather_fma4<C, EPL>(gb, i, p, 4, acc);
+    if (valid) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            o.v[v] = acc[v] + gs * __ldg(a_src + sub * VEC + v) + gd * __ldg(a_dst + sub * VEC + v);
+        o.store(out_tot + (int64_t)row * C + sub * VEC);
+        if (sub == 0) gsd[2 * (int64_t)row] = gs;
+    }
+}
+
+template <int C, bool PIPE>
+__global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
+    const int32_t* __restrict__ cscptr, const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
+    const float* __restrict__ P, const float* __restrict__ DU, const float* __restrict__ G,
+    const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out_tot,
+    float* __restrict__ gsd, int N, int rows_per_cta, int ahead) {
+    using M = GatMap<C>;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int sub = lane % LANES, grow = lane / LANES;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    const int stride = nwarp * RPW;
+    const int base = r0 + warp * RPW;
+    const float* gb = G + sub * VEC;
+    if constexpr (!PIPE) {
+        for (int b = base; b < r1; b += stride) {
+            const int row = b + grow;
+            const bool valid = row < r1;
+            const int rr = valid ? row : r1 - 1;
+            const int beg = __ldg(cscptr + rr);
+            const int deg = __ldg(cscptr + rr + 1) - beg;
+            const int maxdeg = __reduce_max_sync(kFull, deg);
+            if (maxdeg > CAP) {
+                if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd);
+                continue;
+            }
+            int i[EPL];
+            float p[EPL], du[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const bool ok = sub + k * LANES < deg;
+                i[k] = ok ? __ldg(cscrow + beg + sub + k * LANES) : rr;
+                const int e = ok ? __ldg(perm + beg + sub + k * LANES) : 0;
+                p[k] = ok ? P[e] : 0.f;
+                du[k] = ok ? DU[e] : 0.f;
+            }
+            gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i, p, du, gsd[2 * (int64_t)rr + 1], gb, a_src, a_dst, out_tot, gsd);
+        }
+    } else {
+        if (base >= r1) return;
+        auto row_at = [&](int it) -> int {
+            const int r = base + (it > 0 ? it : 0) * stride + grow;
+            return r < r1 ? r : r1 - 1;
+        };
+        int beg2 = 0, deg2 = 0, deg1 = 0, deg0 = 0;
+        int i1[EPL], e1[EPL], i0[EPL];
+        float p0[EPL], du0[EPL], gd0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            i1[k] = i0[k] = row_at(0);
+            e1[k] = 0;
+            p0[k] = du0[k] = 0.f;
+        }
+        const int niter = (r1 - base + stride - 1) / stride;
+        for (int it = -3; it < niter; ++it) {
+            const int r3 = row_at(it + 3);
+            const int beg3 = __ldg(cscptr + r3);
+            const int deg3 = __ldg(cscptr + r3 + 1) - beg3;
+            const int r2 = row_at(it + 2);
+            int i2[EPL], e2[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const bool ok = sub + k * LANES < deg2;
+                i2[k] = ok ? __ldg(cscrow + beg2 + sub + k * LANES) : r2;
+                e2[k] = ok ? __ldg(perm + beg2 + sub + k * LANES) : 0;
+            }
+            const int rc = row_at(it + 1);
+            float p1[EPL], du1[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const bool ok = sub + k * LANES < deg1;
+                p1[k] = ok ? P[e1[k]] : 0.f;
+                du1[k] = ok ? DU[e1[k]] : 0.f;
+                prefetch_far_row<C>(G, i1[k], rc, ok);
+            }
+            const float gd1 = gsd[2 * (int64_t)rc + 1];
+            prefetch_stream<C>(G, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            if (it >= 0) {
+                const int row = base + it * stride + grow;
+                const bool valid = row < r1;
+                const int maxdeg = __reduce_max_sync(kFull, deg0);
+                if (maxdeg > CAP) {
+                    if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd);
+                } else {
+                    gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i0, p0, du0, gd0, gb, a_src, a_dst, out_tot, gsd);
+                }
+            }
+            deg0 = deg1, gd0 = gd1;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) i0[k] = i1[k], p0[k] = p1[k], du0[k] = du1[k], i1[k] = i2[k], e1[k] = e2[k];
+            deg1 = deg2;
+            beg2 = beg3, deg2 = deg3;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -300,32 +740,49 @@ __global__ void __launch_bounds__(kThreads) gat_bwd2_dst_kernel(
     if (sub == 0) sdt[2 * row + 1] = dt;
 }
 
-// Prefetch distance in rows: ~2 waves of resident CTAs ahead; 0 (off) for graphs whose working set is L2-resident anyway.
+// Launch geometry.  Small graphs (working set L2-resident, latency-bound): 256-thread CTAs, one sweep iteration each
+// where possible.  Large graphs: SMs x `cps` CTAs of `threads` threads, each sweeping one contiguous row chunk.
+// bg_tune() overrides (used by the kernel sweep in bench.py --workload c4).
+static int g_tune[8] = {1024, 2, 256, 1, 0, 0, 0, 0};  // see bg_tune() in include/bg_b200.h
+struct GatCfg {
+    unsigned grid, threads;
+    int rows_per_cta, ahead;
+    bool pipe;
+};
 template <int C>
-static int prefetch_rows(int64_t N) {
-    static const int env = getenv("BG_GAT_PF") ? atoi(getenv("BG_GAT_PF")) : -1;
-    if (env >= 0) return env * RowMap<C>::RPC;
-    if (N * C * 4 < (int64_t)(24 << 20)) return 0;
-    return 2 * kSMs * 5 * RowMap<C>::RPC;
+static GatCfg gat_cfg(int64_t N) {
+    const bool small = !g_tune[4] && N * C * 4 < (int64_t)(24 << 20);
+    const int threads = small ? 256 : g_tune[0];
+    const int64_t cap = small ? (int64_t)kSMs * 8 : (int64_t)kSMs * g_tune[1];
+    const int64_t rows_iter = (int64_t)(threads / 32) * RowMap<C>::RPW;
+    const int64_t iters = ceil_div(N, rows_iter);
+    int64_t grid = iters < cap ? iters : cap;
+    const int64_t rpc = ceil_div(iters, grid) * rows_iter;
+    grid = ceil_div(N, rpc);
+    return GatCfg{(unsigned)grid, (unsigned)threads, (int)rpc, (int)ceil_div(g_tune[2], rows_iter), !small && g_tune[3] != 0};
 }
+#define BG_GAT_LAUNCH(KERNEL, ...)                                                      \
+    do {                                                                                \
+        if (C >= 8 && c.pipe) /* narrower rows hold 8 edge slots per lane: the pipeline registers would spill */ \
+            KERNEL<C, (C >= 8)><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.rows_per_cta, c.ahead);  \
+        else                                                                            \
+            KERNEL<C, false><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.rows_per_cta, c.ahead); \
+    } while (0)
 
 template <int C>
 static int launch_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                       float* out, float* m, float* z, float slope, cudaStream_t st) {
-    const int64_t grid = ceil_div(g->N, RowMap<C>::RPC);
-    gat_fwd_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, h, s, d, bias, out, m, z, g->N, slope,
-                                                          prefetch_rows<C>(g->N));
+    const GatCfg c = gat_cfg<C>(g->N);
+    BG_GAT_LAUNCH(gat_fwd_kernel, g->rowptr, g->col, h, s, d, bias, out, m, z, (int)g->N, slope);
     return check_launch("bg_gat_fwd");
 }
 template <int C>
 static int launch_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
                       const float* m, const float* z, const float* a_src, const float* a_dst, float* P,
                       float* DU, float* gh_tot, float* gsd, float slope, cudaStream_t st) {
-    const int64_t grid = ceil_div(g->N, RowMap<C>::RPC);
-    gat_bwd_dst_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
-                                                              g->N, slope);
-    gat_bwd_src_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src,
-                                                              a_dst, gh_tot, gsd, g->N);
+    const GatCfg c = gat_cfg<C>(g->N);
+    BG_GAT_LAUNCH(gat_bwd_dst_kernel, g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd, (int)g->N, slope);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src, a_dst, gh_tot, gsd, (int)g->N);
     return check_launch("bg_gat_bwd");
 }
 template <int C>
@@ -337,8 +794,8 @@ static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const
     float *A0 = scratch, *A1 = scratch + g->E, *A2 = scratch + 2 * g->E, *A3 = scratch + 3 * g->E;
     gat_bwd2_dst_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, Ht, St, Dt, gout, h, s, d, m, z,
                                                                A0, A1, A2, A3, gt, sdt, g->N, slope);
-    gat_bwd_src_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->cscptr, g->cscrow, g->perm, A1, A2, gout, a_src,
-                                                              a_dst, ht_tot, sdt, g->N);
+    const GatCfg c = gat_cfg<C>(g->N);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, A1, A2, gout, a_src, a_dst, ht_tot, sdt, (int)g->N);
     return check_launch("bg_gat_bwd2");
 }
 
@@ -359,6 +816,7 @@ static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const
 
 static int check_graph(const BgGraph* g) {
     BG_REQUIRE(g && g->rowptr && g->col && g->cscptr && g->cscrow && g->perm, BG_EINVAL, "BgGraph has null arrays");
+    BG_REQUIRE(g->N < (int64_t)1 << 31 && g->E < (int64_t)1 << 31, BG_EINVAL, "BgGraph: N and E must fit int32");
     BG_REQUIRE(g->N > 0 && g->E >= g->N, BG_EINVAL, "BgGraph: need N>0 and E>=N (self loops), got N=%lld E=%lld",
                (long long)g->N, (long long)g->E);
     return BG_OK;
@@ -367,6 +825,15 @@ static int check_graph(const BgGraph* g) {
 }  // namespace bg
 
 using namespace bg;
+
+extern "C" int bg_tune(int32_t key, int32_t value) {
+    BG_REQUIRE(key >= 0 && key < 8, BG_EINVAL, "bg_tune: unknown key %d", (int)key);
+    BG_REQUIRE(key != 0 || (value >= 32 && value <= kGatMaxThreads && value % 32 == 0), BG_EINVAL,
+               "bg_tune: threads must be a multiple of 32 in [32, 1024]");
+    BG_REQUIRE(key != 1 || value >= 1, BG_EINVAL, "bg_tune: CTAs per SM must be >= 1");
+    g_tune[key] = value;
+    return BG_OK;
+}
 
 extern "C" int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                           float* out, float* m, float* z, int32_t C, float slope, void* stream) {

@@ -77,6 +77,7 @@ SIGNATURES = {
     "bg_wgrad_multi": (C.c_int, [C.POINTER(BgWgrad), _I32, _P, _SZ, _P]),
     "bg_ln_act_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
     "bg_ln_act_bwd_ws": (_SZ, [_I64, _I32]),
+    "bg_tune": (C.c_int, [_I32, _I32]),
     "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),

@@ -85,6 +85,58 @@ def test_gat_bwd2(C):
     assert_close(ht_k, ht_tot_ref, 1e-5, f"gat_bwd2 ht_tot C={C}")
 
 
+def _hub_graph(n=300, seed=0):
+    """Irregular graph whose degrees straddle every register-slot capacity of the aggregation kernels (8 / 16 / 32):
+    a ring, plus hubs with 5..70 extra in- AND out-edges (symmetric), plus some input self loops (stripped by the CSR)."""
+    from building_gan_b200 import graph
+    g = torch.Generator().manual_seed(seed)
+    src = list(range(n)) + [(i + 1) % n for i in range(n)]
+    dst = [(i + 1) % n for i in range(n)] + list(range(n))
+    for hub, extra in ((3, 5), (40, 9), (41, 13), (90, 20), (150, 33), (151, 70)):
+        others = torch.randperm(n, generator=g)[:extra + 3].tolist()
+        others = [o for o in others if o not in (hub, (hub + 1) % n, (hub - 1) % n)][:extra]
+        src += others + [hub] * len(others)
+        dst += [hub] * len(others) + others
+    src += [7, 8]
+    dst += [7, 8]
+    ei = torch.tensor([src, dst], dtype=torch.int64)
+    return n, pyg.gat_edges(ei, n), graph.VoxelCSR.build(ei, n).to(DEV)
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+def test_gat_high_degree_rows(C):
+    """Rows with more in/out edges than the kernels hold in registers take the generic per-row path; both paths and
+    mixed warps must agree with the oracle (forward, backward)."""
+    n, edges, csr = _hub_graph()
+    assert csr.max_deg > 64
+    h, s, d = (_rand(n, C, seed=1).requires_grad_(), _rand(n, seed=2).requires_grad_(), _rand(n, seed=3).requires_grad_())
+    a_s, a_d, gout, b = _rand(C, seed=5), _rand(C, seed=6), _rand(n, C, seed=7), _rand(C, seed=4)
+    out = pyg.gat_core(h, s, d, edges)
+    gh, gs, gd = torch.autograd.grad(out, (h, s, d), gout)
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    o, m, z = lib.gat_fwd(csr, f(h), f(s), f(d), f(b))
+    assert_close(o, out.detach() + b, 1e-5, f"gat_fwd hub C={C}")
+    gh_tot, gsd, P, DU = lib.gat_bwd(csr, f(gout), f(h), f(s), f(d), m, z, f(a_s), f(a_d))
+    assert_close(gh_tot, gh + gs[:, None] * a_s + gd[:, None] * a_d, 1e-5, f"gat_bwd hub gh_tot C={C}")
+    assert_close(gsd[:, 0], gs, 1e-5, "gat_bwd hub gs")
+    assert_close(gsd[:, 1], gd, 1e-5, "gat_bwd hub gd")
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("pipe", [0, 1])
+def test_gat_large_graph_kernels(C, pipe):
+    """The large-graph launch geometry (contiguous row chunk per CTA, optional software pipeline) forced on small graphs:
+    same results as the oracle, on the building batch and on the hub graph."""
+    L = lib.load()
+    L.bg_tune(4, 1), L.bg_tune(3, pipe), L.bg_tune(0, 128), L.bg_tune(1, 1), L.bg_tune(2, 40)
+    try:
+        test_gat_fwd(C, False)
+        test_gat_bwd(C)
+        test_gat_high_degree_rows(C)
+    finally:
+        L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 2), L.bg_tune(2, 256)
+
+
 def test_gat_deterministic():
     vb, edges, csr = _graph()
     n, C = vb.num_nodes, 64
