@@ -42,13 +42,50 @@ constexpr int kGatMaxThreads = 1024;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNearRows = 512;  // neighbours closer than this are L1/L2-resident through the sweep itself
 
+// Lane mapping of the aggregation kernels: a group of LANES lanes owns one row; a lane holds HALVES 128-bit pieces of
+// it (channels [4*sub, 4*sub+4) of each half-row), so rows of 64 / 128 floats take 8 / 16 lanes and a warp carries
+// 4 / 2 of them: the per-row scalar work and the slot shuffles (which share the LSU data pipe with the gathers - the
+// saturated unit in r01e, 89%) are amortised over twice as many rows, while every 128-bit load instruction still
+// covers whole 128-byte lines.
 template <int C>
-struct GatMap : RowMap<C> {
-    static constexpr int LANES_ = RowMap<C>::LANES;
-    static constexpr int EPL = LANES_ >= 8 ? 1 : 8 / LANES_;  // edge slots per lane
-    static constexpr int CAP = 8;                              // edge slots per row
-    static constexpr int LINES = (C * 4 + 127) / 128;          // 128-byte lines per feature row
+struct GatMap {
+    static constexpr int HALVES = C >= 64 ? 2 : 1;
+    static constexpr int VEC = C >= 4 ? 4 : C;
+    static constexpr int NV = VEC * HALVES;                  // floats per lane
+    static constexpr int LANES = C / NV;
+    static constexpr int RPW = 32 / LANES;                   // rows per warp
+    static constexpr int EPL = LANES >= 8 ? 1 : 8 / LANES;   // edge slots per lane
+    static constexpr int CAP = 8;                            // edge slots per row
+    static constexpr int LINES = (C * 4 + 127) / 128;        // 128-byte lines per feature row
 };
+template <int C>
+__device__ __forceinline__ void row_load(float (&v)[GatMap<C>::NV], const float* __restrict__ xrow, int sub) {
+    using M = GatMap<C>;
+#pragma unroll
+    for (int hh = 0; hh < M::HALVES; ++hh) {
+        Vec<M::VEC> t;
+        t.load(xrow + hh * (C / 2) + sub * M::VEC);
+#pragma unroll
+        for (int q = 0; q < M::VEC; ++q) v[hh * M::VEC + q] = t.v[q];
+    }
+}
+template <int C>
+__device__ __forceinline__ void row_store(const float (&v)[GatMap<C>::NV], float* __restrict__ xrow, int sub) {
+    using M = GatMap<C>;
+#pragma unroll
+    for (int hh = 0; hh < M::HALVES; ++hh) {
+        Vec<M::VEC> t;
+#pragma unroll
+        for (int q = 0; q < M::VEC; ++q) t.v[q] = v[hh * M::VEC + q];
+        t.store(xrow + hh * (C / 2) + sub * M::VEC);
+    }
+}
+// channel index of element q of a lane's row piece
+template <int C>
+__device__ __forceinline__ int chan(int sub, int q) {
+    using M = GatMap<C>;
+    return (q / M::VEC) * (C / 2) + sub * M::VEC + q % M::VEC;
+}
 
 __device__ __forceinline__ float rcp_fast(float x) {  // x >= 1 here (softmax denominators): MUFU.RCP, <= 1 ulp
     float y;
@@ -69,22 +106,65 @@ __device__ __forceinline__ T slot_get(const T (&a)[EPL], int t) {
 // acc += sum_{q < 4} w[t0+q] * X[idx[t0+q], :]   (4 independent 128-bit gathers in flight)
 template <int C, int EPL>
 __device__ __forceinline__ void gather_fma4(const float* __restrict__ xb, const int (&idx)[EPL], const float (&w)[EPL],
-                                            int t0, float (&acc)[RowMap<C>::VEC]) {
-    constexpr int VEC = RowMap<C>::VEC, LANES = RowMap<C>::LANES;
-    int jj[4];
-    float pp[4];
-    Vec<VEC> xv[4];
+                                            int t0, float (&acc)[GatMap<C>::NV]) {
+    constexpr int VEC = GatMap<C>::VEC, LANES = GatMap<C>::LANES, HALVES = GatMap<C>::HALVES;
+    constexpr int NB = 4 / HALVES;  // 4 independent 128-bit loads in flight per lane
 #pragma unroll
-    for (int q = 0; q < 4; ++q) jj[q] = slot_get<LANES, EPL>(idx, t0 + q);
+    for (int b = 0; b < 4; b += NB) {
+        int jj[NB];
+        float pp[NB];
+        Vec<VEC> xv[NB][HALVES];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xv[q].load(xb + (int64_t)jj[q] * C);
+        for (int q = 0; q < NB; ++q) jj[q] = slot_get<LANES, EPL>(idx, t0 + b + q);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pp[q] = slot_get<LANES, EPL>(w, t0 + q);
+        for (int q = 0; q < NB; ++q)
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+            for (int hh = 0; hh < HALVES; ++hh) xv[q][hh].load(xb + (int64_t)jj[q] * C + hh * (C / 2));
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(pp[q], xv[q].v[v], acc[v]);
+        for (int q = 0; q < NB; ++q) pp[q] = slot_get<LANES, EPL>(w, t0 + b + q);
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int hh = 0; hh < HALVES; ++hh)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[hh * VEC + v] = fmaf(pp[q], xv[q][hh].v[v], acc[hh * VEC + v]);
+    }
 }
+
+// Sweep schedule: the rows are cut into chunks of `chunk_rows` (a multiple of the CTA's rows per iteration) that are
+// dealt round-robin to the CTAs, and a CTA sweeps each of its chunks front to back.  Inside a chunk the sweep is
+// contiguous (x / y neighbours hit L1); across the grid all CTAs advance through the same moving window of
+// gridDim.x * chunk_rows rows, which is sized to stay L2-resident, so the floor +-1 neighbours (thousands of rows away)
+// are served by L2 whatever the floor size - every feature row comes from HBM once.  (A plain 1/gridDim.x split only
+// does that when the chunk length happens to divide the floor stride: measured 0.45 vs 0.59 of peak, sweep4.)
+// Small graphs use ONE chunk per CTA (ipc_shift = 30).
+struct Sweep {
+    int chunk_rows, ipc_shift, stride, lane_off, N, niter;
+    __device__ __forceinline__ Sweep(int N_, int chunk_rows_, int ipc_shift_, int rpw, int grow) {
+        N = N_, chunk_rows = chunk_rows_, ipc_shift = ipc_shift_;
+        const int warp = threadIdx.x >> 5;
+        stride = (blockDim.x >> 5) * rpw;
+        lane_off = warp * rpw + grow;
+        const int nchunks = (N + chunk_rows - 1) / chunk_rows;
+        const int nmy = ((int)blockIdx.x < nchunks) ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        niter = 0;
+        if (nmy > 0) {
+            const int r0l = ((int)blockIdx.x + (nmy - 1) * (int)gridDim.x) * chunk_rows;
+            const int left = min(N, r0l + chunk_rows) - (r0l + warp * rpw);
+            niter = ((nmy - 1) << ipc_shift) + (left > 0 ? (left + stride - 1) / stride : 0);
+        }
+    }
+    // this lane's row in sweep iteration max(it, 0) (may be >= N in the last chunk)
+    __device__ __forceinline__ int raw(int it) const {
+        const int itc = it > 0 ? it : 0;
+        return ((int)blockIdx.x + (itc >> ipc_shift) * (int)gridDim.x) * chunk_rows +
+               (itc & ((1 << ipc_shift) - 1)) * stride + lane_off;
+    }
+    __device__ __forceinline__ int at(int it) const {
+        const int r = raw(it);
+        return r < N ? r : N - 1;
+    }
+};
 
 // L2 prefetch of the feature row `j` by the slot's owner lane when the row is far from the sweep position
 template <int C>
@@ -98,7 +178,11 @@ __device__ __forceinline__ void prefetch_far_row(const float* __restrict__ x, in
 // sequential prefetch stream of the rows a warp will own `ahead` iterations later (first touch of the row itself)
 template <int C>
 __device__ __forceinline__ void prefetch_stream(const float* __restrict__ x, int row_ahead, int r1, int sub) {
-    if (row_ahead < r1 && ((sub * RowMap<C>::VEC * 4) & 127) == 0) prefetch_l2(x + (int64_t)row_ahead * C + sub * RowMap<C>::VEC);
+    using M = GatMap<C>;
+    if (row_ahead < r1 && ((sub * M::VEC * 4) & 127) == 0) {
+#pragma unroll
+        for (int hh = 0; hh < M::HALVES; ++hh) prefetch_l2(x + (int64_t)row_ahead * C + hh * (C / 2) + sub * M::VEC);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -110,8 +194,8 @@ __device__ __noinline__ void gat_fwd_row_generic(int row, int sub, unsigned gm, 
                                                  const float* __restrict__ s, const float* __restrict__ d,
                                                  const float* __restrict__ bias, float* __restrict__ out,
                                                  float* __restrict__ m_out, float* __restrict__ z_out, float slope) {
-    using M = RowMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES;
+    using M = GatMap<C>;
+    constexpr int NV = M::NV, LANES = M::LANES;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const float di = __ldg(d + row);
     float mx = -INFINITY;
@@ -121,22 +205,20 @@ __device__ __noinline__ void gat_fwd_row_generic(int row, int sub, unsigned gm, 
     for (int e = beg + sub; e < end; e += LANES) zs += expf(lrelu(__ldg(s + __ldg(col + e)) + di, slope) - mx);
     zs = gsum<LANES>(zs, gm) + 1e-16f;
     const float inv = rcp_fast(zs);
-    float acc[VEC];
+    float acc[NV];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    const float* hb = h + sub * VEC;
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
     for (int e = beg; e < end; ++e) {
         const int j = __ldg(col + e);
-        Vec<VEC> hv;
-        hv.load(hb + (int64_t)j * C);
+        float hv[NV];
+        row_load<C>(hv, h + (int64_t)j * C, sub);
         const float p = expf(lrelu(__ldg(s + j) + di, slope) - mx) * inv;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p, hv.v[v], acc[v]);
+        for (int v = 0; v < NV; ++v) acc[v] = fmaf(p, hv[v], acc[v]);
     }
-    Vec<VEC> o;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) o.v[v] = acc[v] + (bias ? __ldg(bias + sub * VEC + v) : 0.f);
-    o.store(out + (int64_t)row * C + sub * VEC);
+    for (int v = 0; v < NV; ++v) acc[v] += bias ? __ldg(bias + chan<C>(sub, v)) : 0.f;
+    row_store<C>(acc, out + (int64_t)row * C, sub);
     if (sub == 0) {
         m_out[row] = mx;
         z_out[row] = zs;
@@ -151,7 +233,7 @@ __device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg
                                                  float* __restrict__ out, float* __restrict__ m_out,
                                                  float* __restrict__ z_out) {
     using M = GatMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
+    constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
     float p[EPL];
     float mx = u[0];
 #pragma unroll
@@ -167,16 +249,15 @@ __device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg
     const float inv = rcp_fast(zs);
 #pragma unroll
     for (int k = 0; k < EPL; ++k) p[k] *= inv;
-    float acc[VEC];
+    float acc[NV];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
     gather_fma4<C, EPL>(hb, j, p, 0, acc);
     if (maxdeg > 4) gather_fma4<C, EPL>(hb, j, p, 4, acc);
     if (valid) {
-        Vec<VEC> o;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) o.v[v] = acc[v] + (bias ? __ldg(bias + sub * VEC + v) : 0.f);
-        o.store(out + (int64_t)row * C + sub * VEC);
+        for (int v = 0; v < NV; ++v) acc[v] += bias ? __ldg(bias + chan<C>(sub, v)) : 0.f;
+        row_store<C>(acc, out + (int64_t)row * C, sub);
         if (sub == 0) {
             m_out[row] = mx;
             z_out[row] = zs;
@@ -189,21 +270,19 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ h,
     const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
     float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int N, float slope,
-    int rows_per_cta, int ahead) {
+    int chunk_rows, int ipc_shift, int ahead) {
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
-    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-    const int stride = nwarp * RPW;
-    const int base = r0 + warp * RPW;
+    const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
     const float* hb = h + sub * VEC;
     if constexpr (!PIPE) {
-        for (int b = base; b < r1; b += stride) {
-            const int row = b + grow;
-            const bool valid = row < r1;
-            const int rr = valid ? row : r1 - 1;
+        for (int it = 0; it < sw.niter; ++it) {
+            const int row = sw.raw(it);
+            const bool valid = row < N;
+            const int rr = valid ? row : N - 1;
             const int beg = __ldg(rowptr + rr);
             const int deg = __ldg(rowptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
@@ -223,33 +302,28 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
             gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j, u, hb, bias, out, m_out, z_out);
         }
     } else {
-        if (base >= r1) return;
-        auto row_at = [&](int it) -> int {  // this lane's (clamped) row in sweep iteration max(it, 0)
-            const int r = base + (it > 0 ? it : 0) * stride + grow;
-            return r < r1 ? r : r1 - 1;
-        };
+        if (sw.niter == 0) return;
         int beg2 = 0, deg2 = 0, deg1 = 0, deg0 = 0;
         int j1[EPL], j0[EPL];
         float s0[EPL], d1 = 0.f, d0 = 0.f;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
-            j1[k] = j0[k] = row_at(0);
+            j1[k] = j0[k] = sw.at(0);
             s0[k] = 0.f;
         }
-        const int niter = (r1 - base + stride - 1) / stride;
-        for (int it = -3; it < niter; ++it) {
+        for (int it = -3; it < sw.niter; ++it) {
             // A: rowptr of iteration it+3
-            const int r3 = row_at(it + 3);
+            const int r3 = sw.at(it + 3);
             const int beg3 = __ldg(rowptr + r3);
             const int deg3 = __ldg(rowptr + r3 + 1) - beg3;
             // B: col / d of iteration it+2
-            const int r2 = row_at(it + 2);
+            const int r2 = sw.at(it + 2);
             int j2[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) j2[k] = sub + k * LANES < deg2 ? __ldg(col + beg2 + sub + k * LANES) : r2;
             const float d2 = __ldg(d + r2);
             // C: s[j] of iteration it+1, prefetch of its far gather rows and of the row stream `ahead` iterations on
-            const int rc = row_at(it + 1);
+            const int rc = sw.at(it + 1);
             float s1[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -257,11 +331,11 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
                 s1[k] = __ldg(s + j1[k]);
                 prefetch_far_row<C>(h, j1[k], rc, ok);
             }
-            prefetch_stream<C>(h, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            prefetch_stream<C>(h, sw.raw(it + 1 + ahead), N, sub);
             // D: softmax + aggregation of iteration it
             if (it >= 0) {
-                const int row = base + it * stride + grow;
-                const bool valid = row < r1;
+                const int row = sw.raw(it);
+                const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
                     if (valid) gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
@@ -293,21 +367,20 @@ __device__ __noinline__ void gat_bwd_dst_row_generic(int row, int sub, unsigned 
                                                      const float* __restrict__ d, const float* __restrict__ m_in,
                                                      const float* __restrict__ z_in, float* __restrict__ P,
                                                      float* __restrict__ DU, float* __restrict__ gsd, float slope) {
-    using M = RowMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES;
+    using M = GatMap<C>;
+    constexpr int NV = M::NV, LANES = M::LANES;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const float di = __ldg(d + row), mi = __ldg(m_in + row), inv = rcp_fast(__ldg(z_in + row));
-    Vec<VEC> gi;
-    gi.load(gout + (int64_t)row * C + sub * VEC);
-    const float* hb = h + sub * VEC;
+    float gi[NV];
+    row_load<C>(gi, gout + (int64_t)row * C, sub);
     float r = 0.f;
     for (int e = beg; e < end; ++e) {
         const int j = __ldg(col + e);
-        Vec<VEC> hv;
-        hv.load(hb + (int64_t)j * C);
+        float hv[NV];
+        row_load<C>(hv, h + (int64_t)j * C, sub);
         float c = 0.f;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) c = fmaf(gi.v[v], hv.v[v], c);
+        for (int v = 0; v < NV; ++v) c = fmaf(gi[v], hv[v], c);
         c = gsum<LANES>(c, gm);
         const float p = expf(lrelu(__ldg(s + j) + di, slope) - mi) * inv;
         r = fmaf(p, c, r);
@@ -331,26 +404,34 @@ __device__ __noinline__ void gat_bwd_dst_row_generic(int row, int sub, unsigned 
 // c[slot] = g_i . h_j for 4 slots: gather, partial dots, butterfly, the slot's owner lane keeps the result
 template <int C, int EPL>
 __device__ __forceinline__ void gather_dot4(const float* __restrict__ hb, const int (&j)[EPL],
-                                            const Vec<RowMap<C>::VEC>& gi, int t0, int sub, float (&c)[EPL]) {
-    constexpr int VEC = RowMap<C>::VEC, LANES = RowMap<C>::LANES;
-    int jj[4];
-    Vec<VEC> hv[4];
-    float cc[4];
+                                            const float (&gi)[GatMap<C>::NV], int t0, int sub, float (&c)[EPL]) {
+    constexpr int VEC = GatMap<C>::VEC, LANES = GatMap<C>::LANES, HALVES = GatMap<C>::HALVES;
+    constexpr int NB = 4 / HALVES;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) jj[q] = slot_get<LANES, EPL>(j, t0 + q);
+    for (int b = 0; b < 4; b += NB) {
+        int jj[NB];
+        Vec<VEC> hv[NB][HALVES];
+        float cc[NB];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) hv[q].load(hb + (int64_t)jj[q] * C);
+        for (int q = 0; q < NB; ++q) jj[q] = slot_get<LANES, EPL>(j, t0 + b + q);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        cc[q] = 0.f;
+        for (int q = 0; q < NB; ++q)
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) cc[q] = fmaf(gi.v[v], hv[q].v[v], cc[q]);
-    }
+            for (int hh = 0; hh < HALVES; ++hh) hv[q][hh].load(hb + (int64_t)jj[q] * C + hh * (C / 2));
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        cc[q] = group_sum<LANES>(cc[q]);
-        const int t = t0 + q;
-        if (sub == t % LANES) c[t / LANES] = cc[q];
+        for (int q = 0; q < NB; ++q) {
+            cc[q] = 0.f;
+#pragma unroll
+            for (int hh = 0; hh < HALVES; ++hh)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) cc[q] = fmaf(gi[hh * VEC + v], hv[q][hh].v[v], cc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            cc[q] = group_sum<LANES>(cc[q]);
+            const int t = t0 + b + q;
+            if (sub == t % LANES) c[t / LANES] = cc[q];
+        }
     }
 }
 
@@ -362,9 +443,9 @@ __device__ __forceinline__ void gat_bwd_dst_row_fast(int row, bool valid, int be
                                                      float* __restrict__ DU, float* __restrict__ gsd, float slope,
                                                      int rr) {
     using M = GatMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
-    Vec<VEC> gi;
-    gi.load(gout + (int64_t)rr * C + sub * VEC);
+    constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
+    float gi[NV];
+    row_load<C>(gi, gout + (int64_t)rr * C, sub);
     const float inv = rcp_fast(zi);
     float p[EPL], lg[EPL], c[EPL];
 #pragma unroll
@@ -400,21 +481,19 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ gout,
     const float* __restrict__ h, const float* __restrict__ s, const float* __restrict__ d,
     const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
-    float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int rows_per_cta, int ahead) {
+    float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int chunk_rows, int ipc_shift, int ahead) {
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
-    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-    const int stride = nwarp * RPW;
-    const int base = r0 + warp * RPW;
+    const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
     const float* hb = h + sub * VEC;
     if constexpr (!PIPE) {
-        for (int b = base; b < r1; b += stride) {
-            const int row = b + grow;
-            const bool valid = row < r1;
-            const int rr = valid ? row : r1 - 1;
+        for (int it = 0; it < sw.niter; ++it) {
+            const int row = sw.raw(it);
+            const bool valid = row < N;
+            const int rr = valid ? row : N - 1;
             const int beg = __ldg(rowptr + rr);
             const int deg = __ldg(rowptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
@@ -433,30 +512,25 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
                                     __ldg(z_in + rr), gout, hb, P, DU, gsd, slope, rr);
         }
     } else {
-        if (base >= r1) return;
-        auto row_at = [&](int it) -> int {
-            const int r = base + (it > 0 ? it : 0) * stride + grow;
-            return r < r1 ? r : r1 - 1;
-        };
+        if (sw.niter == 0) return;
         int beg2 = 0, deg2 = 0, beg1 = 0, deg1 = 0, beg0 = 0, deg0 = 0;
         int j1[EPL], j0[EPL];
         float s0[EPL], d1 = 0.f, d0 = 0.f, m0 = 0.f, z0 = 1.f;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
-            j1[k] = j0[k] = row_at(0);
+            j1[k] = j0[k] = sw.at(0);
             s0[k] = 0.f;
         }
-        const int niter = (r1 - base + stride - 1) / stride;
-        for (int it = -3; it < niter; ++it) {
-            const int r3 = row_at(it + 3);
+        for (int it = -3; it < sw.niter; ++it) {
+            const int r3 = sw.at(it + 3);
             const int beg3 = __ldg(rowptr + r3);
             const int deg3 = __ldg(rowptr + r3 + 1) - beg3;
-            const int r2 = row_at(it + 2);
+            const int r2 = sw.at(it + 2);
             int j2[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) j2[k] = sub + k * LANES < deg2 ? __ldg(col + beg2 + sub + k * LANES) : r2;
             const float d2 = __ldg(d + r2);
-            const int rc = row_at(it + 1);
+            const int rc = sw.at(it + 1);
             float s1[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -464,18 +538,18 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
                 prefetch_far_row<C>(h, j1[k], rc, sub + k * LANES < deg1);
             }
             const float m1 = __ldg(m_in + rc), z1 = __ldg(z_in + rc);
-            prefetch_stream<C>(h, base + (it + 1 + ahead) * stride + grow, r1, sub);
-            prefetch_stream<C>(gout, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            prefetch_stream<C>(h, sw.raw(it + 1 + ahead), N, sub);
+            prefetch_stream<C>(gout, sw.raw(it + 1 + ahead), N, sub);
             if (it >= 0) {
-                const int row = base + it * stride + grow;
-                const bool valid = row < r1;
+                const int row = sw.raw(it);
+                const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
                     if (valid)
                         gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
                 } else {
                     gat_bwd_dst_row_fast<C>(row, valid, beg0, deg0, maxdeg, sub, j0, s0, d0, m0, z0, gout, hb, P, DU, gsd,
-                                            slope, valid ? row : r1 - 1);
+                                            slope, valid ? row : N - 1);
                 }
             }
             beg0 = beg1, deg0 = deg1, d0 = d1, m0 = m1, z0 = z1;
@@ -499,29 +573,26 @@ __device__ __noinline__ void gat_bwd_src_row_generic(int row, int sub, const int
                                                      const float* __restrict__ G, const float* __restrict__ a_src,
                                                      const float* __restrict__ a_dst, float* __restrict__ out_tot,
                                                      float* __restrict__ gsd) {
-    using M = RowMap<C>;
-    constexpr int VEC = M::VEC;
+    using M = GatMap<C>;
+    constexpr int NV = M::NV;
     const int beg = __ldg(cscptr + row), end = __ldg(cscptr + row + 1);
-    float acc[VEC];
+    float acc[NV];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
     float gs = 0.f;
-    const float* gb = G + sub * VEC;
     for (int k = beg; k < end; ++k) {
         const int i = __ldg(cscrow + k), e = __ldg(perm + k);
-        Vec<VEC> gv;
-        gv.load(gb + (int64_t)i * C);
+        float gv[NV];
+        row_load<C>(gv, G + (int64_t)i * C, sub);
         const float p = P[e];
         gs += DU[e];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(p, gv.v[v], acc[v]);
+        for (int v = 0; v < NV; ++v) acc[v] = fmaf(p, gv[v], acc[v]);
     }
     const float gd = gsd[2 * (int64_t)row + 1];
-    Vec<VEC> o;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v)
-        o.v[v] = acc[v] + gs * __ldg(a_src + sub * VEC + v) + gd * __ldg(a_dst + sub * VEC + v);
-    o.store(out_tot + (int64_t)row * C + sub * VEC);
+    for (int v = 0; v < NV; ++v) acc[v] += gs * __ldg(a_src + chan<C>(sub, v)) + gd * __ldg(a_dst + chan<C>(sub, v));
+    row_store<C>(acc, out_tot + (int64_t)row * C, sub);
     if (sub == 0) gsd[2 * (int64_t)row] = gs;
 }
 
@@ -533,22 +604,20 @@ __device__ __forceinline__ void gat_bwd_src_row_fast(int row, bool valid, int ma
                                                      const float* __restrict__ a_dst, float* __restrict__ out_tot,
                                                      float* __restrict__ gsd) {
     using M = GatMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL;
+    constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
     float gs = 0.f;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) gs += du[k];
     gs = group_sum<LANES>(gs);
-    float acc[VEC];
+    float acc[NV];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
     gather_fma4<C, EPL>(gb, i, p, 0, acc);
     if (maxdeg > 4) gather_fma4<C, EPL>(gb, i, p, 4, acc);
     if (valid) {
-        Vec<VEC> o;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            o.v[v] = acc[v] + gs * __ldg(a_src + sub * VEC + v) + gd * __ldg(a_dst + sub * VEC + v);
-        o.store(out_tot + (int64_t)row * C + sub * VEC);
+        for (int v = 0; v < NV; ++v) acc[v] += gs * __ldg(a_src + chan<C>(sub, v)) + gd * __ldg(a_dst + chan<C>(sub, v));
+        row_store<C>(acc, out_tot + (int64_t)row * C, sub);
         if (sub == 0) gsd[2 * (int64_t)row] = gs;
     }
 }
@@ -558,20 +627,18 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
     const int32_t* __restrict__ cscptr, const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
     const float* __restrict__ P, const float* __restrict__ DU, const float* __restrict__ G,
     const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out_tot,
-    float* __restrict__ gsd, int N, int rows_per_cta, int ahead) {
+    float* __restrict__ gsd, int N, int chunk_rows, int ipc_shift, int ahead) {
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
-    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-    const int stride = nwarp * RPW;
-    const int base = r0 + warp * RPW;
+    const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
     const float* gb = G + sub * VEC;
     if constexpr (!PIPE) {
-        for (int b = base; b < r1; b += stride) {
-            const int row = b + grow;
-            const bool valid = row < r1;
-            const int rr = valid ? row : r1 - 1;
+        for (int it = 0; it < sw.niter; ++it) {
+            const int row = sw.raw(it);
+            const bool valid = row < N;
+            const int rr = valid ? row : N - 1;
             const int beg = __ldg(cscptr + rr);
             const int deg = __ldg(cscptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
@@ -592,26 +659,21 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
             gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i, p, du, gsd[2 * (int64_t)rr + 1], gb, a_src, a_dst, out_tot, gsd);
         }
     } else {
-        if (base >= r1) return;
-        auto row_at = [&](int it) -> int {
-            const int r = base + (it > 0 ? it : 0) * stride + grow;
-            return r < r1 ? r : r1 - 1;
-        };
+        if (sw.niter == 0) return;
         int beg2 = 0, deg2 = 0, deg1 = 0, deg0 = 0;
         int i1[EPL], e1[EPL], i0[EPL];
         float p0[EPL], du0[EPL], gd0 = 0.f;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
-            i1[k] = i0[k] = row_at(0);
+            i1[k] = i0[k] = sw.at(0);
             e1[k] = 0;
             p0[k] = du0[k] = 0.f;
         }
-        const int niter = (r1 - base + stride - 1) / stride;
-        for (int it = -3; it < niter; ++it) {
-            const int r3 = row_at(it + 3);
+        for (int it = -3; it < sw.niter; ++it) {
+            const int r3 = sw.at(it + 3);
             const int beg3 = __ldg(cscptr + r3);
             const int deg3 = __ldg(cscptr + r3 + 1) - beg3;
-            const int r2 = row_at(it + 2);
+            const int r2 = sw.at(it + 2);
             int i2[EPL], e2[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -619,7 +681,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
                 i2[k] = ok ? __ldg(cscrow + beg2 + sub + k * LANES) : r2;
                 e2[k] = ok ? __ldg(perm + beg2 + sub + k * LANES) : 0;
             }
-            const int rc = row_at(it + 1);
+            const int rc = sw.at(it + 1);
             float p1[EPL], du1[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -629,10 +691,10 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
                 prefetch_far_row<C>(G, i1[k], rc, ok);
             }
             const float gd1 = gsd[2 * (int64_t)rc + 1];
-            prefetch_stream<C>(G, base + (it + 1 + ahead) * stride + grow, r1, sub);
+            prefetch_stream<C>(G, sw.raw(it + 1 + ahead), N, sub);
             if (it >= 0) {
-                const int row = base + it * stride + grow;
-                const bool valid = row < r1;
+                const int row = sw.raw(it);
+                const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
                     if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd);
@@ -743,30 +805,39 @@ __global__ void __launch_bounds__(kThreads) gat_bwd2_dst_kernel(
 // Launch geometry.  Small graphs (working set L2-resident, latency-bound): 256-thread CTAs, one sweep iteration each
 // where possible.  Large graphs: SMs x `cps` CTAs of `threads` threads, each sweeping one contiguous row chunk.
 // bg_tune() overrides (used by the kernel sweep in bench.py --workload c4).
-static int g_tune[8] = {1024, 2, 256, 1, 0, 0, 0, 0};  // see bg_tune() in include/bg_b200.h
+static int g_tune[8] = {1024, 1, 128, 1, 0, 64, 0, 0};  // see bg_tune() in include/bg_b200.h
 struct GatCfg {
     unsigned grid, threads;
-    int rows_per_cta, ahead;
+    int chunk_rows, ipc_shift, ahead;
     bool pipe;
 };
 template <int C>
 static GatCfg gat_cfg(int64_t N) {
     const bool small = !g_tune[4] && N * C * 4 < (int64_t)(24 << 20);
     const int threads = small ? 256 : g_tune[0];
-    const int64_t cap = small ? (int64_t)kSMs * 8 : (int64_t)kSMs * g_tune[1];
-    const int64_t rows_iter = (int64_t)(threads / 32) * RowMap<C>::RPW;
+    const int64_t rows_iter = (int64_t)(threads / 32) * GatMap<C>::RPW;
     const int64_t iters = ceil_div(N, rows_iter);
-    int64_t grid = iters < cap ? iters : cap;
-    const int64_t rpc = ceil_div(iters, grid) * rows_iter;
-    grid = ceil_div(N, rpc);
-    return GatCfg{(unsigned)grid, (unsigned)threads, (int)rpc, (int)ceil_div(g_tune[2], rows_iter), !small && g_tune[3] != 0};
+    if (small) {  // one contiguous chunk per CTA, one sweep iteration each while the grid fits 8 CTAs per SM
+        const int64_t cap = (int64_t)kSMs * 8;
+        int64_t grid = iters < cap ? iters : cap;
+        const int64_t rpc = ceil_div(iters, grid) * rows_iter;
+        grid = ceil_div(N, rpc);
+        return GatCfg{(unsigned)grid, (unsigned)threads, (int)rpc, 30, 0, false};
+    }
+    // chunks of ~g_tune[5] KiB of feature rows (power-of-two iterations per chunk), dealt round-robin
+    int shift = 0;
+    while (shift < 12 && (rows_iter << (shift + 1)) * C * 4 <= (int64_t)g_tune[5] * 1024) ++shift;
+    const int64_t chunk = rows_iter << shift;
+    const int64_t nchunks = ceil_div(N, chunk), cap = g_tune[6] > 0 ? g_tune[6] : (int64_t)kSMs * g_tune[1];
+    const int64_t grid = nchunks < cap ? nchunks : cap;
+    return GatCfg{(unsigned)grid, (unsigned)threads, (int)chunk, shift, (int)ceil_div(g_tune[2], rows_iter), g_tune[3] != 0};
 }
 #define BG_GAT_LAUNCH(KERNEL, ...)                                                      \
     do {                                                                                \
         if (C >= 8 && c.pipe) /* narrower rows hold 8 edge slots per lane: the pipeline registers would spill */ \
-            KERNEL<C, (C >= 8)><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.rows_per_cta, c.ahead);  \
+            KERNEL<C, (C >= 8)><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead);  \
         else                                                                            \
-            KERNEL<C, false><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.rows_per_cta, c.ahead); \
+            KERNEL<C, false><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead); \
     } while (0)
 
 template <int C>
@@ -816,7 +887,7 @@ static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const
 
 static int check_graph(const BgGraph* g) {
     BG_REQUIRE(g && g->rowptr && g->col && g->cscptr && g->cscrow && g->perm, BG_EINVAL, "BgGraph has null arrays");
-    BG_REQUIRE(g->N < (int64_t)1 << 31 && g->E < (int64_t)1 << 31, BG_EINVAL, "BgGraph: N and E must fit int32");
+    BG_REQUIRE(g->N < ((int64_t)1 << 31) - ((int64_t)1 << 27) && g->E < (int64_t)1 << 31, BG_EINVAL, "BgGraph: N and E must fit int32");
     BG_REQUIRE(g->N > 0 && g->E >= g->N, BG_EINVAL, "BgGraph: need N>0 and E>=N (self loops), got N=%lld E=%lld",
                (long long)g->N, (long long)g->E);
     return BG_OK;

@@ -54,9 +54,10 @@ typedef struct BgGraph {
 int bg_version(void);
 const char* bg_last_error(void);
 /* Launch-geometry knobs of the aggregation kernels on graphs larger than L2 (no reference counterpart; used by the
- * kernel sweep of `bench.py --workload c4` and by the tests): key 0 = threads per CTA (default 1024), 1 = CTAs per SM
- * (2), 2 = distance in rows of the sequential L2 prefetch stream (256), 3 = use the software-pipelined kernels (1),
- * 4 = use the large-graph geometry for every graph (test hook, 0). */
+ * kernel sweep in scratch/gat_sweep.py and by the tests).  key: 0 = threads per CTA (default 1024), 1 = CTAs per SM (1),
+ * 2 = distance in rows of the sequential L2 prefetch stream (128), 3 = use the software-pipelined kernels (1),
+ * 4 = use the large-graph geometry for every graph (test hook, 0), 5 = KiB of feature rows per sweep chunk (64),
+ * 6 = grid size cap (test hook, 0 = SMs x key 1). */
 int bg_tune(int32_t key, int32_t value);
 
 /* ---- H1: collation (reference data.py:156-163 Batch.from_data_list; PyG GATConv's

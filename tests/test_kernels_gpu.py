@@ -128,13 +128,13 @@ def test_gat_large_graph_kernels(C, pipe):
     """The large-graph launch geometry (contiguous row chunk per CTA, optional software pipeline) forced on small graphs:
     same results as the oracle, on the building batch and on the hub graph."""
     L = lib.load()
-    L.bg_tune(4, 1), L.bg_tune(3, pipe), L.bg_tune(0, 128), L.bg_tune(1, 1), L.bg_tune(2, 40)
+    L.bg_tune(4, 1), L.bg_tune(3, pipe), L.bg_tune(0, 128), L.bg_tune(1, 1), L.bg_tune(2, 40), L.bg_tune(5, 4), L.bg_tune(6, 5)
     try:
         test_gat_fwd(C, False)
         test_gat_bwd(C)
         test_gat_high_degree_rows(C)
     finally:
-        L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 2), L.bg_tune(2, 256)
+        L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 1), L.bg_tune(2, 128), L.bg_tune(5, 64), L.bg_tune(6, 0)
 
 
 def test_gat_deterministic():
