@@ -39,6 +39,8 @@ struct FoldBatch {
 struct WgradQueue {
     static constexpr int kPhases = 4;
     std::vector<FoldEntry> phase[kPhases];
+    std::vector<BgWgrad> pending;  // deferred mode: problems recorded by wgrad_launch, launched by wgrad_flush
+    bool defer = false;
     float* buf = nullptr;
     size_t cap = 0, used = 0;  // floats
 };

@@ -226,16 +226,16 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
 // ------------------------------------------------------------------------------------------
 struct WgProblem {
     const float* gz;
-    int64_t ld_gz;
+    int64_t ld_gz, N, rows_per_split;  // every problem has its own row count (the 7-row type table next to N voxels)
     int Cout, K;
     SegView x;
     float* partial;  // [S][Cout*K]
     int tiles_k, tile_base, ntiles;
 };
+constexpr int kWgMax = 16;  // problems per launch (keeps the parameter block under 4 KiB)
 struct WgBatch {
-    int64_t N, rows_per_split;
     int nprob, S;
-    WgProblem p[BG_MAX_WGRAD];
+    WgProblem p[kWgMax];
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) {
@@ -243,14 +243,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     __shared__ float Gs[RB][T + 4];
     __shared__ float Xs[RB][T + 4];
     int pi = 0;
-#pragma unroll
-    for (int q = 1; q < BG_MAX_WGRAD; ++q)
-        if (q < b.nprob && (int)blockIdx.x >= b.p[q].tile_base) pi = q;
+#pragma unroll 1
+    for (int q = 1; q < b.nprob; ++q)
+        if ((int)blockIdx.x >= b.p[q].tile_base) pi = q;
     const WgProblem& p = b.p[pi];
     const int lt = blockIdx.x - p.tile_base;
     const int k0 = (lt % p.tiles_k) * T, o0 = (lt / p.tiles_k) * T;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-    const int64_t rbeg = (int64_t)blockIdx.y * b.rows_per_split, rend = min(b.N, rbeg + b.rows_per_split);
+    const int64_t rbeg = (int64_t)blockIdx.y * p.rows_per_split, rend = min(p.N, rbeg + p.rows_per_split);
     const int no = min(T, p.Cout - o0), nk = min(T, p.K - k0);  // valid extent of this tile
     float acc[4][4];
 #pragma unroll
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb
 static inline int wgrad_splits(int64_t N, int total_tiles) {
     // small outputs (a handful of tiles) are pure latency: use many short row ranges (the folds of a whole pass run as
     // one parallel launch, so more partials are cheap); large outputs keep the partial traffic bounded
-    int64_t ns = ceil_div(total_tiles <= 4 ? 4 * kSMs : 2 * kSMs, total_tiles);
+    int64_t ns = ceil_div(4 * kSMs, total_tiles);
     const int64_t maxs = ceil_div(N, 64);
     const int64_t cap = total_tiles <= 4 ? 128 : 64;
     if (ns > maxs) ns = maxs;
@@ -351,29 +351,28 @@ static inline int wgrad_splits(int64_t N, int total_tiles) {
 }
 static int wgrad_tiles(int Cout, int K) { return (int)(ceil_div(K, 64) * ceil_div(Cout, 64)); }
 
-// Launch the partial-sum kernel for `nprob` problems and queue their folds.
-int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st) {
-    BG_REQUIRE(nprob >= 1 && nprob <= BG_MAX_WGRAD, BG_EINVAL, "wgrad: nprob %d out of range [1,%d]", nprob, BG_MAX_WGRAD);
+// One partial-sum launch for up to kWgMax problems (any mix of row counts); queues their folds.
+static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st) {
     WgBatch b;
-    b.N = probs[0].N;
     b.nprob = nprob;
     int tiles = 0;
+    int64_t nmax = 0;
     for (int i = 0; i < nprob; ++i) {
         const BgWgrad& a = probs[i];
         BG_REQUIRE(a.gz && (a.dW || a.dbias), BG_EINVAL, "wgrad: problem %d has null pointers", i);
-        BG_REQUIRE(a.N == b.N, BG_EINVAL, "wgrad: problems of one launch must share N");
         WgProblem& p = b.p[i];
-        p.gz = a.gz; p.ld_gz = a.ld_gz; p.Cout = a.Cout;
+        p.gz = a.gz; p.ld_gz = a.ld_gz; p.Cout = a.Cout; p.N = a.N;
         if (int rc = fill_segview(p.x, a.nseg, a.seg, &p.K)) return rc;
         p.tiles_k = (int)ceil_div(p.K, 64);
         p.tile_base = tiles;
         p.ntiles = wgrad_tiles(p.Cout, p.K);
         tiles += p.ntiles;
+        if (a.N > nmax) nmax = a.N;
     }
-    b.S = wgrad_splits(b.N, tiles);
-    b.rows_per_split = ceil_div(ceil_div(b.N, b.S), 32) * 32;
+    b.S = wgrad_splits(nmax, tiles);
     for (int i = 0; i < nprob; ++i) {
         WgProblem& p = b.p[i];
+        p.rows_per_split = ceil_div(ceil_div(p.N, b.S), 32) * 32;
         const size_t need = (size_t)b.S * p.Cout * p.K;
         BG_REQUIRE(q.used + need <= q.cap, BG_EINVAL, "wgrad: partial-sum workspace too small (%zu + %zu > %zu floats)", q.used,
                    need, q.cap);
@@ -403,8 +402,27 @@ int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st
     return check_launch("wgrad");
 }
 
+// Immediate mode: launch now.  Deferred mode (q.defer, used by the whole-pass executors, whose operands stay alive
+// until the end of the pass): only record the problems; wgrad_flush() then runs ALL weight gradients of the pass as
+// one launch per kWgMax problems - ~25 tiny latency-bound launches per backward pass become 2.
+int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st) {
+    BG_REQUIRE(nprob >= 1, BG_EINVAL, "wgrad: nprob %d out of range", nprob);
+    if (q.defer) {
+        q.pending.insert(q.pending.end(), probs, probs + nprob);
+        return BG_OK;
+    }
+    for (int i = 0; i < nprob; i += kWgMax)
+        if (int rc = wgrad_launch_batch(probs + i, nprob - i < kWgMax ? nprob - i : kWgMax, q, st)) return rc;
+    return BG_OK;
+}
+
 // Fold every queued problem: one launch per phase (and per kMaxFold entries).
 int wgrad_flush(WgradQueue& q, cudaStream_t st) {
+    for (size_t i = 0; i < q.pending.size(); i += kWgMax) {
+        const size_t n = q.pending.size() - i < (size_t)kWgMax ? q.pending.size() - i : (size_t)kWgMax;
+        if (int rc = wgrad_launch_batch(q.pending.data() + i, (int)n, q, st)) return rc;
+    }
+    q.pending.clear();
     for (int ph = 0; ph < WgradQueue::kPhases; ++ph) {
         std::vector<FoldEntry>& v = q.phase[ph];
         for (size_t base = 0; base < v.size(); base += FoldBatch::kMax) {
@@ -595,6 +613,7 @@ extern "C" size_t bg_wgrad_multi_ws(int64_t N, int32_t nprob, const int32_t* Cou
 
 extern "C" int bg_wgrad_multi(const BgWgrad* probs, int32_t nprob, float* workspace, size_t ws_bytes, void* stream) {
     BG_REQUIRE(probs && workspace, BG_EINVAL, "bg_wgrad_multi: null pointer");
+    BG_REQUIRE(nprob >= 1 && nprob <= BG_MAX_WGRAD, BG_EINVAL, "bg_wgrad_multi: nprob %d out of range [1,%d]", (int)nprob, BG_MAX_WGRAD);
     BG_REQUIRE(ws_bytes > (size_t)kCounterBytes, BG_EINVAL, "bg_wgrad_multi: workspace too small");
     WgradQueue q;
     q.buf = workspace + kCounterBytes / sizeof(float);

@@ -22,8 +22,14 @@ constexpr float kKeepProb = 0.8f;  // nn.Dropout(0.2), hard-coded in the referen
 struct Arena {
     char* base;
     size_t off;
+    size_t cap = ~(size_t)0;  // bytes; an allocation past it sets `overflow` and returns the arena base (in bounds)
+    bool overflow = false;
     float* f(size_t n) {
         const size_t a = align_up(off, 256);
+        if (a + n * sizeof(float) > cap) {
+            overflow = true;
+            return reinterpret_cast<float*>(base);
+        }
         off = a + n * sizeof(float);
         return base ? reinterpret_cast<float*>(base + a) : nullptr;
     }
@@ -174,7 +180,8 @@ struct Ctx {
     size_t red_bytes;
     void* st;
     int accumulate;
-    WgradQueue* q;           // deferred weight-gradient folds of this pass
+    WgradQueue* q;           // deferred weight gradients of this pass (launched and folded once, at the end)
+    Arena* X;                // per-layer scratch (per-edge arrays); everything a weight gradient reads lives in the pass arena
     float* g(int pidx) const { return (G && pidx >= 0) ? G + goff[pidx] : nullptr; }
 };
 
@@ -184,6 +191,7 @@ static int init_queue(WgradQueue& q, float* red, size_t red_bytes) {
     q.buf = red + kWgradOffsetBytes / sizeof(float);
     q.cap = (red_bytes - kWgradOffsetBytes) / sizeof(float);
     q.used = 0;
+    q.defer = true;  // operands of every weight gradient stay alive until wgrad_flush() at the end of the pass
     return BG_OK;
 }
 
@@ -253,8 +261,9 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
     float* gh = keep ? L.b_gh : T.f((size_t)c.N * C);
     float* gsd = keep ? L.b_gsd : T.f((size_t)c.N * 2);
     float* bst = keep ? L.b_bstats : T.f((size_t)2 * C);
-    float* Pe = T.f((size_t)c.graph->E);
-    float* DU = T.f((size_t)c.graph->E);
+    c.X->off = 0;
+    float* Pe = c.X->f((size_t)c.graph->E);
+    float* DU = c.X->f((size_t)c.graph->E);
     float* gnpar = c.G ? c.g(L.p_gw) : T.f((size_t)3 * C);
     if (gx1) {
         BG_TRY(bg_graphnorm_bwd(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, go, gnpar,
@@ -295,7 +304,8 @@ static int conv_backward2(const Ctx& c, const ConvL& L, const float* Xt, float k
     float* Dt = T.f((size_t)c.N);
     float* gt = T.f((size_t)c.N * C);
     float* sdt = T.f((size_t)c.N * 2);
-    float* scratch = T.f((size_t)4 * c.graph->E);
+    c.X->off = 0;
+    float* scratch = c.X->f((size_t)4 * c.graph->E);
     BG_TRY(matmul_nt(c, Xt, c.N, c.P[L.p_W], C, L.cin, 0, L.cin, Ht, c.P[L.p_as], c.P[L.p_ad], St, Dt));
     BG_TRY(bg_gat_bwd2(c.graph, Ht, St, Dt, L.b_go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], scratch, gt, ht, sdt, C,
                        0.2f, c.st));
@@ -418,11 +428,31 @@ extern "C" int bg_gen_forward(const BgModelDesc* md, const float* const* params,
     return bg_gumbel_st_fwd(logits, noise, seed, offset + 1000, N, K, soft, hard, nullptr, stream);
 }
 
+// Scratch layout of the backward passes: [0, scratch_bytes) = per-layer scratch (per-edge arrays, rewound by every
+// block), rest = pass arena.  Nothing in the pass arena is reused before the end of the pass: every gradient a weight
+// gradient reads stays alive until the single deferred wgrad launch (wgrad_flush).
+static size_t scratch_bytes(int64_t E) { return align_up((size_t)4 * (size_t)E * sizeof(float), 256) + 4096; }
+struct Tally {  // mirrors Arena::f for size queries
+    size_t off = 0;
+    void f(size_t n) { off = align_up(off, 256) + n * sizeof(float); }
+};
+static void tally_conv_bwd(Tally& t, const ConvL& L, int64_t N, bool keep) {
+    if (!keep) { t.f((size_t)N * L.cout); t.f((size_t)N * L.cout); t.f((size_t)N * 2); t.f((size_t)2 * L.cout); }
+    t.f((size_t)3 * L.cout);
+    t.f((size_t)N * L.cin);
+}
+
 extern "C" size_t bg_gen_bwd_ws(const BgModelDesc* md, int64_t N, int64_t E) {
-    if (!md) return 0;
-    // temporaries: a handful of [N, max width] gradients + per-edge scratch; generous fixed bound
-    const size_t wmax = (size_t)(md->g_hidden > md->le_dim ? md->g_hidden : md->le_dim);
-    return (size_t)(10 * (size_t)N * wmax + 4 * (size_t)E + 16 * 1024) * sizeof(float) * 2;
+    GenNet g;
+    if (!md || build_gen(*md, g)) return 0;
+    const size_t K = md->num_classes, le = md->le_dim, gh = md->g_hidden;
+    Tally t;
+    t.f(N * gh); t.f(N * le); t.f(N * le); t.f(K * le); t.f(K * le); t.f(N * K);
+    for (int i = g.n_dec - 1; i >= 0; --i) { t.f((size_t)N * g.dec[i].cout); t.f((size_t)N * (i ? g.dec[i].cin : g.conv[g.n_conv - 1].cout)); }
+    for (int k = 0; k < g.n_conv; ++k) tally_conv_bwd(t, g.conv[k], N, false);
+    for (int i = 0; i < g.n_mlp; ++i) { t.f(N * gh); t.f(N * gh); }
+    for (int i = 0; i < g.n_menc + 2; ++i) { t.f(K * le); t.f(K * le); }
+    return scratch_bytes(E) + align_up(t.off, 256) + 65536;
 }
 
 extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params, const BgGraph* graph, const BgBatchIn* in,
@@ -443,18 +473,15 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     BG_TRY(init_queue(queue, red, red_bytes));
     Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, accumulate ? 1 : 0, &queue};
     const int K = md->num_classes, le = md->le_dim, gh = md->g_hidden;
-    Arena T{static_cast<char*>(tmp), 0};
-    const size_t wide = (size_t)N * (gh > le ? gh : le);
-    float* ga = T.f(wide);  // ping-pong gradient buffers
-    float* gb = T.f(wide);
-    float* gzb = T.f(wide);
+    Arena X{static_cast<char*>(tmp), 0, scratch_bytes(graph->E)};
+    Arena T{static_cast<char*>(tmp) + scratch_bytes(graph->E), 0, tmp_bytes - scratch_bytes(graph->E)};
+    c.X = &X;
     float* g_skip = T.f((size_t)N * gh);
     float* g_e1 = T.f((size_t)N * le);
     float* g_e2 = T.f((size_t)N * le);
     float* ge = T.f((size_t)K * le);
     float* ge2 = T.f((size_t)K * le);
     float* gl = T.f((size_t)N * K);
-    const size_t t_mark = T.off;
     // gumbel straight-through
     const float* g = g_logits;
     if (g_hard || g_soft) {
@@ -466,64 +493,59 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     const BgSeg enc = seg(e_last, le, le, in->type32);
     const BgSeg vx = seg(in->vx, md->voxel_dim, md->voxel_dim), zz = seg(z, md->z_dim, md->z_dim);
     const float* x = net.mlp[net.n_mlp - 1].out;
-    // decoder, last to second layer
-    float* cur = ga;
-    float* nxt = gb;
+    // decoder, last to second layer (every layer gets fresh buffers: see scratch_bytes())
     for (int i = net.n_dec - 1; i >= 1; --i) {
         BgSeg s = seg(net.dec[i - 1].out, net.dec[i].cin, net.dec[i].cin);
         int win[1][2] = {{0, net.dec[i].cin}};
-        float* gin[1] = {nxt};
+        float* gzb = T.f((size_t)N * net.dec[i].cout);
+        float* gin[1] = {T.f((size_t)N * net.dec[i].cin)};
         BG_TRY(dense_backward(c, net.dec[i], N, &s, 1, g, gzb, win, gin, 1, nullptr));
-        g = nxt;
-        float* t = cur; cur = nxt; nxt = t;
+        g = gin[0];
     }
     {
         const int eo = net.conv[net.n_conv - 1].cout;
         BgSeg s5[5] = {seg(net.conv[net.n_conv - 1].x1, eo, eo), seg(x, gh, gh), enc, vx, zz};
         int win[3][2] = {{0, eo}, {eo, eo + gh}, {eo + gh, eo + gh + le}};
-        float* gin[3] = {nxt, g_skip, g_e1};
+        float* gzb = T.f((size_t)N * net.dec[0].cout);
+        float* gin[3] = {T.f((size_t)N * eo), g_skip, g_e1};
         BG_TRY(dense_backward(c, net.dec[0], N, s5, 5, g, gzb, win, gin, 3, nullptr));
-        g = nxt;
-        float* t = cur; cur = nxt; nxt = t;
+        g = gin[0];
     }
     for (int k = net.n_conv - 1; k >= 0; --k) {
         const float* x_in = k == 0 ? x : net.conv[k - 1].x1;
-        T.off = t_mark;
-        BG_TRY(conv_backward(c, net.conv[k], x_in, g, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr, false, T, nxt));
-        g = nxt;
-        float* t = cur; cur = nxt; nxt = t;
+        float* gx = T.f((size_t)N * net.conv[k].cin);
+        BG_TRY(conv_backward(c, net.conv[k], x_in, g, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr, false, T, gx));
+        g = gx;
     }
     BG_TRY(bg_axpy(const_cast<float*>(g), g_skip, 1.f, N * gh, stream));
     for (int i = net.n_mlp - 1; i >= 1; --i) {
         BgSeg s = seg(net.mlp[i - 1].out, gh, gh);
         int win[1][2] = {{0, gh}};
-        float* gin[1] = {nxt};
+        float* gzb = T.f((size_t)N * gh);
+        float* gin[1] = {T.f((size_t)N * gh)};
         BG_TRY(dense_backward(c, net.mlp[i], N, &s, 1, g, gzb, win, gin, 1, nullptr));
-        g = nxt;
-        float* t = cur; cur = nxt; nxt = t;
+        g = gin[0];
     }
     {
         BgSeg s3[3] = {enc, vx, zz};
         int win[1][2] = {{0, le}};
         float* gin[1] = {g_e2};
-        BG_TRY(dense_backward(c, net.mlp[0], N, s3, 3, g, gzb, win, gin, 1, nullptr));
+        BG_TRY(dense_backward(c, net.mlp[0], N, s3, 3, g, T.f((size_t)N * gh), win, gin, 1, nullptr));
     }
     BG_TRY(bg_type_scatter_sum(g_e1, le, in->type32, N, le, K, ge, red, red_bytes, stream));
     BG_TRY(bg_type_scatter_sum(g_e2, le, in->type32, N, le, K, ge2, red, red_bytes, stream));
     BG_TRY(bg_axpy(ge, ge2, 1.f, (int64_t)K * le, stream));
     const float* gcur = ge;
-    float* small_a = ge2;            // [K, le] ping-pong (le == every menc width)
-    float* small_gz = T.f((size_t)K * le);
-    float* small_b = T.f((size_t)K * le);
     for (int i = net.n_menc - 1; i >= 0; --i) {
         const float* xin = i == 0 ? in->table : net.menc[i - 1].out;
         BgSeg s = seg(xin, net.menc[i].cin, net.menc[i].cin);
         int win[1][2] = {{0, net.menc[i].cin}};
-        float* dst = (gcur == small_a) ? small_b : small_a;
-        float* gin[1] = {dst};
+        float* small_gz = T.f((size_t)K * le);
+        float* gin[1] = {T.f((size_t)K * le)};
         BG_TRY(dense_backward(c, net.menc[i], K, &s, 1, gcur, small_gz, win, gin, i > 0 ? 1 : 0, nullptr));
-        gcur = dst;
+        gcur = gin[0];
     }
+    BG_REQUIRE(!T.overflow && !X.overflow, BG_EINVAL, "bg_gen_backward: scratch too small");
     return wgrad_flush(queue, as_stream(stream));
 }
 
@@ -579,9 +601,31 @@ extern "C" size_t bg_disc_bwd_saved_ws(const BgModelDesc* md, int64_t N, int64_t
     (void)E;
     return align_up(A.off, 256);
 }
+static size_t disc_bwd_floats_bytes(const BgModelDesc* md, const DiscNet& d, int64_t N, bool keep) {
+    const size_t dh = md->d_hidden;
+    Tally t;
+    for (int i = 3; i >= 0; --i) { t.f((size_t)N * d.dec[i].cout); t.f((size_t)N * d.dec[i].cin); }
+    for (int k = 0; k < d.n_conv; ++k) tally_conv_bwd(t, d.conv[k], N, keep);
+    t.f(N * dh); t.f(N * dh); t.f(N * dh);
+    return align_up(t.off, 256);
+}
+// scratch of bg_disc_backward; bg_disc_backward2 takes twice this
 extern "C" size_t bg_disc_tmp_ws(const BgModelDesc* md, int64_t N, int64_t E) {
-    if (!md) return 0;
-    return (size_t)(16 * (size_t)N * md->d_hidden + 8 * (size_t)E + 64 * (size_t)N + 16 * 1024) * sizeof(float);
+    DiscNet d;
+    if (!md || build_disc(*md, d)) return 0;
+    const size_t dh = md->d_hidden;
+    const size_t bwd = disc_bwd_floats_bytes(md, d, N, false);
+    Tally t;  // second-order sweep, then the injected first-order sweep
+    t.f(N * dh); t.f(N * dh); t.f(N * dh); t.f(N * dh);
+    for (int k = 0; k < d.n_conv; ++k) {
+        const size_t C = d.conv[k].cout;
+        t.f(N * C); t.f(N * C);                                              // injections
+        t.f(N * C); t.f(N); t.f(N); t.f(N * C); t.f(N * 2); t.f(N * C);   // Ht, St, Dt, gt, sdt, cotangent out
+    }
+    for (int i = 0; i < 4; ++i) { t.f((size_t)N * d.dec[i].cout); t.f((size_t)N * d.dec[i].cout); }
+    const size_t bwd2 = align_up(t.off, 256) + bwd;
+    const size_t need = bwd > (bwd2 + 1) / 2 ? bwd : (bwd2 + 1) / 2;
+    return scratch_bytes(E) + need + 65536;
 }
 
 // First-order backward.  g_score may be null together with inject != null (second-order sweep's forward-graph
@@ -591,13 +635,7 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
                               bool keep, Arena& T, float* g_label) {
     const int64_t N = c.N;
     const int dh = md->d_hidden;
-    float* ga = T.f((size_t)N * dh);
-    float* gb = T.f((size_t)N * dh);
-    float* gzb = T.f((size_t)N * dh);
-    const size_t t_mark = T.off;
     const float* g = g_score;
-    float* cur = ga;
-    float* nxt = gb;
     if (g) {
         for (int i = 3; i >= 0; --i) {
             const float* xin = i == 0 ? d.conv[d.n_conv - 1].x1 : d.dec[i - 1].out;
@@ -605,8 +643,8 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
             DenseL l = d.dec[i];
             if (i == 3) l.out = const_cast<float*>(score);
             int win[1][2] = {{0, l.cin}};
-            float* gin[1] = {nxt};
-            float* gzbuf = keep ? l.b_gz : gzb;
+            float* gin[1] = {T.f((size_t)N * l.cin)};
+            float* gzbuf = keep ? l.b_gz : T.f((size_t)N * l.cout);
             const float* gz_used = nullptr;
             BG_TRY(dense_backward(c, l, N, &s, 1, g, gzbuf, win, gin, 1, &gz_used));
             if (keep && gz_used != gzbuf)  // bare Linear: gz == gout, keep a copy for the second-order sweep
@@ -614,24 +652,22 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
                                cudaSuccess
                            ? BG_OK
                            : BG_ECUDA);
-            g = nxt;
-            float* t = cur; cur = nxt; nxt = t;
+            g = gin[0];
         }
     }
     for (int k = d.n_conv - 1; k >= 0; --k) {
         const float* x_in = k == 0 ? d.pre[1].out : d.conv[k - 1].x1;
-        T.off = t_mark;
+        float* gx = T.f((size_t)N * d.conv[k].cin);
         BG_TRY(conv_backward(c, d.conv[k], x_in, g, training_scale, inj_o ? inj_o[k] : nullptr, inj_h ? inj_h[k] : nullptr, keep, T,
-                             nxt));
-        g = nxt;
-        float* t = cur; cur = nxt; nxt = t;
+                             gx));
+        g = gx;
     }
     {
         BgSeg s = seg(d.pre[0].out, dh, dh);
         int win[1][2] = {{0, dh}};
-        float* gin[1] = {nxt};
-        BG_TRY(dense_backward(c, d.pre[1], N, &s, 1, g, keep ? d.pre[1].b_gz : gzb, win, gin, 1, nullptr));
-        g = nxt;
+        float* gin[1] = {T.f((size_t)N * dh)};
+        BG_TRY(dense_backward(c, d.pre[1], N, &s, 1, g, keep ? d.pre[1].b_gz : T.f((size_t)N * dh), win, gin, 1, nullptr));
+        g = gin[0];
     }
     {
         const int lo = md->local_dim + md->voxel_dim;
@@ -639,7 +675,7 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
                        seg(label, md->num_classes, md->num_classes)};
         int win[1][2] = {{lo, lo + md->num_classes}};
         float* gin[1] = {g_label};
-        BG_TRY(dense_backward(c, d.pre[0], N, s3, 3, g, keep ? d.pre[0].b_gz : gzb, win, gin, g_label ? 1 : 0, nullptr));
+        BG_TRY(dense_backward(c, d.pre[0], N, s3, 3, g, keep ? d.pre[0].b_gz : T.f((size_t)N * dh), win, gin, g_label ? 1 : 0, nullptr));
     }
     return BG_OK;
 }
@@ -663,10 +699,13 @@ extern "C" int bg_disc_backward(const BgModelDesc* md, const float* const* param
     BG_REQUIRE(tmp_bytes >= bg_disc_tmp_ws(md, N, graph->E), BG_EINVAL, "bg_disc_backward: scratch too small");
     WgradQueue queue;
     BG_TRY(init_queue(queue, red, red_bytes));
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, accumulate ? 1 : 0, &queue};
-    Arena T{static_cast<char*>(tmp), 0};
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, accumulate ? 1 : 0, &queue, nullptr};
+    Arena X{static_cast<char*>(tmp), 0, scratch_bytes(graph->E)};
+    Arena T{static_cast<char*>(tmp) + scratch_bytes(graph->E), 0, tmp_bytes - scratch_bytes(graph->E)};
+    c.X = &X;
     BG_TRY(disc_backward_impl(md, d, c, in, label, score, g_score, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr,
                               saved != nullptr, T, g_label));
+    BG_REQUIRE(!T.overflow && !X.overflow, BG_EINVAL, "bg_disc_backward: scratch too small");
     return wgrad_flush(queue, as_stream(stream));
 }
 
@@ -688,10 +727,12 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
     BG_REQUIRE(tmp_bytes >= 2 * bg_disc_tmp_ws(md, N, graph->E), BG_EINVAL, "bg_disc_backward2: scratch too small");
     WgradQueue queue;
     BG_TRY(init_queue(queue, red, red_bytes));
-    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 1, &queue};
+    Ctx c{params, grad_flat, grad_off, graph, N, red, red_bytes, stream, 1, &queue, nullptr};
     const float keep_scale = training ? 1.f / kKeepProb : 1.f;
     const int dh = md->d_hidden, K = md->num_classes, lo = md->local_dim + md->voxel_dim;
-    Arena T{static_cast<char*>(tmp), 0};
+    Arena X{static_cast<char*>(tmp), 0, scratch_bytes(graph->E)};
+    Arena T{static_cast<char*>(tmp) + scratch_bytes(graph->E), 0, tmp_bytes - scratch_bytes(graph->E)};
+    c.X = &X;
     float* ta = T.f((size_t)N * dh);
     float* tb = T.f((size_t)N * dh);
     float* inj_o[kMaxConvs];
@@ -700,7 +741,6 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         inj_o[k] = T.f((size_t)N * d.conv[k].cout);
         inj_h[k] = T.f((size_t)N * d.conv[k].cout);
     }
-    const size_t t_mark = T.off;
     // pre[0] backward was: gz0 = g_a * [x_a > 0] ; g_label = gz0 @ W0[:, lo:lo+K]
     {
         BgSeg lt = seg(Lt, K, K);
@@ -714,15 +754,16 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         BgSeg ts = seg(tb, dh, dh);
         BgWgrad pr = wg(N, d.pre[1].b_gz, dh, dh, &ts, 1, c.g(d.pre[1].pW), dh, nullptr, 1);
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
-        BG_TRY(matmul_nt(c, tb, N, params[d.pre[1].pW], dh, dh, 0, dh, ta));                         // cot(gz1)
-        BG_TRY(bg_ln_act_bwd(ta, d.pre[1].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
+        float* tc = T.f((size_t)N * dh);
+        BG_TRY(matmul_nt(c, tb, N, params[d.pre[1].pW], dh, dh, 0, dh, tc));                         // cot(gz1)
+        tb = T.f((size_t)N * dh);  // the previous tb is a queued weight-gradient operand: leave it alone
+        BG_TRY(bg_ln_act_bwd(tc, d.pre[1].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
     }
-    float* t = tb;       // cotangent flowing up the backward chain
-    float* other = ta;
+    float* t = tb;       // cotangent flowing up the backward chain (fresh buffer per layer)
     for (int k = 0; k < d.n_conv; ++k) {
-        T.off = t_mark;
-        BG_TRY(conv_backward2(c, d.conv[k], t, keep_scale, T, other, inj_o[k], inj_h[k]));
-        float* sw = t; t = other; other = sw;
+        float* out = T.f((size_t)N * d.conv[k].cout);
+        BG_TRY(conv_backward2(c, d.conv[k], t, keep_scale, T, out, inj_o[k], inj_h[k]));
+        t = out;
     }
     for (int i = 0; i < 4; ++i) {
         // backward was: gz = g_y * act'(y) ; g_in = gz @ W        (t = cot(g_in))
@@ -731,11 +772,13 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         BgWgrad pr = wg(N, l.b_gz, l.cout, l.cout, &ts, 1, c.g(l.pW), l.cin, nullptr, 1);
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
         if (i == 3 && !gt_score) break;
-        BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, other));                  // cot(gz)
+        float* cz = T.f((size_t)N * l.cout);
+        BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, cz));                     // cot(gz)
         if (l.act != BG_ACT_NONE) {
-            BG_TRY(bg_ln_act_bwd(other, l.out, nullptr, nullptr, nullptr, N, l.cout, l.act, t, nullptr, nullptr, 0, nullptr, 0, stream));
+            t = T.f((size_t)N * l.cout);
+            BG_TRY(bg_ln_act_bwd(cz, l.out, nullptr, nullptr, nullptr, N, l.cout, l.act, t, nullptr, nullptr, 0, nullptr, 0, stream));
         } else {
-            float* sw = t; t = other; other = sw;
+            t = cz;
         }
     }
     if (gt_score)
@@ -744,8 +787,8 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
                    : BG_ECUDA);
     // forward-graph sweep with the injected cotangents (nothing flows in from the top: the score itself is
     // not part of the second-order loss)
-    T.off = t_mark;
     BG_TRY(disc_backward_impl(md, d, c, in, label, score, nullptr, keep_scale, inj_o, inj_h, false, T, nullptr));
+    BG_REQUIRE(!T.overflow && !X.overflow, BG_EINVAL, "bg_disc_backward2: scratch too small");
     return wgrad_flush(queue, as_stream(stream));
 }
 
