@@ -68,8 +68,11 @@ class DenseSpec:
 
 
 class ConvSpec:
-    def __init__(self, conv: str, norm: str, cin: int, cout: int):
-        self.conv, self.norm, self.cin, self.cout = conv, norm, cin, cout
+    """One [conv, GraphNorm, ReLU, Dropout] block.  ``kind`` in GATCONV / GCNCONV / GRAPHCONV / GATV2CONV
+    (reference models.py:22-31,166-175)."""
+
+    def __init__(self, conv: str, norm: str, cin: int, cout: int, kind: str = "GATCONV"):
+        self.conv, self.norm, self.cin, self.cout, self.kind = conv, norm, cin, cout, kind
 
 
 # ------------------------------------------------------------------------------------------------
@@ -109,11 +112,139 @@ def _wgrad_with_bias(gz: Tensor, segs, dW: Tensor, db: Tensor, accumulate: bool)
     lib.dense_wgrad(gz, list(segs) + [None], dW=dW, accumulate=accumulate, dbias=db)
 
 
+def _colsum(rows: Tensor, dst: Tensor, accumulate: bool) -> None:
+    """dst[C] (+)= column sums of rows[N,C] (deterministic: the weight-gradient kernel against a column of ones)."""
+    lib.dense_wgrad(rows, [None], dW=dst.view(-1, 1), accumulate=accumulate)
+
+
+def _gcn_weights(csr) -> Tensor:
+    w = getattr(csr, "_gcn_w", None)
+    if w is None or w.device != csr.device:
+        w = lib.gcn_norm(csr)
+        csr._gcn_w = w
+    return w
+
+
+# ---- aggregation part of a block, per conv type --------------------------------------------------
+# forward:   (o, saved)                                       o = conv(x) incl. its bias
+# backward:  gx from go (= d loss / d o); ``inj`` = cotangent(s) injected at the conv's intermediate (second-order
+#            sweep); parameter gradients into G; with keep_for_bwd2 the intermediates are kept in ``sv``
+# backward2: (gt, inj) from Xt (= cotangent on gx): gt = cotangent on go, inj = what the injected first-order sweep
+#            adds at the intermediate; direct parameter cotangents are accumulated into G2
+def _agg_forward(P, spec: ConvSpec, csr, x: Tensor):
+    cv = spec.conv
+    if spec.kind == "GATCONV":
+        a_s, a_d = P[cv + ".att_src"].view(-1), P[cv + ".att_dst"].view(-1)
+        lin = lib.dense_fwd([x], P[cv + ".lin.weight"], att=(a_s, a_d))
+        o, m, z = lib.gat_fwd(csr, lin["out"], lin["s"], lin["d"], P[cv + ".bias"])
+        return o, dict(h=lin["out"], s=lin["s"], d=lin["d"], m=m, z=z)
+    if spec.kind == "GCNCONV":
+        h = lib.dense_fwd([x], P[cv + ".lin.weight"])["out"]
+        return lib.spmm(csr, h, _gcn_weights(csr), P[cv + ".bias"]), dict(h=h)
+    if spec.kind == "GRAPHCONV":
+        if getattr(csr, "num_input_self_loops", 0):
+            raise RuntimeError("GRAPHCONV: the voxel graph has self loops in edge_index; the CSR strips them and GraphConv "
+                               "(which adds none) would lose their contribution")
+        agg = lib.spmm(csr, x, None, None, self_loops=False)
+        o = lib.dense_fwd([agg], P[cv + ".lin_rel.weight"], P[cv + ".lin_rel.bias"])["out"]
+        lib.axpy_(o, lib.dense_fwd([x], P[cv + ".lin_root.weight"])["out"])
+        return o, dict(agg=agg)
+    if spec.kind == "GATV2CONV":
+        xl = lib.dense_fwd([x], P[cv + ".lin_l.weight"], P[cv + ".lin_l.bias"])["out"]
+        xr = lib.dense_fwd([x], P[cv + ".lin_r.weight"], P[cv + ".lin_r.bias"])["out"]
+        o, logit, m, z = lib.gatv2_fwd(csr, xl, xr, P[cv + ".att"].view(-1), P[cv + ".bias"])
+        return o, dict(xl=xl, xr=xr, logit=logit, m=m, z=z)
+    raise ValueError(f"Invalid conv_type: {spec.kind}")
+
+
+def _agg_backward(P, G, spec: ConvSpec, csr, sv, go: Tensor, accumulate: bool, inj, keep_for_bwd2: bool) -> Tensor:
+    cv, x = spec.conv, sv["x"]
+    if spec.kind == "GATCONV":
+        a_s, a_d = P[cv + ".att_src"].view(-1), P[cv + ".att_dst"].view(-1)
+        gh, gsd, Pe, DU = lib.gat_bwd(csr, go, sv["h"], sv["s"], sv["d"], sv["m"], sv["z"], a_s, a_d)
+        if G is not None:
+            _colsum(go, G[cv + ".bias"], accumulate)
+            lib.dense_wgrad(gsd, [sv["h"]], dW=G["__att__" + cv], accumulate=accumulate)
+        if inj is not None:
+            lib.axpy_(gh, inj)
+        if G is not None:
+            lib.dense_wgrad(gh, [x], dW=G[cv + ".lin.weight"], accumulate=accumulate)
+        if keep_for_bwd2:
+            sv["b_gh"], sv["b_gsd"] = gh, gsd
+        return lib.dense_fwd([gh], P[cv + ".lin.weight"], transposed=True)["out"]
+    if spec.kind == "GCNCONV":
+        gh = lib.spmm(csr, go, _gcn_weights(csr), None, transpose=True)
+        if inj is not None:
+            lib.axpy_(gh, inj)
+        if G is not None:
+            _colsum(go, G[cv + ".bias"], accumulate)
+            lib.dense_wgrad(gh, [x], dW=G[cv + ".lin.weight"], accumulate=accumulate)
+        if keep_for_bwd2:
+            sv["b_gh"] = gh
+        return lib.dense_fwd([gh], P[cv + ".lin.weight"], transposed=True)["out"]
+    if spec.kind == "GRAPHCONV":
+        g_agg = lib.dense_fwd([go], P[cv + ".lin_rel.weight"], transposed=True)["out"]
+        gx = lib.dense_fwd([go], P[cv + ".lin_root.weight"], transposed=True)["out"]
+        lib.axpy_(gx, lib.spmm(csr, g_agg, None, None, transpose=True, self_loops=False))
+        if G is not None:
+            _wgrad_with_bias(go, [sv["agg"]], G[cv + ".lin_rel.weight"], G[cv + ".lin_rel.bias"], accumulate)
+            lib.dense_wgrad(go, [x], dW=G[cv + ".lin_root.weight"], accumulate=accumulate)
+        return gx
+    if spec.kind == "GATV2CONV":
+        att = P[cv + ".att"].view(-1)
+        gxl, gxr, garow = lib.gatv2_bwd(csr, go, sv["xl"], sv["xr"], att, sv["logit"], sv["m"], sv["z"])
+        if inj is not None:
+            lib.axpy_(gxl, inj[0])
+            lib.axpy_(gxr, inj[1])
+        if G is not None:
+            _colsum(go, G[cv + ".bias"], accumulate)
+            _colsum(garow, G[cv + ".att"], accumulate)
+            _wgrad_with_bias(gxl, [x], G[cv + ".lin_l.weight"], G[cv + ".lin_l.bias"], accumulate)
+            _wgrad_with_bias(gxr, [x], G[cv + ".lin_r.weight"], G[cv + ".lin_r.bias"], accumulate)
+        if keep_for_bwd2:
+            sv["b_gxl"], sv["b_gxr"] = gxl, gxr
+        gx = lib.dense_fwd([gxl], P[cv + ".lin_l.weight"], transposed=True)["out"]
+        return lib.axpy_(gx, lib.dense_fwd([gxr], P[cv + ".lin_r.weight"], transposed=True)["out"])
+    raise ValueError(f"Invalid conv_type: {spec.kind}")
+
+
+def _agg_backward2(P, G2, spec: ConvSpec, csr, sv, Xt: Tensor):
+    cv = spec.conv
+    if spec.kind == "GATCONV":
+        a_s, a_d = P[cv + ".att_src"].view(-1), P[cv + ".att_dst"].view(-1)
+        lin = lib.dense_fwd([Xt], P[cv + ".lin.weight"], att=(a_s, a_d))                       # Ht = Xt W^T, St, Dt
+        lib.dense_wgrad(sv["b_gh"], [Xt], dW=G2[cv + ".lin.weight"], accumulate=True)
+        lib.dense_wgrad(sv["b_gsd"], [lin["out"]], dW=G2["__att__" + cv], accumulate=True)
+        gt, ht, sdt = lib.gat_bwd2(csr, lin["out"], lin["s"], lin["d"], sv["b_go"], sv["h"], sv["s"], sv["d"], sv["m"], sv["z"],
+                                   a_s, a_d)
+        lib.dense_wgrad(sdt, [sv["h"]], dW=G2["__att__" + cv], accumulate=True)
+        return gt, ht
+    if spec.kind == "GCNCONV":  # gx = gh W, gh = A^T go: linear in go, no dependence on the activations
+        Ht = lib.dense_fwd([Xt], P[cv + ".lin.weight"])["out"]
+        lib.dense_wgrad(sv["b_gh"], [Xt], dW=G2[cv + ".lin.weight"], accumulate=True)
+        return lib.spmm(csr, Ht, _gcn_weights(csr), None), None
+    if spec.kind == "GRAPHCONV":  # gx = go W_root + S^T (go W_rel)
+        SXt = lib.spmm(csr, Xt, None, None, self_loops=False)
+        gt = lib.dense_fwd([Xt], P[cv + ".lin_root.weight"])["out"]
+        lib.axpy_(gt, lib.dense_fwd([SXt], P[cv + ".lin_rel.weight"])["out"])
+        lib.dense_wgrad(sv["b_go"], [Xt], dW=G2[cv + ".lin_root.weight"], accumulate=True)
+        lib.dense_wgrad(sv["b_go"], [SXt], dW=G2[cv + ".lin_rel.weight"], accumulate=True)
+        return gt, None
+    if spec.kind == "GATV2CONV":
+        att = P[cv + ".att"].view(-1)
+        Hl = lib.dense_fwd([Xt], P[cv + ".lin_l.weight"])["out"]
+        Hr = lib.dense_fwd([Xt], P[cv + ".lin_r.weight"])["out"]
+        lib.dense_wgrad(sv["b_gxl"], [Xt], dW=G2[cv + ".lin_l.weight"], accumulate=True)
+        lib.dense_wgrad(sv["b_gxr"], [Xt], dW=G2[cv + ".lin_r.weight"], accumulate=True)
+        gt, cxl, cxr, carow = lib.gatv2_bwd2(csr, Hl, Hr, sv["b_go"], sv["xl"], sv["xr"], att, sv["logit"], sv["m"], sv["z"])
+        _colsum(carow, G2[cv + ".att"], True)
+        return gt, (cxl, cxr)
+    raise ValueError(f"Invalid conv_type: {spec.kind}")
+
+
 def conv_forward(P, spec: ConvSpec, csr, x: Tensor, keep, save: bool):
     """keep: None (eval), an explicit uint8 mask, or ("philox", seed, offset) for in-kernel masks."""
-    a_s, a_d = P[spec.conv + ".att_src"].view(-1), P[spec.conv + ".att_dst"].view(-1)
-    lin = lib.dense_fwd([x], P[spec.conv + ".lin.weight"], att=(a_s, a_d))
-    o, m, z = lib.gat_fwd(csr, lin["out"], lin["s"], lin["d"], P[spec.conv + ".bias"])
+    o, agg = _agg_forward(P, spec, csr, x)
     gnp = (P[spec.norm + ".weight"], P[spec.norm + ".bias"], P[spec.norm + ".mean_scale"])
     if keep is None:
         x1, stats = lib.graphnorm_fwd(o, *gnp, None, 1.0)
@@ -123,15 +254,13 @@ def conv_forward(P, spec: ConvSpec, csr, x: Tensor, keep, save: bool):
         x1, stats = lib.graphnorm_fwd(o, *gnp, keep, KEEP_P)
     sv = None
     if save:
-        sv = dict(x=x, h=lin["out"], s=lin["s"], d=lin["d"], o=o, m=m, z=z, x1=x1, stats=stats,
-                  scale=KEEP_SCALE if keep is not None else 1.0)
+        sv = dict(x=x, o=o, x1=x1, stats=stats, scale=KEEP_SCALE if keep is not None else 1.0, **agg)
     return x1, sv
 
 
 def conv_backward(P, G, spec: ConvSpec, csr, sv, gx1: Optional[Tensor], accumulate: bool, inject=None, keep_for_bwd2=False):
-    """First-order backward of one [GATConv, GraphNorm, ReLU, Dropout] block.  ``inject`` = (ot, ht)
-    cotangents added at o and h (second-order sweep).  Returns gx (gradient at the block input)."""
-    a_s, a_d = P[spec.conv + ".att_src"].view(-1), P[spec.conv + ".att_dst"].view(-1)
+    """First-order backward of one [conv, GraphNorm, ReLU, Dropout] block.  ``inject`` = (ot, it) cotangents added at o
+    and at the conv's intermediate (second-order sweep).  Returns gx (gradient at the block input)."""
     nrm = spec.norm
     if gx1 is not None:
         dpar = None if G is None else G["__gn__" + nrm]
@@ -141,35 +270,20 @@ def conv_backward(P, G, spec: ConvSpec, csr, sv, gx1: Optional[Tensor], accumula
             lib.axpy_(go, inject[0])
     else:
         go, bstats = inject[0], None
-    gh, gsd, Pe, DU = lib.gat_bwd(csr, go, sv["h"], sv["s"], sv["d"], sv["m"], sv["z"], a_s, a_d)
-    if G is not None:
-        lib.dense_wgrad(go, [None], dW=G[spec.conv + ".bias"].view(-1, 1), accumulate=accumulate)
-        lib.dense_wgrad(gsd, [sv["h"]], dW=G["__att__" + spec.conv], accumulate=accumulate)
-    if inject is not None:
-        lib.axpy_(gh, inject[1])
-    if G is not None:
-        lib.dense_wgrad(gh, [sv["x"]], dW=G[spec.conv + ".lin.weight"], accumulate=accumulate)
-    gx = lib.dense_fwd([gh], P[spec.conv + ".lin.weight"], transposed=True)["out"]
+    gx = _agg_backward(P, G, spec, csr, sv, go, accumulate, None if inject is None else inject[1], keep_for_bwd2)
     if keep_for_bwd2:
-        sv["b_gx1"], sv["b_go"], sv["b_gh"], sv["b_gsd"], sv["b_bstats"] = gx1, go, gh, gsd, bstats
+        sv["b_gx1"], sv["b_go"], sv["b_bstats"] = gx1, go, bstats
     return gx
 
 
 def conv_backward2(P, G2, spec: ConvSpec, csr, sv, Xt: Tensor):
-    """Second-order step through (lin-bwd, gat-bwd, gn-bwd) of one block, in that order.  Xt = cotangent
-    on the block's input gradient gx.  Returns (cotangent on gx1, (ot, ht) to inject at o / h)."""
-    a_s, a_d = P[spec.conv + ".att_src"].view(-1), P[spec.conv + ".att_dst"].view(-1)
-    W = P[spec.conv + ".lin.weight"]
-    lin = lib.dense_fwd([Xt], W, att=(a_s, a_d))                       # Ht = Xt W^T, St, Dt
-    lib.dense_wgrad(sv["b_gh"], [Xt], dW=G2[spec.conv + ".lin.weight"], accumulate=True)
-    lib.dense_wgrad(sv["b_gsd"], [lin["out"]], dW=G2["__att__" + spec.conv], accumulate=True)
-    gt, ht, sdt = lib.gat_bwd2(csr, lin["out"], lin["s"], lin["d"], sv["b_go"], sv["h"], sv["s"], sv["d"], sv["m"], sv["z"],
-                               a_s, a_d)
-    lib.dense_wgrad(sdt, [sv["h"]], dW=G2["__att__" + spec.conv], accumulate=True)
+    """Second-order step through (conv-bwd, gn-bwd) of one block, in that order.  Xt = cotangent on the block's input
+    gradient gx.  Returns (cotangent on gx1, (ot, it) to inject at o / the conv's intermediate)."""
+    gt, it = _agg_backward2(P, G2, spec, csr, sv, Xt)
     nrm = spec.norm
     gx1t, ot, _ = lib.graphnorm_bwd2(gt, sv["b_gx1"], sv["o"], sv["x1"], P[nrm + ".weight"], P[nrm + ".mean_scale"],
                                      sv["stats"], sv["b_bstats"], sv["scale"], G2["__gn__" + nrm], True)
-    return gx1t, (ot, ht)
+    return gx1t, (ot, it)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,9 +297,10 @@ def grad_views(layout: ParamLayout, flat: Tensor, convs: Sequence[ConvSpec]) -> 
         o = layout.offsets[c.norm + ".weight"]
         assert layout.offsets[c.norm + ".bias"] == o + n and layout.offsets[c.norm + ".mean_scale"] == o + 2 * n
         G["__gn__" + c.norm] = flat[o: o + 3 * n].view(3, n)
-        o = layout.offsets[c.conv + ".att_src"]
-        assert layout.offsets[c.conv + ".att_dst"] == o + n
-        G["__att__" + c.conv] = flat[o: o + 2 * n].view(2, n)
+        if c.kind == "GATCONV":
+            o = layout.offsets[c.conv + ".att_src"]
+            assert layout.offsets[c.conv + ".att_dst"] == o + n
+            G["__att__" + c.conv] = flat[o: o + 2 * n].view(2, n)
     return G
 
 
@@ -193,5 +308,6 @@ def conv_groups(convs: Sequence[ConvSpec]) -> List[List[str]]:
     out = []
     for c in convs:
         out.append([c.norm + ".weight", c.norm + ".bias", c.norm + ".mean_scale"])
-        out.append([c.conv + ".att_src", c.conv + ".att_dst"])
+        if c.kind == "GATCONV":
+            out.append([c.conv + ".att_src", c.conv + ".att_dst"])
     return out

@@ -78,8 +78,10 @@ class VoxelCSR:
 
     FIELDS = ("rowptr", "col", "cscptr", "cscrow", "perm", "graph_ptr")
 
-    def __init__(self, num_nodes: int, num_edges: int, num_graphs: int, max_deg: int, **arrays: Tensor):
+    def __init__(self, num_nodes: int, num_edges: int, num_graphs: int, max_deg: int, num_input_self_loops: int = 0,
+                 **arrays: Tensor):
         self.num_nodes, self.num_edges, self.num_graphs, self.max_deg = num_nodes, num_edges, num_graphs, max_deg
+        self.num_input_self_loops = num_input_self_loops  # stripped by the build (GraphConv, which adds none, refuses them)
         for f in self.FIELDS:
             setattr(self, f, arrays[f])
         self._c = None
@@ -92,19 +94,19 @@ class VoxelCSR:
             graph_ptr = torch.tensor([0, num_nodes])
         gp = graph_ptr.detach().to("cpu", torch.int32).contiguous()
         arrays, e_out, max_deg = lib.csr_build_host(ei, num_nodes)
-        return cls(num_nodes, e_out, gp.numel() - 1, max_deg, graph_ptr=gp, **arrays)
+        return cls(num_nodes, e_out, gp.numel() - 1, max_deg, int(ei.shape[1]) + num_nodes - e_out, graph_ptr=gp, **arrays)
 
     @property
     def device(self) -> torch.device:
         return self.rowptr.device
 
     def to(self, device, non_blocking: bool = False) -> "VoxelCSR":
-        out = VoxelCSR(self.num_nodes, self.num_edges, self.num_graphs, self.max_deg,
+        out = VoxelCSR(self.num_nodes, self.num_edges, self.num_graphs, self.max_deg, self.num_input_self_loops,
                        **{f: getattr(self, f).to(device, non_blocking=non_blocking) for f in self.FIELDS})
         return out
 
     def pin_memory(self) -> "VoxelCSR":
-        return VoxelCSR(self.num_nodes, self.num_edges, self.num_graphs, self.max_deg,
+        return VoxelCSR(self.num_nodes, self.num_edges, self.num_graphs, self.max_deg, self.num_input_self_loops,
                         **{f: getattr(self, f).pin_memory() for f in self.FIELDS})
 
     def c_struct(self):
@@ -194,7 +196,8 @@ class Batch(Data):
                         for d in shape:
                             n *= d
                         arrays[key[7:]] = dbuf[off: off + n * dtype.itemsize].view(dtype).view(shape)
-                self._fields["bg_csr"] = VoxelCSR(old.num_nodes, old.num_edges, old.num_graphs, old.max_deg, **arrays)
+                self._fields["bg_csr"] = VoxelCSR(old.num_nodes, old.num_edges, old.num_graphs, old.max_deg,
+                                                  old.num_input_self_loops, **arrays)
             object.__setattr__(self, "_pack", None)
             self._fields.pop("_bg_cache", None)
             return self

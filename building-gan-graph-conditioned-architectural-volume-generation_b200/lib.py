@@ -81,6 +81,11 @@ SIGNATURES = {
     "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),
+    "bg_gcn_norm": (C.c_int, [C.POINTER(BgGraph), _P, _P]),
+    "bg_spmm": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _I32, _I32, _I32, _P]),
+    "bg_gatv2_fwd": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 8 + [_I32, _F, _P]),
+    "bg_gatv2_bwd": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 12 + [_I32, _F, _P]),
+    "bg_gatv2_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 14 + [_I32, _F, _P]),
     "bg_graphnorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _U64, _U64, _I64, _I32, _F, _P, _P, _P, _SZ, _P]),
     "bg_graphnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _I64, _I32, _P, _P, _I32, _P, _P, _SZ, _P]),
     "bg_graphnorm_bwd2": (C.c_int, [_P] * 8 + [_F, _I64, _I32, _P, _P, _P, _I32, _P, _SZ, _P]),
@@ -467,6 +472,74 @@ def gat_bwd2(csr, Ht: Tensor, St: Tensor, Dt: Tensor, gout: Tensor, h: Tensor, s
                            s.data_ptr(), d.data_ptr(), m.data_ptr(), z.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
                            scratch.data_ptr(), gt.data_ptr(), ht.data_ptr(), sdt.data_ptr(), c, slope, _stream()))
     return gt, ht, sdt
+
+
+# ------------------------------------------------------------------------------------------------
+# non-default conv types (GCNConv / GraphConv / GATv2Conv aggregation)
+# ------------------------------------------------------------------------------------------------
+@_op("gcn_norm", 1)
+def gcn_norm(csr) -> Tensor:
+    """Per-edge symmetric normalisation weights of GCNConv in CSR order."""
+    lib = load()
+    w = torch.empty(csr.num_edges, dtype=torch.float32, device=csr.device)
+    _check(lib.bg_gcn_norm(C.byref(csr.c_struct()), w.data_ptr(), _stream()))
+    return w
+
+
+@_op("spmm", 1)
+def spmm(csr, x: Tensor, w: Optional[Tensor] = None, bias: Optional[Tensor] = None, transpose: bool = False,
+         self_loops: bool = True) -> Tensor:
+    """Weighted neighbour sum over the in-edges (transpose=False) or out-edges (True) of every node."""
+    lib = load()
+    _cf32(x, "x")
+    out = torch.empty_like(x)
+    _check(lib.bg_spmm(C.byref(csr.c_struct()), _p(w), x.data_ptr(), _p(bias), out.data_ptr(), x.shape[1], int(transpose),
+                       int(self_loops), _stream()))
+    return out
+
+
+@_op("gatv2_fwd", 1)
+def gatv2_fwd(csr, xl: Tensor, xr: Tensor, att: Tensor, bias: Optional[Tensor], slope: float = 0.2):
+    lib = load()
+    _cf32(xl, "xl"), _cf32(xr, "xr")
+    n, c = xl.shape
+    out = torch.empty_like(xl)
+    logit = torch.empty(csr.num_edges, dtype=torch.float32, device=xl.device)
+    m = torch.empty(n, dtype=torch.float32, device=xl.device)
+    z = torch.empty(n, dtype=torch.float32, device=xl.device)
+    _check(lib.bg_gatv2_fwd(C.byref(csr.c_struct()), xl.data_ptr(), xr.data_ptr(), att.data_ptr(), _p(bias), out.data_ptr(),
+                            logit.data_ptr(), m.data_ptr(), z.data_ptr(), c, slope, _stream()))
+    return out, logit, m, z
+
+
+@_op("gatv2_bwd", 2)
+def gatv2_bwd(csr, gout: Tensor, xl: Tensor, xr: Tensor, att: Tensor, logit: Tensor, m: Tensor, z: Tensor, slope: float = 0.2):
+    """Returns gxl, gxr, garow (column sum = attention-vector gradient)."""
+    lib = load()
+    _cf32(gout, "gout")
+    c = xl.shape[1]
+    P = torch.empty(csr.num_edges, dtype=torch.float32, device=xl.device)
+    DL = torch.empty_like(P)
+    gxl, gxr, garow = torch.empty_like(xl), torch.empty_like(xl), torch.empty_like(xl)
+    _check(lib.bg_gatv2_bwd(C.byref(csr.c_struct()), gout.data_ptr(), xl.data_ptr(), xr.data_ptr(), att.data_ptr(),
+                            logit.data_ptr(), m.data_ptr(), z.data_ptr(), P.data_ptr(), DL.data_ptr(), gxl.data_ptr(),
+                            gxr.data_ptr(), garow.data_ptr(), c, slope, _stream()))
+    return gxl, gxr, garow
+
+
+@_op("gatv2_bwd2", 2)
+def gatv2_bwd2(csr, Hl: Tensor, Hr: Tensor, gout: Tensor, xl: Tensor, xr: Tensor, att: Tensor, logit: Tensor, m: Tensor,
+               z: Tensor, slope: float = 0.2):
+    """Cotangents (Hl, Hr) on (gxl, gxr) -> gt (on gout), cxl, cxr, carow (column sum = cotangent on att)."""
+    lib = load()
+    _cf32(Hl, "Hl"), _cf32(Hr, "Hr")
+    c = xl.shape[1]
+    scratch = torch.empty(6 * csr.num_edges, dtype=torch.float32, device=xl.device)
+    gt, cxl, cxr, carow = torch.empty_like(xl), torch.empty_like(xl), torch.empty_like(xl), torch.empty_like(xl)
+    _check(lib.bg_gatv2_bwd2(C.byref(csr.c_struct()), Hl.data_ptr(), Hr.data_ptr(), gout.data_ptr(), xl.data_ptr(), xr.data_ptr(),
+                             att.data_ptr(), logit.data_ptr(), m.data_ptr(), z.data_ptr(), scratch.data_ptr(), gt.data_ptr(),
+                             cxl.data_ptr(), cxr.data_ptr(), carow.data_ptr(), c, slope, _stream()))
+    return gt, cxl, cxr, carow
 
 
 # ------------------------------------------------------------------------------------------------

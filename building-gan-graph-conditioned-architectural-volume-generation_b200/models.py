@@ -47,8 +47,7 @@ class GATConv(nn.Module):
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
-        if out_channels not in lib.SUPPORTED_WIDTHS or in_channels > 128:
-            raise ValueError(f"GATConv({in_channels}, {out_channels}): libbgb200 supports widths {lib.SUPPORTED_WIDTHS}")
+        _check_widths("GATConv", in_channels, out_channels)
         self.in_channels, self.out_channels = in_channels, out_channels
         self.lin = _PygLinearParams(in_channels, out_channels)
         self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
@@ -57,6 +56,59 @@ class GATConv(nn.Module):
         _glorot(self.lin.weight)  # PyG's reset_parameters() re-draws lin before the attention vectors
         _glorot(self.att_src)
         _glorot(self.att_dst)
+
+
+def _check_widths(name: str, in_channels: int, out_channels: int) -> None:
+    if out_channels not in lib.SUPPORTED_WIDTHS or in_channels > 128:
+        raise ValueError(f"{name}({in_channels}, {out_channels}): libbgb200 supports widths {lib.SUPPORTED_WIDTHS}")
+
+
+class _PygLinearBias(nn.Module):
+    """torch_geometric.nn.dense.Linear(in, out, bias=True): ``weight`` [out, in], ``bias`` [out] (zeros)."""
+
+    def __init__(self, cin: int, cout: int, init: str = "glorot"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        if init == "glorot":
+            _glorot(self.weight)
+        else:
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+
+class GCNConv(nn.Module):
+    """Parameters of tgnn.GCNConv(in, out): bias[C], lin.weight[C, Cin] (glorot, no bias)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        _check_widths("GCNConv", in_channels, out_channels)
+        self.lin = _PygLinearParams(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+
+class GraphConv(nn.Module):
+    """Parameters of tgnn.GraphConv(in, out): lin_rel.{weight,bias}, lin_root.weight (kaiming-uniform Linears)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        _check_widths("GraphConv", in_channels, out_channels)
+        self.lin_rel = _PygLinearBias(in_channels, out_channels, init="kaiming")
+        self.lin_root = _PygLinearParams(in_channels, out_channels)
+        nn.init.kaiming_uniform_(self.lin_root.weight, a=math.sqrt(5))
+
+
+class GATv2Conv(nn.Module):
+    """Parameters of tgnn.GATv2Conv(in, out) (heads=1, share_weights=False): att[1,1,C], bias[C],
+    lin_l.{weight,bias}, lin_r.{weight,bias}."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        _check_widths("GATv2Conv", in_channels, out_channels)
+        self.lin_l = _PygLinearBias(in_channels, out_channels)
+        self.lin_r = _PygLinearBias(in_channels, out_channels)
+        self.att = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        _glorot(self.att)
 
 
 class GraphNorm(nn.Module):
@@ -68,19 +120,23 @@ class GraphNorm(nn.Module):
         self.mean_scale = nn.Parameter(torch.ones(channels))
 
 
+_CONVS = {"GCNCONV": GCNConv, "GRAPHCONV": GraphConv, "GATCONV": GATConv, "GATV2CONV": GATv2Conv}
+
+
 class _GnnStack(nn.Module):
     """Registers children as ``module_{i}`` exactly like tgnn.Sequential (models.py:90,210)."""
 
-    def __init__(self, widths: List[int]):
+    def __init__(self, widths: List[int], kind: str = "GATCONV"):
         super().__init__()
         self.specs: List[ConvSpec] = []
+        conv = _CONVS[kind]
         i = 0
         for a, b in zip(widths[:-1], widths[1:]):
-            setattr(self, f"module_{i}", GATConv(a, b))
+            setattr(self, f"module_{i}", conv(a, b))
             setattr(self, f"module_{i + 1}", GraphNorm(b))
             setattr(self, f"module_{i + 2}", nn.ReLU(True))
             setattr(self, f"module_{i + 3}", nn.Dropout(0.2))
-            self.specs.append(ConvSpec(f"module_{i}", f"module_{i + 1}", a, b))
+            self.specs.append(ConvSpec(f"module_{i}", f"module_{i + 1}", a, b, kind))
             i += 4
 
 
@@ -98,17 +154,20 @@ def _hourglass(hidden: int, repeat: int) -> List[int]:
     return down + down[-2::-1]
 
 
-def _require_gat(kind: str) -> None:
-    if kind not in ("GCNCONV", "GRAPHCONV", "GATCONV", "GATV2CONV"):
+def _executor_for(kind: str) -> str:
+    return EXECUTOR if kind == "GATCONV" else "python"
+
+
+def _conv_kind(kind: str) -> str:
+    if kind not in _CONVS:
         raise ValueError(f"Invalid conv_type: {kind}")  # models.py:31,175
-    if kind != "GATCONV":
-        raise NotImplementedError(
-            f"conv_type {kind}: only GATCONV (the reference default, config.py:89,93) has sm_100a kernels so far; "
-            "there is no torch fallback")
+    return kind
 
 
 # "native" (default): one C call per pass (csrc/bg_passes.cu).  "python": the same passes composed op by op in
-# executor.py (kept as the readable specification of the pass structure and for debugging).
+# executor.py (kept as the readable specification of the pass structure and for debugging).  The native pass executor
+# covers the reference's default conv type (GATCONV, config.py:89,93); models built with GCNCONV / GRAPHCONV / GATV2CONV
+# run the op-by-op executor on the same kernel library (per-model ``_executor``).
 EXECUTOR = os.environ.get("BG_EXECUTOR", "native")
 # "philox" (default): dropout masks / Gumbel noise generated inside the kernels (Philox4x32-10, seeded from
 # torch.cuda.initial_seed()).  "torch": drawn with torch's device generator in the reference's draw order
@@ -247,12 +306,13 @@ class VoxelGNNGenerator(nn.Module):
         c = configuration
         self.configuration = c
         self.local_graph_dim, self.voxel_graph_dim = local_graph_dim, voxel_graph_dim
-        _require_gat(c.GENERATOR_CONV_TYPE)
+        kind = _conv_kind(c.GENERATOR_CONV_TYPE)
+        self._kind = kind
         le, gh = c.LOCAL_ENCODER_HIDDEN_DIM, c.GENERATOR_HIDDEN_DIM
         self.matched_features_encoder = _ln_mlp([local_graph_dim] + [le] * (c.LOCAL_GRAPH_ENCODER_REPEAT + 1))
         self.mlp_encoder = _ln_mlp([le + voxel_graph_dim + c.Z_DIM] + [gh] * (c.GENERATOR_MLP_ENCODER_REPEAT + 1))
         widths = _hourglass(gh, c.GENERATOR_ENCODER_REPEAT)
-        self.encoder = _GnnStack(widths)
+        self.encoder = _GnnStack(widths, kind)
         self.decoder = _ln_mlp([le + voxel_graph_dim + c.Z_DIM + widths[-1] + gh, gh, gh // 2, gh // 4, gh // 8],
                                final_plain=c.NUM_CLASSES)
         self._le, self._gh, self._enc_out = le, gh, widths[-1]
@@ -260,13 +320,13 @@ class VoxelGNNGenerator(nn.Module):
                       for i in range(c.LOCAL_GRAPH_ENCODER_REPEAT + 1)]
         self._mlp = [DenseSpec(f"mlp_encoder.{3 * i}", f"mlp_encoder.{3 * i + 1}", ACT_LRELU)
                      for i in range(c.GENERATOR_MLP_ENCODER_REPEAT + 1)]
-        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout) for s in self.encoder.specs]
+        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout, s.kind) for s in self.encoder.specs]
         self._dec = [DenseSpec(f"decoder.{3 * i}", f"decoder.{3 * i + 1}", ACT_LRELU) for i in range(4)]
         self._dec.append(DenseSpec("decoder.12", None, ACT_NONE))
         self._names = [n for n, _ in self.named_parameters()]
         self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
         self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
-        assert lib.load().bg_gen_num_params(C.byref(self._native.md)) == len(self._names)
+        assert kind != "GATCONV" or lib.load().bg_gen_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
     def forward(self, local_graph, voxel_graph, z, gumbel_noise: Optional[Tensor] = None, keeps=None):
@@ -277,6 +337,7 @@ class VoxelGNNGenerator(nn.Module):
         bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
         zz = z.squeeze(0).to(bc.vx.device, torch.float32).contiguous()
         seed, offset = _philox_ticket()
+        EXECUTOR = _executor_for(self._kind)
         if keeps is None and self.training and (RNG_MODE == "torch" or EXECUTOR == "python"):
             keeps = _draw_keeps(bc.n, self._convs, True, bc.vx.device)
         if gumbel_noise is None and (RNG_MODE == "torch" or EXECUTOR == "python"):
@@ -473,11 +534,12 @@ class VoxelGNNDiscriminator(nn.Module):
         c = configuration
         self.configuration = c
         self.local_graph_dim, self.voxel_graph_dim = local_graph_dim, voxel_graph_dim
-        _require_gat(c.DISCRIMINATOR_CONV_TYPE)
+        kind = _conv_kind(c.DISCRIMINATOR_CONV_TYPE)
+        self._kind = kind
         dh = c.DISCRIMINATOR_HIDDEN_DIM
         self.mlp_encoder = nn.Sequential(nn.Linear(local_graph_dim + voxel_graph_dim + c.NUM_CLASSES, dh), nn.ReLU(True),
                                          nn.Linear(dh, dh), nn.ReLU(True))
-        self.encoder = _GnnStack(_hourglass(dh, c.DISCRIMINATOR_ENCODER_REPEAT))
+        self.encoder = _GnnStack(_hourglass(dh, c.DISCRIMINATOR_ENCODER_REPEAT), kind)
         tail: List[nn.Module] = [nn.Linear(dh, dh // 2), nn.ReLU(True), nn.Linear(dh // 2, dh // 4), nn.ReLU(True),
                                  nn.Linear(dh // 4, dh // 8), nn.ReLU(True), nn.Linear(dh // 8, 1)]
         if not c.USE_WGANGP:
@@ -485,14 +547,14 @@ class VoxelGNNDiscriminator(nn.Module):
                                       "the reference default is WGAN-GP (config.py:106)")
         self.decoder = nn.Sequential(*tail)
         self._pre = [DenseSpec("mlp_encoder.0", None, ACT_RELU), DenseSpec("mlp_encoder.2", None, ACT_RELU)]
-        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout) for s in self.encoder.specs]
+        self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout, s.kind) for s in self.encoder.specs]
         self._dec = [DenseSpec("decoder.0", None, ACT_RELU), DenseSpec("decoder.2", None, ACT_RELU),
                      DenseSpec("decoder.4", None, ACT_RELU), DenseSpec("decoder.6", None, ACT_NONE)]
         self._names = [n for n, _ in self.named_parameters()]
         self._layout = ex.ParamLayout(list(self.named_parameters()), ex.conv_groups(self._convs))
         self._label_lo = local_graph_dim + voxel_graph_dim
         self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
-        assert lib.load().bg_disc_num_params(C.byref(self._native.md)) == len(self._names)
+        assert kind != "GATCONV" or lib.load().bg_disc_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
     def forward(self, local_graph, voxel_graph, label_hard, keeps=None):
@@ -506,6 +568,7 @@ class VoxelGNNDiscriminator(nn.Module):
             label = bc.real_onehot[1]
         label = label.to(bc.vx.device).contiguous()
         seed, offset = _philox_ticket()
+        EXECUTOR = _executor_for(self._kind)
         if keeps is None and self.training and (RNG_MODE == "torch" or EXECUTOR == "python"):
             keeps = _draw_keeps(bc.n, self._convs, True, bc.vx.device)
         params = list(self.parameters())

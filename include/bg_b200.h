@@ -152,6 +152,31 @@ int bg_ln_act_bwd(const float* gout, const float* out, const float* xhat, const 
                   float* dgamma, float* dbeta, int32_t accumulate, float* workspace, size_t ws_bytes, void* stream);
 size_t bg_ln_act_bwd_ws(int64_t N, int32_t C);
 
+/* ---- H14: the non-default conv types of GENERATOR_CONV_TYPE / DISCRIMINATOR_CONV_TYPE (reference models.py:22-31,
+ * 166-175; config.py:89,93).  GCNConv: h = x W^T (bg_dense_fwd), out = bg_spmm(w = bg_gcn_norm, h) + bias.
+ * GraphConv: out = lin_rel(bg_spmm(no weights, no self loops, x)) + lin_root(x).  Both aggregations are linear, so
+ * the backward is the transposed product (transpose = 1) and the second-order backward the forward product again. */
+/* w[E'] (CSR order) = deg(dst)^-1/2 deg(src)^-1/2, deg = in-degree incl. the self loop (PyG gcn_norm, fill 1). */
+int bg_gcn_norm(const BgGraph* g, float* w, void* stream);
+/* out[r,:] = sum over row r of w[edge] * x[other end,:] (+ bias).  transpose 0: rows = destinations (CSR);
+ * 1: rows = sources (CSC, weights looked up through perm).  w NULL = ones.  self_loops 0 skips the self loop. */
+int bg_spmm(const BgGraph* g, const float* w, const float* x, const float* bias, float* out, int32_t C,
+            int32_t transpose, int32_t self_loops, void* stream);
+/* GATv2Conv (heads=1, share_weights=False): xl = lin_l(x), xr = lin_r(x) come from bg_dense_fwd;
+ * out_i = sum_e softmax_i(att . LeakyReLU(xl_j + xr_i)) xl_j + bias.  Saves logit[E'] (CSR order), m[N], z[N]. */
+int bg_gatv2_fwd(const BgGraph* g, const float* xl, const float* xr, const float* att, const float* bias, float* out,
+                 float* logit, float* m, float* z, int32_t C, float slope, void* stream);
+/* First-order backward: gxl[N,C], gxr[N,C], garow[N,C] (column sum = d loss / d att), scratch P[E'], DL[E']. */
+int bg_gatv2_bwd(const BgGraph* g, const float* gout, const float* xl, const float* xr, const float* att,
+                 const float* logit, const float* m, const float* z, float* P, float* DL, float* gxl, float* gxr,
+                 float* garow, int32_t C, float slope, void* stream);
+/* Second-order backward (WGAN-GP): cotangents Hl, Hr on (gxl, gxr) -> gt (on gout), cxl, cxr (on xl, xr),
+ * carow[N,C] (column sum = cotangent on att).  scratch: 6*E' floats. */
+int bg_gatv2_bwd2(const BgGraph* g, const float* Hl, const float* Hr, const float* gout, const float* xl,
+                  const float* xr, const float* att, const float* logit, const float* m, const float* z,
+                  float* scratch, float* gt, float* cxl, float* cxr, float* carow, int32_t C, float slope,
+                  void* stream);
+
 /* ---- H5a/H9: GATConv attention aggregation (PyG 2.6.1 GATConv.edge_update + message +
  * aggregate; reference call sites models.py:72,82,192,202).  h = x W^T, s = h.a_src,
  * d = h.a_dst come from bg_dense_fwd.  out_i = sum_e softmax_i(LeakyReLU(s_j+d_i)) h_j + bias.

@@ -1,0 +1,209 @@
+"""the non-default conv types of GENERATOR_CONV_TYPE / DISCRIMINATOR_CONV_TYPE
+(reference models.py:22-31,166-175) - GCNConv, GraphConv, GATv2Conv.
+
+Kernel level: bg_gcn_norm / bg_spmm / bg_gatv2_{fwd,bwd,bwd2} against the oracle (oracle/pyg.py evaluated in fp64 with
+torch autograd, including the second-order products the WGAN-GP penalty needs).  Model level: the drop-in generator /
+discriminator built with each conv type against the oracle models with identical weights: forward, first-order
+gradients, and the gradient penalty's second-order parameter gradients.  Tolerances as in test_kernels_gpu.py /
+test_models_gpu.py (rel 1e-5 of max magnitude per kernel; 1e-4 / 1e-3 for parameter gradients through the stacks)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pyg
+from test_kernels_gpu import _graph, _hub_graph, _rand
+from test_models_gpu import (D_WIDTHS, G_WIDTHS, _act_close, _fp32_twin, _grads_close, _inject_masks, _keeps, _setup,
+                             _sync_patterns)
+from util import assert_close
+
+from building_gan_b200 import Configuration, lib
+from building_gan_b200.models import VoxelGNNDiscriminator, VoxelGNNGenerator
+
+pytestmark = pytest.mark.gpu
+WIDTHS = [1, 2, 4, 8, 16, 32, 64, 128]
+DEV = "cuda"
+KINDS = ["GCNCONV", "GRAPHCONV", "GATV2CONV"]
+f = lambda t: t.detach().float().to(DEV).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hub", [False, True])
+def test_gcn_norm(hub):
+    if hub:
+        n, edges, csr = _hub_graph()
+    else:
+        vb, edges, csr = _graph()
+        n = vb.num_nodes
+    deg = pyg.scatter(torch.ones(edges.size(1), dtype=torch.float64), edges[1], n)
+    ref = deg.pow(-0.5)[edges[0]] * deg.pow(-0.5)[edges[1]]
+    # CSR order = destination-sorted, per-row COO order: a stable sort of the oracle's edge list by destination
+    order = torch.sort(edges[1], stable=True).indices
+    assert_close(lib.gcn_norm(csr), ref[order], 1e-6, "gcn_norm")
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("weighted,self_loops", [(True, True), (False, False), (False, True)])
+def test_spmm_forward_and_transpose(C, weighted, self_loops):
+    n, edges, csr = _hub_graph()
+    x = _rand(n, C, seed=1)
+    order = torch.sort(edges[1], stable=True).indices
+    w_coo = _rand(edges.size(1), seed=2).abs() + 0.1 if weighted else torch.ones(edges.size(1), dtype=torch.float64)
+    if not self_loops:
+        w_coo = w_coo * (edges[0] != edges[1])
+    A = torch.zeros(n, n, dtype=torch.float64).index_put_((edges[1], edges[0]), w_coo, accumulate=True)  # [dst, src]
+    w = f(w_coo[order]) if weighted else None
+    b = _rand(C, seed=3)
+    assert_close(lib.spmm(csr, f(x), w, f(b), self_loops=self_loops), A @ x + b, 1e-5, f"spmm C={C}")
+    assert_close(lib.spmm(csr, f(x), w, None, transpose=True, self_loops=self_loops), A.t() @ x, 1e-5, f"spmm^T C={C}")
+
+
+def _gatv2_core(xl, xr, att, edges, n):
+    src, dst = edges[0], edges[1]
+    logit = (F.leaky_relu(xl[src] + xr[dst], 0.2) * att).sum(-1)
+    p = pyg.segment_softmax(logit, dst, n)
+    return pyg.scatter(p.unsqueeze(-1) * xl[src], dst, n)
+
+
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("hub", [False, True])
+def test_gatv2_fwd_bwd_bwd2(C, hub):
+    if hub:
+        n, edges, csr = _hub_graph()
+    else:
+        vb, edges, csr = _graph()
+        n = vb.num_nodes
+    xl, xr, att, gout = (_rand(n, C, seed=1).requires_grad_(), _rand(n, C, seed=2).requires_grad_(),
+                         _rand(C, seed=3).requires_grad_(), _rand(n, C, seed=4).requires_grad_())
+    b = _rand(C, seed=5)
+    out = _gatv2_core(xl, xr, att, edges, n)
+    o, logit, m, z = lib.gatv2_fwd(csr, f(xl), f(xr), f(att), f(b))
+    assert_close(o, out.detach() + b, 1e-5, f"gatv2_fwd C={C}")
+    gxl, gxr, gatt = torch.autograd.grad(out, (xl, xr, att), gout, create_graph=True)
+    k_gxl, k_gxr, k_garow = lib.gatv2_bwd(csr, f(gout), f(xl), f(xr), f(att), logit, m, z)
+    assert_close(k_gxl, gxl, 1e-5, "gatv2_bwd gxl")
+    assert_close(k_gxr, gxr, 1e-5, "gatv2_bwd gxr")
+    assert_close(k_garow.double().sum(0).cpu(), gatt, 3e-5, "gatv2_bwd gatt")
+    # second order: VJP of (gxl, gxr) with cotangents (Hl, Hr) w.r.t. (gout, xl, xr, att)
+    Hl, Hr = _rand(n, C, seed=6), _rand(n, C, seed=7)
+    gt, cxl, cxr, catt = torch.autograd.grad((gxl, gxr), (gout, xl, xr, att), (Hl, Hr))
+    k_gt, k_cxl, k_cxr, k_carow = lib.gatv2_bwd2(csr, f(Hl), f(Hr), f(gout), f(xl), f(xr), f(att), logit, m, z)
+    assert_close(k_gt, gt, 1e-5, "gatv2_bwd2 gt")
+    assert_close(k_cxl, cxl, 1e-5, "gatv2_bwd2 cxl")
+    assert_close(k_cxr, cxr, 1e-5, "gatv2_bwd2 cxr")
+    assert_close(k_carow.double().sum(0).cpu(), catt, 3e-5, "gatv2_bwd2 catt")
+
+
+# ------------------------------------------------------------------------------------------------
+# models
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+def test_state_dict_keys_match_oracle(kind):
+    from oracle import models as omodels
+    cfg = Configuration()
+    cfg.GENERATOR_CONV_TYPE = cfg.DISCRIMINATOR_CONV_TYPE = kind
+    for ours, theirs in ((VoxelGNNGenerator(cfg, 17, 12), omodels.OracleGenerator(cfg, 17, 12)),
+                         (VoxelGNNDiscriminator(cfg, 17, 12), omodels.OracleDiscriminator(cfg, 17, 12))):
+        a, b = ours.state_dict(), theirs.state_dict()
+        assert sorted(a) == sorted(b)
+        assert all(tuple(a[k].shape) == tuple(b[k].shape) for k in a)
+
+
+def test_invalid_conv_type_raises_like_the_reference():
+    cfg = Configuration()
+    cfg.GENERATOR_CONV_TYPE = "SAGECONV"
+    with pytest.raises(ValueError, match="Invalid conv_type"):
+        VoxelGNNGenerator(cfg, 17, 12)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("train", [False, True])
+def test_generator_with_conv_type(kind, train):
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup(conv=kind)
+    n = vb.num_nodes
+    z = torch.randn(1, n, cfg.Z_DIM, generator=torch.Generator().manual_seed(5))
+    noise = -torch.empty(n, 7).exponential_(generator=torch.Generator().manual_seed(6)).log()
+    keeps = _keeps(n, G_WIDTHS, 7) if train else [None] * 14
+    G.train(train), oG.train(train)
+    _inject_masks(oG, keeps)
+    ologits, ohard, osoft = oG(olb, ovb, z.double(), noise.double())
+    oG32, lb32, vb32 = _fp32_twin(oG, olb, ovb)
+    l32, _, s32 = oG32(lb32, vb32, z, noise)
+    kk = [None if k is None else k.to(torch.uint8).to(DEV) for k in keeps]
+    G.debug_keep_saved = True
+    logits, hard, soft = G(lb, vb, z.to(DEV), noise.to(DEV), keeps=kk)
+    _act_close(logits, ologits, l32.detach(), 1e-4, f"{kind} logits")
+    _act_close(soft, osoft, s32.detach(), 1e-4, f"{kind} label_soft")
+    w1, w2, w3 = (torch.randn(n, 7, generator=torch.Generator().manual_seed(s), dtype=torch.float64) for s in (8, 9, 10))
+    _sync_patterns(oG, G.debug_saved, ovb.type)
+    plogits, phard, psoft = oG(olb, ovb, z.double(), noise.double())
+    ((plogits * w1).sum() + (phard * w2).sum() + (psoft * w3).sum()).backward()
+    oG32b, lb32b, vb32b = _fp32_twin(oG, olb, ovb)
+    ql, qh, qs = oG32b(lb32b, vb32b, z, noise)
+    ((ql * w1.float()).sum() + (qh * w2.float()).sum() + (qs * w3.float()).sum()).backward()
+    ((logits * w1.float().to(DEV)).sum() + (hard * w2.float().to(DEV)).sum() + (soft * w3.float().to(DEV)).sum()).backward()
+    _grads_close(G, oG, 1e-3, f"generator {kind}", oG32b)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("train", [False, True])
+def test_discriminator_and_gradient_penalty_with_conv_type(kind, train):
+    """trainer.py:291-316 through a discriminator built with each conv type: score, d score / d label, first-order
+    parameter gradients, then autograd.grad(create_graph=True) + backward through that gradient."""
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup(conv=kind)
+    n = vb.num_nodes
+    keeps = _keeps(n, D_WIDTHS, 4) if train else [None] * 6
+    D.train(train), oD.train(train)
+    _inject_masks(oD, keeps)
+    kk = [None if k is None else k.to(torch.uint8).to(DEV) for k in keeps]
+    label = torch.rand(1, n, 7, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    ol = label.clone().requires_grad_()
+    l = label.float().to(DEV).requires_grad_()
+    D.debug_keep_saved = True
+    score = D(lb, vb, l, keeps=kk)
+    oscore = oD(olb, ovb, ol)
+    oD32, lb32, vb32 = _fp32_twin(oD, olb, ovb)
+    _act_close(score, oscore, oD32(lb32, vb32, label.float()).detach(), 1e-5, f"{kind} critic score")
+    w = torch.randn(n, 1, generator=torch.Generator().manual_seed(8), dtype=torch.float64)
+    _sync_patterns(oD, D.debug_saved)
+    (oD(olb, ovb, ol) * w).sum().backward()
+    (score * w.float().to(DEV)).sum().backward()
+    assert_close(l.grad, ol.grad, 5e-5, f"{kind} d score / d label")
+    _grads_close(D, oD, 2e-4, f"discriminator {kind}")
+    D.zero_grad(), oD.zero_grad()
+
+    def gp(model, lg, vg, xin, **kw):
+        xin = xin.requires_grad_(True)
+        s = model(lg, vg, xin.unsqueeze(0), **kw)
+        (g,) = torch.autograd.grad(s, xin, torch.ones_like(s), create_graph=True, only_inputs=True)
+        return ((g.norm(dim=1) - 1) ** 2).mean() * 10.0, g
+
+    x = torch.rand(n, 7, generator=torch.Generator().manual_seed(13), dtype=torch.float64)
+    kgp, kg = gp(D, lb, vb, x.float().to(DEV), keeps=kk)
+    _sync_patterns(oD, D.debug_saved)
+    ogp, og = gp(oD, olb, ovb, x.clone())
+    # the same (pattern-synced) oracle in fp32 = the rounding envelope of a correct fp32 implementation: GATv2's
+    # internal LeakyReLU sits inside the conv (its on/off pattern cannot be synced from outside), so sites within
+    # rounding distance of 0 may flip
+    oD32b, lb32b, vb32b = _fp32_twin(oD, olb, ovb)
+    ogp32, og32 = gp(oD32b, lb32b, vb32b, x.float())
+    _act_close(kg, og, og32.detach(), 5e-5, f"{kind} d D / d x")
+    _act_close(kgp.reshape(1), ogp.reshape(1), ogp32.detach().reshape(1), 5e-5, f"{kind} gradient penalty")
+    ogp.backward()
+    ogp32.backward()
+    kgp.backward()
+    _grads_close(D, oD, 2e-4, f"gradient-penalty param grads {kind}", oD32b)
+
+
+def test_graphconv_refuses_input_self_loops():
+    """GraphConv adds no self loops; the CSR strips the ones in edge_index, so a graph that has them must be refused."""
+    from building_gan_b200 import executor as ex
+    from building_gan_b200 import graph
+    n = 6
+    ei = torch.tensor([[0, 1, 2, 3, 4, 5, 2], [1, 2, 3, 4, 5, 0, 2]])
+    csr = graph.VoxelCSR.build(ei, n).to(DEV)
+    assert csr.num_input_self_loops == 1
+    spec = ex.ConvSpec("c", "n", 4, 4, "GRAPHCONV")
+    with pytest.raises(RuntimeError, match="self loops"):
+        ex._agg_forward({}, spec, csr, torch.zeros(n, 4, device=DEV))

@@ -70,8 +70,10 @@ def _inject_masks(oracle_model, keeps):
         setattr(oracle_model.encoder, f"module_{4 * k + 3}", _FixedDrop(keep) if keep is not None else nn.Identity())
 
 
-def _setup(ids=(21, 22), seed=0, dtype=torch.float64):
+def _setup(ids=(21, 22), seed=0, dtype=torch.float64, conv=None):
     cfg = Configuration()
+    if conv is not None:
+        cfg.GENERATOR_CONV_TYPE = cfg.DISCRIMINATOR_CONV_TYPE = conv
     pairs = [synth.building_pair(i) for i in ids]
     lb, vb = graph.collate_fn(pairs)
     olb = pyg.Batch.from_data_list([pyg.Data(**p[0]._fields) for p in pairs])
