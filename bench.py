@@ -236,15 +236,20 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     # ---- roofline of the aggregation kernel at the bench shapes (rank 0): the 46 gat_fwd launches of one step's layer
     # widths (6 generator passes x 14 + 16 discriminator passes x 6 widths), CUDA-graph replayed so the CPU launch cost
     # is out of the picture, timed with CUDA events on the launching stream, L2 flushed before every replay.
-    roofline, ops = None, None
+    roofline, ops, roof_step, agg = None, None, None, None
     if rank == 0:
-        roofline = _gat_roofline(resident[0][1], G, D, flush)
+        roof_step = _gat_roofline(resident[0][1], G, D, flush)
+        if not args.no_hbm_roofline:
+            roofline, agg = _hbm_roofline(dev, flush)
+        if roofline is None:
+            roofline = roof_step
         # local step (no gradient all-reduce: the other ranks do not take part in this extra step)
         ops = _kernel_shares(lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=None,
                                                      sync_losses=False))
-    cpu_baseline = None
+    cpu_baseline, torch_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = _cpu_baseline(host)
+        torch_gpu = _torch_gpu_baseline(host, dev)
 
     if rank == 0:
         val = world * args.steps / (ms * 1e-3)
@@ -261,7 +266,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "steps/s",
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * (cfg.N_CRITIC + 1),
                         "ms_per_step": round(ms_e2e / args.steps, 3)},
-                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": ops}
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "torch_b200_baseline": torch_gpu, "roofline_step_shapes": roof_step, "aggregation_hbm": agg, "kernels": ops}
         print(json.dumps(line), flush=True)
 
 
@@ -305,6 +311,93 @@ def _gat_roofline(vb, G, D, flush):
             "note": f"N={n}, E'={e}: the batch-32 working set (<= 8 MB per layer) is L2-resident and every launch is "
                     "latency-bound, so this fraction is NOT an HBM number; cold-L2 HBM-sized runs (N=1e5/1e6): "
                     "`bench.py --workload c4`, results in profiles/"}
+
+
+def _hbm_roofline(dev, flush):
+    """BASELINE config 4 / SURVEY section 8(d) cold-cache rule: the aggregation kernels on a 10-graph batch of 1e5-voxel
+    irregular grids (N = 1e6, compulsory bytes >= 4x L2), L2 flushed before every launch, CUDA events on the launching
+    stream, median of 7.  Returns (roofline object for gat_fwd at C=64, per-kernel table for C in 16/64/128)."""
+    from building_gan_b200 import graph, lib, synth
+    from building_gan_b200.benchmarks import _peak, _time
+    peak, src = _peak()
+    pairs = [synth.large_grid_pair(900 + i) for i in range(10)]
+    _, vb = graph.collate_fn(pairs)
+    csr = vb.bg_csr.to(dev)
+    n, e = csr.num_nodes, csr.num_edges
+    table, roof = {}, None
+    for c in (16, 64, 128):
+        h, s, d = torch.randn(n, c, device=dev), torch.randn(n, device=dev), torch.randn(n, device=dev)
+        b, a1, a2 = torch.zeros(c, device=dev), torch.randn(c, device=dev), torch.randn(c, device=dev)
+        g = torch.randn(n, c, device=dev)
+        one, zero = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        o, m, z = lib.gat_fwd(csr, h, s, d, b)
+        x1, stats = lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1, 2)
+        for _ in range(2):
+            lib.gat_bwd(csr, g, h, s, d, m, z, a1, a2)
+            lib.graphnorm_bwd(g, o, x1, one, one, stats, 1.25)
+        cases = (("gat_fwd", lambda: lib.gat_fwd(csr, h, s, d, b), _gat_fwd_bytes(n, e, c)),
+                 ("gat_bwd", lambda: lib.gat_bwd(csr, g, h, s, d, m, z, a1, a2), 4 * (4 * n * c + 8 * n + 3 * e + c + 2)),
+                 ("graphnorm_fwd", lambda: lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1, 2), 4 * (2 * n * c + 4 * c)),
+                 ("graphnorm_bwd", lambda: lib.graphnorm_bwd(g, o, x1, one, one, stats, 1.25), 4 * (3 * n * c + 6 * c)))
+        row = {}
+        for name, fn, by in cases:
+            t = _time(fn, flush)
+            row[name] = {"us": round(t * 1e6, 1), "GBs": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak, 3)}
+            if name == "gat_fwd" and c == 64:
+                roof = {"kernel": "gat_fwd_kernel<64, pipelined>: GATConv edge-softmax + aggregation (BASELINE config 4: 10 x 1e5-voxel "
+                                  "irregular 6-neighbour grids, N=1e6, E'=6.76e6, C=64)", "bound": "hbm",
+                        "achieved": round(by / t / 1e9, 1), "peak": peak, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
+                        "unit": "GB/s", "frac": round(by / t / 1e9 / peak, 4), "traffic": _ncu_traffic("gat_fwd_kernel"),
+                        "avg_launch_us": round(t * 1e6, 1), "algorithmic_bytes_per_launch": by,
+                        "timing": "CUDA events around one launch, L2 flushed (256 MiB write) before each, median of 7",
+                        "note": "the training step's own batch-32 shapes are L2-resident and latency-bound: see roofline_step_shapes"}
+        table[f"C={c}"] = row
+        del h, g, o, x1
+    return roof, {"N": n, "E": e, "cold_l2": True, "peak_gbs": peak, "kernels": table}
+
+
+def _ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` summary."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full_gat_c64_N1e6.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            col = next(i for i, h in enumerate(rows[0]) if kernel in h)
+            vals = {r[0]: r for r in rows[1:]}
+            mb = float(vals["dram__bytes_read.sum"][col]) + float(vals["dram__bytes_write.sum"][col])
+            return {"bytes": int(mb * 1e6), "source": os.path.basename(path)}
+        except Exception:
+            continue
+    return None
+
+
+def _torch_gpu_baseline(host_batches, dev):
+    """The reference algorithm (oracle restatement: plain torch ops, scatter_add / index_select, autograd double backward)
+    on the SAME B200 - the stand-in for "the reference's single-B200 PyTorch path" of the north star (torch_geometric
+    itself is not installable).  TF32 off.  Bounded: 1 warm-up + 3 steps."""
+    try:
+        from building_gan_b200 import Configuration
+        from oracle import models as omodels, pyg as opyg, trainer as otrainer
+        torch.backends.cuda.matmul.allow_tf32 = False
+        cfg = Configuration()
+        torch.manual_seed(777)
+        G, D = omodels.OracleGenerator(cfg, 17, 12).to(dev), omodels.OracleDiscriminator(cfg, 17, 12).to(dev)
+        og = torch.optim.Adam(G.parameters(), lr=cfg.LEARNING_RATE_GENERATOR, betas=cfg.BETAS)
+        od = torch.optim.Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
+        batches = [(_to_oracle(lb, opyg).to(dev), _to_oracle(vb, opyg).to(dev)) for lb, vb in host_batches[:2]]
+        otrainer.train_step(G, D, og, od, *batches[0], cfg)
+        torch.cuda.synchronize()
+        n = 3
+        t0 = time.perf_counter()
+        for i in range(n):
+            otrainer.train_step(G, D, og, od, *batches[(i + 1) % 2], cfg)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": round(n / dt, 4), "unit": "steps/s", "kind": "port on cuda:0 (plain torch ops, fp32, TF32 off)",
+                "sample": f"{n} full batch-32 steps (after 1 warm-up) of the oracle restatement of trainer.py:467-495"}
+    except Exception as exc:  # informational
+        return {"error": repr(exc)[:200]}
 
 
 def _kernel_shares(run_step):
@@ -359,6 +452,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "sample", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = _env_int("RANK", 0), _env_int("LOCAL_RANK", 0), _env_int("WORLD_SIZE", 1)

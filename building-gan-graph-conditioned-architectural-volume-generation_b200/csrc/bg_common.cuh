@@ -39,8 +39,13 @@ struct FoldBatch {
 struct WgradQueue {
     static constexpr int kPhases = 4;
     std::vector<FoldEntry> phase[kPhases];
-    std::vector<BgWgrad> pending;  // deferred mode: problems recorded by wgrad_launch, launched by wgrad_flush
+    std::vector<BgWgrad> pending;  // deferred mode: problems recorded by wgrad_launch, launched in batches of kWgMax
     bool defer = false;
+    // deferred mode with overlap: batches run on a library-owned side stream, forked from / joined back into the caller's
+    // stream with events (capturable), so the weight gradients overlap the latency-bound dgrad chain of the same pass
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool forked = false;
     float* buf = nullptr;
     size_t cap = 0, used = 0;  // floats
 };

@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "bg_common.cuh"
 
 namespace bg {
@@ -233,6 +235,7 @@ struct WgProblem {
     int tiles_k, tile_base, ntiles;
 };
 constexpr int kWgMax = 16;  // problems per launch (keeps the parameter block under 4 KiB)
+constexpr int kWgKick = 8;  // deferred mode: a batch leaves for the side stream as soon as this many problems are queued
 struct WgBatch {
     int nprob, S;
     WgProblem p[kWgMax];
@@ -240,8 +243,9 @@ struct WgBatch {
 
 __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) {
     constexpr int T = 64, RB = 32;
-    __shared__ float Gs[RB][T + 4];
-    __shared__ float Xs[RB][T + 4];
+    __shared__ float smem[2][RB][T + 4];
+    float(*Gs)[T + 4] = smem[0];
+    float(*Xs)[T + 4] = smem[1];
     int pi = 0;
 #pragma unroll 1
     for (int q = 1; q < b.nprob; ++q)
@@ -249,9 +253,20 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     const WgProblem& p = b.p[pi];
     const int lt = blockIdx.x - p.tile_base;
     const int k0 = (lt % p.tiles_k) * T, o0 = (lt / p.tiles_k) * T;
-    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int tid = threadIdx.x;
     const int64_t rbeg = (int64_t)blockIdx.y * p.rows_per_split, rend = min(p.N, rbeg + p.rows_per_split);
     const int no = min(T, p.Cout - o0), nk = min(T, p.K - k0);  // valid extent of this tile
+    // Thread mapping.  A full 64x64 tile is a 16x16 grid of 4x4 micro-tiles = 256 threads.  Most tiles of this model
+    // are much smaller (C <= 64 in the discriminator, [2,C] attention and [C,1] bias gradients): their to x tk micro-
+    // tiles occupy only `tiles` threads, so the CTA is split into R = 256 / tiles row groups that each take every
+    // R-th row of a slab and are summed in group order at the end (fixed order => deterministic).  r01f before this:
+    // 68 us per batched launch with 7/8 of the warps idle at the barriers.
+    const int to = (no + 3) >> 2, tk = (nk + 3) >> 2, tiles = to * tk;
+    int R = 1;
+    while (R < RB && 2 * R * tiles <= kThreads) R <<= 1;
+    const int grp = tid / tiles, slot = tid - grp * tiles;
+    const bool active = grp < R;
+    const int ty = slot / tk, tx = slot - ty * tk;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -287,9 +302,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
         }
         __syncthreads();
         if (r0 + RB < rend) fetch(r0 + RB);
-        if (ty * 4 < no && tx * 4 < nk) {
-#pragma unroll
-            for (int rr = 0; rr < RB; ++rr) {
+        if (active) {
+            for (int rr = grp; rr < RB; rr += R) {
                 float g[4], x[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) g[i] = Gs[rr][ty * 4 + i];
@@ -303,6 +317,28 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
         }
         __syncthreads();
     }
+    if (R > 1) {  // fold the row groups through shared memory (Gs and Xs are free now: 2*32*68 >= 256*16 floats)
+        float* red = &smem[0][0][0];
+        static_assert(sizeof(smem) >= kThreads * 16 * sizeof(float), "fold buffer");
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) red[(i * 4 + j) * kThreads + tid] = acc[i][j];
+        }
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float t = 0.f;
+                    for (int q = 0; q < R; ++q) t += red[(i * 4 + j) * kThreads + q * tiles + slot];
+                    acc[i][j] = t;
+                }
+        }
+    }
+    if (grp != 0) return;
     float* mine = p.partial + (int64_t)blockIdx.y * p.Cout * p.K;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -405,10 +441,52 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
 // Immediate mode: launch now.  Deferred mode (q.defer, used by the whole-pass executors, whose operands stay alive
 // until the end of the pass): only record the problems; wgrad_flush() then runs ALL weight gradients of the pass as
 // one launch per kWgMax problems - ~25 tiny latency-bound launches per backward pass become 2.
+// Side stream + fork/join events of the overlap mode: one set per device, created on first use, never destroyed (the
+// only library-owned CUDA objects; BG_WGRAD_OVERLAP=0 keeps everything on the caller's stream).
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+    static const bool enabled = !(getenv("BG_WGRAD_OVERLAP") && atoi(getenv("BG_WGRAD_OVERLAP")) == 0);
+    if (!enabled) return nullptr;
+    static SideStream pool[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStream& s = pool[dev];
+    if (!s.st) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    }
+    return &s;
+}
+
+// Launch the first `n` pending problems: on the side stream (after everything enqueued so far on `st`) when available
+static int wgrad_kick(WgradQueue& q, size_t n, cudaStream_t st) {
+    cudaStream_t where = st;
+    if (!q.side) {
+        if (SideStream* s = side_stream()) { q.side = s->st; q.ev_fork = s->fork; q.ev_join = s->join; }
+    }
+    if (q.side) {
+        if (cudaEventRecord(q.ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(q.side, q.ev_fork, 0) != cudaSuccess) {
+            set_error("wgrad: fork to the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return BG_ECUDA;
+        }
+        where = q.side;
+        q.forked = true;
+    }
+    const int rc = wgrad_launch_batch(q.pending.data(), (int)n, q, where);
+    q.pending.erase(q.pending.begin(), q.pending.begin() + n);
+    return rc;
+}
+
 int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st) {
     BG_REQUIRE(nprob >= 1, BG_EINVAL, "wgrad: nprob %d out of range", nprob);
     if (q.defer) {
         q.pending.insert(q.pending.end(), probs, probs + nprob);
+        while (q.pending.size() >= (size_t)kWgKick)
+            if (int rc = wgrad_kick(q, kWgKick, st)) return rc;
         return BG_OK;
     }
     for (int i = 0; i < nprob; i += kWgMax)
@@ -418,11 +496,15 @@ int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st
 
 // Fold every queued problem: one launch per phase (and per kMaxFold entries).
 int wgrad_flush(WgradQueue& q, cudaStream_t st) {
-    for (size_t i = 0; i < q.pending.size(); i += kWgMax) {
-        const size_t n = q.pending.size() - i < (size_t)kWgMax ? q.pending.size() - i : (size_t)kWgMax;
-        if (int rc = wgrad_launch_batch(q.pending.data() + i, (int)n, q, st)) return rc;
+    while (!q.pending.empty())
+        if (int rc = wgrad_kick(q, q.pending.size() < (size_t)kWgMax ? q.pending.size() : (size_t)kWgMax, st)) return rc;
+    if (q.forked) {  // join: the folds (and everything the caller enqueues next) wait for the side-stream batches
+        if (cudaEventRecord(q.ev_join, q.side) != cudaSuccess || cudaStreamWaitEvent(st, q.ev_join, 0) != cudaSuccess) {
+            set_error("wgrad: join from the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return BG_ECUDA;
+        }
+        q.forked = false;
     }
-    q.pending.clear();
     for (int ph = 0; ph < WgradQueue::kPhases; ++ph) {
         std::vector<FoldEntry>& v = q.phase[ph];
         for (size_t base = 0; base < v.size(); base += FoldBatch::kMax) {

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
     const bool fused = (keep == nullptr) && keep_prob < 1.f;
     const float keep_scale = (keep != nullptr || fused) ? 1.f / keep_prob : 1.f;
     const int64_t n4 = total / 4;
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(o) + i);
         const int c0 = (int)((i * 4) % C);
@@ -131,7 +132,11 @@ __device__ __forceinline__ void moments_body(const F& f, int64_t N, int G, unsig
     float acc[K * VEC];
 #pragma unroll
     for (int i = 0; i < K * VEC; ++i) acc[i] = 0.f;
-    for (int64_t r = r0 + rs; r < r1; r += RPI) f.template accumulate<C>(r, cv, acc);
+    // 4 independent row loads in flight per thread (a single dependent load per trip left the kernel latency-bound at
+    // ~50% of HBM bandwidth on graphs larger than L2); the summation order per thread is unchanged
+    int64_t r = r0 + rs;
+    for (; r + 3 * RPI < r1; r += 4 * RPI) f.template accumulate4<C>(r, RPI, cv, acc);
+    for (; r < r1; r += RPI) f.template accumulate<C>(r, cv, acc);
     cta_colsum<C, K>(acc, red);
     for (int i = threadIdx.x; i < K * C; i += kThreads) partials[(int64_t)blockIdx.x * K * C + i] = red[i];
     is_last = hier_fold(partials, partials + (int64_t)G * K * C, K * C, counters, red, sums_out);
@@ -145,17 +150,32 @@ __device__ __forceinline__ void moments_body(const F& f, int64_t N, int G, unsig
 struct StatsAcc {
     const float* o;
     template <int CC>
-    __device__ __forceinline__ void accumulate(int64_t r, int cv, float* acc) const {
+    __device__ __forceinline__ void consume(const Vec<ColMap<CC>::VEC>& x, const Vec<ColMap<CC>::VEC>& sh, float* acc) const {
         constexpr int VEC = ColMap<CC>::VEC;
-        Vec<VEC> x, sh;
-        x.load(o + r * CC + cv * VEC);
-        sh.load(o + cv * VEC);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const float d = x.v[v] - sh.v[v];
             acc[v] += d;
             acc[VEC + v] = fmaf(d, d, acc[VEC + v]);
         }
+    }
+    template <int CC>
+    __device__ __forceinline__ void accumulate(int64_t r, int cv, float* acc) const {
+        constexpr int VEC = ColMap<CC>::VEC;
+        Vec<VEC> x, sh;
+        x.load(o + r * CC + cv * VEC);
+        sh.load(o + cv * VEC);
+        consume<CC>(x, sh, acc);
+    }
+    template <int CC>
+    __device__ __forceinline__ void accumulate4(int64_t r, int64_t step, int cv, float* acc) const {
+        constexpr int VEC = ColMap<CC>::VEC;
+        Vec<VEC> x[4], sh;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q].load(o + (r + q * step) * CC + cv * VEC);
+        sh.load(o + cv * VEC);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) consume<CC>(x[q], sh, acc);
     }
 };
 
@@ -186,13 +206,9 @@ template <int C>
 struct BwdAcc {
     BwdMoments p;
     template <int CC>
-    __device__ __forceinline__ void accumulate(int64_t r, int cv, float* acc) const {
+    __device__ __forceinline__ void consume(const Vec<ColMap<CC>::VEC>& g, const Vec<ColMap<CC>::VEC>& ov,
+                                            const Vec<ColMap<CC>::VEC>& xv, int cv, float* acc) const {
         constexpr int VEC = ColMap<CC>::VEC;
-        Vec<VEC> g, ov, xv;
-        const int64_t off = r * CC + cv * VEC;
-        g.load(p.gx1 + off);
-        ov.load(p.o + off);
-        xv.load(p.x1 + off);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int c = cv * VEC + v;
@@ -201,6 +217,30 @@ struct BwdAcc {
             acc[v] += gy;
             acc[VEC + v] = fmaf(gy, oh, acc[VEC + v]);
         }
+    }
+    template <int CC>
+    __device__ __forceinline__ void accumulate(int64_t r, int cv, float* acc) const {
+        constexpr int VEC = ColMap<CC>::VEC;
+        Vec<VEC> g, ov, xv;
+        const int64_t off = r * CC + cv * VEC;
+        g.load(p.gx1 + off);
+        ov.load(p.o + off);
+        xv.load(p.x1 + off);
+        consume<CC>(g, ov, xv, cv, acc);
+    }
+    template <int CC>
+    __device__ __forceinline__ void accumulate4(int64_t r, int64_t step, int cv, float* acc) const {
+        constexpr int VEC = ColMap<CC>::VEC;
+        Vec<VEC> g[4], ov[4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t off = (r + q * step) * CC + cv * VEC;
+            g[q].load(p.gx1 + off);
+            ov[q].load(p.o + off);
+            xv[q].load(p.x1 + off);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) consume<CC>(g[q], ov[q], xv[q], cv, acc);
     }
 };
 
@@ -249,10 +289,40 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(BwdMoments p, co
         sh[c] = a * mu;
     }
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
-        const int c = (int)(i % C);
-        const float gy = p.x1[i] > 0.f ? p.gx1[i] * p.keep_scale : 0.f;
-        go[i] = gy * k1[c] - (p.o[i] - sh[c]) * k2[c] - k3[c];
+    const int64_t n4 = total / 4;  // 128-bit loads/stores (C >= 4: a float4 never straddles a row)
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    auto one4 = [&](int64_t i, const float4& xa, const float4& ga, const float4& oa) {
+        const int c0 = (int)((i * 4) % C);
+        const float xv[4] = {xa.x, xa.y, xa.z, xa.w}, gv[4] = {ga.x, ga.y, ga.z, ga.w}, ov[4] = {oa.x, oa.y, oa.z, oa.w};
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = (c0 + k) % C;
+            const float gy = xv[k] > 0.f ? gv[k] * p.keep_scale : 0.f;
+            r[k] = gy * k1[c] - (ov[k] - sh[c]) * k2[c] - k3[c];
+        }
+        reinterpret_cast<float4*>(go)[i] = make_float4(r[0], r[1], r[2], r[3]);
+    };
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // 12 independent 128-bit loads in flight per thread
+        float4 xa[4], ga[4], oa[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            xa[q] = __ldg(reinterpret_cast<const float4*>(p.x1) + i + q * stride);
+            ga[q] = __ldg(reinterpret_cast<const float4*>(p.gx1) + i + q * stride);
+            oa[q] = __ldg(reinterpret_cast<const float4*>(p.o) + i + q * stride);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) one4(i + q * stride, xa[q], ga[q], oa[q]);
+    }
+    for (; i < n4; i += stride)
+        one4(i, __ldg(reinterpret_cast<const float4*>(p.x1) + i), __ldg(reinterpret_cast<const float4*>(p.gx1) + i),
+             __ldg(reinterpret_cast<const float4*>(p.o) + i));
+    if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
+        const int64_t t = n4 * 4 + threadIdx.x;
+        const int c = (int)(t % C);
+        const float gy = p.x1[t] > 0.f ? p.gx1[t] * p.keep_scale : 0.f;
+        go[t] = gy * k1[c] - (p.o[t] - sh[c]) * k2[c] - k3[c];
     }
 }
 
@@ -277,6 +347,11 @@ struct Bwd2Acc {
             acc[VEC + v] = fmaf(xt.v[v], gy, acc[VEC + v]);
             acc[2 * VEC + v] = fmaf(xt.v[v], oh, acc[2 * VEC + v]);
         }
+    }
+    template <int CC>
+    __device__ __forceinline__ void accumulate4(int64_t r, int64_t step, int cv, float* acc) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) accumulate<CC>(r + q * step, cv, acc);
     }
 };
 

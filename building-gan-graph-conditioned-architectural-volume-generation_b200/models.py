@@ -154,6 +154,17 @@ def _hourglass(hidden: int, repeat: int) -> List[int]:
     return down + down[-2::-1]
 
 
+def _param_list(model) -> List[nn.Parameter]:
+    """``list(model.parameters())`` cached on the model: walking the module tree costs ~0.1 ms and every pass of the
+    training step (46 per step) needs the list.  nn.Module keeps the Parameter objects across .to()/.cuda()/load_state_dict
+    (their .data is swapped in place); re-registering a parameter by hand must be followed by ``model._bg_params = None``."""
+    cached = model.__dict__.get("_bg_params")
+    if cached is None:
+        cached = list(model.parameters())
+        model.__dict__["_bg_params"] = cached
+    return cached
+
+
 def _executor_for(kind: str) -> str:
     return EXECUTOR if kind == "GATCONV" else "python"
 
@@ -329,6 +340,10 @@ class VoxelGNNGenerator(nn.Module):
         assert kind != "GATCONV" or lib.load().bg_gen_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_bg_params"] = None  # .to() / .cuda() may re-create the Parameter objects
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, local_graph, voxel_graph, z, gumbel_noise: Optional[Tensor] = None, keeps=None):
         """(logits, label_hard, label_soft), reference models.py:119-155.  ``gumbel_noise`` [N,7] / ``keeps`` (one
         uint8 [N,C] keep-mask per conv block) inject the random draws explicitly (parity tests); by default they
@@ -344,7 +359,7 @@ class VoxelGNNGenerator(nn.Module):
             gumbel_noise = -torch.empty(bc.n, self.configuration.NUM_CLASSES, device=bc.vx.device).exponential_().log()
         if gumbel_noise is not None:
             gumbel_noise = gumbel_noise.to(torch.float32).contiguous()
-        params = list(self.parameters())
+        params = _param_list(self)
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         fn = _GenFn if EXECUTOR == "python" else _GenNativeFn
         if EXECUTOR == "python" and keeps is None:
@@ -479,7 +494,7 @@ class _GenNativeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: VoxelGNNGenerator, bc, zz, noise, keeps, need, ticket, *tensors):
         L, st = lib.load(), model._native
-        params = list(model.parameters())
+        params = _param_list(model)
         dev, n, e, k = zz.device, bc.n, bc.csr.num_edges, model.configuration.NUM_CLASSES
         ws = lib.u8_buffer(L.bg_gen_fwd_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
@@ -506,7 +521,7 @@ class _GenNativeFn(torch.autograd.Function):
             raise RuntimeError("generator backward called but the forward ran without grad")
         L, model, bc = lib.load(), ctx.model, ctx.bc
         st = model._native
-        params = list(model.parameters())
+        params = _param_list(model)
         logits, soft = ctx.saved_tensors
         dev, n, e = logits.device, bc.n, bc.csr.num_edges
         flat = st.bind_grads(params) if ctx.bucket_mode else torch.empty(st.layout.total, dtype=torch.float32, device=dev)
@@ -557,6 +572,10 @@ class VoxelGNNDiscriminator(nn.Module):
         assert kind != "GATCONV" or lib.load().bg_disc_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
 
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_bg_params"] = None  # .to() / .cuda() may re-create the Parameter objects
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, local_graph, voxel_graph, label_hard, keeps=None):
         """Per-voxel critic score [N,1], reference models.py:229-245.  ``keeps`` injects explicit dropout masks."""
         lib.load()
@@ -571,7 +590,7 @@ class VoxelGNNDiscriminator(nn.Module):
         EXECUTOR = _executor_for(self._kind)
         if keeps is None and self.training and (RNG_MODE == "torch" or EXECUTOR == "python"):
             keeps = _draw_keeps(bc.n, self._convs, True, bc.vx.device)
-        params = list(self.parameters())
+        params = _param_list(self)
         need = torch.is_grad_enabled() and (label.requires_grad or any(p.requires_grad for p in params))
         if EXECUTOR == "python":
             return _DiscFn.apply(self, bc, keeps if keeps is not None else [None] * len(self._convs), need, label, *params)
@@ -707,7 +726,7 @@ class _DiscNativeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: VoxelGNNDiscriminator, bc, keeps, need, ticket, label, *tensors):
         L, st = lib.load(), model._native
-        params = list(model.parameters())
+        params = _param_list(model)
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         ws = lib.u8_buffer(L.bg_disc_fwd_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
@@ -741,7 +760,7 @@ class _DiscNativeBwdFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, flags, score, g_score, label, *tensors):
         L, st = lib.load(), model._native
-        params = list(model.parameters())
+        params = _param_list(model)
         second_order, bucket_mode = flags
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         if bucket_mode:  # under create_graph only the input gradient is wanted (autograd.grad(..., only_inputs=True))
@@ -773,7 +792,7 @@ class _DiscNativeBwdFn(torch.autograd.Function):
             raise RuntimeError("second-order backward requested but the first backward ran without create_graph=True")
         L, model, bc = lib.load(), ctx.model, ctx.bc
         st = model._native
-        params = list(model.parameters())
+        params = _param_list(model)
         label, score = ctx.saved_tensors
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         flat2 = st.bind_grads(params) if ctx.bucket_mode else torch.zeros(st.layout.total, dtype=torch.float32, device=dev)
