@@ -275,6 +275,44 @@ extern "C" int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_
     return check_launch("bg_segment_softmax");
 }
 
+// Per-segment confusion matrices: cm[s, t, p] = #{rows of segment s with target t and prediction p}, prediction =
+// argmax of a score row (first maximum, like torch.argmax).  One CTA per segment, integer shared-memory counters
+// (integer addition is associative: deterministic).  Replaces the B+4 sklearn calls per step of trainer.py:387-443.
+__global__ void __launch_bounds__(kThreads) segment_confusion_kernel(const float* __restrict__ score,
+                                                                     const int64_t* __restrict__ target,
+                                                                     const int32_t* __restrict__ seg_ptr, int K,
+                                                                     int32_t* __restrict__ cm) {
+    __shared__ int cnt[16 * 16];
+    for (int i = threadIdx.x; i < K * K; i += kThreads) cnt[i] = 0;
+    __syncthreads();
+    const int s = blockIdx.x;
+    for (int r = seg_ptr[s] + threadIdx.x; r < seg_ptr[s + 1]; r += kThreads) {
+        const float* row = score + (int64_t)r * K;
+        int best = 0;
+        float bv = __ldg(row);
+        for (int k = 1; k < K; ++k) {
+            const float v = __ldg(row + k);
+            if (v > bv) {
+                bv = v;
+                best = k;
+            }
+        }
+        const int t = (int)target[r];
+        if (t >= 0 && t < K) atomicAdd(&cnt[t * K + best], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += kThreads) cm[(int64_t)s * K * K + i] = cnt[i];
+}
+
+extern "C" int bg_segment_confusion(const float* score, const int64_t* target, const int32_t* seg_ptr, int64_t S, int32_t K,
+                                    int32_t* cm, void* stream) {
+    BG_REQUIRE(score && target && seg_ptr && cm, BG_EINVAL, "bg_segment_confusion: null pointer");
+    BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_segment_confusion: K=%d out of range [1,16]", (int)K);
+    if (S <= 0) return BG_OK;
+    segment_confusion_kernel<<<(unsigned)S, kThreads, 0, as_stream(stream)>>>(score, target, seg_ptr, K, cm);
+    return check_launch("bg_segment_confusion");
+}
+
 extern "C" int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S, int32_t C, int32_t mode, float* out,
                                void* stream) {
     BG_REQUIRE(x && seg_ptr && out, BG_EINVAL, "bg_segment_pool: null pointer");

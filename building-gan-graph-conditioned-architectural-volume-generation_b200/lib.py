@@ -94,6 +94,7 @@ SIGNATURES = {
     "bg_gumbel_st_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "bg_segment_softmax": (C.c_int, [_P, _P, _I64, _P, _P]),
     "bg_segment_pool": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "bg_segment_confusion": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "bg_gen_num_params": (C.c_int32, [_MD]),
     "bg_disc_num_params": (C.c_int32, [_MD]),
     "bg_gen_fwd_ws": (_SZ, [_MD, _I64, _I64]),
@@ -635,6 +636,18 @@ def segment_softmax(v: Tensor, seg_ptr: Tensor) -> Tensor:
     out = torch.empty_like(v)
     _check(lib.bg_segment_softmax(v.data_ptr(), seg_ptr.data_ptr(), seg_ptr.numel() - 1, out.data_ptr(), _stream()))
     return out
+
+
+@_op("segment_confusion", 1)
+def segment_confusion(score: Tensor, target: Tensor, seg_ptr: Tensor) -> Tensor:
+    """cm[S,K,K] int32: per-segment confusion counts of argmax(score) against int64 targets."""
+    lib = load()
+    _cf32(score, "score")
+    assert target.dtype == torch.int64 and target.is_contiguous() and seg_ptr.dtype == torch.int32
+    s, k = seg_ptr.numel() - 1, score.shape[1]
+    cm = torch.empty(s, k, k, dtype=torch.int32, device=score.device)
+    _check(lib.bg_segment_confusion(score.data_ptr(), target.data_ptr(), seg_ptr.data_ptr(), s, k, cm.data_ptr(), _stream()))
+    return cm
 
 
 @_op("segment_pool", 1)

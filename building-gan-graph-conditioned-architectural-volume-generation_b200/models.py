@@ -558,8 +558,7 @@ class VoxelGNNDiscriminator(nn.Module):
         tail: List[nn.Module] = [nn.Linear(dh, dh // 2), nn.ReLU(True), nn.Linear(dh // 2, dh // 4), nn.ReLU(True),
                                  nn.Linear(dh // 4, dh // 8), nn.ReLU(True), nn.Linear(dh // 8, 1)]
         if not c.USE_WGANGP:
-            raise NotImplementedError("USE_WGANGP=False (sigmoid + BCE critic) has no sm_100a kernel yet; "
-                                      "the reference default is WGAN-GP (config.py:106)")
+            tail.append(nn.Sigmoid())  # models.py:222-223; applied to the kernel path's score in forward()
         self.decoder = nn.Sequential(*tail)
         self._pre = [DenseSpec("mlp_encoder.0", None, ACT_RELU), DenseSpec("mlp_encoder.2", None, ACT_RELU)]
         self._convs = [ConvSpec("encoder." + s.conv, "encoder." + s.norm, s.cin, s.cout, s.kind) for s in self.encoder.specs]
@@ -593,10 +592,15 @@ class VoxelGNNDiscriminator(nn.Module):
         params = _param_list(self)
         need = torch.is_grad_enabled() and (label.requires_grad or any(p.requires_grad for p in params))
         if EXECUTOR == "python":
-            return _DiscFn.apply(self, bc, keeps if keeps is not None else [None] * len(self._convs), need, label, *params)
-        if GRAD_MODE == "bucket":
-            return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, True), label, self._native.get_anchor(label.device))
-        return _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, False), label, *params)
+            score = _DiscFn.apply(self, bc, keeps if keeps is not None else [None] * len(self._convs), need, label, *params)
+        elif GRAD_MODE == "bucket":
+            score = _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, True), label,
+                                        self._native.get_anchor(label.device))
+        else:
+            score = _DiscNativeFn.apply(self, bc, keeps, need, (seed, offset, False), label, *params)
+        # vanilla-GAN critic (USE_WGANGP=False): the [N,1] score goes through the decoder's final Sigmoid (one tiny
+        # elementwise op; its autograd backward feeds g_score of the kernel path)
+        return score if self.configuration.USE_WGANGP else torch.sigmoid(score)
 
     # -- passes -----------------------------------------------------------------------------------
     def _forward_pass(self, P, bc: _BatchCtx, label: Tensor, keeps, save: bool):

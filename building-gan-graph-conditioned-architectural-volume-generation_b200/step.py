@@ -43,8 +43,8 @@ def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tens
                        rng: str = "cpu") -> Tensor:
     d_real = discriminator(local_graph, voxel_graph, voxel_graph.types_onehot.unsqueeze(0))
     d_fake = discriminator(local_graph, voxel_graph, label_hard)
-    if not cfg.USE_WGANGP:
-        raise NotImplementedError("USE_WGANGP=False is not on the B200 path")
+    if not cfg.USE_WGANGP:  # trainer.py:326-330 (the discriminator then ends in a sigmoid, models.py:222-223)
+        return F.binary_cross_entropy(d_fake, torch.zeros_like(d_fake)) + F.binary_cross_entropy(d_real, torch.ones_like(d_real))
     return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng)
 
 
@@ -69,7 +69,8 @@ def far_loss(voxel_graph, label_hard: Tensor, cfg) -> Tensor:
 
 def generator_loss(discriminator, local_graph, voxel_graph, logits: Tensor, label_hard: Tensor, cfg) -> Tensor:
     d_fake = discriminator(local_graph, voxel_graph, label_hard)
-    adv = -d_fake.mean() * cfg.LAMBDA_ADV
+    adv = -d_fake.mean() if cfg.USE_WGANGP else F.binary_cross_entropy(d_fake, torch.ones_like(d_fake))  # trainer.py:337-341
+    adv = adv * cfg.LAMBDA_ADV
     ce = F.cross_entropy(logits, voxel_graph.type) * cfg.LAMBDA_LABEL
     n = voxel_graph.num_nodes
     ratio_g = label_hard.squeeze(0).sum(dim=0) / n
@@ -77,6 +78,37 @@ def generator_loss(discriminator, local_graph, voxel_graph, logits: Tensor, labe
     r_main = F.mse_loss(ratio_g[:-2], ratio[:-2]) * cfg.LAMBDA_RATIO
     r_void = F.mse_loss(ratio_g[-2:], ratio[-2:]) * cfg.LAMBDA_RATIO_VOID
     return adv + r_main + ce + r_void + far_loss(voxel_graph, label_hard, cfg)
+
+
+def _prf(cm: Tensor):
+    """sklearn precision / recall / f1 with average="macro", zero_division=0 from confusion counts cm[..., K, K]
+    (rows = target, columns = prediction): per class over the classes present in the targets or the predictions."""
+    cm = cm.to(torch.float64)
+    tp = cm.diagonal(dim1=-2, dim2=-1)
+    pred, true = cm.sum(-2), cm.sum(-1)
+    present = (pred + true) > 0
+    n = present.sum(-1).clamp_min(1)
+    safe = lambda a, b: torch.where(b > 0, a / b.clamp_min(1), torch.zeros_like(a))
+    prec, rec, f1 = safe(tp, pred), safe(tp, true), safe(2 * tp, pred + true)
+    avg = lambda v: (v * present).sum(-1) / n
+    return avg(prec), avg(rec), avg(f1)
+
+
+def compute_metrics(voxel_graph, label_hard: Tensor, cfg):
+    """trainer.py:387-443 without sklearn and without per-building D2H copies: ONE confusion-matrix kernel
+    (bg_segment_confusion, [B,7,7] counts) and a handful of tiny tensor ops.  Returns device tensors
+    (f1, f1 per building [B], precision, recall, accuracy) equal to sklearn's macro scores with zero_division=0;
+    call ``.item()`` / ``.tolist()`` where the reference logs them."""
+    if cfg.METRICS_AVERAGE != "macro":
+        raise NotImplementedError(f"METRICS_AVERAGE={cfg.METRICS_AVERAGE!r}: only 'macro' (config.py:81) is on the B200 path")
+    ptr = voxel_graph.ptr
+    ptr32 = (ptr.to(torch.int32) if ptr.dtype != torch.int32 else ptr).contiguous()
+    cm = lib.segment_confusion(label_hard.squeeze(0).detach().to(torch.float32).contiguous(), voxel_graph.type.contiguous(), ptr32)
+    _, _, f1_each = _prf(cm)
+    tot = cm.sum(0)
+    prec, rec, f1 = _prf(tot)
+    acc = tot.diagonal().sum().to(torch.float64) / tot.sum().clamp_min(1)
+    return f1, f1_each, prec, rec, acc
 
 
 def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng: str = "cpu",

@@ -234,6 +234,10 @@ int bg_gumbel_st_bwd(const float* g_hard, const float* g_soft, const float* soft
 /* ---- generic segment primitives named by north_star (same machinery as the edge softmax and
  * the GraphNorm statistics, exposed with an arbitrary segment pointer). */
 int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_t S, float* out, void* stream);
+/* N1 (trainer.py:387-443 `_compute_metrics`: one sklearn call per building + 4 per batch, each with D2H copies):
+ * cm[S,K,K] (int32), cm[s,t,p] = rows of segment s with target class t and predicted class p = argmax(score row). */
+int bg_segment_confusion(const float* score, const int64_t* target, const int32_t* seg_ptr, int64_t S, int32_t K,
+                         int32_t* cm, void* stream);
 /* mode 0 = mean, 1 = max, 2 = sum; x[N,C] -> out[S,C] */
 int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S, int32_t C, int32_t mode,
                     float* out, void* stream);

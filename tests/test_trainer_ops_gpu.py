@@ -1,0 +1,91 @@
+"""SURVEY section 8(f) N1 + the USE_WGANGP=False branch: the trainer-side pieces around the models.
+
+* ``step.compute_metrics`` (one confusion-matrix kernel) against sklearn called exactly like trainer.py:387-443;
+* the vanilla-GAN critic (sigmoid tail, BCE losses; trainer.py:326-330,340-341; models.py:222-223) against the oracle."""
+import numpy as np
+import pytest
+import torch
+from sklearn import metrics as skm
+
+from oracle import trainer as otrainer
+from test_models_gpu import _grads_close, _setup
+from util import assert_close
+
+from building_gan_b200 import lib, step
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_segment_confusion_counts_are_exact():
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 300, 2, 1025]
+    ptr = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    n, k = int(ptr[-1]), 7
+    score = torch.randn(n, k, generator=g)
+    score[5] = 0.0  # a full tie: argmax takes the first index
+    target = torch.randint(0, k, (n,), generator=g)
+    cm = lib.segment_confusion(score.to(DEV), target.to(DEV), ptr.to(DEV)).cpu()
+    pred = score.argmax(1)
+    for s in range(len(sizes)):
+        ref = torch.zeros(k, k, dtype=torch.int32)
+        for t, p in zip(target[ptr[s]:ptr[s + 1]].tolist(), pred[ptr[s]:ptr[s + 1]].tolist()):
+            ref[t, p] += 1
+        assert torch.equal(cm[s], ref)
+
+
+@pytest.mark.parametrize("skew", [False, True])
+def test_metrics_match_sklearn_like_the_reference_calls_it(skew):
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup(ids=(31, 32, 33))
+    n = vb.num_nodes
+    g = torch.Generator().manual_seed(9)
+    hard = torch.zeros(n, 7)
+    idx = torch.randint(0, 3 if skew else 7, (n,), generator=g)  # skew: classes missing from the predictions
+    hard[torch.arange(n), idx] = 1.0
+    f1, f1_each, prec, rec, acc = step.compute_metrics(vb, hard.unsqueeze(0).to(DEV), cfg)
+    y, yp = ovb.type.numpy(), idx.numpy()
+    assert abs(float(f1) - skm.f1_score(y, yp, average="macro", zero_division=0)) < 1e-12
+    assert abs(float(prec) - skm.precision_score(y, yp, average="macro", zero_division=0)) < 1e-12
+    assert abs(float(rec) - skm.recall_score(y, yp, average="macro", zero_division=0)) < 1e-12
+    assert abs(float(acc) - skm.accuracy_score(y, yp)) < 1e-12
+    ptr = ovb.ptr.tolist()
+    for gi in range(ovb.num_graphs):
+        want = skm.f1_score(y[ptr[gi]:ptr[gi + 1]], yp[ptr[gi]:ptr[gi + 1]], average="macro", zero_division=0)
+        assert abs(float(f1_each[gi]) - want) < 1e-12
+
+
+def test_vanilla_gan_branch_use_wgangp_false():
+    """USE_WGANGP=False: discriminator ends in a sigmoid, critic / generator losses are BCE."""
+    from building_gan_b200 import Configuration
+    from building_gan_b200.models import VoxelGNNDiscriminator
+    from oracle import models as omodels
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
+    cfg.USE_WGANGP = False
+    D2 = VoxelGNNDiscriminator(cfg, 17, 12)
+    assert isinstance(D2.decoder[-1], torch.nn.Sigmoid)
+    D2.load_state_dict(D.state_dict())
+    oD2 = omodels.OracleDiscriminator(cfg, 17, 12)
+    oD2.load_state_dict({k: v.cpu() for k, v in D.state_dict().items()})
+    oD2 = oD2.double().eval()
+    D2 = D2.to(DEV).eval()
+    G.eval(), oG.eval()
+    n = vb.num_nodes
+    z = torch.randn(1, n, cfg.Z_DIM, generator=torch.Generator().manual_seed(5))
+    noise = -torch.empty(n, 7).exponential_(generator=torch.Generator().manual_seed(6)).log()
+    with torch.no_grad():
+        _, hard, soft = G(lb, vb, z.to(DEV), noise.to(DEV))
+    ohard, osoft = hard.cpu().double(), soft.cpu().double()
+    kd = step.discriminator_loss(D2, lb, vb, hard.unsqueeze(0), soft.unsqueeze(0), cfg)
+    od = otrainer.discriminator_loss(oD2, olb, ovb, ohard.unsqueeze(0), osoft.unsqueeze(0), cfg)
+    assert_close(kd.reshape(1), od.reshape(1), 1e-5, "BCE critic loss")
+    kd.backward(), od.backward()
+    # two forwards (real, fake) share the weights, so the oracle's ReLU patterns cannot be pinned to the kernel path's here:
+    # sites within rounding distance of 0 may flip (see test_models_gpu._PatternAct), hence 1e-3 instead of 1e-4
+    _grads_close(D2, oD2, 1e-3, "BCE critic gradients")
+    # generator side: BCE(D(fake), 1) with the straight-through labels
+    D2.zero_grad(), oD2.zero_grad()
+    logits, h2, s2 = G(lb, vb, z.to(DEV), noise.to(DEV))
+    ol, oh, os_ = oG(olb, ovb, z.double(), noise.double())
+    kg = step.generator_loss(D2, lb, vb, logits, h2.unsqueeze(0), cfg)
+    og = otrainer.generator_loss(oD2, olb, ovb, ol, oh.unsqueeze(0), cfg)
+    assert_close(kg.reshape(1), og.reshape(1), 2e-5, "BCE generator loss")
