@@ -338,6 +338,9 @@ def _hbm_roofline(dev, flush):
         cases = (("gat_fwd", lambda: lib.gat_fwd(csr, h, s, d, b), _gat_fwd_bytes(n, e, c)),
                  ("gat_bwd", lambda: lib.gat_bwd(csr, g, h, s, d, m, z, a1, a2), 4 * (4 * n * c + 8 * n + 3 * e + c + 2)),
                  ("graphnorm_fwd", lambda: lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1, 2), 4 * (2 * n * c + 4 * c)),
+                 # what the model passes run: statistics fused into the aggregation epilogue + one elementwise pass
+                 ("gat_fwd+graphnorm_fwd_fused", lambda: lib.gat_fwd_gn(csr, h, s, d, b, one, zero, one, None, 0.8, 1, 2),
+                  _gat_fwd_bytes(n, e, c) + 4 * (2 * n * c + 4 * c)),
                  ("graphnorm_bwd", lambda: lib.graphnorm_bwd(g, o, x1, one, one, stats, 1.25), 4 * (3 * n * c + 6 * c)))
         row = {}
         for name, fn, by in cases:

@@ -255,4 +255,43 @@ __device__ __forceinline__ bool hier_fold(float* partials, float* gpartials, int
     return true;
 }
 
+// hier_fold for CTAs of any size: only the first kThreads threads fold (the others just take part in the barriers).
+__device__ __forceinline__ void fold_partials_any(const float* partials, int G, int L, float* red /*>= kThreads*/,
+                                                  float* result /*shared, >= L*/) {
+    for (int base = 0; base < L; base += kThreads) {
+        const int Lt = min(L - base, kThreads);
+        int Lp = 1;
+        while (Lp < Lt) Lp <<= 1;
+        const int S = kThreads / Lp;
+        for (int vt = threadIdx.x; vt < kThreads; vt += blockDim.x) {  // kThreads virtual folding threads
+            const int i = vt % Lp, sl = vt / Lp;
+            float t = 0.f;
+            if (i < Lt)
+#pragma unroll 8
+                for (int g = sl; g < G; g += S) t += partials[(int64_t)g * L + base + i];
+            red[vt] = t;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < Lt; t += blockDim.x) {
+            float a = 0.f;
+            for (int q = 0; q < S; ++q) a += red[q * Lp + t];
+            result[base + t] = a;
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ bool hier_fold_any(float* partials, float* gpartials, int L, unsigned int* counters, float* red,
+                                              float* result) {
+    const int G = gridDim.x;
+    const int group = blockIdx.x / kFoldGroup, ngroups = (G + kFoldGroup - 1) / kFoldGroup;
+    const int gsize = min(kFoldGroup, G - group * kFoldGroup);
+    if (!ticket_last(counters + 1 + group, gsize)) return false;
+    fold_partials_any(partials + (int64_t)group * kFoldGroup * L, gsize, L, red, result);
+    if (ngroups == 1) return true;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) gpartials[(int64_t)group * L + i] = result[i];
+    if (!ticket_last(counters, ngroups)) return false;
+    fold_partials_any(gpartials, ngroups, L, red, result);
+    return true;
+}
+
 }  // namespace bg

@@ -231,7 +231,9 @@ __device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg
                                                  const int (&j)[GatMap<C>::EPL], const float (&u)[GatMap<C>::EPL],
                                                  const float* __restrict__ hb, const float* __restrict__ bias,
                                                  float* __restrict__ out, float* __restrict__ m_out,
-                                                 float* __restrict__ z_out) {
+                                                 float* __restrict__ z_out, float (&st1)[GatMap<C>::NV],
+                                                 float (&st2)[GatMap<C>::NV], bool stats /* compile-time at the call sites */,
+                                                 const float* __restrict__ kshift) {
     using M = GatMap<C>;
     constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
     float p[EPL];
@@ -255,6 +257,15 @@ __device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg
     gather_fma4<C, EPL>(hb, j, p, 0, acc);
     if (maxdeg > 4) gather_fma4<C, EPL>(hb, j, p, 4, acc);
     if (valid) {
+        if (stats) {  // GraphNorm moments of (out - bias - k), k = row 0's aggregate: one shift common to every CTA, so the
+                      // partial sums simply add, and a sample of the column keeps S2/n - (S1/n)^2 free of cancellation
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float a = acc[v] - kshift[chan<C>(sub, v)];
+                st1[v] += a;
+                st2[v] = fmaf(a, a, st2[v]);
+            }
+        }
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] += bias ? __ldg(bias + chan<C>(sub, v)) : 0.f;
         row_store<C>(acc, out + (int64_t)row * C, sub);
@@ -265,19 +276,136 @@ __device__ __forceinline__ void gat_fwd_row_fast(int row, bool valid, int maxdeg
     }
 }
 
-template <int C, bool PIPE>
-__global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
+// GraphNorm statistics fused into the aggregation (mu, then var of o - alpha*mu over ALL rows): per-lane moment
+// sums -> warp (lanes holding the same channels) -> CTA -> per-CTA partial -> two-level last-CTA fold (fixed order,
+// bitwise reproducible) -> stats[3C] = (mean, rstd, var), exactly what gn_stats_kernel writes.
+struct GnFuse {
+    float* partials;         // [gridDim.x][2C]; NULL = no statistics
+    float* gpartials;        // [ceil(gridDim.x / 16)][2C]
+    unsigned int* counters;  // self-resetting tickets
+    const float* alpha;      // GraphNorm mean_scale
+    float* stats;            // out: [3C]
+    float eps;
+    int64_t n_rows;
+};
+
+template <int C>
+__device__ __forceinline__ void gat_fwd_row_stats_from_out(int row, int sub, const float* __restrict__ out,
+                                                           const float* __restrict__ bias, float (&st1)[GatMap<C>::NV],
+                                                           float (&st2)[GatMap<C>::NV], const float* __restrict__ kshift) {
+    float o[GatMap<C>::NV];
+    row_load<C>(o, out + (int64_t)row * C, sub);  // written by this lane a moment ago (generic high-degree path)
+#pragma unroll
+    for (int v = 0; v < GatMap<C>::NV; ++v) {
+        const float a = o[v] - (bias ? __ldg(bias + chan<C>(sub, v)) : 0.f) - kshift[chan<C>(sub, v)];
+        st1[v] += a;
+        st2[v] = fmaf(a, a, st2[v]);
+    }
+}
+
+// k = sum_e p_e h_j of row 0 (no bias), computed by the first lane group of warp 0 of EVERY CTA (same arithmetic => the
+// same bits everywhere) and left in shared memory.
+template <int C>
+__device__ __forceinline__ void gat_fwd_row0_shift(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                   const float* __restrict__ h, const float* __restrict__ s,
+                                                   const float* __restrict__ d, float slope, float* kshift) {
+    using M = GatMap<C>;
+    constexpr int NV = M::NV, LANES = M::LANES;
+    if (threadIdx.x < LANES) {
+        const int sub = threadIdx.x;
+        const unsigned gm = group_mask<LANES>(sub);
+        const int beg = __ldg(rowptr), end = __ldg(rowptr + 1);
+        const float di = __ldg(d);
+        float mx = -INFINITY;
+        for (int e = beg + sub; e < end; e += LANES) mx = fmaxf(mx, lrelu(__ldg(s + __ldg(col + e)) + di, slope));
+        mx = gmax<LANES>(mx, gm);
+        float zs = 0.f;
+        for (int e = beg + sub; e < end; e += LANES) zs += expf(lrelu(__ldg(s + __ldg(col + e)) + di, slope) - mx);
+        zs = gsum<LANES>(zs, gm) + 1e-16f;
+        const float inv = rcp_fast(zs);
+        float acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+        for (int e = beg; e < end; ++e) {
+            const int j = __ldg(col + e);
+            float hv[NV];
+            row_load<C>(hv, h + (int64_t)j * C, sub);
+            const float p = expf(lrelu(__ldg(s + j) + di, slope) - mx) * inv;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = fmaf(p, hv[v], acc[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) kshift[chan<C>(sub, v)] = acc[v];
+    }
+    __syncthreads();
+}
+
+template <int C>
+__device__ __forceinline__ void gat_fwd_finish_stats(const GnFuse& gn, const float* __restrict__ bias, int sub,
+                                                     float (&st1)[GatMap<C>::NV], float (&st2)[GatMap<C>::NV],
+                                                     const float* __restrict__ kshift) {
+    using M = GatMap<C>;
+    constexpr int NV = M::NV, LANES = M::LANES;
+    __shared__ float red[(kGatMaxThreads / 32) * 2 * C > kThreads ? (kGatMaxThreads / 32) * 2 * C : kThreads];
+    __shared__ float sums[2 * C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1) {
+            st1[v] += __shfl_xor_sync(kFull, st1[v], o);
+            st2[v] += __shfl_xor_sync(kFull, st2[v], o);
+        }
+    if (lane < LANES) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            red[warp * 2 * C + chan<C>(sub, v)] = st1[v];
+            red[warp * 2 * C + C + chan<C>(sub, v)] = st2[v];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nwarp; ++w) t += red[w * 2 * C + i];
+        gn.partials[(int64_t)blockIdx.x * 2 * C + i] = t;
+    }
+    __syncthreads();
+    if (!hier_fold_any(gn.partials, gn.gpartials, 2 * C, gn.counters, red, sums)) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float n = (float)gn.n_rows;
+        const float md = sums[c] / n;
+        const float mean = (bias ? __ldg(bias + c) : 0.f) + kshift[c] + md;
+        const float M2 = fmaxf(sums[C + c] - sums[c] * md, 0.f);
+        const float shift = mean * (1.f - __ldg(gn.alpha + c));  // mean of (o - alpha*mu)
+        const float var = (M2 + n * shift * shift) / n;
+        gn.stats[c] = mean;
+        gn.stats[C + c] = 1.f / sqrtf(var + gn.eps);
+        gn.stats[2 * C + c] = var;
+    }
+}
+
+// STATS variants carry 2*NV more live registers per lane: they are built for 768-thread CTAs (85 registers) instead of
+// spilling inside the gather loop at the 64-register cap of a 1024-thread CTA.
+constexpr int kGatStatsThreads = 768;
+template <int C, bool PIPE, bool STATS>
+__global__ void __launch_bounds__(STATS ? kGatStatsThreads : kGatMaxThreads, 1) gat_fwd_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ h,
     const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
     float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int N, float slope,
-    int chunk_rows, int ipc_shift, int ahead) {
+    int chunk_rows, int ipc_shift, int ahead, const GnFuse gn) {
     using M = GatMap<C>;
-    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
+    constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW, NV = M::NV;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
     const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
     const float* hb = h + sub * VEC;
+    constexpr bool stats = STATS;  // a compile-time switch: the 2*NV accumulators must not cost the plain kernel registers
+    __shared__ float kshift[STATS ? C : 1];
+    if constexpr (STATS) gat_fwd_row0_shift<C>(rowptr, col, h, s, d, slope, kshift);
+    float st1[NV], st2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) st1[v] = st2[v] = 0.f;
     if constexpr (!PIPE) {
         for (int it = 0; it < sw.niter; ++it) {
             const int row = sw.raw(it);
@@ -287,7 +415,10 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
             const int deg = __ldg(rowptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
             if (maxdeg > CAP) {
-                if (valid) gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                if (valid) {
+                    gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                    if (stats) gat_fwd_row_stats_from_out<C>(row, sub, out, bias, st1, st2, kshift);
+                }
                 continue;
             }
             const float di = __ldg(d + rr);
@@ -299,10 +430,10 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
                 j[k] = ok ? __ldg(col + beg + sub + k * LANES) : rr;
                 u[k] = ok ? lrelu(__ldg(s + j[k]) + di, slope) : -INFINITY;
             }
-            gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j, u, hb, bias, out, m_out, z_out);
+            gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j, u, hb, bias, out, m_out, z_out, st1, st2, stats, kshift);
         }
     } else {
-        if (sw.niter == 0) return;
+        if (sw.niter == 0 && !stats) return;
         int beg2 = 0, deg2 = 0, deg1 = 0, deg0 = 0;
         int j1[EPL], j0[EPL];
         float s0[EPL], d1 = 0.f, d0 = 0.f;
@@ -338,12 +469,15 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
                 const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
-                    if (valid) gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                    if (valid) {
+                        gat_fwd_row_generic<C>(row, sub, gm, rowptr, col, h, s, d, bias, out, m_out, z_out, slope);
+                        if (stats) gat_fwd_row_stats_from_out<C>(row, sub, out, bias, st1, st2, kshift);
+                    }
                 } else {
                     float u[EPL];
 #pragma unroll
                     for (int k = 0; k < EPL; ++k) u[k] = sub + k * LANES < deg0 ? lrelu(s0[k] + d0, slope) : -INFINITY;
-                    gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j0, u, hb, bias, out, m_out, z_out);
+                    gat_fwd_row_fast<C>(row, valid, maxdeg, sub, j0, u, hb, bias, out, m_out, z_out, st1, st2, stats, kshift);
                 }
             }
             // rotate the pipeline registers
@@ -354,6 +488,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_fwd_kernel(
             beg2 = beg3, deg2 = deg3;
         }
     }
+    if (stats) gat_fwd_finish_stats<C>(gn, bias, sub, st1, st2, kshift);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -812,9 +947,9 @@ struct GatCfg {
     bool pipe;
 };
 template <int C>
-static GatCfg gat_cfg(int64_t N) {
+static GatCfg gat_cfg(int64_t N, int max_threads = kGatMaxThreads) {
     const bool small = !g_tune[4] && N * C * 4 < (int64_t)(24 << 20);
-    const int threads = small ? 256 : g_tune[0];
+    const int threads = small ? 256 : (g_tune[0] < max_threads ? g_tune[0] : max_threads);
     const int64_t rows_iter = (int64_t)(threads / 32) * GatMap<C>::RPW;
     const int64_t iters = ceil_div(N, rows_iter);
     if (small) {  // one contiguous chunk per CTA, one sweep iteration each while the grid fits 8 CTAs per SM
@@ -842,9 +977,25 @@ static GatCfg gat_cfg(int64_t N) {
 
 template <int C>
 static int launch_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
-                      float* out, float* m, float* z, float slope, cudaStream_t st) {
-    const GatCfg c = gat_cfg<C>(g->N);
-    BG_GAT_LAUNCH(gat_fwd_kernel, g->rowptr, g->col, h, s, d, bias, out, m, z, (int)g->N, slope);
+                      float* out, float* m, float* z, float slope, cudaStream_t st, const float* gn_alpha = nullptr,
+                      float gn_eps = 0.f, float* gn_stats = nullptr, float* ws = nullptr) {
+    const GatCfg c = gat_cfg<C>(g->N, gn_stats ? kGatStatsThreads : kGatMaxThreads);
+    GnFuse gn{};
+    if (gn_stats) {  // workspace: [counters 4 KiB][partials grid x 2C][group partials]
+        gn.counters = reinterpret_cast<unsigned int*>(ws);
+        gn.partials = ws + kCounterBytes / sizeof(float);
+        gn.gpartials = gn.partials + (size_t)c.grid * 2 * C;
+        gn.alpha = gn_alpha, gn.stats = gn_stats, gn.eps = gn_eps, gn.n_rows = g->N;
+    }
+#define BG_FWD(PIPE_, STATS_)                                                                                              \
+    gat_fwd_kernel<C, PIPE_, STATS_><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, h, s, d, bias, out, m, z, (int)g->N, slope, \
+                                                                   c.chunk_rows, c.ipc_shift, c.ahead, gn)
+    if (C >= 8 && c.pipe) {
+        if (gn_stats) BG_FWD((C >= 8), true); else BG_FWD((C >= 8), false);
+    } else {
+        if (gn_stats) BG_FWD(false, true); else BG_FWD(false, false);
+    }
+#undef BG_FWD
     return check_launch("bg_gat_fwd");
 }
 template <int C>
@@ -911,6 +1062,25 @@ extern "C" int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, cons
     if (int rc = check_graph(g)) return rc;
     BG_REQUIRE(h && s && d && out && m && z, BG_EINVAL, "bg_gat_fwd: null pointer");
 #define CALL(CC) launch_fwd<CC>(g, h, s, d, bias, out, m, z, slope, as_stream(stream))
+    BG_DISPATCH_C(C, CALL)
+#undef CALL
+}
+
+// Upper bound of the grid any launch geometry uses: 8 CTAs per SM (small graphs) or g_tune CTAs per SM.
+extern "C" size_t bg_gat_fwd_gn_ws(int64_t N, int32_t C) {
+    (void)N;
+    const size_t gmax = (size_t)kSMs * (g_tune[1] > 8 ? g_tune[1] : 8) + 16;
+    return (size_t)kCounterBytes + (gmax + gmax / kFoldGroup + 2) * 2 * (size_t)C * sizeof(float);
+}
+
+extern "C" int bg_gat_fwd_gn(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias, float* out,
+                             float* m, float* z, int32_t C, float slope, const float* gn_alpha, float gn_eps, float* gn_stats,
+                             float* workspace, size_t ws_bytes, void* stream) {
+    if (int rc = check_graph(g)) return rc;
+    BG_REQUIRE(h && s && d && out && m && z && gn_alpha && gn_stats && workspace, BG_EINVAL, "bg_gat_fwd_gn: null pointer");
+    BG_REQUIRE(ws_bytes >= bg_gat_fwd_gn_ws(g->N, C), BG_EINVAL, "bg_gat_fwd_gn: workspace too small");
+    BG_REQUIRE(g_tune[6] == 0 || g_tune[6] <= kSMs * 8, BG_EINVAL, "bg_gat_fwd_gn: grid cap too large");
+#define CALL(CC) launch_fwd<CC>(g, h, s, d, bias, out, m, z, slope, as_stream(stream), gn_alpha, gn_eps, gn_stats, workspace)
     BG_DISPATCH_C(C, CALL)
 #undef CALL
 }

@@ -486,6 +486,19 @@ extern "C" int bg_graphnorm_fwd(const float* o, const float* w, const float* bet
     return check_launch("bg_graphnorm_fwd");
 }
 
+// The apply half alone: statistics come from bg_gat_fwd_gn (fused into the aggregation) or any other producer.
+extern "C" int bg_graphnorm_apply(const float* o, const float* w, const float* beta, const float* alpha, const float* stats,
+                                  const uint8_t* keep, float keep_prob, uint64_t seed, uint64_t offset, int64_t N, int32_t C,
+                                  float* x1, void* stream) {
+    BG_REQUIRE(o && w && beta && alpha && stats && x1, BG_EINVAL, "bg_graphnorm_apply: null pointer");
+    BG_REQUIRE(N > 0 && C >= 1 && C <= 128, BG_EINVAL, "bg_graphnorm_apply: bad shape");
+    BG_REQUIRE(keep_prob > 0.f && keep_prob <= 1.f, BG_EINVAL, "bg_graphnorm_apply: keep_prob must be in (0,1]");
+    const int64_t total = N * C;
+    gn_apply_kernel<<<flat_grid(total), kThreads, 0, as_stream(stream)>>>(o, w, beta, alpha, stats, keep, keep_prob, seed, offset,
+                                                                          total, C, x1);
+    return check_launch("bg_graphnorm_apply");
+}
+
 extern "C" int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x1, const float* w, const float* alpha,
                                 const float* stats, float keep_scale, int64_t N, int32_t C, float* go, float* dparams,
                                 int32_t accumulate, float* bstats, float* workspace, size_t ws_bytes, void* stream) {

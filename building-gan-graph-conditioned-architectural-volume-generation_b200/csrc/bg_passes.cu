@@ -247,9 +247,11 @@ static BgWgrad wg(int64_t N, const float* gz, int ld_gz, int Cout, const BgSeg* 
 static int conv_forward(const Ctx& c, const ConvL& L, const float* x, const uint8_t* keep, float keep_prob, uint64_t seed,
                         uint64_t offset) {
     BG_TRY(matmul_nt(c, x, c.N, c.P[L.p_W], L.cout, L.cin, 0, L.cin, L.h, c.P[L.p_as], c.P[L.p_ad], L.s, L.d));
-    BG_TRY(bg_gat_fwd(c.graph, L.h, L.s, L.d, c.P[L.p_bias], L.o, L.m, L.z, L.cout, 0.2f, c.st));
-    return bg_graphnorm_fwd(L.o, c.P[L.p_gw], c.P[L.p_gb], c.P[L.p_ga], keep, keep_prob, seed, offset, c.N, L.cout, 1e-5f, L.x1,
-                            L.stats, c.red, c.red_bytes, c.st);
+    // aggregation with the GraphNorm statistics fused into its epilogue, then ONE elementwise pass
+    BG_TRY(bg_gat_fwd_gn(c.graph, L.h, L.s, L.d, c.P[L.p_bias], L.o, L.m, L.z, L.cout, 0.2f, c.P[L.p_ga], 1e-5f, L.stats, c.red,
+                         c.red_bytes < kWgradOffsetBytes ? c.red_bytes : kWgradOffsetBytes, c.st));
+    return bg_graphnorm_apply(L.o, c.P[L.p_gw], c.P[L.p_gb], c.P[L.p_ga], L.stats, keep, keep_prob, seed, offset, c.N, L.cout,
+                              L.x1, c.st);
 }
 
 // First-order backward of one block.  gx1 may be null (then `inj_o` IS the gradient at o).  Temporaries come

@@ -79,6 +79,9 @@ SIGNATURES = {
     "bg_ln_act_bwd_ws": (_SZ, [_I64, _I32]),
     "bg_tune": (C.c_int, [_I32, _I32]),
     "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
+    "bg_gat_fwd_gn_ws": (_SZ, [_I64, _I32]),
+    "bg_gat_fwd_gn": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P, _F, _P, _P, _SZ, _P]),
+    "bg_graphnorm_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, C.c_uint64, C.c_uint64, _I64, _I32, _P, _P]),
     "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),
     "bg_gcn_norm": (C.c_int, [C.POINTER(BgGraph), _P, _P]),
@@ -437,6 +440,30 @@ def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope:
     _check(lib.bg_gat_fwd(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
                           m.data_ptr(), z.data_ptr(), c, slope, _stream()))
     return out, m, z
+
+
+@_op("gat_fwd_gn", 2)
+def gat_fwd_gn(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], gn_w: Tensor, gn_beta: Tensor, gn_alpha: Tensor,
+               keep: Optional[Tensor] = None, keep_prob: float = 1.0, seed: int = 0, offset: int = 0, slope: float = 0.2,
+               eps: float = 1e-5):
+    """GATConv aggregation with the following GraphNorm's statistics fused into its epilogue, then the elementwise
+    GraphNorm + ReLU + dropout pass.  Returns (o, m, z, x1, stats) like gat_fwd + graphnorm_fwd."""
+    lib = load()
+    _cf32(h, "h")
+    n, c = h.shape
+    dev = h.device
+    out = torch.empty_like(h)
+    m = torch.empty(n, dtype=torch.float32, device=dev)
+    z = torch.empty(n, dtype=torch.float32, device=dev)
+    stats = torch.empty(3 * c, dtype=torch.float32, device=dev)
+    ws = workspace(lib.bg_gat_fwd_gn_ws(n, c), dev)
+    _check(lib.bg_gat_fwd_gn(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
+                             m.data_ptr(), z.data_ptr(), c, slope, gn_alpha.data_ptr(), eps, stats.data_ptr(), ws.data_ptr(),
+                             ws.numel() * 4, _stream()))
+    x1 = torch.empty_like(h)
+    _check(lib.bg_graphnorm_apply(out.data_ptr(), gn_w.data_ptr(), gn_beta.data_ptr(), gn_alpha.data_ptr(), stats.data_ptr(),
+                                  _p(keep), keep_prob, seed, offset, n, c, x1.data_ptr(), _stream()))
+    return out, m, z, x1, stats
 
 
 @_op("gat_bwd", 2)

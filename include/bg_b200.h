@@ -183,6 +183,16 @@ int bg_gatv2_bwd2(const BgGraph* g, const float* Hl, const float* Hr, const floa
  * Saves the per-row softmax max `m` and denominator `z` (incl. PyG's +1e-16). */
 int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                float* out, float* m, float* z, int32_t C, float slope, void* stream);
+/* The same aggregation with the statistics of the GraphNorm that follows it (models.py:72-73) fused into its epilogue:
+ * gn_stats[3C] = (mean, rstd, var of out - mean_scale*mean) over all N rows, as bg_graphnorm_fwd computes them, so that
+ * the normalisation is one elementwise pass (bg_graphnorm_apply) and `out` is not re-read for its moments.  The moment
+ * sums are shifted by a sample of the column (row 0's aggregate, recomputed by every CTA) and folded in a fixed order
+ * (deterministic).  workspace: bg_gat_fwd_gn_ws bytes,
+ * first 4096 bytes zero on first use. */
+size_t bg_gat_fwd_gn_ws(int64_t N, int32_t C);
+int bg_gat_fwd_gn(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias, float* out,
+                  float* m, float* z, int32_t C, float slope, const float* gn_alpha, float gn_eps, float* gn_stats,
+                  float* workspace, size_t ws_bytes, void* stream);
 /* First-order backward.  Inputs gout[N,C] (= d loss/d out), h, s, d, m, z, a_src, a_dst.
  * Outputs: gh_tot[N,C] = d loss/d h including the s- and d-paths, gsd[N,2] = (d loss/d s,
  * d loss/d d) for the attention-vector gradients, and the per-edge scratch P[E], DU[E]
@@ -207,6 +217,9 @@ int bg_gat_bwd2(const BgGraph* g, const float* Ht, const float* St, const float*
  * order); keep == NULL && keep_prob < 1: Philox4x32-10 mask from (seed, offset) generated in the
  * kernel; keep == NULL && keep_prob == 1: eval (no dropout).  The backward kernels take
  * keep_scale = 1/keep_prob (1 in eval) and recover the mask from x1 > 0. */
+int bg_graphnorm_apply(const float* o, const float* w, const float* beta, const float* alpha, const float* stats,
+                       const uint8_t* keep, float keep_prob, uint64_t seed, uint64_t offset, int64_t N, int32_t C,
+                       float* x1, void* stream); /* the elementwise half alone (statistics from bg_gat_fwd_gn) */
 int bg_graphnorm_fwd(const float* o, const float* w, const float* beta, const float* alpha,
                      const uint8_t* keep, float keep_prob, uint64_t seed, uint64_t offset, int64_t N, int32_t C,
                      float eps, float* x1, float* stats, float* workspace, size_t ws_bytes, void* stream);

@@ -137,6 +137,42 @@ def test_gat_large_graph_kernels(C, pipe):
         L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 1), L.bg_tune(2, 128), L.bg_tune(5, 64), L.bg_tune(6, 0)
 
 
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("geometry", ["small", "large", "large-pipelined"])
+def test_gat_fwd_with_fused_graphnorm_statistics(C, geometry):
+    """bg_gat_fwd_gn + bg_graphnorm_apply == bg_gat_fwd + bg_graphnorm_fwd == the oracle (GATConv then GraphNorm over all
+    rows, ReLU): the moments accumulated in the aggregation epilogue (shifted by a sample row, folded across CTAs in a
+    fixed order) give the same mean / rstd / var; on the building batch and on the hub graph (generic high-degree rows)."""
+    L = lib.load()
+    if geometry != "small":
+        L.bg_tune(4, 1), L.bg_tune(3, int(geometry == "large-pipelined")), L.bg_tune(0, 128), L.bg_tune(1, 1), L.bg_tune(5, 4)
+        L.bg_tune(6, 5)
+    try:
+        for hub in (False, True):
+            if hub:
+                n, edges, csr = _hub_graph()
+            else:
+                vb, edges, csr = _graph()
+                n = vb.num_nodes
+            h, s, d, b = _rand(n, C, seed=1), _rand(n, seed=2), _rand(n, seed=3), _rand(C, seed=4) * 3.0
+            w, beta, alpha = _rand(C, seed=5) * 0.3 + 1, _rand(C, seed=6) * 0.3, _rand(C, seed=7) * 0.3 + 1
+            f = lambda t: t.float().to(DEV).contiguous()
+            o, m, z, x1, stats = lib.gat_fwd_gn(csr, f(h), f(s), f(d), f(b), f(w), f(beta), f(alpha))
+            o_ref = pyg.gat_core(h, s, d, edges) + b
+            x1_ref, mu, var = _gn_ref(o_ref, w, beta, alpha, None, 1.0)
+            assert_close(o, o_ref, 1e-5, f"fused o C={C}")
+            assert_close(stats[:C], mu, 3e-5, "fused mean")
+            assert_close(stats[2 * C:], var, 3e-5, "fused var")
+            assert_close(x1, x1_ref, 3e-5, f"fused x1 C={C}")
+            o2, m2, z2 = lib.gat_fwd(csr, f(h), f(s), f(d), f(b))
+            assert torch.equal(o, o2) and torch.equal(m, m2) and torch.equal(z, z2)
+            # deterministic: the fold order is fixed
+            again = lib.gat_fwd_gn(csr, f(h), f(s), f(d), f(b), f(w), f(beta), f(alpha))
+            assert torch.equal(stats, again[4]) and torch.equal(x1, again[3])
+    finally:
+        L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 1), L.bg_tune(2, 128), L.bg_tune(5, 64), L.bg_tune(6, 0)
+
+
 def test_gat_deterministic():
     vb, edges, csr = _graph()
     n, C = vb.num_nodes, 64
