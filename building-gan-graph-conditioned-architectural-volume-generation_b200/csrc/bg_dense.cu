@@ -76,6 +76,9 @@ struct DenseParams {
     float* out;
     int64_t ld_out;
     float *xhat, *rstd, *s, *d;
+    const float* gate;
+    int64_t ld_gate;
+    float gate_slope;
 };
 
 template <int BN, int TM, int TN>
@@ -201,6 +204,12 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
                 p.s[grow] = ss;
                 p.d[grow] = dd;
             }
+        }
+        if (p.gate && grow < p.N) {  // fused activation backward of the layer below: zero / scale where its output was off
+            const float* grw = p.gate + grow * p.ld_gate + col0 + tx * TN;
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                if (col0 + tx * TN + j < p.Cout) y[j] *= (__ldg(grw + j) > 0.f ? 1.f : p.gate_slope);
         }
         if (grow < p.N) {
             float* orow = p.out + grow * p.ld_out + col0 + tx * TN;
@@ -659,12 +668,13 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     p.bias = a->bias; p.gamma = a->ln_gamma; p.beta = a->ln_beta;
     p.att_src = a->att_src; p.att_dst = a->att_dst; p.act = a->act;
     p.out = a->out; p.ld_out = a->ld_out; p.xhat = a->xhat; p.rstd = a->rstd; p.s = a->s; p.d = a->d;
+    p.gate = a->gate; p.ld_gate = a->ld_gate; p.gate_slope = a->gate_slope;
     const bool rowwise = a->ln_gamma || a->att_src;
     BG_REQUIRE(!a->ln_gamma || a->ln_beta, BG_EINVAL, "bg_dense_fwd: LayerNorm needs gamma and beta");
     BG_REQUIRE(!a->att_src || (a->att_dst && a->s && a->d), BG_EINVAL, "bg_dense_fwd: attention dots need att_dst, s, d");
     BG_REQUIRE(!rowwise || a->Cout <= 128, BG_EUNSUPPORTED, "bg_dense_fwd: row-wise epilogue needs Cout<=128 (got %d)", a->Cout);
     {  // 128/64-wide layers with plain row-major weights go to the tensor cores (tcgen05, 3xTF32 split: fp32-accurate)
-        const int rc = dense_tc_try(a, p.K, as_stream(stream));
+        const int rc = a->gate ? 1 : dense_tc_try(a, p.K, as_stream(stream));
         if (rc <= 0) return rc;
     }
     int bn = 8;

@@ -211,21 +211,26 @@ static int dense_fwd_call(const Ctx& c, const DenseL& l, int64_t rows, const BgS
 }
 
 // out[rows, hi-lo] = X[rows, Kx] @ W[:, lo:hi]   (W is [Kx, ldw] row-major: the backward-input product)
-static int matmul_nn(const Ctx& c, const float* X, int64_t rows, int Kx, const float* W, int ldw, int lo, int hi, float* out) {
+// `gate` (optional, [rows, hi-lo]): the ReLU backward of the layer below fused into the epilogue (out *= gate > 0)
+static int matmul_nn(const Ctx& c, const float* X, int64_t rows, int Kx, const float* W, int ldw, int lo, int hi, float* out,
+                     const float* gate = nullptr) {
     BgDense a{};
     a.N = rows; a.nseg = 1; a.seg[0] = seg(X, Kx, Kx);
     a.W = W + lo; a.w_so = 1; a.w_sk = ldw; a.Cout = hi - lo;
     a.act = BG_ACT_NONE; a.out = out; a.ld_out = hi - lo;
+    a.gate = gate; a.ld_gate = hi - lo; a.gate_slope = 0.f;
     return bg_dense_fwd(&a, c.st);
 }
 // out[rows, Cout] = X[rows, hi-lo] @ W[:, lo:hi]^T   (W is [Cout, ldw] row-major)
 static int matmul_nt(const Ctx& c, const float* X, int64_t rows, const float* W, int Cout, int ldw, int lo, int hi, float* out,
-                     const float* a_src = nullptr, const float* a_dst = nullptr, float* s = nullptr, float* d = nullptr) {
+                     const float* a_src = nullptr, const float* a_dst = nullptr, float* s = nullptr, float* d = nullptr,
+                     const float* gate = nullptr) {
     BgDense a{};
     a.N = rows; a.nseg = 1; a.seg[0] = seg(X, hi - lo, hi - lo);
     a.W = W + lo; a.w_so = ldw; a.w_sk = 1; a.Cout = Cout;
     a.act = BG_ACT_NONE; a.out = out; a.ld_out = Cout;
     a.att_src = a_src; a.att_dst = a_dst; a.s = s; a.d = d;
+    a.gate = gate; a.ld_gate = Cout; a.gate_slope = 0.f;
     return bg_dense_fwd(&a, c.st);
 }
 
@@ -257,7 +262,7 @@ static int conv_forward(const Ctx& c, const ConvL& L, const float* x, const uint
 // First-order backward of one block.  gx1 may be null (then `inj_o` IS the gradient at o).  Temporaries come
 // from T; when `keep` the intermediates are written to the block's b_* buffers instead (second-order sweep).
 static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float* gx1, float keep_scale, const float* inj_o,
-                         const float* inj_h, bool keep, Arena& T, float* gx_out) {
+                         const float* inj_h, bool keep, Arena& T, float* gx_out, const float* gate_x = nullptr) {
     const int C = L.cout;
     float* go = keep ? L.b_go : T.f((size_t)c.N * C);
     float* gh = keep ? L.b_gh : T.f((size_t)c.N * C);
@@ -288,7 +293,7 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
                          wg(c.N, gsd, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, c.accumulate)};
         BG_TRY(wgrad_launch(pr, inj_h ? 1 : 3, *c.q, as_stream(c.st)));
     }
-    if (gx_out) BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out));
+    if (gx_out) BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out, gate_x));
     if (keep && gx1) BG_TRY(cudaMemcpyAsync(L.b_gx1, gx1, (size_t)c.N * C * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) ==
                                     cudaSuccess
                                 ? BG_OK
@@ -324,10 +329,16 @@ static int conv_backward2(const Ctx& c, const ConvL& L, const float* Xt, float k
 
 // Backward of one dense layer: gz (pre-activation gradient), parameter gradients, and the input gradient for
 // the requested column windows of the layer input.
+// `gout_is_gz`: the incoming gradient already went through this layer's activation backward (the producer's epilogue
+// was gated with this layer's output).  `gate_below`: this layer's input is the ReLU output of a plain layer - gate the
+// first backward-input product with it, so that layer needs no activation-backward launch of its own.
 static int dense_backward(const Ctx& c, const DenseL& l, int64_t rows, const BgSeg* segs, int nseg, const float* gout, float* gz_buf,
-                          const int (*win)[2], float* const* gin, int nwin, const float** gz_out) {
+                          const int (*win)[2], float* const* gin, int nwin, const float** gz_out, bool gout_is_gz = false,
+                          const float* gate_below = nullptr) {
     const float* gz = gout;
-    if (l.pg >= 0) {
+    if (gout_is_gz) {
+        BG_REQUIRE(l.pg < 0, BG_EINVAL, "dense_backward: a fused activation backward needs a layer without LayerNorm");
+    } else if (l.pg >= 0) {
         float* dgam = c.G ? c.g(l.pg) : nullptr;
         float* dbet = c.G ? c.g(l.pbeta) : nullptr;
         BG_REQUIRE(c.G, BG_EINVAL, "LayerNorm backward needs a grad bucket");
@@ -345,7 +356,8 @@ static int dense_backward(const Ctx& c, const DenseL& l, int64_t rows, const BgS
         BgWgrad pr = wg(rows, gz, l.cout, l.cout, all, nseg + 1, c.g(l.pW), l.cin, c.g(l.pb), c.accumulate);
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(c.st)));
     }
-    for (int i = 0; i < nwin; ++i) BG_TRY(matmul_nn(c, gz, rows, l.cout, c.P[l.pW], l.cin, win[i][0], win[i][1], gin[i]));
+    for (int i = 0; i < nwin; ++i)
+        BG_TRY(matmul_nn(c, gz, rows, l.cout, c.P[l.pW], l.cin, win[i][0], win[i][1], gin[i], i == 0 ? gate_below : nullptr));
     if (gz_out) *gz_out = gz;
     return BG_OK;
 }
@@ -638,6 +650,8 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
     const int64_t N = c.N;
     const int dh = md->d_hidden;
     const float* g = g_score;
+    bool g_is_gz = false;  // g already carries the activation backward of the layer it enters (fused gate)
+    auto plain_relu = [](const DenseL& l) { return l.pg < 0 && l.act == BG_ACT_RELU; };
     if (g) {
         for (int i = 3; i >= 0; --i) {
             const float* xin = i == 0 ? d.conv[d.n_conv - 1].x1 : d.dec[i - 1].out;
@@ -645,31 +659,38 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
             DenseL l = d.dec[i];
             if (i == 3) l.out = const_cast<float*>(score);
             int win[1][2] = {{0, l.cin}};
-            float* gin[1] = {T.f((size_t)N * l.cin)};
-            float* gzbuf = keep ? l.b_gz : T.f((size_t)N * l.cout);
+            const bool gate = i > 0 && plain_relu(d.dec[i - 1]);  // dec[i-1]'s ReLU backward rides on this dgrad
+            float* gin[1] = {gate && keep ? d.dec[i - 1].b_gz : T.f((size_t)N * l.cin)};
+            float* gzbuf = g_is_gz ? nullptr : (keep ? l.b_gz : T.f((size_t)N * l.cout));
             const float* gz_used = nullptr;
-            BG_TRY(dense_backward(c, l, N, &s, 1, g, gzbuf, win, gin, 1, &gz_used));
-            if (keep && gz_used != gzbuf)  // bare Linear: gz == gout, keep a copy for the second-order sweep
+            BG_TRY(dense_backward(c, l, N, &s, 1, g, gzbuf, win, gin, 1, &gz_used, g_is_gz, gate ? d.dec[i - 1].out : nullptr));
+            if (keep && !g_is_gz && gz_used != gzbuf)  // bare Linear: gz == gout, keep a copy for the second-order sweep
                 BG_TRY(cudaMemcpyAsync(gzbuf, gz_used, (size_t)N * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) ==
                                cudaSuccess
                            ? BG_OK
                            : BG_ECUDA);
             g = gin[0];
+            g_is_gz = gate;
         }
     }
     for (int k = d.n_conv - 1; k >= 0; --k) {
         const float* x_in = k == 0 ? d.pre[1].out : d.conv[k - 1].x1;
-        float* gx = T.f((size_t)N * d.conv[k].cin);
+        const bool gate = k == 0 && plain_relu(d.pre[1]);
+        float* gx = gate && keep ? d.pre[1].b_gz : T.f((size_t)N * d.conv[k].cin);
         BG_TRY(conv_backward(c, d.conv[k], x_in, g, training_scale, inj_o ? inj_o[k] : nullptr, inj_h ? inj_h[k] : nullptr, keep, T,
-                             gx));
+                             gx, gate ? d.pre[1].out : nullptr));
         g = gx;
+        g_is_gz = gate;
     }
     {
         BgSeg s = seg(d.pre[0].out, dh, dh);
         int win[1][2] = {{0, dh}};
-        float* gin[1] = {T.f((size_t)N * dh)};
-        BG_TRY(dense_backward(c, d.pre[1], N, &s, 1, g, keep ? d.pre[1].b_gz : T.f((size_t)N * dh), win, gin, 1, nullptr));
+        const bool gate = plain_relu(d.pre[0]);
+        float* gin[1] = {gate && keep ? d.pre[0].b_gz : T.f((size_t)N * dh)};
+        float* gzbuf = g_is_gz ? nullptr : (keep ? d.pre[1].b_gz : T.f((size_t)N * dh));
+        BG_TRY(dense_backward(c, d.pre[1], N, &s, 1, g, gzbuf, win, gin, 1, nullptr, g_is_gz, gate ? d.pre[0].out : nullptr));
         g = gin[0];
+        g_is_gz = gate;
     }
     {
         const int lo = md->local_dim + md->voxel_dim;
@@ -677,7 +698,8 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
                        seg(label, md->num_classes, md->num_classes)};
         int win[1][2] = {{lo, lo + md->num_classes}};
         float* gin[1] = {g_label};
-        BG_TRY(dense_backward(c, d.pre[0], N, s3, 3, g, keep ? d.pre[0].b_gz : T.f((size_t)N * dh), win, gin, g_label ? 1 : 0, nullptr));
+        float* gzbuf = g_is_gz ? nullptr : (keep ? d.pre[0].b_gz : T.f((size_t)N * dh));
+        BG_TRY(dense_backward(c, d.pre[0], N, s3, 3, g, gzbuf, win, gin, g_label ? 1 : 0, nullptr, g_is_gz));
     }
     return BG_OK;
 }
@@ -748,18 +770,20 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         BgSeg lt = seg(Lt, K, K);
         BgWgrad pr = wg(N, d.pre[0].b_gz, dh, dh, &lt, 1, c.g(d.pre[0].pW) + lo, d.pre[0].cin, nullptr, 1);
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
-        BG_TRY(matmul_nt(c, Lt, N, params[d.pre[0].pW], dh, d.pre[0].cin, lo, lo + K, ta));          // cot(gz0)
-        BG_TRY(bg_ln_act_bwd(ta, d.pre[0].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
+        // cot(g_a) = cot(gz0) * [x_a > 0], the mask fused into the product's epilogue
+        BG_TRY(matmul_nt(c, Lt, N, params[d.pre[0].pW], dh, d.pre[0].cin, lo, lo + K, tb, nullptr, nullptr, nullptr, nullptr,
+                         d.pre[0].out));
+        (void)ta;
     }
     // pre[1] backward was: gz1 = g_b * [x_b > 0] ; g_a = gz1 @ W1          (tb = cot(g_a))
     {
         BgSeg ts = seg(tb, dh, dh);
         BgWgrad pr = wg(N, d.pre[1].b_gz, dh, dh, &ts, 1, c.g(d.pre[1].pW), dh, nullptr, 1);
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
-        float* tc = T.f((size_t)N * dh);
-        BG_TRY(matmul_nt(c, tb, N, params[d.pre[1].pW], dh, dh, 0, dh, tc));                         // cot(gz1)
-        tb = T.f((size_t)N * dh);  // the previous tb is a queued weight-gradient operand: leave it alone
-        BG_TRY(bg_ln_act_bwd(tc, d.pre[1].out, nullptr, nullptr, nullptr, N, dh, BG_ACT_RELU, tb, nullptr, nullptr, 0, nullptr, 0, stream));
+        float* tc = T.f((size_t)N * dh);  // the previous tb is a queued weight-gradient operand: leave it alone
+        BG_TRY(matmul_nt(c, tb, N, params[d.pre[1].pW], dh, dh, 0, dh, tc, nullptr, nullptr, nullptr, nullptr,
+                         d.pre[1].out));                                                          // cot(g_b) = cot(gz1) * mask
+        tb = tc;
     }
     float* t = tb;       // cotangent flowing up the backward chain (fresh buffer per layer)
     for (int k = 0; k < d.n_conv; ++k) {
@@ -775,12 +799,17 @@ extern "C" int bg_disc_backward2(const BgModelDesc* md, const float* const* para
         BG_TRY(wgrad_launch(&pr, 1, *c.q, as_stream(stream)));
         if (i == 3 && !gt_score) break;
         float* cz = T.f((size_t)N * l.cout);
-        BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, cz));                     // cot(gz)
-        if (l.act != BG_ACT_NONE) {
-            t = T.f((size_t)N * l.cout);
-            BG_TRY(bg_ln_act_bwd(cz, l.out, nullptr, nullptr, nullptr, N, l.cout, l.act, t, nullptr, nullptr, 0, nullptr, 0, stream));
-        } else {
+        if (l.act == BG_ACT_RELU) {  // cot(g_y) = cot(gz) * [y > 0], fused
+            BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, cz, nullptr, nullptr, nullptr, nullptr, l.out));
             t = cz;
+        } else {
+            BG_TRY(matmul_nt(c, t, N, params[l.pW], l.cout, l.cin, 0, l.cin, cz));                 // cot(gz)
+            if (l.act != BG_ACT_NONE) {
+                t = T.f((size_t)N * l.cout);
+                BG_TRY(bg_ln_act_bwd(cz, l.out, nullptr, nullptr, nullptr, N, l.cout, l.act, t, nullptr, nullptr, 0, nullptr, 0, stream));
+            } else {
+                t = cz;
+            }
         }
     }
     if (gt_score)

@@ -40,7 +40,8 @@ class BgDense(C.Structure):
                 ("w_so", C.c_int64), ("w_sk", C.c_int64), ("Cout", C.c_int32), ("bias", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("act", C.c_int32), ("att_src", C.c_void_p),
                 ("att_dst", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64), ("xhat", C.c_void_p),
-                ("rstd", C.c_void_p), ("s", C.c_void_p), ("d", C.c_void_p)]
+                ("rstd", C.c_void_p), ("s", C.c_void_p), ("d", C.c_void_p), ("gate", C.c_void_p), ("ld_gate", C.c_int64),
+                ("gate_slope", C.c_float)]
 
 
 class BgModelDesc(C.Structure):
@@ -334,7 +335,8 @@ def _fill_segs(arr, segs: Sequence[Seg]) -> Tuple[int, int]:
 @_op("dense_fwd", 1)
 def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln: Optional[Tuple[Tensor, Tensor]] = None,
               act: int = ACT_NONE, att: Optional[Tuple[Tensor, Tensor]] = None, transposed: bool = False,
-              save_ln: bool = False, out: Optional[Tensor] = None, cols: Optional[Tuple[int, int]] = None):
+              save_ln: bool = False, out: Optional[Tensor] = None, cols: Optional[Tuple[int, int]] = None,
+              gate: Optional[Tensor] = None, gate_slope: float = 0.0):
     """out = act(LN(X @ Wop^T + bias)).  ``transposed=False``: Wop = W ([Cout,K]).  ``transposed=True``:
     Wop = W^T, i.e. out = X @ W (the backward-input product); ``cols=(a,b)`` then restricts the output to
     columns a..b of W (only those input gradients are needed).  Returns a dict of the produced tensors."""
@@ -371,6 +373,10 @@ def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln:
         res["d"] = torch.empty(n, dtype=torch.float32, device=dev)
         a.s, a.d = res["s"].data_ptr(), res["d"].data_ptr()
     a.out, a.ld_out = out.data_ptr(), out.stride(0)
+    if gate is not None:  # out *= gate > 0 ? 1 : gate_slope  (activation backward of the layer below, fused)
+        _f32(gate, "gate")
+        assert gate.shape == out.shape and gate.stride(1) == 1
+        a.gate, a.ld_gate, a.gate_slope = gate.data_ptr(), gate.stride(0), gate_slope
     _check(lib.bg_dense_fwd(C.byref(a), _stream()))
     return res
 

@@ -112,6 +112,11 @@ typedef struct BgDense {
     float* xhat;                         /* optional [N,Cout] LayerNorm normalised value (saved for backward) */
     float* rstd;                         /* optional [N] */
     float* s; float* d;                  /* optional [N] each */
+    const float* gate;                   /* optional [N,Cout] (leading dimension ld_gate): out *= gate > 0 ? 1 : gate_slope -
+                                            the activation backward of the layer BELOW fused into this backward-input
+                                            product (gate = that layer's saved output) */
+    int64_t ld_gate;
+    float gate_slope;
 } BgDense;
 int bg_dense_fwd(const BgDense* a, void* stream);
 /* 128-wide (K >= 128) and 64-wide (K >= 256) layers with plain row-major weights run on the tensor cores: tcgen05.mma

@@ -85,6 +85,18 @@ def test_gat_bwd2(C):
     assert_close(ht_k, ht_tot_ref, 1e-5, f"gat_bwd2 ht_tot C={C}")
 
 
+@pytest.mark.parametrize("cout", [1, 7, 16, 64])
+def test_dense_backward_input_product_with_fused_relu_gate(cout):
+    """out = (X @ W)[:, :] * (gate > 0): the ReLU backward of the layer below fused into the dgrad epilogue."""
+    n, k = 1031, 48
+    x, w, gate = _rand(n, k, seed=1), _rand(k, cout, seed=2), _rand(n, cout, seed=3)
+    f = lambda t: t.float().to(DEV).contiguous()
+    got = lib.dense_fwd([f(x)], f(w), transposed=True, gate=f(gate))["out"]
+    assert_close(got, (x @ w) * (gate > 0), 1e-5, f"gated dgrad cout={cout}")
+    got = lib.dense_fwd([f(x)], f(w), transposed=True, gate=f(gate), gate_slope=0.2)["out"]
+    assert_close(got, (x @ w) * torch.where(gate > 0, 1.0, 0.2), 1e-5, "gated dgrad (leaky)")
+
+
 def _hub_graph(n=300, seed=0):
     """Irregular graph whose degrees straddle every register-slot capacity of the aggregation kernels (8 / 16 / 32):
     a ring, plus hubs with 5..70 extra in- AND out-edges (symmetric), plus some input self loops (stripped by the CSR)."""
