@@ -196,7 +196,14 @@ def _check(rc: int) -> None:
         raise RuntimeError(f"libbgb200 error {rc}: {last_error()}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """Raw cudaStream_t of torch's current stream on the current device (every launch goes there).  The private fast path
+    skips ~6 us of Python per call (it is called ~100 times per training step); falls back to the public API."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
