@@ -266,7 +266,11 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "steps/s",
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * (cfg.N_CRITIC + 1),
                         "ms_per_step": round(ms_e2e / args.steps, 3)},
-                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": (ops["libbgb200_launches_per_step"] * args.steps
+                                 if isinstance(ops, dict) and "libbgb200_launches_per_step" in ops else launches),
+                "gpu_launches_source": "kernels of libbgb200.so counted by CUPTI over one step x steps (torch's own kernels "
+                                       "excluded); fallback: the Python layer's per-pass estimate",
+                "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "torch_b200_baseline": torch_gpu, "roofline_step_shapes": roof_step, "aggregation_hbm": agg, "kernels": ops}
         print(json.dumps(line), flush=True)
 
@@ -420,6 +424,7 @@ def _kernel_shares(run_step):
         tot = sum(v[1] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]
         return {"gpu_ms_per_step": round(tot / 1e3, 3), "launches_per_step": sum(v[0] for v in agg.values()),
+                "libbgb200_launches_per_step": sum(v[0] for k, v in agg.items() if "bg::" in k),
                 "top": {k: {"launches": c, "ms": round(t / 1e3, 3), "share": round(t / tot, 3)} for k, (c, t) in top}}
     except Exception as exc:  # profiling is best-effort
         return {"error": repr(exc)}
