@@ -8,9 +8,14 @@
  *
  *   - pure C, POD only; device pointers are raw `float*` / `int32_t*`, `stream` is a
  *     `cudaStream_t` passed as `void*` (NULL = legacy default stream);
- *   - the library never allocates, frees or synchronises: inputs, outputs, saved tensors and
- *     workspaces are caller-owned; every launch goes to the caller's stream, so a sequence of
- *     calls is CUDA-graph capturable;
+ *   - the library never allocates or frees device memory and never synchronises: inputs, outputs, saved
+ *     tensors and workspaces are caller-owned; every launch is ordered on the caller's stream, so a
+ *     sequence of calls is CUDA-graph capturable.  The only library-owned CUDA objects are one
+ *     non-blocking side stream + two events per device, created on first use by the whole-pass
+ *     backward entry points: the batched weight-gradient launches of a pass run there, forked from
+ *     and joined back into the caller's stream with events before the pass returns control of its
+ *     buffers (BG_WGRAD_OVERLAP=0 keeps everything on the caller's stream).  Process-global state:
+ *     that pool, the launch-geometry knobs of bg_tune() and the bg_set_dense_tc() switch;
  *   - return 0 on success, a negative BG_E* code otherwise; `bg_last_error()` returns a
  *     thread-local human-readable message.  There is NO CPU fallback.
  *   - all activations are row-major fp32 `[N, C]`; supported GNN channel widths are
