@@ -370,7 +370,10 @@ def _hbm_roofline(dev, flush):
                  # what the model passes run: statistics fused into the aggregation epilogue + one elementwise pass
                  ("gat_fwd+graphnorm_fwd_fused", lambda: lib.gat_fwd_gn(csr, h, s, d, b, one, zero, one, None, 0.8, 1, 2),
                   _gat_fwd_bytes(n, e, c) + 4 * (2 * n * c + 4 * c)),
-                 ("graphnorm_bwd", lambda: lib.graphnorm_bwd(g, o, x1, one, one, stats, 1.25), 4 * (3 * n * c + 6 * c)))
+                 ("graphnorm_bwd", lambda: lib.graphnorm_bwd(g, o, x1, one, one, stats, 1.25), 4 * (3 * n * c + 6 * c)),
+                 # what the model passes run: GraphNorm backward moments + its elementwise half fused into the aggregation backward
+                 ("graphnorm_bwd+gat_bwd_fused", lambda: lib.gat_bwd_gn(csr, g, o, x1, one, one, stats, 1.25, h, s, d, m, z, a1, a2),
+                  4 * (3 * n * c + 6 * c) + 4 * (4 * n * c + 8 * n + 3 * e + c + 2)))
         row = {}
         for name, fn, by in cases:
             t = _time(fn, flush)

@@ -495,6 +495,58 @@ __global__ void __launch_bounds__(STATS ? kGatStatsThreads : kGatMaxThreads, 1) 
 // backward, pass A: per destination row (CSR).  Writes P[e] (softmax weight), DU[e] (d loss /
 // d pre-activation logit u_e = s_j + d_i) and gsd[2i+1] = d loss / d d_i.
 // ------------------------------------------------------------------------------------------
+// GraphNorm backward "apply" fused into the destination pass (SURVEY H5b/H5c backward): the gradient at the conv output,
+//   go = w r gy - w r^3 G1 (o - alpha mu) - alpha M[..]   with gy = gx1 * keep_scale * [x1 > 0]   (+ an injected cotangent),
+// is computed by the lane group that owns the row right where the aggregation backward needs it (its g_i), and written
+// once for the source pass / the bias gradient - instead of a separate elementwise launch that writes go and this kernel
+// reading it back.  The per-channel constants are the ones gn_bwd_apply_kernel uses, evaluated by every CTA into shared
+// memory (same expressions => same bits as the unfused pair).
+struct GnBwdFuse {
+    const float *gx1, *o, *x1, *inj;  // inj: optional cotangent added to go (second-order sweep)
+    const float *w, *alpha, *stats, *bstats;
+    float* go_out;
+    float keep_scale;
+};
+template <int C>
+__device__ __forceinline__ void gn_bwd_consts(const GnBwdFuse& f, float* kc) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mu = f.stats[c], r = f.stats[C + c], a = f.alpha[c], wc = f.w[c];
+        const float G0 = f.bstats[c], G1 = f.bstats[C + c];
+        kc[c] = wc * r;
+        kc[C + c] = wc * r * r * r * G1;
+        kc[2 * C + c] = a * (wc * r * G0 - wc * r * r * r * G1 * mu * (1.f - a));
+        kc[3 * C + c] = a * mu;
+    }
+    __syncthreads();
+}
+// g_i of row rr: loaded (FUSE = false) or computed from the GraphNorm backward and stored to go_out (FUSE = true)
+template <int C, bool FUSE>
+__device__ __forceinline__ void load_gi(float (&gi)[GatMap<C>::NV], const float* __restrict__ gout, const GnBwdFuse& f,
+                                        const float* kc, int rr, int sub, bool valid) {
+    constexpr int NV = GatMap<C>::NV;
+    if constexpr (!FUSE) {
+        row_load<C>(gi, gout + (int64_t)rr * C, sub);
+    } else {
+        float g[NV], ov[NV], xv[NV];
+        row_load<C>(g, f.gx1 + (int64_t)rr * C, sub);
+        row_load<C>(ov, f.o + (int64_t)rr * C, sub);
+        row_load<C>(xv, f.x1 + (int64_t)rr * C, sub);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int c = chan<C>(sub, v);
+            const float gy = xv[v] > 0.f ? g[v] * f.keep_scale : 0.f;
+            gi[v] = gy * kc[c] - (ov[v] - kc[3 * C + c]) * kc[C + c] - kc[2 * C + c];
+        }
+        if (f.inj) {
+            float iv[NV];
+            row_load<C>(iv, f.inj + (int64_t)rr * C, sub);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) gi[v] += iv[v];
+        }
+        if (valid) row_store<C>(gi, f.go_out + (int64_t)rr * C, sub);
+    }
+}
+
 template <int C>
 __device__ __noinline__ void gat_bwd_dst_row_generic(int row, int sub, unsigned gm, const int32_t* __restrict__ rowptr,
                                                      const int32_t* __restrict__ col, const float* __restrict__ gout,
@@ -570,17 +622,17 @@ __device__ __forceinline__ void gather_dot4(const float* __restrict__ hb, const 
     }
 }
 
-template <int C>
+template <int C, bool FUSE>
 __device__ __forceinline__ void gat_bwd_dst_row_fast(int row, bool valid, int beg, int deg, int maxdeg, int sub,
                                                      const int (&j)[GatMap<C>::EPL], const float (&sj)[GatMap<C>::EPL],
                                                      float di, float mi, float zi, const float* __restrict__ gout,
                                                      const float* __restrict__ hb, float* __restrict__ P,
                                                      float* __restrict__ DU, float* __restrict__ gsd, float slope,
-                                                     int rr) {
+                                                     int rr, const GnBwdFuse& fuse, const float* kc) {
     using M = GatMap<C>;
     constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
     float gi[NV];
-    row_load<C>(gi, gout + (int64_t)rr * C, sub);
+    load_gi<C, FUSE>(gi, gout, fuse, kc, rr, sub, valid);
     const float inv = rcp_fast(zi);
     float p[EPL], lg[EPL], c[EPL];
 #pragma unroll
@@ -611,14 +663,18 @@ __device__ __forceinline__ void gat_bwd_dst_row_fast(int row, bool valid, int be
     if (valid && sub == 0) gsd[2 * (int64_t)row + 1] = gd;
 }
 
-template <int C, bool PIPE>
-__global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ gout,
+template <int C, bool PIPE, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kGatStatsThreads : kGatMaxThreads, 1) gat_bwd_dst_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ gout_in,
     const float* __restrict__ h, const float* __restrict__ s, const float* __restrict__ d,
     const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
-    float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int chunk_rows, int ipc_shift, int ahead) {
+    float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int chunk_rows, int ipc_shift, int ahead,
+    const GnBwdFuse fuse) {
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
+    __shared__ float kc[FUSE ? 4 * C : 1];
+    if constexpr (FUSE) gn_bwd_consts<C>(fuse, kc);
+    const float* gout = FUSE ? fuse.go_out : gout_in;  // the generic row path reads the row back from where it was stored
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
@@ -633,7 +689,13 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
             const int deg = __ldg(rowptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
             if (maxdeg > CAP) {
-                if (valid) gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
+                if (valid) {
+                    if constexpr (FUSE) {
+                        float gi[M::NV];
+                        load_gi<C, true>(gi, gout, fuse, kc, row, sub, true);
+                    }
+                    gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
+                }
                 continue;
             }
             int j[EPL];
@@ -643,8 +705,8 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
                 j[k] = sub + k * LANES < deg ? __ldg(col + beg + sub + k * LANES) : rr;
                 sj[k] = __ldg(s + j[k]);
             }
-            gat_bwd_dst_row_fast<C>(row, valid, beg, deg, maxdeg, sub, j, sj, __ldg(d + rr), __ldg(m_in + rr),
-                                    __ldg(z_in + rr), gout, hb, P, DU, gsd, slope, rr);
+            gat_bwd_dst_row_fast<C, FUSE>(row, valid, beg, deg, maxdeg, sub, j, sj, __ldg(d + rr), __ldg(m_in + rr),
+                                          __ldg(z_in + rr), gout, hb, P, DU, gsd, slope, rr, fuse, kc);
         }
     } else {
         if (sw.niter == 0) return;
@@ -674,17 +736,28 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_dst_kernel(
             }
             const float m1 = __ldg(m_in + rc), z1 = __ldg(z_in + rc);
             prefetch_stream<C>(h, sw.raw(it + 1 + ahead), N, sub);
-            prefetch_stream<C>(gout, sw.raw(it + 1 + ahead), N, sub);
+            if constexpr (FUSE) {
+                prefetch_stream<C>(fuse.gx1, sw.raw(it + 1 + ahead), N, sub);
+                prefetch_stream<C>(fuse.o, sw.raw(it + 1 + ahead), N, sub);
+                prefetch_stream<C>(fuse.x1, sw.raw(it + 1 + ahead), N, sub);
+            } else {
+                prefetch_stream<C>(gout, sw.raw(it + 1 + ahead), N, sub);
+            }
             if (it >= 0) {
                 const int row = sw.raw(it);
                 const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
-                    if (valid)
+                    if (valid) {
+                        if constexpr (FUSE) {
+                            float gi[M::NV];
+                            load_gi<C, true>(gi, gout, fuse, kc, row, sub, true);
+                        }
                         gat_bwd_dst_row_generic<C>(row, sub, gm, rowptr, col, gout, h, s, d, m_in, z_in, P, DU, gsd, slope);
+                    }
                 } else {
-                    gat_bwd_dst_row_fast<C>(row, valid, beg0, deg0, maxdeg, sub, j0, s0, d0, m0, z0, gout, hb, P, DU, gsd,
-                                            slope, valid ? row : N - 1);
+                    gat_bwd_dst_row_fast<C, FUSE>(row, valid, beg0, deg0, maxdeg, sub, j0, s0, d0, m0, z0, gout, hb, P, DU, gsd,
+                                                  slope, valid ? row : N - 1, fuse, kc);
                 }
             }
             beg0 = beg1, deg0 = deg1, d0 = d1, m0 = m1, z0 = z1;
@@ -1003,9 +1076,31 @@ static int launch_bwd(const BgGraph* g, const float* gout, const float* h, const
                       const float* m, const float* z, const float* a_src, const float* a_dst, float* P,
                       float* DU, float* gh_tot, float* gsd, float slope, cudaStream_t st) {
     const GatCfg c = gat_cfg<C>(g->N);
-    BG_GAT_LAUNCH(gat_bwd_dst_kernel, g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd, (int)g->N, slope);
+    const GnBwdFuse nofuse{};
+    if (C >= 8 && c.pipe)
+        gat_bwd_dst_kernel<C, (C >= 8), false><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
+                                                                            (int)g->N, slope, c.chunk_rows, c.ipc_shift, c.ahead, nofuse);
+    else
+        gat_bwd_dst_kernel<C, false, false><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
+                                                                         (int)g->N, slope, c.chunk_rows, c.ipc_shift, c.ahead, nofuse);
     BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src, a_dst, gh_tot, gsd, (int)g->N);
     return check_launch("bg_gat_bwd");
+}
+// destination pass with the GraphNorm backward fused in (go is produced here), then the source pass on that go
+template <int C>
+static int launch_bwd_gn(const BgGraph* g, const GnBwdFuse& f, const float* h, const float* s, const float* d, const float* m,
+                         const float* z, const float* a_src, const float* a_dst, float* P, float* DU, float* gh_tot, float* gsd,
+                         float slope, cudaStream_t st) {
+    const GatCfg cd = gat_cfg<C>(g->N, kGatStatsThreads);
+    if (C >= 8 && cd.pipe)
+        gat_bwd_dst_kernel<C, (C >= 8), true><<<cd.grid, cd.threads, 0, st>>>(g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
+                                                                             (int)g->N, slope, cd.chunk_rows, cd.ipc_shift, cd.ahead, f);
+    else
+        gat_bwd_dst_kernel<C, false, true><<<cd.grid, cd.threads, 0, st>>>(g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
+                                                                          (int)g->N, slope, cd.chunk_rows, cd.ipc_shift, cd.ahead, f);
+    const GatCfg c = gat_cfg<C>(g->N);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, f.go_out, a_src, a_dst, gh_tot, gsd, (int)g->N);
+    return check_launch("bg_gat_bwd_gn");
 }
 template <int C>
 static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const float* Dt, const float* gout,
@@ -1092,6 +1187,21 @@ extern "C" int bg_gat_bwd(const BgGraph* g, const float* gout, const float* h, c
     BG_REQUIRE(gout && h && s && d && m && z && a_src && a_dst && P && DU && gh_tot && gsd, BG_EINVAL,
                "bg_gat_bwd: null pointer");
 #define CALL(CC) launch_bwd<CC>(g, gout, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream))
+    BG_DISPATCH_C(C, CALL)
+#undef CALL
+}
+
+extern "C" int bg_gat_bwd_gn(const BgGraph* g, const float* gx1, const float* o, const float* x1, const float* gn_w,
+                             const float* gn_alpha, const float* gn_stats, const float* gn_bstats, float keep_scale,
+                             const float* inj_o, const float* h, const float* s, const float* d, const float* m, const float* z,
+                             const float* a_src, const float* a_dst, float* P, float* DU, float* go, float* gh_tot, float* gsd,
+                             int32_t C, float slope, void* stream) {
+    if (int rc = check_graph(g)) return rc;
+    BG_REQUIRE(gx1 && o && x1 && gn_w && gn_alpha && gn_stats && gn_bstats && h && s && d && m && z && a_src && a_dst && P && DU &&
+                   go && gh_tot && gsd,
+               BG_EINVAL, "bg_gat_bwd_gn: null pointer");
+    const GnBwdFuse f{gx1, o, x1, inj_o, gn_w, gn_alpha, gn_stats, gn_bstats, go, keep_scale};
+#define CALL(CC) launch_bwd_gn<CC>(g, f, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream))
     BG_DISPATCH_C(C, CALL)
 #undef CALL
 }

@@ -521,6 +521,28 @@ extern "C" int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x
     return check_launch("bg_graphnorm_bwd");
 }
 
+// The moments half of bg_graphnorm_bwd alone (parameter gradients + bstats): the elementwise half is fused into the
+// aggregation backward (bg_gat_bwd_gn).
+extern "C" int bg_graphnorm_bwd_moments(const float* gx1, const float* o, const float* x1, const float* w, const float* alpha,
+                                        const float* stats, float keep_scale, int64_t N, int32_t C, float* dparams,
+                                        int32_t accumulate, float* bstats, float* workspace, size_t ws_bytes, void* stream) {
+    BG_REQUIRE(gx1 && o && x1 && w && alpha && stats && dparams && bstats && workspace, BG_EINVAL,
+               "bg_graphnorm_bwd_moments: null pointer");
+    BG_REQUIRE(ws_bytes >= bg_graphnorm_ws(N, C), BG_EINVAL, "bg_graphnorm_bwd_moments: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    float* partials = workspace + kCounterBytes / sizeof(float);
+    BwdMoments p{gx1, o, x1, alpha, stats, keep_scale};
+#define CALL(CC)                                                                                                     \
+    {                                                                                                                \
+        const int G = gn_splits<CC>(N);                                                                              \
+        gn_bwd_moments_kernel<CC><<<G, kThreads, 0, st>>>(p, w, N, G, dparams, accumulate, bstats, counter, partials); \
+    }
+    BG_GN_DISPATCH(C, CALL)
+#undef CALL
+    return check_launch("bg_graphnorm_bwd_moments");
+}
+
 extern "C" int bg_graphnorm_bwd2(const float* Xt, const float* gx1, const float* o, const float* x1, const float* w,
                                  const float* alpha, const float* stats, const float* bstats, float keep_scale, int64_t N,
                                  int32_t C, float* gx1t, float* ot, float* dparams2, int32_t accumulate, float* workspace,

@@ -273,13 +273,16 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
     float* DU = c.X->f((size_t)c.graph->E);
     float* gnpar = c.G ? c.g(L.p_gw) : T.f((size_t)3 * C);
     if (gx1) {
-        BG_TRY(bg_graphnorm_bwd(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, go, gnpar,
-                                c.G ? c.accumulate : 0, bst, c.red, c.red_bytes, c.st));
-        if (inj_o) BG_TRY(bg_axpy(go, inj_o, 1.f, c.N * C, c.st));
+        // GraphNorm backward: column moments (+ parameter gradients) as one launch; the elementwise half (and the injected
+        // cotangent at o) rides in the prologue of the aggregation backward's destination pass
+        BG_TRY(bg_graphnorm_bwd_moments(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, gnpar,
+                                        c.G ? c.accumulate : 0, bst, c.red, c.red_bytes, c.st));
+        BG_TRY(bg_gat_bwd_gn(c.graph, gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, bst, keep_scale, inj_o, L.h, L.s, L.d, L.m,
+                             L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, go, gh, gsd, C, 0.2f, c.st));
     } else {
         go = const_cast<float*>(inj_o);
+        BG_TRY(bg_gat_bwd(c.graph, go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, gh, gsd, C, 0.2f, c.st));
     }
-    BG_TRY(bg_gat_bwd(c.graph, go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, gh, gsd, C, 0.2f, c.st));
     BgSeg ones = seg(nullptr, 1, 0), hseg = seg(L.h, C, C), xseg = seg(x_in, L.cin, L.cin);
     if (c.G && inj_h) {  // bias, [att_src; att_dst] see gh BEFORE the injection at h (those cotangents are h-path only)
         BgWgrad pr[2] = {wg(c.N, go, C, C, &ones, 1, c.g(L.p_bias), 1, nullptr, c.accumulate),

@@ -85,6 +85,8 @@ SIGNATURES = {
     "bg_graphnorm_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, C.c_uint64, C.c_uint64, _I64, _I32, _P, _P]),
     "bg_gat_bwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
     "bg_gat_bwd2": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 15 + [_I32, _F, _P]),
+    "bg_gat_bwd_gn": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 7 + [_F] + [_P] * 13 + [_I32, _F, _P]),
+    "bg_graphnorm_bwd_moments": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _I64, _I32, _P, _I32, _P, _P, _SZ, _P]),
     "bg_gcn_norm": (C.c_int, [C.POINTER(BgGraph), _P, _P]),
     "bg_spmm": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "bg_gatv2_fwd": (C.c_int, [C.POINTER(BgGraph)] + [_P] * 8 + [_I32, _F, _P]),
@@ -495,6 +497,33 @@ def gat_bwd(csr, gout: Tensor, h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Te
                           z.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), P.data_ptr(), DU.data_ptr(), gh.data_ptr(),
                           gsd.data_ptr(), c, slope, _stream()))
     return gh, gsd, P, DU
+
+
+@_op("gat_bwd_gn", 3)
+def gat_bwd_gn(csr, gx1: Tensor, o: Tensor, x1: Tensor, gn_w: Tensor, gn_alpha: Tensor, stats: Tensor, keep_scale: float,
+               h: Tensor, s: Tensor, d: Tensor, m: Tensor, z: Tensor, a_src: Tensor, a_dst: Tensor,
+               inj_o: Optional[Tensor] = None, slope: float = 0.2):
+    """GraphNorm backward (moments launch + elementwise half fused into the aggregation backward) followed by the GAT
+    backward.  Returns (go, gn dparams[3,C], gh_tot, gsd)."""
+    lib = load()
+    _cf32(gx1, "gx1")
+    n, c = h.shape
+    dev = h.device
+    dpar = torch.empty(3, c, dtype=torch.float32, device=dev)
+    bst = torch.empty(2 * c, dtype=torch.float32, device=dev)
+    ws = workspace(lib.bg_graphnorm_ws(n, c), dev)
+    _check(lib.bg_graphnorm_bwd_moments(gx1.data_ptr(), o.data_ptr(), x1.data_ptr(), gn_w.data_ptr(), gn_alpha.data_ptr(),
+                                        stats.data_ptr(), keep_scale, n, c, dpar.data_ptr(), 0, bst.data_ptr(), ws.data_ptr(),
+                                        ws.numel() * 4, _stream()))
+    P = torch.empty(csr.num_edges, dtype=torch.float32, device=dev)
+    DU = torch.empty_like(P)
+    go, gh = torch.empty_like(h), torch.empty_like(h)
+    gsd = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    _check(lib.bg_gat_bwd_gn(C.byref(csr.c_struct()), gx1.data_ptr(), o.data_ptr(), x1.data_ptr(), gn_w.data_ptr(),
+                             gn_alpha.data_ptr(), stats.data_ptr(), bst.data_ptr(), keep_scale, _p(inj_o), h.data_ptr(),
+                             s.data_ptr(), d.data_ptr(), m.data_ptr(), z.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
+                             P.data_ptr(), DU.data_ptr(), go.data_ptr(), gh.data_ptr(), gsd.data_ptr(), c, slope, _stream()))
+    return go, dpar, gh, gsd
 
 
 @_op("gat_bwd2", 2)

@@ -210,6 +210,18 @@ int bg_gat_fwd_gn(const BgGraph* g, const float* h, const float* s, const float*
 int bg_gat_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
                const float* m, const float* z, const float* a_src, const float* a_dst,
                float* P, float* DU, float* gh_tot, float* gsd, int32_t C, float slope, void* stream);
+/* The same backward with the elementwise half of the preceding GraphNorm backward fused into the destination pass:
+ * go[N,C] = d loss / d (conv output) is computed from (gx1, o, x1, the GraphNorm parameters, stats, and the bstats written
+ * by bg_graphnorm_bwd_moments) (+ inj_o, an optional injected cotangent) by the lane group that needs it, and written once
+ * for the source pass and the bias gradient.  Equals bg_graphnorm_bwd (+ bg_axpy) followed by bg_gat_bwd. */
+int bg_gat_bwd_gn(const BgGraph* g, const float* gx1, const float* o, const float* x1, const float* gn_w,
+                  const float* gn_alpha, const float* gn_stats, const float* gn_bstats, float keep_scale,
+                  const float* inj_o, const float* h, const float* s, const float* d, const float* m, const float* z,
+                  const float* a_src, const float* a_dst, float* P, float* DU, float* go, float* gh_tot, float* gsd,
+                  int32_t C, float slope, void* stream);
+int bg_graphnorm_bwd_moments(const float* gx1, const float* o, const float* x1, const float* w, const float* alpha,
+                             const float* stats, float keep_scale, int64_t N, int32_t C, float* dparams,
+                             int32_t accumulate, float* bstats, float* workspace, size_t ws_bytes, void* stream);
 /* Second-order backward (WGAN-GP, reference trainer.py:306-312 create_graph=True): given the
  * cotangents Ht[N,C], St[N], Dt[N] on (gh, gs, gd) of bg_gat_bwd, returns
  * gt[N,C] (cotangent on gout), ht_tot[N,C] (cotangent on h incl. s/d paths) and sdt[N,2]

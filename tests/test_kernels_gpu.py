@@ -185,6 +185,43 @@ def test_gat_fwd_with_fused_graphnorm_statistics(C, geometry):
         L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 1), L.bg_tune(2, 128), L.bg_tune(5, 64), L.bg_tune(6, 0)
 
 
+@pytest.mark.parametrize("C", WIDTHS)
+@pytest.mark.parametrize("geometry", ["small", "large", "large-pipelined"])
+def test_gat_bwd_with_fused_graphnorm_backward(C, geometry):
+    """bg_graphnorm_bwd_moments + bg_gat_bwd_gn == bg_graphnorm_bwd (+ injected cotangent) + bg_gat_bwd, bit for bit on go
+    (same per-channel constants, same expression) and on everything downstream; building batch and hub graph."""
+    L = lib.load()
+    if geometry != "small":
+        L.bg_tune(4, 1), L.bg_tune(3, int(geometry == "large-pipelined")), L.bg_tune(0, 128), L.bg_tune(1, 1), L.bg_tune(5, 4)
+        L.bg_tune(6, 5)
+    try:
+        for hub in (False, True):
+            if hub:
+                n, edges, csr = _hub_graph()
+            else:
+                vb, edges, csr = _graph()
+                n = vb.num_nodes
+            f = lambda t: t.float().to(DEV).contiguous()
+            h, s, d, b = f(_rand(n, C, seed=1)), f(_rand(n, seed=2)), f(_rand(n, seed=3)), f(_rand(C, seed=4))
+            w, beta, alpha = f(_rand(C, seed=5) * 0.3 + 1), f(_rand(C, seed=6) * 0.3), f(_rand(C, seed=7) * 0.3 + 1)
+            a_s, a_d, gx1, inj = f(_rand(C, seed=8)), f(_rand(C, seed=9)), f(_rand(n, C, seed=10)), f(_rand(n, C, seed=11))
+            keep = (torch.rand(n, C, generator=torch.Generator().manual_seed(5)) < 0.8).to(torch.uint8).to(DEV)
+            o, m, z = lib.gat_fwd(csr, h, s, d, b)
+            x1, stats = lib.graphnorm_fwd(o, w, beta, alpha, keep, 0.8)
+            for inject in (None, inj):
+                go_ref, dpar_ref, _ = lib.graphnorm_bwd(gx1, o, x1, w, alpha, stats, 1.25)
+                if inject is not None:
+                    go_ref = go_ref + inject
+                gh_ref, gsd_ref, _, _ = lib.gat_bwd(csr, go_ref.contiguous(), h, s, d, m, z, a_s, a_d)
+                go, dpar, gh, gsd = lib.gat_bwd_gn(csr, gx1, o, x1, w, alpha, stats, 1.25, h, s, d, m, z, a_s, a_d, inject)
+                assert torch.equal(dpar, dpar_ref)
+                assert_close(go, go_ref, 1e-6, f"fused go C={C}")
+                assert_close(gh, gh_ref, 1e-5, f"fused gh C={C}")
+                assert_close(gsd, gsd_ref, 1e-5, f"fused gsd C={C}")
+    finally:
+        L.bg_tune(4, 0), L.bg_tune(3, 1), L.bg_tune(0, 1024), L.bg_tune(1, 1), L.bg_tune(2, 128), L.bg_tune(5, 64), L.bg_tune(6, 0)
+
+
 def test_gat_deterministic():
     vb, edges, csr = _graph()
     n, C = vb.num_nodes, 64
