@@ -55,6 +55,28 @@ int wgrad_flush(WgradQueue& q, cudaStream_t st);
 // tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 
+// ---- launches: every kernel of the library goes through launch_k().  With programmatic dependent launch (PDL, BG_PDL=1;
+// default off, see pdl_enabled()) kernel N+1 is scheduled while kernel N drains: each kernel starts with pdl_prologue() =
+// `griddepcontrol.launch_dependents` (the next kernel may be made resident once all CTAs of this one have started) followed by
+// `griddepcontrol.wait` (block until the previous kernel has completed and its writes are visible) BEFORE its first global
+// access, so stream order is preserved exactly.  Measured on the batch-32 training step (scratch/timeline.py): 4400 kernels
+// per two steps left 7.5 ms of 2-5 us idle gaps between dependent launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define BG_REQUIRE(cond, code, ...)      \
     do {                                 \
         if (!(cond)) {                   \
@@ -79,6 +101,11 @@ static inline int reduce_splits(int64_t N, int rows_per_cta_iter) {
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <int VEC>
 struct Vec;
 template <>

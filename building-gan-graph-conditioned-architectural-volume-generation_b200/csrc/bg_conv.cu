@@ -28,6 +28,7 @@ namespace bg {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) gcn_norm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                             float* __restrict__ w, int64_t N) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= N) return;
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const int32_t* __restric
                                                         const int32_t* __restrict__ perm, const float* __restrict__ w,
                                                         const float* __restrict__ x, const float* __restrict__ bias,
                                                         float* __restrict__ out, int64_t N, int self_loops) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(kThreads) gatv2_fwd_kernel(
     const float* __restrict__ xr, const float* __restrict__ att, const float* __restrict__ bias,
     float* __restrict__ out, float* __restrict__ logit, float* __restrict__ m_out, float* __restrict__ z_out, int64_t N,
     float slope) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(kThreads) gatv2_bwd_dst_kernel(
     const float* __restrict__ xl, const float* __restrict__ xr, const float* __restrict__ att,
     const float* __restrict__ logit, const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
     float* __restrict__ DL, float* __restrict__ gxr, float* __restrict__ garow, int64_t N, float slope) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(kThreads) gatv2_bwd_src_kernel(
     const int32_t* __restrict__ cscptr, const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
     const float* __restrict__ PA, const float* __restrict__ PB, const float* __restrict__ G, const float* __restrict__ xl,
     const float* __restrict__ xr, const float* __restrict__ att, float* __restrict__ out, int64_t N, float slope) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) gatv2_bwd2_dst_kernel(
     const float* __restrict__ z_in, float* __restrict__ S0, float* __restrict__ S1, float* __restrict__ S2,
     float* __restrict__ S3, float* __restrict__ S4, float* __restrict__ S5, float* __restrict__ gt, float* __restrict__ cxr,
     float* __restrict__ carow, int64_t N, float slope) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -359,7 +365,7 @@ using namespace bg;
 extern "C" int bg_gcn_norm(const BgGraph* g, float* w, void* stream) {
     if (int rc = check_graph_conv(g)) return rc;
     BG_REQUIRE(w, BG_EINVAL, "bg_gcn_norm: null pointer");
-    gcn_norm_kernel<<<(unsigned)ceil_div(g->N, kThreads), kThreads, 0, as_stream(stream)>>>(g->rowptr, g->col, w, g->N);
+    launch_k(gcn_norm_kernel, (unsigned)ceil_div(g->N, kThreads), kThreads, 0, as_stream(stream), g->rowptr, g->col, w, g->N);
     return check_launch("bg_gcn_norm");
 }
 
@@ -372,9 +378,9 @@ extern "C" int bg_spmm(const BgGraph* g, const float* w, const float* x, const f
     do {                                                                                                                \
         const unsigned grid = (unsigned)ceil_div(g->N, RowMap<CC>::RPC);                                                \
         if (transpose)                                                                                                  \
-            spmm_kernel<CC, true><<<grid, kThreads, 0, st>>>(g->cscptr, g->cscrow, g->perm, w, x, bias, out, g->N, self_loops); \
+            launch_k(spmm_kernel<CC, true>, grid, kThreads, 0, st, g->cscptr, g->cscrow, g->perm, w, x, bias, out, g->N, self_loops); \
         else                                                                                                            \
-            spmm_kernel<CC, false><<<grid, kThreads, 0, st>>>(g->rowptr, g->col, nullptr, w, x, bias, out, g->N, self_loops);   \
+            launch_k(spmm_kernel<CC, false>, grid, kThreads, 0, st, g->rowptr, g->col, nullptr, w, x, bias, out, g->N, self_loops);   \
     } while (0)
     BG_CONV_DISPATCH_C(C, CALL)
 #undef CALL
@@ -387,7 +393,7 @@ extern "C" int bg_gatv2_fwd(const BgGraph* g, const float* xl, const float* xr, 
     BG_REQUIRE(xl && xr && att && out && logit && m && z, BG_EINVAL, "bg_gatv2_fwd: null pointer");
     cudaStream_t st = as_stream(stream);
 #define CALL(CC)                                                                                               \
-    gatv2_fwd_kernel<CC><<<(unsigned)ceil_div(g->N, RowMap<CC>::RPC), kThreads, 0, st>>>(g->rowptr, g->col, xl, xr, att, bias, \
+    launch_k(gatv2_fwd_kernel<CC>, (unsigned)ceil_div(g->N, RowMap<CC>::RPC), kThreads, 0, st, g->rowptr, g->col, xl, xr, att, bias, \
                                                                                           out, logit, m, z, g->N, slope)
     BG_CONV_DISPATCH_C(C, CALL)
 #undef CALL
@@ -404,9 +410,9 @@ extern "C" int bg_gatv2_bwd(const BgGraph* g, const float* gout, const float* xl
 #define CALL(CC)                                                                                                          \
     do {                                                                                                                  \
         const unsigned grid = (unsigned)ceil_div(g->N, RowMap<CC>::RPC);                                                  \
-        gatv2_bwd_dst_kernel<CC><<<grid, kThreads, 0, st>>>(g->rowptr, g->col, gout, xl, xr, att, logit, m, z, P, DL, gxr, \
+        launch_k(gatv2_bwd_dst_kernel<CC>, grid, kThreads, 0, st, g->rowptr, g->col, gout, xl, xr, att, logit, m, z, P, DL, gxr, \
                                                             garow, g->N, slope);                                          \
-        gatv2_bwd_src_kernel<CC><<<grid, kThreads, 0, st>>>(g->cscptr, g->cscrow, g->perm, P, DL, gout, xl, xr, att, gxl,  \
+        launch_k(gatv2_bwd_src_kernel<CC>, grid, kThreads, 0, st, g->cscptr, g->cscrow, g->perm, P, DL, gout, xl, xr, att, gxl,  \
                                                             g->N, slope);                                                 \
     } while (0)
     BG_CONV_DISPATCH_C(C, CALL)
@@ -427,9 +433,9 @@ extern "C" int bg_gatv2_bwd2(const BgGraph* g, const float* Hl, const float* Hr,
 #define CALL(CC)                                                                                                             \
     do {                                                                                                                     \
         const unsigned grid = (unsigned)ceil_div(g->N, RowMap<CC>::RPC);                                                     \
-        gatv2_bwd2_dst_kernel<CC><<<grid, kThreads, 0, st>>>(g->rowptr, g->col, Hl, Hr, gout, xl, xr, att, logit, m, z, S[0], \
+        launch_k(gatv2_bwd2_dst_kernel<CC>, grid, kThreads, 0, st, g->rowptr, g->col, Hl, Hr, gout, xl, xr, att, logit, m, z, S[0], \
                                                              S[1], S[2], S[3], S[4], S[5], gt, cxr, carow, g->N, slope);     \
-        gatv2_bwd_src_kernel<CC><<<grid, kThreads, 0, st>>>(g->cscptr, g->cscrow, g->perm, S[4], S[5], gout, xl, xr, att, cxl, \
+        launch_k(gatv2_bwd_src_kernel<CC>, grid, kThreads, 0, st, g->cscptr, g->cscrow, g->perm, S[4], S[5], gout, xl, xr, att, cxl, \
                                                             g->N, slope);                                                    \
     } while (0)
     BG_CONV_DISPATCH_C(C, CALL)

@@ -83,6 +83,7 @@ struct DenseParams {
 
 template <int BN, int TM, int TN>
 __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p) {
+    pdl_prologue();
     constexpr int TX = BN / TN, TY = BM / TM;
     static_assert(TX * TY == kThreads, "tile/thread mismatch");
     __shared__ float Xs[BK][BM + 1];
@@ -251,6 +252,7 @@ struct WgBatch {
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) {
+    pdl_prologue();
     constexpr int T = 64, RB = 32;
     __shared__ float smem[2][RB][T + 4];
     float(*Gs)[T + 4] = smem[0];
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
 }
 
 __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb) {
+    pdl_prologue();
     int e = 0;
 #pragma unroll 1
     for (int q = 1; q < fb.n; ++q)
@@ -443,7 +446,7 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
         q.phase[phase].push_back(f);
     }
     dim3 grid((unsigned)tiles, (unsigned)b.S);
-    wgrad_multi_kernel<<<grid, kThreads, 0, st>>>(b);
+    launch_k(wgrad_multi_kernel, grid, kThreads, 0, st, b);
     return check_launch("wgrad");
 }
 
@@ -525,7 +528,7 @@ int wgrad_flush(WgradQueue& q, cudaStream_t st) {
                 fb.e[i].block_base = blocks;
                 blocks += (int)ceil_div((int64_t)fb.e[i].Cout * fb.e[i].K, kThreads);
             }
-            wgrad_fold_kernel<<<blocks, kThreads, 0, st>>>(fb);
+            launch_k(wgrad_fold_kernel, blocks, kThreads, 0, st, fb);
         }
         v.clear();
     }
@@ -542,6 +545,7 @@ __global__ void __launch_bounds__(kThreads) ln_act_bwd_kernel(const float* __res
                                                               const float* __restrict__ gamma, int64_t N, int G, int act,
                                                               float* __restrict__ gz, float* dgamma, float* dbeta,
                                                               int accumulate, unsigned int* counter, float* partials) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, RPC = M::RPC;
     __shared__ float red[kThreads * 2 * VEC];
@@ -612,6 +616,7 @@ __global__ void __launch_bounds__(kThreads) ln_act_bwd_kernel(const float* __res
 
 __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                                            int64_t total, int act, float* __restrict__ gz) {
+    pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
         const float o = out[i], g = gout[i];
         gz[i] = act == BG_ACT_RELU ? (o > 0.f ? g : 0.f) : act == BG_ACT_LRELU ? (o > 0.f ? g : 0.2f * g) : g;
@@ -622,10 +627,12 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const float* __restri
 // small utilities
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+    pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
         y[i] = fmaf(a, x[i], y[i]);
 }
 __global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ y, float v, int64_t n) {
+    pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) y[i] = v;
 }
 
@@ -684,11 +691,11 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     dim3 grid((unsigned)ceil_div(a->N, BM), (unsigned)ceil_div(a->Cout, bn));
     cudaStream_t st = as_stream(stream);
     switch (bn) {
-        case 8: dense_fwd_kernel<8, 2, 1><<<grid, kThreads, 0, st>>>(p); break;
-        case 16: dense_fwd_kernel<16, 2, 2><<<grid, kThreads, 0, st>>>(p); break;
-        case 32: dense_fwd_kernel<32, 2, 4><<<grid, kThreads, 0, st>>>(p); break;
-        case 64: dense_fwd_kernel<64, 4, 4><<<grid, kThreads, 0, st>>>(p); break;
-        default: dense_fwd_kernel<128, 4, 8><<<grid, kThreads, 0, st>>>(p); break;
+        case 8: launch_k(dense_fwd_kernel<8, 2, 1>, grid, kThreads, 0, st, p); break;
+        case 16: launch_k(dense_fwd_kernel<16, 2, 2>, grid, kThreads, 0, st, p); break;
+        case 32: launch_k(dense_fwd_kernel<32, 2, 4>, grid, kThreads, 0, st, p); break;
+        case 64: launch_k(dense_fwd_kernel<64, 4, 4>, grid, kThreads, 0, st, p); break;
+        default: launch_k(dense_fwd_kernel<128, 4, 8>, grid, kThreads, 0, st, p); break;
     }
     return check_launch("bg_dense_fwd");
 }
@@ -734,7 +741,7 @@ extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* x
     cudaStream_t st = as_stream(stream);
     if (!xhat) {
         const int64_t total = N * C;
-        act_bwd_kernel<<<flat_grid(total), kThreads, 0, st>>>(gout, out, total, act, gz);
+        launch_k(act_bwd_kernel, flat_grid(total), kThreads, 0, st, gout, out, total, act, gz);
         return check_launch("bg_ln_act_bwd(act)");
     }
     BG_REQUIRE(rstd && gamma && dgamma && dbeta && workspace, BG_EINVAL, "bg_ln_act_bwd: LayerNorm path needs rstd/gamma/dgamma/dbeta/workspace");
@@ -744,7 +751,7 @@ extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* x
 #define CALL(CC)                                                                                                   \
     {                                                                                                              \
         const int G = reduce_splits(N, RowMap<CC>::RPC);                                                           \
-        ln_act_bwd_kernel<CC><<<G, kThreads, 0, st>>>(gout, out, xhat, rstd, gamma, N, G, act, gz, dgamma, dbeta, \
+        launch_k(ln_act_bwd_kernel<CC>, G, kThreads, 0, st, gout, out, xhat, rstd, gamma, N, G, act, gz, dgamma, dbeta, \
                                                       accumulate, counter, partials);                              \
     }
     switch (C) {
@@ -764,13 +771,13 @@ extern "C" int bg_ln_act_bwd(const float* gout, const float* out, const float* x
 extern "C" int bg_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
     BG_REQUIRE(y && x, BG_EINVAL, "bg_axpy: null pointer");
     if (n <= 0) return BG_OK;
-    axpy_kernel<<<flat_grid(n), kThreads, 0, as_stream(stream)>>>(y, x, a, n);
+    launch_k(axpy_kernel, flat_grid(n), kThreads, 0, as_stream(stream), y, x, a, n);
     return check_launch("bg_axpy");
 }
 
 extern "C" int bg_fill(float* y, float v, int64_t n, void* stream) {
     BG_REQUIRE(y, BG_EINVAL, "bg_fill: null pointer");
     if (n <= 0) return BG_OK;
-    fill_kernel<<<flat_grid(n), kThreads, 0, as_stream(stream)>>>(y, v, n);
+    launch_k(fill_kernel, flat_grid(n), kThreads, 0, as_stream(stream), y, v, n);
     return check_launch("bg_fill");
 }

@@ -112,6 +112,7 @@ __device__ __forceinline__ int swz(int row, int k) { return row * 128 + ((((k >>
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcParams p) {
+    pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = TC_M * 128, B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -349,12 +350,12 @@ int dense_tc_try(const BgDense* a, int K, cudaStream_t st) {
         constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 128 * 128) + 1024 + 64;
         static bool once = (cudaFuncSetAttribute(dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
         (void)once;
-        dense_tc_kernel<128><<<grid, kThreads, smem, st>>>(p);
+        launch_k(dense_tc_kernel<128>, grid, kThreads, smem, st, p);
     } else {
         constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 64 * 128) + 1024 + 64;
         static bool once = (cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
         (void)once;
-        dense_tc_kernel<64><<<grid, kThreads, smem, st>>>(p);
+        launch_k(dense_tc_kernel<64>, grid, kThreads, smem, st, p);
     }
     return check_launch("bg_dense_fwd(tcgen05)");
 }

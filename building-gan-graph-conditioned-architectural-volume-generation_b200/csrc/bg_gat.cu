@@ -39,6 +39,8 @@ namespace bg {
 // register-free prefetches.  Stages that refer to an iteration < 0 redo iteration 0 with degree 0.
 // ------------------------------------------------------------------------------------------
 constexpr int kGatMaxThreads = 1024;
+template <int C>
+constexpr bool kPipeOK = C >= 8;  // narrower rows hold 8 edge slots per lane: the pipeline registers would spill
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNearRows = 512;  // neighbours closer than this are L1/L2-resident through the sweep itself
 
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(STATS ? kGatStatsThreads : kGatMaxThreads, 1) 
     const float* __restrict__ s, const float* __restrict__ d, const float* __restrict__ bias,
     float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ z_out, int N, float slope,
     int chunk_rows, int ipc_shift, int ahead, const GnFuse gn) {
+    pdl_prologue();
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW, NV = M::NV;
     const int lane = threadIdx.x & 31;
@@ -670,6 +673,7 @@ __global__ void __launch_bounds__(FUSE ? kGatStatsThreads : kGatMaxThreads, 1) g
     const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ P,
     float* __restrict__ DU, float* __restrict__ gsd, int N, float slope, int chunk_rows, int ipc_shift, int ahead,
     const GnBwdFuse fuse) {
+    pdl_prologue();
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
     __shared__ float kc[FUSE ? 4 * C : 1];
@@ -836,6 +840,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
     const float* __restrict__ P, const float* __restrict__ DU, const float* __restrict__ G,
     const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out_tot,
     float* __restrict__ gsd, int N, int chunk_rows, int ipc_shift, int ahead) {
+    pdl_prologue();
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
     const int lane = threadIdx.x & 31;
@@ -935,6 +940,7 @@ __global__ void __launch_bounds__(kThreads) gat_bwd2_dst_kernel(
     const float* __restrict__ m_in, const float* __restrict__ z_in, float* __restrict__ A0,
     float* __restrict__ A1, float* __restrict__ A2, float* __restrict__ A3, float* __restrict__ gt,
     float* __restrict__ sdt, int64_t N, float slope) {
+    pdl_prologue();
     using M = RowMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1042,10 +1048,10 @@ static GatCfg gat_cfg(int64_t N, int max_threads = kGatMaxThreads) {
 }
 #define BG_GAT_LAUNCH(KERNEL, ...)                                                      \
     do {                                                                                \
-        if (C >= 8 && c.pipe) /* narrower rows hold 8 edge slots per lane: the pipeline registers would spill */ \
-            KERNEL<C, (C >= 8)><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead);  \
+        if (kPipeOK<C> && c.pipe) /* narrower rows hold 8 edge slots per lane: the pipeline registers would spill */ \
+            launch_k(KERNEL<C, kPipeOK<C>>, c.grid, c.threads, 0, st, __VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead);  \
         else                                                                            \
-            KERNEL<C, false><<<c.grid, c.threads, 0, st>>>(__VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead); \
+            launch_k(KERNEL<C, false>, c.grid, c.threads, 0, st, __VA_ARGS__, c.chunk_rows, c.ipc_shift, c.ahead); \
     } while (0)
 
 template <int C>
@@ -1061,10 +1067,10 @@ static int launch_fwd(const BgGraph* g, const float* h, const float* s, const fl
         gn.alpha = gn_alpha, gn.stats = gn_stats, gn.eps = gn_eps, gn.n_rows = g->N;
     }
 #define BG_FWD(PIPE_, STATS_)                                                                                              \
-    gat_fwd_kernel<C, PIPE_, STATS_><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, h, s, d, bias, out, m, z, (int)g->N, slope, \
+    launch_k(gat_fwd_kernel<C, PIPE_, STATS_>, c.grid, c.threads, 0, st, g->rowptr, g->col, h, s, d, bias, out, m, z, (int)g->N, slope, \
                                                                    c.chunk_rows, c.ipc_shift, c.ahead, gn)
-    if (C >= 8 && c.pipe) {
-        if (gn_stats) BG_FWD((C >= 8), true); else BG_FWD((C >= 8), false);
+    if (kPipeOK<C> && c.pipe) {
+        if (gn_stats) BG_FWD(kPipeOK<C>, true); else BG_FWD(kPipeOK<C>, false);
     } else {
         if (gn_stats) BG_FWD(false, true); else BG_FWD(false, false);
     }
@@ -1077,11 +1083,11 @@ static int launch_bwd(const BgGraph* g, const float* gout, const float* h, const
                       float* DU, float* gh_tot, float* gsd, float slope, cudaStream_t st) {
     const GatCfg c = gat_cfg<C>(g->N);
     const GnBwdFuse nofuse{};
-    if (C >= 8 && c.pipe)
-        gat_bwd_dst_kernel<C, (C >= 8), false><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
+    if (kPipeOK<C> && c.pipe)
+        launch_k(gat_bwd_dst_kernel<C, kPipeOK<C>, false>, c.grid, c.threads, 0, st, g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
                                                                             (int)g->N, slope, c.chunk_rows, c.ipc_shift, c.ahead, nofuse);
     else
-        gat_bwd_dst_kernel<C, false, false><<<c.grid, c.threads, 0, st>>>(g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
+        launch_k(gat_bwd_dst_kernel<C, false, false>, c.grid, c.threads, 0, st, g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
                                                                          (int)g->N, slope, c.chunk_rows, c.ipc_shift, c.ahead, nofuse);
     BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src, a_dst, gh_tot, gsd, (int)g->N);
     return check_launch("bg_gat_bwd");
@@ -1092,11 +1098,11 @@ static int launch_bwd_gn(const BgGraph* g, const GnBwdFuse& f, const float* h, c
                          const float* z, const float* a_src, const float* a_dst, float* P, float* DU, float* gh_tot, float* gsd,
                          float slope, cudaStream_t st) {
     const GatCfg cd = gat_cfg<C>(g->N, kGatStatsThreads);
-    if (C >= 8 && cd.pipe)
-        gat_bwd_dst_kernel<C, (C >= 8), true><<<cd.grid, cd.threads, 0, st>>>(g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
+    if (kPipeOK<C> && cd.pipe)
+        launch_k(gat_bwd_dst_kernel<C, kPipeOK<C>, true>, cd.grid, cd.threads, 0, st, g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
                                                                              (int)g->N, slope, cd.chunk_rows, cd.ipc_shift, cd.ahead, f);
     else
-        gat_bwd_dst_kernel<C, false, true><<<cd.grid, cd.threads, 0, st>>>(g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
+        launch_k(gat_bwd_dst_kernel<C, false, true>, cd.grid, cd.threads, 0, st, g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
                                                                           (int)g->N, slope, cd.chunk_rows, cd.ipc_shift, cd.ahead, f);
     const GatCfg c = gat_cfg<C>(g->N);
     BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, f.go_out, a_src, a_dst, gh_tot, gsd, (int)g->N);
@@ -1109,7 +1115,7 @@ static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const
                        float* sdt, float slope, cudaStream_t st) {
     const int64_t grid = ceil_div(g->N, RowMap<C>::RPC);
     float *A0 = scratch, *A1 = scratch + g->E, *A2 = scratch + 2 * g->E, *A3 = scratch + 3 * g->E;
-    gat_bwd2_dst_kernel<C><<<(unsigned)grid, kThreads, 0, st>>>(g->rowptr, g->col, Ht, St, Dt, gout, h, s, d, m, z,
+    launch_k(gat_bwd2_dst_kernel<C>, (unsigned)grid, kThreads, 0, st, g->rowptr, g->col, Ht, St, Dt, gout, h, s, d, m, z,
                                                                A0, A1, A2, A3, gt, sdt, g->N, slope);
     const GatCfg c = gat_cfg<C>(g->N);
     BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, A1, A2, gout, a_src, a_dst, ht_tot, sdt, (int)g->N);

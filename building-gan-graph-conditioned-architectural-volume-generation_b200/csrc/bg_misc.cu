@@ -5,7 +5,18 @@
 
 #include "bg_common.cuh"
 
+#include <stdlib.h>
+
 namespace bg {
+
+bool pdl_enabled() {
+    // default OFF: the batch-32 training step is bound by the host's launch rate (~3.5 us per launch), not by the gaps
+    // between dependent kernels - with PDL on the small gaps disappear from the timeline (scratch/timeline.py: 7.5 -> 0.9 ms
+    // per two steps) but the step is not faster.  BG_PDL=1 turns it on (useful under CUDA-graph replay / a faster host).
+    static const bool on = getenv("BG_PDL") && atoi(getenv("BG_PDL")) != 0;
+    return on;
+}
+
 
 static thread_local char g_err[512] = "";
 
@@ -31,6 +42,7 @@ int check_launch(const char* what) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) type_table_kernel(const float* __restrict__ lx, const int64_t* __restrict__ ltype,
                                                               int64_t M, int F, int K, float* __restrict__ table) {
+    pdl_prologue();
     const int w = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= K * F) return;
     const int t = w / F, f = w % F;
@@ -50,6 +62,7 @@ __global__ void __launch_bounds__(kThreads) type_table_kernel(const float* __res
 __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __restrict__ g, int64_t ld, const int32_t* __restrict__ type,
                                                                 int64_t N, int C, int K, int G, float* out,
                                                                 unsigned int* counter, float* partials) {
+    pdl_prologue();
     extern __shared__ float acc[];  // [K*C]
     const int64_t chunk = ceil_div(N, G);
     const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
@@ -73,6 +86,7 @@ __global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(const float* __res
                                                               uint64_t seed, uint64_t offset, int64_t N, int K,
                                                               float* __restrict__ soft, float* __restrict__ hard,
                                                               int32_t* __restrict__ amax) {
+    pdl_prologue();
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (r >= N) return;
     float v[16], mx = -INFINITY;
@@ -114,6 +128,7 @@ __global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(kThreads) gumbel_bwd_kernel(const float* __restrict__ g_hard, const float* __restrict__ g_soft,
                                                               const float* __restrict__ soft, int64_t N, int K,
                                                               float* __restrict__ g_logits) {
+    pdl_prologue();
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (r >= N) return;
     float g[16], dot = 0.f;
@@ -129,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) gumbel_bwd_kernel(const float* __res
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) segment_softmax_kernel(const float* __restrict__ v, const int32_t* __restrict__ ptr,
                                                                    int64_t S, float* __restrict__ out) {
+    pdl_prologue();
     const int64_t sgm = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (sgm >= S) return;
@@ -144,6 +160,7 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_kernel(const float* 
 
 __global__ void __launch_bounds__(kThreads) segment_pool_kernel(const float* __restrict__ x, const int32_t* __restrict__ ptr,
                                                                 int64_t S, int C, int mode, float* __restrict__ out) {
+    pdl_prologue();
     // one CTA per segment; thread c owns column c and walks the rows in order
     const int64_t sgm = blockIdx.x;
     if (sgm >= S) return;
@@ -225,7 +242,7 @@ extern "C" int bg_type_table(const float* local_x, const int64_t* local_type, in
     BG_REQUIRE(local_x && local_type && table, BG_EINVAL, "bg_type_table: null pointer");
     BG_REQUIRE(M >= 0 && F > 0 && K > 0, BG_EINVAL, "bg_type_table: bad sizes");
     const int warps = K * F;
-    type_table_kernel<<<(unsigned)ceil_div(warps * 32, kThreads), kThreads, 0, as_stream(stream)>>>(local_x, local_type, M, F, K, table);
+    launch_k(type_table_kernel, (unsigned)ceil_div(warps * 32, kThreads), kThreads, 0, as_stream(stream), local_x, local_type, M, F, K, table);
     return check_launch("bg_type_table");
 }
 
@@ -246,7 +263,7 @@ extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* ty
     BG_REQUIRE(ws_bytes >= bg_type_scatter_sum_ws(N, C, K), BG_EINVAL, "bg_type_scatter_sum: workspace too small");
     BG_REQUIRE((size_t)K * C * sizeof(float) <= 48 * 1024, BG_EUNSUPPORTED, "bg_type_scatter_sum: K*C too large");
     const int G = scatter_splits(N);
-    type_scatter_kernel<<<G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream)>>>(
+    launch_k(type_scatter_kernel, G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream), 
         g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
     return check_launch("bg_type_scatter_sum");
 }
@@ -255,7 +272,7 @@ extern "C" int bg_gumbel_st_fwd(const float* logits, const float* noise, uint64_
                                 float* soft, float* hard, int32_t* argmax, void* stream) {
     BG_REQUIRE(logits && soft && hard, BG_EINVAL, "bg_gumbel_st_fwd: null pointer");
     BG_REQUIRE(K >= 1 && K <= 12, BG_EUNSUPPORTED, "bg_gumbel_st_fwd: K=%d not in [1,12]", K);
-    gumbel_fwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(logits, noise, seed, offset, N, K, soft,
+    launch_k(gumbel_fwd_kernel, (unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream), logits, noise, seed, offset, N, K, soft,
                                                                                           hard, argmax);
     return check_launch("bg_gumbel_st_fwd");
 }
@@ -264,14 +281,14 @@ extern "C" int bg_gumbel_st_bwd(const float* g_hard, const float* g_soft, const 
                                 float* g_logits, void* stream) {
     BG_REQUIRE(soft && g_logits && (g_hard || g_soft), BG_EINVAL, "bg_gumbel_st_bwd: null pointer");
     BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_gumbel_st_bwd: K=%d not in [1,16]", K);
-    gumbel_bwd_kernel<<<(unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream)>>>(g_hard, g_soft, soft, N, K, g_logits);
+    launch_k(gumbel_bwd_kernel, (unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream), g_hard, g_soft, soft, N, K, g_logits);
     return check_launch("bg_gumbel_st_bwd");
 }
 
 extern "C" int bg_segment_softmax(const float* v, const int32_t* seg_ptr, int64_t S, float* out, void* stream) {
     BG_REQUIRE(v && seg_ptr && out, BG_EINVAL, "bg_segment_softmax: null pointer");
     if (S <= 0) return BG_OK;
-    segment_softmax_kernel<<<(unsigned)ceil_div(S * 32, kThreads), kThreads, 0, as_stream(stream)>>>(v, seg_ptr, S, out);
+    launch_k(segment_softmax_kernel, (unsigned)ceil_div(S * 32, kThreads), kThreads, 0, as_stream(stream), v, seg_ptr, S, out);
     return check_launch("bg_segment_softmax");
 }
 
@@ -282,6 +299,7 @@ __global__ void __launch_bounds__(kThreads) segment_confusion_kernel(const float
                                                                      const int64_t* __restrict__ target,
                                                                      const int32_t* __restrict__ seg_ptr, int K,
                                                                      int32_t* __restrict__ cm) {
+    pdl_prologue();
     __shared__ int cnt[16 * 16];
     for (int i = threadIdx.x; i < K * K; i += kThreads) cnt[i] = 0;
     __syncthreads();
@@ -309,7 +327,7 @@ extern "C" int bg_segment_confusion(const float* score, const int64_t* target, c
     BG_REQUIRE(score && target && seg_ptr && cm, BG_EINVAL, "bg_segment_confusion: null pointer");
     BG_REQUIRE(K >= 1 && K <= 16, BG_EUNSUPPORTED, "bg_segment_confusion: K=%d out of range [1,16]", (int)K);
     if (S <= 0) return BG_OK;
-    segment_confusion_kernel<<<(unsigned)S, kThreads, 0, as_stream(stream)>>>(score, target, seg_ptr, K, cm);
+    launch_k(segment_confusion_kernel, (unsigned)S, kThreads, 0, as_stream(stream), score, target, seg_ptr, K, cm);
     return check_launch("bg_segment_confusion");
 }
 
@@ -318,6 +336,6 @@ extern "C" int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S
     BG_REQUIRE(x && seg_ptr && out, BG_EINVAL, "bg_segment_pool: null pointer");
     BG_REQUIRE(mode >= 0 && mode <= 2, BG_EINVAL, "bg_segment_pool: mode must be 0 (mean), 1 (max) or 2 (sum)");
     if (S <= 0) return BG_OK;
-    segment_pool_kernel<<<(unsigned)S, kThreads, 0, as_stream(stream)>>>(x, seg_ptr, S, C, mode, out);
+    launch_k(segment_pool_kernel, (unsigned)S, kThreads, 0, as_stream(stream), x, seg_ptr, S, C, mode, out);
     return check_launch("bg_segment_pool");
 }

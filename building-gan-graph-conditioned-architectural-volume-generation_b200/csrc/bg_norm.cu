@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
                                                             const float* __restrict__ stats, const uint8_t* __restrict__ keep,
                                                             float keep_prob, uint64_t seed, uint64_t offset, int64_t total, int C,
                                                             float* __restrict__ x1) {
+    pdl_prologue();
     __shared__ float sc[128], sh[128];  // y = o*sc + sh
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const float mu = stats[c], r = stats[C + c];
@@ -183,6 +184,7 @@ template <int C>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ o, const float* __restrict__ alpha,
                                                             int64_t N, int G, float eps, float* __restrict__ stats,
                                                             unsigned int* counters, float* partials) {
+    pdl_prologue();
     __shared__ float sums[2 * C];
     bool is_last;
     StatsAcc f{o};
@@ -249,6 +251,7 @@ template <int C>
 __global__ void __launch_bounds__(kThreads) gn_bwd_moments_kernel(BwdMoments p, const float* __restrict__ w, int64_t N, int G,
                                                                   float* dparams, int accumulate, float* bstats,
                                                                   unsigned int* counter, float* partials) {
+    pdl_prologue();
     __shared__ float sums[2 * C];
     bool is_last;
     BwdAcc<C> f{p};
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_moments_kernel(BwdMoments p, 
 __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(BwdMoments p, const float* __restrict__ w,
                                                                 const float* __restrict__ bstats, int64_t total, int C,
                                                                 float* __restrict__ go) {
+    pdl_prologue();
     __shared__ float k1[128], k2[128], k3[128], sh[128];  // go = gy*k1 - ohat*k2 - k3 ; ohat = o - sh
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const float mu = p.stats[c], r = p.stats[C + c], a = p.alpha[c], wc = w[c];
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd2_moments_kernel(Bwd2Moments p
                                                                    const float* __restrict__ bstats, int64_t N, int G,
                                                                    float* dparams2, int accumulate, float* b2,
                                                                    unsigned int* counter, float* partials) {
+    pdl_prologue();
     __shared__ float sums[3 * C];
     bool is_last;
     Bwd2Acc<C> f{p};
@@ -402,6 +407,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd2_apply_kernel(Bwd2Moments p, 
                                                                  const float* __restrict__ bstats, const float* __restrict__ b2,
                                                                  int64_t total, int C, float* __restrict__ gx1t,
                                                                  float* __restrict__ ot) {
+    pdl_prologue();
     __shared__ float wr[128], wr3[128], Qs[128], G1s[128], cf[128], sh[128], aA0[128], aMPhi[128];
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const float mu = p.stats[c], r = p.stats[C + c], a = p.alpha[c], wc = w[c];
@@ -477,12 +483,12 @@ extern "C" int bg_graphnorm_fwd(const float* o, const float* w, const float* bet
 #define CALL(CC)                                                                                            \
     {                                                                                                       \
         const int G = gn_splits<CC>(N);                                                                     \
-        gn_stats_kernel<CC><<<G, kThreads, 0, st>>>(o, alpha, N, G, eps, stats, counter, partials);         \
+        launch_k(gn_stats_kernel<CC>, G, kThreads, 0, st, o, alpha, N, G, eps, stats, counter, partials);         \
     }
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
     const int64_t total = N * C;
-    gn_apply_kernel<<<flat_grid(total), kThreads, 0, st>>>(o, w, beta, alpha, stats, keep, keep_prob, seed, offset, total, C, x1);
+    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, st, o, w, beta, alpha, stats, keep, keep_prob, seed, offset, total, C, x1);
     return check_launch("bg_graphnorm_fwd");
 }
 
@@ -494,7 +500,7 @@ extern "C" int bg_graphnorm_apply(const float* o, const float* w, const float* b
     BG_REQUIRE(N > 0 && C >= 1 && C <= 128, BG_EINVAL, "bg_graphnorm_apply: bad shape");
     BG_REQUIRE(keep_prob > 0.f && keep_prob <= 1.f, BG_EINVAL, "bg_graphnorm_apply: keep_prob must be in (0,1]");
     const int64_t total = N * C;
-    gn_apply_kernel<<<flat_grid(total), kThreads, 0, as_stream(stream)>>>(o, w, beta, alpha, stats, keep, keep_prob, seed, offset,
+    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, as_stream(stream), o, w, beta, alpha, stats, keep, keep_prob, seed, offset,
                                                                           total, C, x1);
     return check_launch("bg_graphnorm_apply");
 }
@@ -512,12 +518,12 @@ extern "C" int bg_graphnorm_bwd(const float* gx1, const float* o, const float* x
 #define CALL(CC)                                                                                                     \
     {                                                                                                                \
         const int G = gn_splits<CC>(N);                                                                              \
-        gn_bwd_moments_kernel<CC><<<G, kThreads, 0, st>>>(p, w, N, G, dparams, accumulate, bstats, counter, partials); \
+        launch_k(gn_bwd_moments_kernel<CC>, G, kThreads, 0, st, p, w, N, G, dparams, accumulate, bstats, counter, partials); \
     }
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
     const int64_t total = N * C;
-    gn_bwd_apply_kernel<<<flat_grid(total), kThreads, 0, st>>>(p, w, bstats, total, C, go);
+    launch_k(gn_bwd_apply_kernel, flat_grid(total), kThreads, 0, st, p, w, bstats, total, C, go);
     return check_launch("bg_graphnorm_bwd");
 }
 
@@ -536,7 +542,7 @@ extern "C" int bg_graphnorm_bwd_moments(const float* gx1, const float* o, const 
 #define CALL(CC)                                                                                                     \
     {                                                                                                                \
         const int G = gn_splits<CC>(N);                                                                              \
-        gn_bwd_moments_kernel<CC><<<G, kThreads, 0, st>>>(p, w, N, G, dparams, accumulate, bstats, counter, partials); \
+        launch_k(gn_bwd_moments_kernel<CC>, G, kThreads, 0, st, p, w, N, G, dparams, accumulate, bstats, counter, partials); \
     }
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
@@ -558,11 +564,11 @@ extern "C" int bg_graphnorm_bwd2(const float* Xt, const float* gx1, const float*
 #define CALL(CC)                                                                                                        \
     {                                                                                                                   \
         const int G = gn_splits<CC>(N);                                                                                 \
-        gn_bwd2_moments_kernel<CC><<<G, kThreads, 0, st>>>(p, w, bstats, N, G, dparams2, accumulate, b2, counter, partials); \
+        launch_k(gn_bwd2_moments_kernel<CC>, G, kThreads, 0, st, p, w, bstats, N, G, dparams2, accumulate, b2, counter, partials); \
     }
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
     const int64_t total = N * C;
-    gn_bwd2_apply_kernel<<<flat_grid(total), kThreads, 0, st>>>(p, w, bstats, b2, total, C, gx1t, ot);
+    launch_k(gn_bwd2_apply_kernel, flat_grid(total), kThreads, 0, st, p, w, bstats, b2, total, C, gx1t, ot);
     return check_launch("bg_graphnorm_bwd2");
 }
