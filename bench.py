@@ -189,6 +189,12 @@ def _to_oracle(batch, opyg):
 # ----------------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------------
+def _pdl_state(lib) -> bool:
+    prev = lib.set_pdl(False)
+    lib.set_pdl(prev)
+    return prev
+
+
 def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     import torch.distributed as dist
     from building_gan_b200 import Configuration, lib, step
@@ -203,8 +209,15 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     cfg.BATCH_SIZE = BATCH
     torch.manual_seed(777)
     G, D = VoxelGNNGenerator(cfg, 17, 12).to(dev), VoxelGNNDiscriminator(cfg, 17, 12).to(dev)
-    og = torch.optim.Adam(G.parameters(), lr=cfg.LEARNING_RATE_GENERATOR, betas=cfg.BETAS)
-    od = torch.optim.Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
+    # H15: the reference's Adam(lr, betas) (train.py:36-37).  "flat" = building_gan_b200.optim.Adam, the same optimiser as
+    # one kernel launch over the models' flat buffers; "torch" = torch.optim.Adam (foreach) on the same models.
+    if args.adam == "flat":
+        from building_gan_b200.optim import Adam
+    else:
+        Adam = torch.optim.Adam
+    og = Adam(G.parameters(), lr=cfg.LEARNING_RATE_GENERATOR, betas=cfg.BETAS)
+    od = Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
+    OVERLAP = not args.no_overlap
     grad_sync = None
     if world > 1:
         from building_gan_b200.dist import GradSync
@@ -219,13 +232,15 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, fin=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             flush.zero_()  # L2 flush between timed iterations (inside the timed region, ~40 us)
             fn(i)
+        if fin is not None:
+            fin()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -235,15 +250,42 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             ms = float(t.item())
         return ms
 
+    gstep = None
+    if OVERLAP and world == 1 and args.adam == "flat" and not args.no_graph:
+        from building_gan_b200.graphs import GraphedStep
+        gstep = GraphedStep(G, D, og, od, cfg)  # critic update + sampling pass captured once per step, replayed N_CRITIC times
+
     def step_resident(i):
         lb, vb = resident[i % len(resident)]
-        return step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses=False)
+        if gstep is not None:
+            return gstep(lb, vb, sync_losses=False)
+        return step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses=False, overlap=OVERLAP)
 
     result_sink = []
+    pending = []  # (pinned host buffer, copy-done event) of steps whose losses are still on their way to the host
+
+    def drain(keep: int):
+        while len(pending) > keep:
+            buf, ev = pending.pop(0)
+            ev.synchronize()
+            vals = buf.tolist()
+            result_sink.append((vals[:-1], vals[-1]))  # the step's 6 losses (trainer.py:479,493) as floats
 
     def step_e2e(i):
         lb, vb = _clone_to(*host[i % len(host)], dev)  # pinned host -> device, every step
-        d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step")
+        if gstep is not None:
+            # the 6 losses of EVERY step are read back (one async D2H into pinned memory per step); the host looks at step i's
+            # floats while step i+1 is being captured, so capture and execution overlap.  fin_e2e() collects the last one
+            # inside the timed region.
+            gstep(lb, vb, sync_losses=False)
+            buf = torch.empty(cfg.N_CRITIC + 1, dtype=torch.float32, pin_memory=True)
+            buf.copy_(gstep.last_losses, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((buf, ev))
+            drain(1)
+            return
+        d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step", overlap=OVERLAP)
         result_sink.append((d_losses, g_loss))  # the step's 6 losses (trainer.py:479,493) read back as floats, one D2H
 
     for i in range(args.warmup):
@@ -256,7 +298,10 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     clock_info = clocks.stop()
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    drain(0)
+    n_before = len(result_sink)
+    ms_e2e = timed(step_e2e, args.steps, fin=lambda: drain(0))
+    assert len(result_sink) - n_before == args.steps, "every timed end-to-end step must have delivered its losses to the host"
 
     # ---- roofline of the aggregation kernel at the bench shapes (rank 0): the 46 gat_fwd launches of one step's layer
     # widths (6 generator passes x 14 + 16 discriminator passes x 6 widths), CUDA-graph replayed so the CPU launch cost
@@ -286,6 +331,13 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                            "global_batch": BATCH * world, "batches_cycled": NUM_BATCHES,
                            "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
                            "rng": "z / GP mix drawn on device; dropout masks + Gumbel noise from in-kernel Philox (BG_RNG=philox)",
+                           "adam": ("building_gan_b200.optim.Adam (torch.optim.Adam semantics, one launch over flat buffers)"
+                                    if args.adam == "flat" else "torch.optim.Adam (foreach)"),
+                           "overlap": ("independent passes on 4 streams (step.Lanes): sampling passes up front, D(real)/D(fake) beside "
+                                       "the gradient-penalty pass" if OVERLAP else "single stream"),
+                           "cuda_graphs": ("critic update and sampling pass captured once per step, replayed N_CRITIC times "
+                                           "(graphs.GraphedStep)" if gstep is not None else "none"),
+                           "pdl": _pdl_state(lib),
                            "grads": os.environ.get("BG_GRADS", "bucket"), "executor": os.environ.get("BG_EXECUTOR", "native"),
                            "parallelism": f"dp{world}" if world > 1 else "single"},
                 "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "steps/s",
@@ -487,6 +539,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "sample", "c4"])
+    ap.add_argument("--adam", default="flat", choices=["flat", "torch"])
+    ap.add_argument("--no-graph", action="store_true", help="no CUDA-graph replay of the critic updates")
+    ap.add_argument("--no-overlap", action="store_true", help="every pass on one stream in the reference's call order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-roofline", action="store_true")
     args = ap.parse_args()

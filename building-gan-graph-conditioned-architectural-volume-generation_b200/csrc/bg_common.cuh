@@ -62,6 +62,7 @@ int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 // access, so stream order is preserved exactly.  Measured on the batch-32 training step (scratch/timeline.py): 4400 kernels
 // per two steps left 7.5 ms of 2-5 us idle gaps between dependent launches.
 bool pdl_enabled();
+const uint64_t* rng_base();  // bg_set_rng_base
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

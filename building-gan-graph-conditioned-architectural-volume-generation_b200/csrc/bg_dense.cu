@@ -3,6 +3,7 @@
 // s = y.a_src, d = y.a_dst (the `lin` of a GATConv), the split-N deterministic weight gradient
 // and the LayerNorm/activation backward.  fp32 FFMA: this is the rel-1e-5 parity mode.
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include <stdlib.h>
@@ -453,24 +454,36 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
 // Immediate mode: launch now.  Deferred mode (q.defer, used by the whole-pass executors, whose operands stay alive
 // until the end of the pass): only record the problems; wgrad_flush() then runs ALL weight gradients of the pass as
 // one launch per kWgMax problems - ~25 tiny latency-bound launches per backward pass become 2.
-// Side stream + fork/join events of the overlap mode: one set per device, created on first use, never destroyed (the
-// only library-owned CUDA objects; BG_WGRAD_OVERLAP=0 keeps everything on the caller's stream).
+// Side stream + fork/join events of the overlap mode: one set per (device, caller stream) - passes running concurrently on
+// different caller streams (step.py's discriminator lanes) must not share a side stream, or each one's join would wait for the
+// other's weight gradients.  Created on first use, never destroyed (the only library-owned CUDA objects; at most kMaxSide sets,
+// further caller streams stay on their own stream; BG_WGRAD_OVERLAP=0 keeps everything on the caller's stream).
 struct SideStream {
+    int dev = -1;
+    cudaStream_t caller = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-static SideStream* side_stream() {
+static SideStream* side_stream(cudaStream_t caller) {
     static const bool enabled = !(getenv("BG_WGRAD_OVERLAP") && atoi(getenv("BG_WGRAD_OVERLAP")) == 0);
     if (!enabled) return nullptr;
-    static SideStream pool[16];
+    constexpr int kMaxSide = 64;
+    static SideStream pool[kMaxSide];
+    static int used = 0;
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    SideStream& s = pool[dev];
-    if (!s.st) {
-        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+        if (pool[i].dev == dev && pool[i].caller == caller) return &pool[i];
+    if (used == kMaxSide) return nullptr;
+    SideStream& s = pool[used];
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    s.dev = dev;
+    s.caller = caller;
+    ++used;
     return &s;
 }
 
@@ -478,7 +491,7 @@ static SideStream* side_stream() {
 static int wgrad_kick(WgradQueue& q, size_t n, cudaStream_t st) {
     cudaStream_t where = st;
     if (!q.side) {
-        if (SideStream* s = side_stream()) { q.side = s->st; q.ev_fork = s->fork; q.ev_join = s->join; }
+        if (SideStream* s = side_stream(st)) { q.side = s->st; q.ev_fork = s->fork; q.ev_join = s->join; }
     }
     if (q.side) {
         if (cudaEventRecord(q.ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(q.side, q.ev_fork, 0) != cudaSuccess) {
@@ -636,6 +649,36 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ y, f
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) y[i] = v;
 }
 
+// Adam over one flat parameter buffer (H15: torch.optim.Adam semantics, amsgrad/maximize off): one launch per optimiser
+// step instead of torch's foreach sequence over ~190 parameter tensors.  Same update order as torch's _multi_tensor_adam:
+// m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).  The step count comes
+// either from the host (step_size / bc2_sqrt precomputed in double, like torch) or - CUDA-graph replay - from a device
+// counter that the caller increments before the launch.
+__global__ void __launch_bounds__(kThreads) adam_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                             float4* __restrict__ v, int64_t n4, double lr, double b1, double b2d, float b2,
+                                                             float w1, float w2, float eps, float wd, float step_size, float bc2_sqrt, const int64_t* __restrict__ step_dev) {
+    pdl_prologue();
+    if (step_dev) {
+        const double t = (double)*step_dev;
+        step_size = (float)(lr / (1.0 - pow(b1, t)));
+        bc2_sqrt = (float)sqrt(1.0 - pow(b2d, t));
+    }
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = wd != 0.f ? fmaf(wd, P[k], G[k]) : G[k];
+            const float diff = gr - M[k];  // torch lerp: a + w d for |w| < 0.5, else b - d (1 - w)
+            M[k] = w1 < 0.5f ? M[k] + w1 * diff : gr - diff * (1.f - w1);
+            V[k] = V[k] * b2 + w2 * gr * gr;
+            const float denom = sqrtf(V[k]) / bc2_sqrt + eps;
+            P[k] = P[k] - step_size * (M[k] / denom);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
 static inline int flat_grid(int64_t total) {
     int64_t g = ceil_div(total, (int64_t)kThreads * 4);
     if (g < 1) g = 1;
@@ -780,4 +823,24 @@ extern "C" int bg_fill(float* y, float v, int64_t n, void* stream) {
     if (n <= 0) return BG_OK;
     launch_k(fill_kernel, flat_grid(n), kThreads, 0, as_stream(stream), y, v, n);
     return check_launch("bg_fill");
+}
+
+extern "C" int bg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, int64_t step, const int64_t* step_dev, void* stream) {
+    BG_REQUIRE(p && g && m && v, BG_EINVAL, "bg_adam_flat: null pointer");
+    BG_REQUIRE(n >= 0 && n % 4 == 0, BG_EINVAL, "bg_adam_flat: n=%lld must be a multiple of 4 (flat buckets are padded)", (long long)n);
+    BG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, BG_EINVAL, "bg_adam_flat: buffers must be 16-byte aligned");
+    BG_REQUIRE(step_dev || step >= 1, BG_EINVAL, "bg_adam_flat: step=%lld (counts from 1)", (long long)step);
+    if (n == 0) return BG_OK;
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (!step_dev) {
+        step_size = (float)(lr / (1.0 - pow(beta1, (double)step)));
+        bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    }
+    const int64_t grid = std::min<int64_t>(ceil_div(n / 4, (int64_t)kThreads), 8 * kSMs);
+    launch_k(adam_flat_kernel, (int)grid, kThreads, 0, as_stream(stream), reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+             reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, (float)beta2,
+             (float)(1.0 - beta1), (float)(1.0 - beta2),  // torch forms 1 - beta in double, then narrows
+             (float)eps, (float)weight_decay, step_size, bc2_sqrt, step_dev);
+    return check_launch("bg_adam_flat");
 }

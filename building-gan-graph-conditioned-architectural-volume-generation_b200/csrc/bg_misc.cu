@@ -9,14 +9,21 @@
 
 namespace bg {
 
+// Programmatic dependent launch: default ON for single-stream use (BG_PDL=0 turns it off): on the batch-32 training step the
+// 2-5 us idle gaps between dependent kernels (scratch/timeline.py: 7.5 -> 0.9 ms per two steps) are worth 47.5 -> 53.9 steps/s.
+// It does NOT mix with the multi-stream step (step.Lanes): launches carrying the attribute into streams that fork/join through
+// events cost 26.3 vs 15.5 ms per step there, so Lanes switches it off at run time through bg_set_pdl(0).
+static int g_pdl = -1;
 bool pdl_enabled() {
-    // default OFF: the batch-32 training step is bound by the host's launch rate (~3.5 us per launch), not by the gaps
-    // between dependent kernels - with PDL on the small gaps disappear from the timeline (scratch/timeline.py: 7.5 -> 0.9 ms
-    // per two steps) but the step is not faster.  BG_PDL=1 turns it on (useful under CUDA-graph replay / a faster host).
-    static const bool on = getenv("BG_PDL") && atoi(getenv("BG_PDL")) != 0;
-    return on;
+    if (g_pdl < 0) g_pdl = !(getenv("BG_PDL") && atoi(getenv("BG_PDL")) == 0);
+    return g_pdl != 0;
 }
 
+// Device-resident addend for every in-kernel Philox offset (NULL = none).  A CUDA graph freezes kernel arguments, so a
+// captured pass would replay the same dropout masks / Gumbel noise; with a base pointer set during capture the replays read
+// the addend from device memory, which the owner of the graph bumps between replays (graphs.py).
+static const uint64_t* g_rng_base = nullptr;
+const uint64_t* rng_base() { return g_rng_base; }
 
 static thread_local char g_err[512] = "";
 
@@ -83,10 +90,11 @@ __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __r
 // H7: Gumbel-softmax + straight-through, one thread per row (K <= 16)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
-                                                              uint64_t seed, uint64_t offset, int64_t N, int K,
-                                                              float* __restrict__ soft, float* __restrict__ hard,
+                                                              uint64_t seed, uint64_t offset, const uint64_t* __restrict__ base,
+                                                              int64_t N, int K, float* __restrict__ soft, float* __restrict__ hard,
                                                               int32_t* __restrict__ amax) {
     pdl_prologue();
+    if (base) offset += *base;
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (r >= N) return;
     float v[16], mx = -INFINITY;
@@ -181,7 +189,16 @@ __global__ void __launch_bounds__(kThreads) segment_pool_kernel(const float* __r
 
 using namespace bg;
 
-extern "C" int bg_version(void) { return 100; }
+extern "C" int bg_version(void) { return 101; }
+extern "C" int bg_set_pdl(int32_t on) {
+    const int prev = bg::pdl_enabled() ? 1 : 0;
+    bg::g_pdl = on ? 1 : 0;
+    return prev;
+}
+extern "C" int bg_set_rng_base(const uint64_t* base) {
+    bg::g_rng_base = base;
+    return BG_OK;
+}
 extern "C" const char* bg_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,7 +289,7 @@ extern "C" int bg_gumbel_st_fwd(const float* logits, const float* noise, uint64_
                                 float* soft, float* hard, int32_t* argmax, void* stream) {
     BG_REQUIRE(logits && soft && hard, BG_EINVAL, "bg_gumbel_st_fwd: null pointer");
     BG_REQUIRE(K >= 1 && K <= 12, BG_EUNSUPPORTED, "bg_gumbel_st_fwd: K=%d not in [1,12]", K);
-    launch_k(gumbel_fwd_kernel, (unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream), logits, noise, seed, offset, N, K, soft,
+    launch_k(gumbel_fwd_kernel, (unsigned)ceil_div(N, kThreads), kThreads, 0, as_stream(stream), logits, noise, seed, offset, rng_base(), N, K, soft,
                                                                                           hard, argmax);
     return check_launch("bg_gumbel_st_fwd");
 }

@@ -55,9 +55,11 @@ __device__ __forceinline__ void cta_colsum(float (&val)[K * ColMap<C>::VEC], flo
 __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restrict__ o, const float* __restrict__ w,
                                                             const float* __restrict__ beta, const float* __restrict__ alpha,
                                                             const float* __restrict__ stats, const uint8_t* __restrict__ keep,
-                                                            float keep_prob, uint64_t seed, uint64_t offset, int64_t total, int C,
+                                                            float keep_prob, uint64_t seed, uint64_t offset,
+                                                            const uint64_t* __restrict__ base, int64_t total, int C,
                                                             float* __restrict__ x1) {
     pdl_prologue();
+    if (base) offset += *base;
     __shared__ float sc[128], sh[128];  // y = o*sc + sh
     for (int c = threadIdx.x; c < C; c += kThreads) {
         const float mu = stats[c], r = stats[C + c];
@@ -488,7 +490,7 @@ extern "C" int bg_graphnorm_fwd(const float* o, const float* w, const float* bet
     BG_GN_DISPATCH(C, CALL)
 #undef CALL
     const int64_t total = N * C;
-    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, st, o, w, beta, alpha, stats, keep, keep_prob, seed, offset, total, C, x1);
+    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, st, o, w, beta, alpha, stats, keep, keep_prob, seed, offset, rng_base(), total, C, x1);
     return check_launch("bg_graphnorm_fwd");
 }
 
@@ -500,7 +502,7 @@ extern "C" int bg_graphnorm_apply(const float* o, const float* w, const float* b
     BG_REQUIRE(N > 0 && C >= 1 && C <= 128, BG_EINVAL, "bg_graphnorm_apply: bad shape");
     BG_REQUIRE(keep_prob > 0.f && keep_prob <= 1.f, BG_EINVAL, "bg_graphnorm_apply: keep_prob must be in (0,1]");
     const int64_t total = N * C;
-    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, as_stream(stream), o, w, beta, alpha, stats, keep, keep_prob, seed, offset,
+    launch_k(gn_apply_kernel, flat_grid(total), kThreads, 0, as_stream(stream), o, w, beta, alpha, stats, keep, keep_prob, seed, offset, rng_base(),
                                                                           total, C, x1);
     return check_launch("bg_graphnorm_apply");
 }

@@ -11,9 +11,11 @@ torch / CPU fallback - on a machine without the built library or without CUDA ``
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -165,6 +167,14 @@ def _param_list(model) -> List[nn.Parameter]:
     return cached
 
 
+_LIVE = weakref.WeakSet()
+
+
+def live_models():
+    """The generator / discriminator instances alive in this process (optim.Adam finds the owner of a parameter list here)."""
+    return list(_LIVE)
+
+
 def _executor_for(kind: str) -> str:
     return EXECUTOR if kind == "GATCONV" else "python"
 
@@ -221,6 +231,49 @@ class _NativeState:
         self.goff = (C.c_int64 * len(layout.names))(*[layout.offsets[n] for n in layout.names])
         self._ptrs, self._key = None, None
         self.bucket, self.views, self.anchor = None, None, None
+        self.pflat = None
+        self.lane, self.lane_buckets, self.dirty = None, {}, []
+
+    # -- lanes: passes of ONE model running concurrently on different CUDA streams (step.py, critic update) ---------------
+    # The backward kernels add parameter gradients into the bucket with plain read-modify-write stores, so two passes in
+    # flight at once need separate destinations: a pass whose forward ran inside ``with model.lane(k)`` delivers its parameter
+    # gradients into the private bucket of lane k (overwrite mode: no zeroing needed), and ``merge_lanes()`` - called by the
+    # owner of the streams once they are joined - adds the dirty lane buckets into the real one in a fixed order.
+    def lane_bucket(self, lane, device):
+        """(flat, accumulate) for a backward pass that ran in ``lane``."""
+        b = self.lane_buckets.get(lane)
+        if b is None or b.device != device:
+            b = torch.zeros(self.layout.total, dtype=torch.float32, device=device)
+            self.lane_buckets[lane] = b
+        again = lane in self.dirty
+        if not again:
+            self.dirty.append(lane)
+        return b, again
+
+    def merge_lanes(self, params) -> None:
+        if not self.dirty:
+            return
+        bucket = self.bind_grads(params)
+        for lane in sorted(self.dirty):
+            lib.axpy_(bucket, self.lane_buckets[lane])
+        self.dirty = []
+
+    def flat_params(self, params) -> Tensor:
+        """Re-home every ``p.data`` as a view of ONE flat fp32 buffer laid out like the gradient bucket (optim.Adam steps the
+        flat buffers with one launch).  Idempotent; redone if .to()/.cuda()/load_state_dict(assign=True) replaced the storage."""
+        lay, pf = self.layout, self.pflat
+        first, last = lay.names[0], lay.names[-1]
+        if pf is not None and pf.device == params[0].device and params[0].data_ptr() == pf.data_ptr() + 4 * lay.offsets[first] \
+                and params[-1].data_ptr() == pf.data_ptr() + 4 * lay.offsets[last]:
+            return pf
+        pf = torch.zeros(lay.total, dtype=torch.float32, device=params[0].device)
+        with torch.no_grad():
+            for p, n in zip(params, lay.names):
+                v = lay.view(pf, n)
+                v.copy_(p.data)
+                p.data = v
+        self.pflat = pf
+        return pf
 
     def get_anchor(self, device) -> Tensor:
         """1-element leaf that carries the autograd edge of a bucket-mode pass (parameters are not autograd inputs)."""
@@ -298,6 +351,18 @@ def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
     return ctx
 
 
+def prepare_batch(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
+    """Build every lazily cached per-batch tensor now (type table, CSR handles, the float copy of the real one-hot labels):
+    nothing is allocated-and-cached during the model calls afterwards (required before CUDA-graph capture, graphs.py)."""
+    bc = _batch_ctx(local_graph, voxel_graph, num_types)
+    label = voxel_graph.types_onehot
+    if label.dtype != torch.float32 and (bc.real_onehot is None or bc.real_onehot[0] != label.data_ptr()):
+        bc.real_onehot = (label.data_ptr(), label.to(bc.vx.device, torch.float32).contiguous())
+    _batch_in(bc)
+    bc.csr.c_struct()
+    return bc
+
+
 def _draw_keeps(n: int, specs: List[ConvSpec], training: bool, device) -> List[Optional[Tensor]]:
     """Dropout keep-masks, one per block, drawn with torch's own dropout kernel in layer order so the
     device RNG stream is consumed exactly as the reference consumes it (SURVEY appendix C #9)."""
@@ -339,6 +404,7 @@ class VoxelGNNGenerator(nn.Module):
         self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
         assert kind != "GATCONV" or lib.load().bg_gen_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
+        _LIVE.add(self)
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__["_bg_params"] = None  # .to() / .cuda() may re-create the Parameter objects
@@ -570,10 +636,26 @@ class VoxelGNNDiscriminator(nn.Module):
         self._native = _NativeState(self, _model_desc(c, local_graph_dim, voxel_graph_dim), self._layout)
         assert kind != "GATCONV" or lib.load().bg_disc_num_params(C.byref(self._native.md)) == len(self._names)
         self.to(c.DEVICE)
+        _LIVE.add(self)
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__["_bg_params"] = None  # .to() / .cuda() may re-create the Parameter objects
         return super()._apply(fn, *args, **kwargs)
+
+    @contextlib.contextmanager
+    def lane(self, key: int):
+        """Passes started inside this context may run concurrently (on another CUDA stream) with other passes of this model:
+        their backward delivers the parameter gradients into a private bucket (``_NativeState.lane_bucket``) until
+        ``merge_lanes()``.  Used by step.discriminator_loss for the D(real) / D(fake) passes of a critic update."""
+        prev, self._native.lane = self._native.lane, key
+        try:
+            yield self
+        finally:
+            self._native.lane = prev
+
+    def merge_lanes(self) -> None:
+        """Add the lane buckets into ``p.grad`` (call on the main stream after the lane streams were joined)."""
+        self._native.merge_lanes(_param_list(self))
 
     def forward(self, local_graph, voxel_graph, label_hard, keeps=None):
         """Per-voxel critic score [N,1], reference models.py:229-245.  ``keeps`` injects explicit dropout masks."""
@@ -742,7 +824,7 @@ class _DiscNativeFn(torch.autograd.Function):
         lib.pass_launches(2 + 4 * len(model._convs) + 4)
         if getattr(model, "debug_keep_saved", False):
             model.debug_saved = _saved_views(model, ws, n, score, False)
-        ctx.need, ctx.bucket_mode = need, ticket[2]
+        ctx.need, ctx.bucket_mode, ctx.lane = need, ticket[2], st.lane
         if need:
             ctx.model, ctx.bc, ctx.ws, ctx.training = model, bc, ws, model.training
             ctx.save_for_backward(label, score, *tensors)
@@ -753,7 +835,10 @@ class _DiscNativeFn(torch.autograd.Function):
         if not ctx.need:
             raise RuntimeError("discriminator backward called but the forward ran without grad")
         label, score, *tensors = ctx.saved_tensors
-        outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training, (torch.is_grad_enabled(), ctx.bucket_mode), score,
+        if ctx.lane is not None:  # runs on the lane's stream (autograd: the forward's stream); g_score came from another one
+            g_score.record_stream(torch.cuda.current_stream())
+        outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training,
+                                      (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score,
                                       g_score.contiguous(), label, *tensors)
         return (None, None, None, None, None) + tuple(outs)
 
@@ -765,10 +850,16 @@ class _DiscNativeBwdFn(torch.autograd.Function):
     def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, flags, score, g_score, label, *tensors):
         L, st = lib.load(), model._native
         params = _param_list(model)
-        second_order, bucket_mode = flags
+        second_order, bucket_mode, lane = flags
         dev, n, e = label.device, bc.n, bc.csr.num_edges
+        accumulate = bucket_mode
         if bucket_mode:  # under create_graph only the input gradient is wanted (autograd.grad(..., only_inputs=True))
-            flat = None if second_order else st.bind_grads(params)
+            if second_order:
+                flat = None
+            elif lane is None:
+                flat = st.bind_grads(params)
+            else:
+                flat, accumulate = st.lane_bucket(lane, dev)
         else:
             flat = torch.empty(st.layout.total, dtype=torch.float32, device=dev)
         saved = lib.u8_buffer(L.bg_disc_bwd_saved_ws(C.byref(st.md), n, e), dev) if second_order else None
@@ -777,7 +868,7 @@ class _DiscNativeBwdFn(torch.autograd.Function):
         g_label = torch.empty_like(label)
         lib._check(L.bg_disc_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
                                       label.data_ptr(), ws.data_ptr(), score.data_ptr(), g_score.data_ptr(), int(training),
-                                      lib._p(flat), st.goff, int(bucket_mode), lib._p(saved), 0 if saved is None else saved.numel(),
+                                      lib._p(flat), st.goff, int(accumulate), lib._p(saved), 0 if saved is None else saved.numel(),
                                       tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4, g_label.data_ptr(),
                                       lib._stream()))
         lib.pass_launches((3 * 4 + 6 * len(model._convs) + 3 * 2) if flat is not None else (2 * 4 + 5 * len(model._convs) + 4))

@@ -14,6 +14,7 @@ GPU (same distributions, no host round trip) - the fast default of the benchmark
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -30,22 +31,64 @@ def _rand(shape, device, rng: str, normal: bool) -> Tensor:
     return torch.randn(*shape, device=device) if normal else torch.rand(*shape, device=device)
 
 
-def gradient_penalty(discriminator, local_graph, voxel_graph, label_soft: Tensor, cfg, rng: str = "cpu") -> Tensor:
+def gradient_penalty(discriminator, local_graph, voxel_graph, label_soft: Tensor, cfg, rng: str = "cpu",
+                     e: Optional[Tensor] = None) -> Tensor:
     n = voxel_graph.types_onehot.shape[0]
-    e = _rand((n, 1), label_soft.device, rng, normal=False)
+    if e is None:
+        e = _rand((n, 1), label_soft.device, rng, normal=False)
     mixed = (e * voxel_graph.types_onehot + (1 - e) * label_soft.squeeze(0)).requires_grad_(True)
     score = discriminator(local_graph, voxel_graph, mixed.unsqueeze(0))
     (grad,) = torch.autograd.grad(score, mixed, torch.ones_like(score), create_graph=True, only_inputs=True)
     return ((grad.norm(dim=1) - 1) ** 2).mean() * cfg.LAMBDA_GP
 
 
+class Lanes:
+    """Side streams of the overlapped training step (``train_step(..., overlap=True)``), one set per device.
+
+    At the reference's batch size every kernel of the step is latency-bound (N ~ 15 k voxels: tens of CTAs on 148 SMs), and
+    the step contains independent work the reference runs back to back: the three critic passes D(real), D(fake), D(mixed)
+    of one update (trainer.py:319-323) and the no-grad generator passes of all N_CRITIC updates (trainer.py:469-473: G does
+    not change inside the critic loop).  Each gets its own stream: ``real`` / ``fake`` for the two plain critic passes (forward
+    and, through autograd's stream affinity, backward), ``gen`` for the sampling passes; the gradient-penalty pass and
+    everything else stay on the caller's stream.  Same arithmetic, same kernels; only the parameter-gradient contributions
+    of the three critic passes are summed in a different order (lane buckets, models._NativeState)."""
+    _per_device = {}
+
+    def __init__(self, device):
+        self.real, self.fake, self.gen = (torch.cuda.Stream(device=device) for _ in range(3))
+        if os.environ.get("BG_PDL") is None:
+            lib.set_pdl(False)  # programmatic dependent launch and event-forked streams do not mix (csrc/bg_misc.cu)
+
+    @classmethod
+    def get(cls, device) -> "Lanes":
+        key = torch.device(device).index
+        if key not in cls._per_device:
+            cls._per_device[key] = cls(device)
+        return cls._per_device[key]
+
+
 def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tensor, label_soft: Tensor, cfg,
-                       rng: str = "cpu") -> Tensor:
-    d_real = discriminator(local_graph, voxel_graph, voxel_graph.types_onehot.unsqueeze(0))
-    d_fake = discriminator(local_graph, voxel_graph, label_hard)
-    if not cfg.USE_WGANGP:  # trainer.py:326-330 (the discriminator then ends in a sigmoid, models.py:222-223)
-        return F.binary_cross_entropy(d_fake, torch.zeros_like(d_fake)) + F.binary_cross_entropy(d_real, torch.ones_like(d_real))
-    return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng)
+                       rng: str = "cpu", lanes: Optional[Lanes] = None, e: Optional[Tensor] = None) -> Tensor:
+    real = voxel_graph.types_onehot.unsqueeze(0)
+    if lanes is None or not cfg.USE_WGANGP or not hasattr(discriminator, "lane"):
+        d_real = discriminator(local_graph, voxel_graph, real)
+        d_fake = discriminator(local_graph, voxel_graph, label_hard)
+        if not cfg.USE_WGANGP:  # trainer.py:326-330 (the discriminator then ends in a sigmoid, models.py:222-223)
+            return F.binary_cross_entropy(d_fake, torch.zeros_like(d_fake)) + F.binary_cross_entropy(d_real, torch.ones_like(d_real))
+        return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng, e)
+    # same three passes in the same host order, on three streams: fork after everything enqueued so far, join before the loss
+    main = torch.cuda.current_stream()
+    fork = main.record_event()
+    with torch.cuda.stream(lanes.real), discriminator.lane(1):
+        lanes.real.wait_event(fork)
+        d_real = discriminator(local_graph, voxel_graph, real)
+    with torch.cuda.stream(lanes.fake), discriminator.lane(2):
+        lanes.fake.wait_event(fork)
+        d_fake = discriminator(local_graph, voxel_graph, label_hard)
+    gp = gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng, e)
+    main.wait_stream(lanes.real)
+    main.wait_stream(lanes.fake)
+    return d_fake.mean() - d_real.mean() + gp
 
 
 def far_loss(voxel_graph, label_hard: Tensor, cfg) -> Tensor:
@@ -112,25 +155,65 @@ def compute_metrics(voxel_graph, label_hard: Tensor, cfg):
 
 
 def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng: str = "cpu",
-               grad_sync=None, sync_losses="each"):
+               grad_sync=None, sync_losses="each", overlap=False):
     """trainer.py:467-495 for one device-resident batch.  ``grad_sync(model)`` (optional) is called after each
     backward, before the optimiser step - the data-parallel gradient all-reduce hooks in here.
     Returns (critic losses, generator loss, label_hard[1,N,7]).  ``sync_losses``: "each" = ``.item()`` right after every
     backward exactly like the reference (6 host syncs per step, trainer.py:479,493); "step" = the same 6 floats read
     back with ONE device->host copy at the end of the step (the host keeps running ahead of the GPU inside the step);
-    False = 0-dim device tensors, no sync."""
+    False = 0-dim device tensors, no sync.
+    ``overlap``: False = every pass on the caller's stream in the reference's call order.  True = the independent passes of
+    the step run concurrently (``Lanes``): the N_CRITIC sampling passes of the generator are issued up front on their own
+    stream (z and the GP mixing factors are still drawn in the reference's order z1, e1, z2, e2, ...), and D(real) / D(fake)
+    of each critic update run beside the gradient-penalty pass.  "order" = the call order of True on a single stream (what
+    the tests compare True against)."""
     dev = voxel_graph.x.device
     n = voxel_graph.num_nodes
     each = sync_losses in (True, "each")
     d_losses = []
-    for _ in range(cfg.N_CRITIC):
-        with torch.no_grad():
-            z = _rand((1, n, cfg.Z_DIM), dev, rng, normal=True)
-            _, hard, soft = generator(local_graph, voxel_graph, z)
-            hard, soft = hard.unsqueeze(0), soft.unsqueeze(0)
+    lanes = Lanes.get(dev) if overlap is True else None
+    samples, es = None, None
+    if overlap:
+        from . import models
+        models._batch_ctx(local_graph, voxel_graph, cfg.NUM_CLASSES)  # per-batch constants: built once, on this stream
+        main = torch.cuda.current_stream()
+        zs, es = [], []
+        for _ in range(cfg.N_CRITIC):
+            zs.append(_rand((1, n, cfg.Z_DIM), dev, rng, normal=True))
+            es.append(_rand((n, 1), dev, rng, normal=False))
+        samples = []
+        start = main.record_event()
+        gen_stream = lanes.gen if lanes is not None else main
+        with torch.no_grad(), torch.cuda.stream(gen_stream):
+            if lanes is not None:
+                gen_stream.wait_event(start)
+            for z in zs:
+                _, hard, soft = generator(local_graph, voxel_graph, z)
+                if lanes is not None:  # produced on the sampling stream, consumed on the other three
+                    for t in (hard, soft):
+                        for s_ in (main, lanes.real, lanes.fake):
+                            t.record_stream(s_)
+                samples.append((hard.unsqueeze(0), soft.unsqueeze(0), gen_stream.record_event() if lanes is not None else None))
+    for it in range(cfg.N_CRITIC):
+        if samples is None:
+            with torch.no_grad():
+                z = _rand((1, n, cfg.Z_DIM), dev, rng, normal=True)
+                _, hard, soft = generator(local_graph, voxel_graph, z)
+                hard, soft = hard.unsqueeze(0), soft.unsqueeze(0)
+            e = None
+        else:
+            hard, soft, ready = samples[it]
+            e = es[it]
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
         opt_d.zero_grad()
-        d_loss = discriminator_loss(discriminator, local_graph, voxel_graph, hard, soft, cfg, rng)
+        d_loss = discriminator_loss(discriminator, local_graph, voxel_graph, hard, soft, cfg, rng, lanes, e)
         d_loss.backward()
+        if lanes is not None:
+            main = torch.cuda.current_stream()
+            main.wait_stream(lanes.real)
+            main.wait_stream(lanes.fake)
+            discriminator.merge_lanes()
         if grad_sync is not None:
             grad_sync(discriminator)
         d_losses.append(d_loss.item() if each else d_loss.detach())

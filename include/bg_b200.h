@@ -334,9 +334,24 @@ int bg_disc_backward2(const BgModelDesc* md, const float* const* params, const B
 int32_t bg_gen_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
 int32_t bg_disc_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
 
+/* ---- process-wide knobs (the only library state besides the per-(device, stream) weight-gradient side streams).
+ * bg_set_pdl: programmatic dependent launch on/off at run time (initial value: env BG_PDL, default on); returns the previous
+ * setting.  bg_set_rng_base: device pointer to a uint64 that every in-kernel Philox offset adds (NULL = none, the default):
+ * set it while capturing a CUDA graph so that replays draw fresh dropout masks / Gumbel noise (the graph owner bumps the
+ * value between replays), reset it to NULL afterwards. */
+int bg_set_pdl(int32_t on);
+int bg_set_rng_base(const uint64_t* base);
+
 /* ---- small utilities used by the host-side executor */
 int bg_axpy(float* y, const float* x, float a, int64_t n, void* stream);          /* y += a*x */
 int bg_fill(float* y, float v, int64_t n, void* stream);
+
+/* ---- H15: torch.optim.Adam.step (reference train.py:36-37, trainer.py:481,495; amsgrad / maximize off) over ONE flat
+ * parameter buffer: p, g, m (exp_avg), v (exp_avg_sq) are index-aligned flat fp32 buffers of n elements (n % 4 == 0,
+ * 16-byte aligned).  step counts from 1 (the value torch's state["step"] has AFTER its increment); if step_dev is not
+ * NULL the count is read from that device counter instead (CUDA-graph replay: the caller increments it in-graph). */
+int bg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                 double weight_decay, int64_t step, const int64_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

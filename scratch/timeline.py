@@ -7,19 +7,22 @@ from building_gan_b200 import Configuration, lib, step
 from building_gan_b200.models import VoxelGNNDiscriminator, VoxelGNNGenerator
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
+OV = os.environ.get("OVERLAP", "1") == "1"
 cfg = Configuration()
 torch.manual_seed(777)
 G, D = VoxelGNNGenerator(cfg, 17, 12).to(dev), VoxelGNNDiscriminator(cfg, 17, 12).to(dev)
-og = torch.optim.Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS)
-od = torch.optim.Adam(D.parameters(), lr=2e-4, betas=cfg.BETAS)
+from building_gan_b200.optim import Adam as _A
+_A = torch.optim.Adam if os.environ.get("ADAM") == "torch" else _A
+og = _A(G.parameters(), lr=2e-4, betas=cfg.BETAS)
+od = _A(D.parameters(), lr=2e-4, betas=cfg.BETAS)
 host = bench._make_batches(0, 1, 32, pin=False)
 lb, vb = bench._clone_to(*host[0], dev)
 for _ in range(3):
-    step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+    step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False, overlap=OV)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(2):
-        step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+        step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False, overlap=OV)
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if str(e.device_type).endswith("CUDA") and e.device_time > 0]
 ev.sort(key=lambda e: e.time_range.start)
@@ -36,6 +39,11 @@ for e in ev:
         cur_end = en
 span = t1 - t0
 print(f"span {span/1e3:.2f} ms for 2 steps; GPU busy (union) {busy/1e3:.2f} ms = {100*busy/span:.1f}%; kernels {len(ev)}; sum of kernel times {sum(e.device_time for e in ev)/1e3:.2f} ms")
+per = collections.defaultdict(lambda: [0, 0.0, 1e30, 0.0])
+for e in ev:
+    k = getattr(e, "stream", None) if hasattr(e, "stream") else None
+    r = per[k]; r[0] += 1; r[1] += e.device_time; r[2] = min(r[2], e.time_range.start); r[3] = max(r[3], e.time_range.end)
+print("per stream: " + "; ".join(f"{k}: {v[0]} kernels, {v[1]/1e3:.2f} ms busy, active {(v[2]-t0)/1e3:.2f}..{(v[3]-t0)/1e3:.2f} ms" for k, v in per.items()))
 hist = collections.Counter()
 tot_gap = sum(g for g, _ in gaps)
 for g, _ in gaps:

@@ -10,8 +10,10 @@ dev = torch.device("cuda", 0)
 cfg = Configuration()
 torch.manual_seed(777)
 G, D = VoxelGNNGenerator(cfg, 17, 12).to(dev), VoxelGNNDiscriminator(cfg, 17, 12).to(dev)
-og = torch.optim.Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS)
-od = torch.optim.Adam(D.parameters(), lr=2e-4, betas=cfg.BETAS)
+from building_gan_b200.optim import Adam as _A
+_A = torch.optim.Adam if os.environ.get("ADAM") == "torch" else _A
+og = _A(G.parameters(), lr=2e-4, betas=cfg.BETAS)
+od = _A(D.parameters(), lr=2e-4, betas=cfg.BETAS)
 host = bench._make_batches(0, 1, 32, pin=False)
 lb, vb = bench._clone_to(*host[0], dev)
 for _ in range(3):

@@ -1,0 +1,166 @@
+"""``building_gan_b200.optim.Adam`` (one bg_adam_flat launch over flat parameter / gradient / moment
+buffers) against ``torch.optim.Adam`` as the reference constructs it (train.py:36-37: lr, betas=(0.5, 0.999), defaults
+otherwise) - same trajectories, same state_dict format in both directions, CosineAnnealingLR on top (train.py:38)."""
+import copy
+import io
+
+import pytest
+import torch
+
+from building_gan_b200 import Configuration
+from building_gan_b200.models import VoxelGNNDiscriminator, VoxelGNNGenerator
+from building_gan_b200.optim import Adam
+
+from util import rel_err
+
+
+def _pair(cls, device):
+    cfg = Configuration()
+    cfg.DEVICE = device
+    torch.manual_seed(11)
+    a = cls(cfg, 17, 12)
+    b = cls(cfg, 17, 12)
+    b.load_state_dict(a.state_dict())
+    return cfg, a, b
+
+
+def _set_grads(model, grads, flat: bool):
+    params = list(model.parameters())
+    if flat:  # the way the backward kernels deliver them: views of the model's flat bucket
+        model._native.bind_grads(params)
+        for v, g in zip(model._native.views, grads):
+            v.copy_(g)
+    else:
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+
+
+def test_constructor_contract_cpu():
+    cfg, D, _ = _pair(VoxelGNNDiscriminator, "cpu")
+    opt = Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
+    ref = torch.optim.Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
+    assert set(opt.param_groups[0]) == set(ref.param_groups[0])
+    for k, v in ref.param_groups[0].items():
+        if k != "params":
+            assert opt.param_groups[0][k] == v, k
+    assert opt.state_dict()["state"] == {} and opt.state_dict()["param_groups"] == ref.state_dict()["param_groups"]
+    with pytest.raises(ValueError):
+        Adam(list(D.parameters())[:3], lr=1e-3)  # not the parameter list of one model
+    with pytest.raises(ValueError):
+        Adam(torch.nn.Linear(3, 3).parameters(), lr=1e-3)
+    with pytest.raises(NotImplementedError):
+        Adam(D.parameters(), lr=1e-3, amsgrad=True)
+    opt.zero_grad()  # no gradients yet: falls through to torch's zero_grad
+    opt.step()       # nothing back-propagated: a no-op, like torch.optim.Adam (no CUDA call)
+    assert opt.state_dict()["state"] == {}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", [VoxelGNNDiscriminator, VoxelGNNGenerator])
+@pytest.mark.parametrize("flat_grads", [True, False])
+def test_matches_torch_adam(cls, flat_grads):
+    cfg, A, B = _pair(cls, "cuda")
+    lr = 2e-3  # 10x the reference's 2e-4 so that 30 steps move the parameters visibly
+    ours = Adam(A.parameters(), lr=lr, betas=cfg.BETAS)
+    ref = torch.optim.Adam(B.parameters(), lr=lr, betas=cfg.BETAS)
+    s_ours = torch.optim.lr_scheduler.CosineAnnealingLR(ours, T_max=20)
+    s_ref = torch.optim.lr_scheduler.CosineAnnealingLR(ref, T_max=20)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    start = [p.detach().clone() for p in A.parameters()]
+    for it in range(30):
+        grads = [torch.randn(p.shape, device="cuda", generator=gen) * (0.1 + (it % 3)) for p in A.parameters()]
+        ours.zero_grad()
+        ref.zero_grad()
+        _set_grads(A, grads, flat_grads)
+        _set_grads(B, grads, False)
+        ours.step()
+        ref.step()
+        if it % 5 == 4:
+            s_ours.step()
+            s_ref.step()
+    moved = max((p.detach() - s).abs().max().item() for p, s in zip(A.parameters(), start))
+    assert moved > 1e-2
+    for (name, p), q in zip(A.named_parameters(), B.parameters()):
+        # tolerance: fp32 rounding of the same expression evaluated in one fused kernel vs torch's foreach sequence,
+        # relative to the distance moved
+        assert (p - q).abs().max().item() <= 2e-6 * max(moved, q.abs().max().item()), name
+    for p, q in zip(A.parameters(), B.parameters()):
+        for key in ("exp_avg", "exp_avg_sq"):
+            assert rel_err(ours.state[p][key], ref.state[q][key]) <= 1e-6, key
+    # parameters stayed views of one flat buffer, in the gradient bucket's layout
+    st = A._native
+    assert all(p.data_ptr() == st.pflat.data_ptr() + 4 * st.layout.offsets[n] for (n, p) in A.named_parameters())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("direction", ["ours->torch", "torch->ours"])
+def test_state_dict_interchange(direction):
+    cfg, A, B = _pair(VoxelGNNDiscriminator, "cuda")
+    mk = {"ours": lambda m: Adam(m.parameters(), lr=1e-3, betas=cfg.BETAS),
+          "torch": lambda m: torch.optim.Adam(m.parameters(), lr=1e-3, betas=cfg.BETAS)}
+    src_kind, dst_kind = direction.split("->")
+    src, dst = mk[src_kind](A), mk[dst_kind](B)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for _ in range(3):
+        grads = [torch.randn(p.shape, device="cuda", generator=gen) for p in A.parameters()]
+        _set_grads(A, grads, src_kind == "ours")
+        src.step()
+    buf = io.BytesIO()
+    torch.save({"discriminator": A.state_dict(), "optimizer_discriminator": src.state_dict()}, buf)  # trainer.py:715-736
+    buf.seek(0)
+    states = torch.load(buf, weights_only=False)
+    B.load_state_dict(states["discriminator"])
+    dst.load_state_dict(states["optimizer_discriminator"])
+    assert float(dst.state_dict()["state"][0]["step"]) == 3.0
+    for _ in range(4):  # both continue identically
+        grads = [torch.randn(p.shape, device="cuda", generator=gen) for p in A.parameters()]
+        _set_grads(A, grads, src_kind == "ours")
+        _set_grads(B, grads, dst_kind == "ours")
+        src.step()
+        dst.step()
+    for (name, p), q in zip(A.named_parameters(), B.parameters()):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1e-2, q.abs().max().item()), name
+    assert float(src.state_dict()["state"][0]["step"]) == float(dst.state_dict()["state"][0]["step"]) == 7.0
+
+
+@pytest.mark.gpu
+def test_capturable_counter_and_training_step():
+    """capturable=True (device step counter) gives the same update; and a real training step through the kernels with
+    optim.Adam equals the same step with torch.optim.Adam."""
+    from building_gan_b200 import step as bstep
+    from util import small_batch
+
+    cfg, A, B = _pair(VoxelGNNDiscriminator, "cuda")
+    a = Adam(A.parameters(), lr=1e-3, betas=cfg.BETAS, capturable=True)
+    b = Adam(B.parameters(), lr=1e-3, betas=cfg.BETAS)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(5):
+        grads = [torch.randn(p.shape, device="cuda", generator=gen) for p in A.parameters()]
+        _set_grads(A, grads, True)
+        _set_grads(B, grads, True)
+        a.step()
+        b.step()
+    for p, q in zip(A.parameters(), B.parameters()):
+        assert (p - q).abs().max().item() <= 1e-6 * max(1e-2, q.abs().max().item())
+    assert float(a.state_dict()["state"][0]["step"]) == 5.0
+
+    cfg, G1, G2 = _pair(VoxelGNNGenerator, "cuda")
+    _, D1, D2 = _pair(VoxelGNNDiscriminator, "cuda")
+    for m in (G1, G2, D1, D2):
+        m.eval()  # no dropout: the two runs see the same arithmetic
+    lb, vb = small_batch()
+    lb, vb = lb.to("cuda"), vb.to("cuda")
+    o1 = (Adam(G1.parameters(), lr=2e-4, betas=cfg.BETAS), Adam(D1.parameters(), lr=2e-4, betas=cfg.BETAS))
+    o2 = (torch.optim.Adam(G2.parameters(), lr=2e-4, betas=cfg.BETAS), torch.optim.Adam(D2.parameters(), lr=2e-4, betas=cfg.BETAS))
+    out = []
+    for G, D, (og, od) in ((G1, D1, o1), (G2, D2, o2)):
+        torch.manual_seed(4)
+        torch.cuda.manual_seed(4)
+        from building_gan_b200 import models as bm
+        bm._philox_calls = 0
+        out.append(bstep.train_step(G, D, og, od, lb, vb, cfg, rng="cpu"))
+    assert max(abs(x - y) for x, y in zip(out[0][0], out[1][0])) <= 1e-4 * max(1.0, max(abs(v) for v in out[1][0]))
+    for m1, m2 in ((G1, G2), (D1, D2)):
+        for (name, p), q in zip(m1.named_parameters(), m2.parameters()):
+            # Adam's first steps move every parameter by ~lr regardless of gradient scale: compare against lr
+            assert (p - q).abs().max().item() <= 0.05 * 2e-4 * 6, name
