@@ -251,9 +251,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         return ms
 
     gstep = None
-    if OVERLAP and world == 1 and args.adam == "flat" and not args.no_graph:
+    if OVERLAP and args.adam == "flat" and not args.no_graph:
         from building_gan_b200.graphs import GraphedStep
-        gstep = GraphedStep(G, D, og, od, cfg)  # critic update + sampling pass captured once per step, replayed N_CRITIC times
+        gstep = GraphedStep(G, D, og, od, cfg, grad_sync=grad_sync)  # critic update + sampling pass captured once per step, replayed N_CRITIC times
 
     def step_resident(i):
         lb, vb = resident[i % len(resident)]
@@ -288,7 +288,11 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step", overlap=OVERLAP)
         result_sink.append((d_losses, g_loss))  # the step's 6 losses (trainer.py:479,493) read back as floats, one D2H
 
-    for i in range(args.warmup):
+    # untimed warm-up: the W steps asked for; with CUDA-graph replay at least one pass over every distinct batch shape plus
+    # the eager first step, so that the graph memory pools reach their steady-state size before the clock starts (a first
+    # capture at a new, larger N grows the pool with cudaMalloc: 30-700 ms once per pool, scratch/graph_steps.py)
+    n_warm = max(args.warmup, NUM_BATCHES + 2) if gstep is not None else args.warmup
+    for i in range(n_warm):
         step_resident(i)
     clocks = _Clocks(local_rank)
     clocks.start()
@@ -314,8 +318,11 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         if roofline is None:
             roofline = roof_step
         # local step (no gradient all-reduce: the other ranks do not take part in this extra step)
-        ops = _kernel_shares(lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=None,
-                                                     sync_losses=False))
+        if gstep is not None and world == 1:
+            ops = _kernel_shares(lambda: gstep(*resident[0], sync_losses=False))
+        else:
+            ops = _kernel_shares(lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=None,
+                                                         sync_losses=False, overlap=OVERLAP))
     cpu_baseline, torch_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = _cpu_baseline(host)
@@ -328,7 +335,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "train.py step (5 critic + 1 generator update), batch 32 per GPU, 6types-like synthetic "
                                        "buildings (mean ~400 voxels, 6-neighbour irregular grids)",
-                           "global_batch": BATCH * world, "batches_cycled": NUM_BATCHES,
+                           "global_batch": BATCH * world, "batches_cycled": NUM_BATCHES, "untimed_warmup_steps": n_warm,
                            "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
                            "rng": "z / GP mix drawn on device; dropout masks + Gumbel noise from in-kernel Philox (BG_RNG=philox)",
                            "adam": ("building_gan_b200.optim.Adam (torch.optim.Adam semantics, one launch over flat buffers)"

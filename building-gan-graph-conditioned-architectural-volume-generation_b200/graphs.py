@@ -19,7 +19,7 @@ What makes the replays differ (a graph freezes every kernel argument):
 * Adam's step count lives in a device counter (optim.Adam(capturable=True) semantics, switched on for the captured step).
 
 Not supported here (use step.train_step): rng="cpu" (host draws cannot be captured), torch.optim.Adam for the critic, the
-non-native conv types, a gradient all-reduce between backward and Adam (multi-GPU runs use the eager overlapped step).
+non-native conv types.
 """
 from __future__ import annotations
 
@@ -42,7 +42,11 @@ class _Captured:
 
 
 class GraphedStep:
-    def __init__(self, generator, discriminator, opt_g, opt_d, cfg):
+    def __init__(self, generator, discriminator, opt_g, opt_d, cfg, grad_sync=None):
+        """``grad_sync(model)``: the data-parallel gradient all-reduce (dist.GradSync), called after each backward and before
+        the optimiser step; for the critic it is captured into the graph (NCCL collectives are capturable; the communicator is
+        created by the eager first step)."""
+        self.grad_sync = grad_sync
         if not isinstance(opt_d, Adam):
             raise TypeError("GraphedStep: the critic optimiser must be building_gan_b200.optim.Adam (its step is captured)")
         if models._executor_for(discriminator._kind) == "python" or models._executor_for(generator._kind) == "python" \
@@ -70,7 +74,8 @@ class GraphedStep:
                 # first call: the eager overlapped step on the same streams creates every lazily cached buffer (per-stream
                 # workspaces, gradient / lane buckets, flat parameters, Adam state) outside any graph pool
                 out = _step.train_step(self.G, self.D, self.opt_g, self.opt_d, local_graph, voxel_graph, self.cfg, rng="device",
-                                       sync_losses=sync_losses if sync_losses == "step" else False, overlap=True)
+                                       grad_sync=self.grad_sync, sync_losses=sync_losses if sync_losses == "step" else False,
+                                       overlap=True)
                 self._warm = True
             else:
                 out = self._run(local_graph, voxel_graph, sync_losses)
@@ -115,6 +120,8 @@ class GraphedStep:
             self.main.wait_stream(self.lanes.real)
             self.main.wait_stream(self.lanes.fake)
             self.D.merge_lanes()
+            if self.grad_sync is not None:
+                self.grad_sync(self.D)
             self.opt_d.step()
             cap.out = d_loss.detach()
             del d_loss
@@ -175,6 +182,8 @@ class GraphedStep:
         g_loss = _step.generator_loss(self.D, lb, vb, logits, hard, cfg)
         g_loss.backward()  # the generator's backward pass runs on the stream of its forward (autograd's stream affinity)
         main.wait_stream(gen)
+        if self.grad_sync is not None:
+            self.grad_sync(self.G)
         losses[R].copy_(g_loss.detach())
         self.opt_g.step()
         self.last_losses = losses

@@ -15,11 +15,17 @@ og = _A(G.parameters(), lr=2e-4, betas=cfg.BETAS)
 od = _A(D.parameters(), lr=2e-4, betas=cfg.BETAS)
 host = bench._make_batches(0, 1, 32, pin=False)
 lb, vb = bench._clone_to(*host[0], dev)
-for _ in range(2):
-    step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+if os.environ.get("GRAPH", "1") == "1":
+    from building_gan_b200.graphs import GraphedStep
+    gs = GraphedStep(G, D, og, od, cfg)
+    run = lambda: gs(lb, vb, sync_losses=False)
+else:
+    run = lambda: step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+for _ in range(3):
+    run()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-step.train_step(G, D, og, od, lb, vb, cfg, rng="device", sync_losses=False)
+run()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("N", vb.num_nodes, "E'", vb.bg_csr.num_edges)
