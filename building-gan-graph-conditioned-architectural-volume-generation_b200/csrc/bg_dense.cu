@@ -3,6 +3,7 @@
 // s = y.a_src, d = y.a_dst (the `lin` of a GATConv), the split-N deterministic weight gradient
 // and the LayerNorm/activation backward.  fp32 FFMA: this is the rel-1e-5 parity mode.
 #include <algorithm>
+#include <type_traits>
 #include <mutex>
 #include <vector>
 
@@ -262,7 +263,7 @@ struct WgBatch {
 __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) {
     pdl_prologue();
     constexpr int T = 64, RB = 32;
-    __shared__ float smem[2][RB][T + 4];
+    __shared__ __align__(16) float smem[2][RB][T + 4];
     float(*Gs)[T + 4] = smem[0];
     float(*Xs)[T + 4] = smem[1];
     int pi = 0;
@@ -297,9 +298,42 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     const float* gcol = mycol < no ? p.gz + o0 + mycol : nullptr;
     // software pipeline: the global loads of slab i+1 are issued (into registers) before slab i is multiplied, so the
     // load latency overlaps the FMAs / the barrier instead of adding to every iteration
-    constexpr int PER = RB * T / kThreads;
+    constexpr int PER = RB * T / kThreads, RSTEP = kThreads / T;  // a thread's q-th element of a slab: row (tid / T) + q * RSTEP
     float gv[PER], xv[PER];
+    // Address arithmetic hoisted out of the slab loop (ncu r01i: FFMA was 17% of the instructions of this kernel, IMAD / ISETP /
+    // LEA / branches of the per-element index math and of seg_load 50%): per thread one base pointer per operand and constant
+    // strides; full slabs (all but possibly the last of a split) carry no row predicates; a gather index or a partial slab
+    // takes the general path.
+    const int rl = tid / T;
+    const float* gp = gcol ? gcol + (rbeg + rl) * p.ld_gz : nullptr;
+    const int64_t gstep = (int64_t)RSTEP * p.ld_gz;
+    const bool xdirect = xcol.base != nullptr && xcol.gather == nullptr;
+    const float* xp = xdirect ? xcol.base + (rbeg + rl) * (int64_t)xcol.ld : nullptr;
+    const int64_t xstep = (int64_t)RSTEP * xcol.ld;
+    const float xconst = (xcol.base == nullptr && xcol.ones) ? 1.f : 0.f;
     auto fetch = [&](int64_t r0) {
+        if (r0 + RB <= rend) {
+            if (gp) {
+                const float* g0 = gp + (r0 - rbeg) * p.ld_gz;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) gv[q] = __ldg(g0 + q * gstep);
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) gv[q] = 0.f;
+            }
+            if (xdirect) {
+                const float* x0 = xp + (r0 - rbeg) * (int64_t)xcol.ld;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = __ldg(x0 + q * xstep);
+            } else if (xcol.base == nullptr) {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = xconst;
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = seg_load(xcol, r0 + rl + q * RSTEP);
+            }
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const int64_t r = r0 + (tid + q * kThreads) / T;
@@ -315,23 +349,34 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
     for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            const int idx = tid + q * kThreads, rr = idx / T, cc = idx % T;
-            Gs[rr][cc] = gv[q];
-            Xs[rr][cc] = xv[q];
+            Gs[rl + q * RSTEP][mycol] = gv[q];
+            Xs[rl + q * RSTEP][mycol] = xv[q];
         }
         __syncthreads();
         if (r0 + RB < rend) fetch(r0 + RB);
         if (active) {
-            for (int rr = grp; rr < RB; rr += R) {
-                float g[4], x[4];
+            // rows grp, grp + R, ... of the slab, fully unrolled per R (same order as a plain loop): constant shared-memory
+            // offsets and one 128-bit load per operand instead of a dynamic row loop with eight scalar loads
+            auto rows = [&](auto rc) {
+                constexpr int RR = decltype(rc)::value;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) g[i] = Gs[rr][ty * 4 + i];
+                for (int i = 0; i < RB / RR; ++i) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(&Gs[grp + i * RR][ty * 4]);
+                    const float4 x4 = *reinterpret_cast<const float4*>(&Xs[grp + i * RR][tx * 4]);
+                    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = Xs[rr][tx * 4 + j];
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], x[j], acc[i][j]);
+                        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(g[a], x[c], acc[a][c]);
+                }
+            };
+            switch (R) {
+                case 1: rows(std::integral_constant<int, 1>{}); break;
+                case 2: rows(std::integral_constant<int, 2>{}); break;
+                case 4: rows(std::integral_constant<int, 4>{}); break;
+                case 8: rows(std::integral_constant<int, 8>{}); break;
+                case 16: rows(std::integral_constant<int, 16>{}); break;
+                default: rows(std::integral_constant<int, 32>{}); break;
             }
         }
         __syncthreads();
