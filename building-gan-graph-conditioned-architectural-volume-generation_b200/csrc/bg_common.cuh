@@ -268,10 +268,19 @@ __device__ __forceinline__ void fold_partials(const float* partials, int G, int 
 // kFoldGroup folds its group, the last group folds the group results.  Both folds are <= ~20 deep, so the
 // critical path stays short even with ~300 CTAs.  counters[0] = global ticket, counters[1+g] = group g.
 // Returns true in exactly one CTA, whose `result` (shared, >= L floats) then holds the column sums.
+// Up to kSingleFold CTAs (the small, L2-resident graphs of the training step: N ~ 15 k rows -> G ~ 120) ONE ticket round is
+// enough: the last CTA sums all G partials itself (<= 40 loads per thread, 8 in flight) instead of paying a second
+// fence -> atomic -> reload round trip (~2 us of a ~10 us launch).  The choice depends on G only, so results stay reproducible.
 constexpr int kFoldGroup = 16;
+constexpr int kSingleFold = 160;
 __device__ __forceinline__ bool hier_fold(float* partials, float* gpartials, int L, unsigned int* counters, float* red,
                                           float* result) {
     const int G = gridDim.x;
+    if (G <= kSingleFold) {
+        if (!ticket_last(counters, G)) return false;
+        fold_partials(partials, G, L, red, result);
+        return true;
+    }
     const int group = blockIdx.x / kFoldGroup, ngroups = (G + kFoldGroup - 1) / kFoldGroup;
     const int gsize = min(kFoldGroup, G - group * kFoldGroup);
     if (!ticket_last(counters + 1 + group, gsize)) return false;
@@ -311,6 +320,11 @@ __device__ __forceinline__ void fold_partials_any(const float* partials, int G, 
 __device__ __forceinline__ bool hier_fold_any(float* partials, float* gpartials, int L, unsigned int* counters, float* red,
                                               float* result) {
     const int G = gridDim.x;
+    if (G <= kSingleFold) {
+        if (!ticket_last(counters, G)) return false;
+        fold_partials_any(partials, G, L, red, result);
+        return true;
+    }
     const int group = blockIdx.x / kFoldGroup, ngroups = (G + kFoldGroup - 1) / kFoldGroup;
     const int gsize = min(kFoldGroup, G - group * kFoldGroup);
     if (!ticket_last(counters + 1 + group, gsize)) return false;

@@ -185,6 +185,92 @@ __global__ void __launch_bounds__(kThreads) segment_pool_kernel(const float* __r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// H11 / H12 loss glue of one critic update (reference trainer.py:298-301, 314, 323): the interpolate between the real one-hot
+// labels and the generated soft labels, and  loss = mean(D(fake)) - mean(D(real)) + lambda * mean((||grad_i||_2 - 1)^2)
+// with its backward.  torch runs this as ~30 elementwise / reduction launches per critic update, all of them on the
+// critical path between the first and the second-order backward of the gradient-penalty pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gp_mix_kernel(const float* __restrict__ e, const int64_t* __restrict__ onehot_i64,
+                                                          const float* __restrict__ onehot_f32, const float* __restrict__ soft,
+                                                          int64_t N, int K, float* __restrict__ mixed) {
+    pdl_prologue();
+    const int64_t total = N * K;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const float ev = __ldg(e + i / K);
+        const float oh = onehot_i64 ? (float)__ldg(onehot_i64 + i) : __ldg(onehot_f32 + i);
+        mixed[i] = ev * oh + (1.f - ev) * __ldg(soft + i);  // e * real + (1 - e) * fake, in torch's evaluation order
+    }
+}
+
+constexpr int kLossTerms = 3;  // sum D(fake), sum D(real), sum (||grad_i|| - 1)^2
+__global__ void __launch_bounds__(kThreads) critic_loss_fwd_kernel(const float* __restrict__ d_fake, const float* __restrict__ d_real,
+                                                                   const float* __restrict__ grad, int64_t N, int K, float lambda,
+                                                                   float* __restrict__ coef, float* partials, unsigned int* counters,
+                                                                   float* __restrict__ out /* loss, mean fake, mean real, gp */) {
+    pdl_prologue();
+    __shared__ float red[kThreads];
+    __shared__ float wsum[kLossTerms][kThreads / 32];
+    __shared__ float result[kLossTerms];
+    const int G = gridDim.x;
+    const int64_t chunk = ceil_div(N, (int64_t)G);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    float acc[kLossTerms] = {0.f, 0.f, 0.f};
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += kThreads) {
+        acc[0] += __ldg(d_fake + i);
+        acc[1] += __ldg(d_real + i);
+        float ss = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float g = __ldg(grad + i * K + k);
+            ss = fmaf(g, g, ss);
+        }
+        const float nrm = sqrtf(ss), dev = nrm - 1.f;
+        acc[2] = fmaf(dev, dev, acc[2]);
+        // d/d grad_i of lambda * mean((||grad_i|| - 1)^2) = coef_i * grad_i; torch's norm backward is 0 at a zero row
+        coef[i] = nrm > 0.f ? lambda * 2.f * dev / ((float)N * nrm) : 0.f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < kLossTerms; ++t) {
+        float v = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[t][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLossTerms) {
+        float v = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) v += wsum[threadIdx.x][w];
+        partials[(int64_t)blockIdx.x * kLossTerms + threadIdx.x] = v;
+    }
+    if (!hier_fold(partials, partials + (int64_t)G * kLossTerms, kLossTerms, counters, red, result)) return;
+    if (threadIdx.x == 0) {
+        const float mf = result[0] / (float)N, mr = result[1] / (float)N, gp = lambda * (result[2] / (float)N);
+        out[0] = mf - mr + gp;
+        out[1] = mf;
+        out[2] = mr;
+        out[3] = gp;
+    }
+}
+
+// upstream gradient g (a device scalar): d loss / d D(fake)_i = g / N, d loss / d D(real)_i = -g / N, d loss / d grad_i = g coef_i grad_i
+__global__ void __launch_bounds__(kThreads) critic_loss_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ coef,
+                                                                   const float* __restrict__ grad, int64_t N, int K,
+                                                                   float* __restrict__ g_fake, float* __restrict__ g_real,
+                                                                   float* __restrict__ g_grad) {
+    pdl_prologue();
+    const float g = __ldg(g_loss);
+    const float inv = g / (float)N;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
+        if (g_fake) g_fake[i] = inv;
+        if (g_real) g_real[i] = -inv;
+        if (g_grad) {
+            const float c = g * __ldg(coef + i);
+            for (int k = 0; k < K; ++k) g_grad[i * K + k] = c * __ldg(grad + i * K + k);
+        }
+    }
+}
 }  // namespace bg
 
 using namespace bg;
@@ -355,4 +441,39 @@ extern "C" int bg_segment_pool(const float* x, const int32_t* seg_ptr, int64_t S
     if (S <= 0) return BG_OK;
     launch_k(segment_pool_kernel, (unsigned)S, kThreads, 0, as_stream(stream), x, seg_ptr, S, C, mode, out);
     return check_launch("bg_segment_pool");
+}
+
+extern "C" int bg_gp_mix(const float* e, const void* onehot, int32_t onehot_is_i64, const float* soft, int64_t N, int32_t K, float* mixed,
+                         void* stream) {
+    BG_REQUIRE(e && onehot && soft && mixed, BG_EINVAL, "bg_gp_mix: null pointer");
+    if (N <= 0) return BG_OK;
+    const int64_t grid = std::min<int64_t>(bg::ceil_div(N * K, (int64_t)bg::kThreads), 8 * bg::kSMs);
+    bg::launch_k(bg::gp_mix_kernel, (int)grid, bg::kThreads, 0, bg::as_stream(stream), e,
+                 onehot_is_i64 ? static_cast<const int64_t*>(onehot) : nullptr, onehot_is_i64 ? nullptr : static_cast<const float*>(onehot),
+                 soft, N, (int)K, mixed);
+    return bg::check_launch("bg_gp_mix");
+}
+
+extern "C" size_t bg_critic_loss_ws(int64_t N) { return bg::kCounterBytes + (size_t)(64 + 8) * bg::kLossTerms * sizeof(float) + 256; }
+
+extern "C" int bg_critic_loss_fwd(const float* d_fake, const float* d_real, const float* grad, int64_t N, int32_t K, float lambda,
+                                  float* coef, float* workspace, size_t ws_bytes, float* out4, void* stream) {
+    BG_REQUIRE(d_fake && d_real && grad && coef && workspace && out4, BG_EINVAL, "bg_critic_loss_fwd: null pointer");
+    BG_REQUIRE(N >= 1 && K >= 1, BG_EINVAL, "bg_critic_loss_fwd: N=%lld K=%d", (long long)N, K);
+    BG_REQUIRE(ws_bytes >= bg_critic_loss_ws(N), BG_EINVAL, "bg_critic_loss_fwd: workspace too small");
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+    float* partials = workspace + bg::kCounterBytes / sizeof(float);
+    const int G = (int)std::min<int64_t>(64, bg::ceil_div(N, (int64_t)bg::kThreads));  // function of N only: reproducible
+    bg::launch_k(bg::critic_loss_fwd_kernel, G, bg::kThreads, 0, bg::as_stream(stream), d_fake, d_real, grad, N, (int)K, lambda, coef, partials,
+                 counters, out4);
+    return bg::check_launch("bg_critic_loss_fwd");
+}
+
+extern "C" int bg_critic_loss_bwd(const float* g_loss, const float* coef, const float* grad, int64_t N, int32_t K, float* g_fake,
+                                  float* g_real, float* g_grad, void* stream) {
+    BG_REQUIRE(g_loss && coef && grad, BG_EINVAL, "bg_critic_loss_bwd: null pointer");
+    if (N <= 0) return BG_OK;
+    const int64_t grid = std::min<int64_t>(bg::ceil_div(N, (int64_t)bg::kThreads), 4 * bg::kSMs);
+    bg::launch_k(bg::critic_loss_bwd_kernel, (int)grid, bg::kThreads, 0, bg::as_stream(stream), g_loss, coef, grad, N, (int)K, g_fake, g_real, g_grad);
+    return bg::check_launch("bg_critic_loss_bwd");
 }

@@ -122,6 +122,10 @@ SIGNATURES = {
     "bg_disc_ws_offsets": (C.c_int32, [_MD, _I64, _P, _I32]),
     "bg_axpy": (C.c_int, [_P, _P, _F, _I64, _P]),
     "bg_fill": (C.c_int, [_P, _F, _I64, _P]),
+    "bg_gp_mix": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
+    "bg_critic_loss_ws": (_SZ, [_I64]),
+    "bg_critic_loss_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _F, _P, _P, _SZ, _P, _P]),
+    "bg_critic_loss_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "bg_set_pdl": (C.c_int, [_I32]),
     "bg_set_rng_base": (C.c_int, [_P]),
     "bg_adam_flat": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64, _P, _P]),
@@ -754,6 +758,46 @@ def fill_(y: Tensor, v: float) -> Tensor:
     _cf32(y, "y")
     _check(lib.bg_fill(y.data_ptr(), v, y.numel(), _stream()))
     return y
+
+
+@_op("gp_mix", 1)
+def gp_mix(e: Tensor, onehot: Tensor, soft: Tensor) -> Tensor:
+    """mixed = e * onehot + (1 - e) * soft (trainer.py:298-301); onehot int64 (as the reference holds it) or fp32."""
+    lib = load()
+    _cf32(e, "e"), _cf32(soft, "soft")
+    n, k = soft.shape
+    assert e.numel() == n and tuple(onehot.shape) == (n, k) and onehot.is_contiguous() and onehot.dtype in (torch.int64, torch.float32)
+    mixed = torch.empty_like(soft)
+    _check(lib.bg_gp_mix(e.data_ptr(), onehot.data_ptr(), int(onehot.dtype == torch.int64), soft.data_ptr(), n, k, mixed.data_ptr(),
+                         _stream()))
+    return mixed
+
+
+@_op("critic_loss_fwd", 1)
+def critic_loss_fwd(d_fake: Tensor, d_real: Tensor, grad: Tensor, lam: float):
+    """(out4 = [loss, mean D(fake), mean D(real), gp], coef[N]) - bg_critic_loss_fwd."""
+    lib = load()
+    _cf32(d_fake, "d_fake"), _cf32(d_real, "d_real"), _cf32(grad, "grad")
+    n, k = grad.shape
+    assert d_fake.numel() == n and d_real.numel() == n
+    coef = torch.empty(n, dtype=torch.float32, device=grad.device)
+    out4 = torch.empty(4, dtype=torch.float32, device=grad.device)
+    ws = workspace(lib.bg_critic_loss_ws(n), grad.device)
+    _check(lib.bg_critic_loss_fwd(d_fake.data_ptr(), d_real.data_ptr(), grad.data_ptr(), n, k, float(lam), coef.data_ptr(),
+                                  ws.data_ptr(), ws.numel() * 4, out4.data_ptr(), _stream()))
+    return out4, coef
+
+
+@_op("critic_loss_bwd", 1)
+def critic_loss_bwd(g_loss: Tensor, coef: Tensor, grad: Tensor, want_fake: bool, want_real: bool, want_grad: bool):
+    lib = load()
+    n, k = grad.shape
+    g_fake = torch.empty(n, 1, dtype=torch.float32, device=grad.device) if want_fake else None
+    g_real = torch.empty(n, 1, dtype=torch.float32, device=grad.device) if want_real else None
+    g_grad = torch.empty_like(grad) if want_grad else None
+    _check(lib.bg_critic_loss_bwd(g_loss.data_ptr(), coef.data_ptr(), grad.data_ptr(), n, k, _p(g_fake), _p(g_real), _p(g_grad),
+                                  _stream()))
+    return g_fake, g_real, g_grad
 
 
 def set_pdl(on: bool) -> bool:

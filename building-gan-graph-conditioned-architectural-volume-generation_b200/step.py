@@ -67,15 +67,49 @@ class Lanes:
         return cls._per_device[key]
 
 
+class _CriticLossFn(torch.autograd.Function):
+    """loss = mean(D(fake)) - mean(D(real)) + lambda * mean((||grad_i||_2 - 1)^2)  (trainer.py:314,323) as one forward and one
+    backward launch (bg_critic_loss_fwd / _bwd) instead of ~25 torch launches on the critical path of every critic update."""
+
+    @staticmethod
+    def forward(ctx, d_fake, d_real, grad, lam):
+        out4, coef = lib.critic_loss_fwd(d_fake.contiguous(), d_real.contiguous(), grad.contiguous(), lam)
+        ctx.save_for_backward(coef, grad)
+        return out4[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        coef, grad = ctx.saved_tensors
+        g_fake, g_real, g_grad = lib.critic_loss_bwd(g.contiguous(), coef, grad.contiguous(), *ctx.needs_input_grad[:3])
+        return g_fake, g_real, g_grad, None
+
+
+def _penalty_gradient(discriminator, local_graph, voxel_graph, label_soft: Tensor, rng: str, e: Optional[Tensor]) -> Tensor:
+    """trainer.py:298-312: the critic's input gradient at the interpolate (differentiable: create_graph=True)."""
+    n = voxel_graph.types_onehot.shape[0]
+    if e is None:
+        e = _rand((n, 1), label_soft.device, rng, normal=False)
+    mixed = lib.gp_mix(e.contiguous(), voxel_graph.types_onehot.contiguous(), label_soft.squeeze(0).contiguous()).requires_grad_(True)
+    score = discriminator(local_graph, voxel_graph, mixed.unsqueeze(0))
+    (grad,) = torch.autograd.grad(score, mixed, torch.ones_like(score), create_graph=True, only_inputs=True)
+    return grad
+
+
 def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tensor, label_soft: Tensor, cfg,
                        rng: str = "cpu", lanes: Optional[Lanes] = None, e: Optional[Tensor] = None) -> Tensor:
+    """trainer.py:318-332.  WGAN-GP on the kernel path: the interpolate and the loss arithmetic are fused launches
+    (bg_gp_mix, bg_critic_loss_*); ``gradient_penalty`` above is the same term spelled with torch ops, as the reference does."""
     real = voxel_graph.types_onehot.unsqueeze(0)
-    if lanes is None or not cfg.USE_WGANGP or not hasattr(discriminator, "lane"):
+    fused = cfg.USE_WGANGP and label_soft.is_cuda and hasattr(discriminator, "_native")
+    if lanes is None or not fused or not hasattr(discriminator, "lane"):
         d_real = discriminator(local_graph, voxel_graph, real)
         d_fake = discriminator(local_graph, voxel_graph, label_hard)
         if not cfg.USE_WGANGP:  # trainer.py:326-330 (the discriminator then ends in a sigmoid, models.py:222-223)
             return F.binary_cross_entropy(d_fake, torch.zeros_like(d_fake)) + F.binary_cross_entropy(d_real, torch.ones_like(d_real))
-        return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng, e)
+        if not fused:
+            return d_fake.mean() - d_real.mean() + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng, e)
+        grad = _penalty_gradient(discriminator, local_graph, voxel_graph, label_soft, rng, e)
+        return _CriticLossFn.apply(d_fake, d_real, grad, cfg.LAMBDA_GP)
     # same three passes in the same host order, on three streams: fork after everything enqueued so far, join before the loss
     main = torch.cuda.current_stream()
     fork = main.record_event()
@@ -85,10 +119,10 @@ def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tens
     with torch.cuda.stream(lanes.fake), discriminator.lane(2):
         lanes.fake.wait_event(fork)
         d_fake = discriminator(local_graph, voxel_graph, label_hard)
-    gp = gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, rng, e)
+    grad = _penalty_gradient(discriminator, local_graph, voxel_graph, label_soft, rng, e)
     main.wait_stream(lanes.real)
     main.wait_stream(lanes.fake)
-    return d_fake.mean() - d_real.mean() + gp
+    return _CriticLossFn.apply(d_fake, d_real, grad, cfg.LAMBDA_GP)
 
 
 def far_loss(voxel_graph, label_hard: Tensor, cfg) -> Tensor:

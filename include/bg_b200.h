@@ -334,6 +334,19 @@ int bg_disc_backward2(const BgModelDesc* md, const float* const* params, const B
 int32_t bg_gen_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
 int32_t bg_disc_ws_offsets(const BgModelDesc* md, int64_t N, int64_t* out, int32_t cap);
 
+/* ---- H11 / H12: the loss glue of one critic update (reference trainer.py:291-332).
+ * bg_gp_mix:          mixed = e * onehot + (1 - e) * soft   (trainer.py:298-301; onehot int64 [N,K] as the reference holds it, or fp32)
+ * bg_critic_loss_fwd: out4 = {loss, mean D(fake), mean D(real), gp},  loss = mean(d_fake) - mean(d_real) + lambda * mean((||grad_i||_2 - 1)^2)
+ *                     (trainer.py:314, 323); coef[N] is saved for the backward.  Deterministic fold, no atomics on floats.
+ * bg_critic_loss_bwd: g_fake[i] = g/N, g_real[i] = -g/N, g_grad[i,:] = g * coef[i] * grad[i,:]  (any output may be NULL); g = *g_loss. */
+int bg_gp_mix(const float* e, const void* onehot, int32_t onehot_is_i64, const float* soft, int64_t N, int32_t K, float* mixed,
+              void* stream);
+size_t bg_critic_loss_ws(int64_t N);
+int bg_critic_loss_fwd(const float* d_fake, const float* d_real, const float* grad, int64_t N, int32_t K, float lambda, float* coef,
+                       float* workspace, size_t ws_bytes, float* out4, void* stream);
+int bg_critic_loss_bwd(const float* g_loss, const float* coef, const float* grad, int64_t N, int32_t K, float* g_fake, float* g_real,
+                       float* g_grad, void* stream);
+
 /* ---- process-wide knobs (the only library state besides the per-(device, stream) weight-gradient side streams).
  * bg_set_pdl: programmatic dependent launch on/off at run time (initial value: env BG_PDL, default on); returns the previous
  * setting.  bg_set_rng_base: device pointer to a uint64 that every in-kernel Philox offset adds (NULL = none, the default):

@@ -89,3 +89,33 @@ def test_vanilla_gan_branch_use_wgangp_false():
     kg = step.generator_loss(D2, lb, vb, logits, h2.unsqueeze(0), cfg)
     og = otrainer.generator_loss(oD2, olb, ovb, ol, oh.unsqueeze(0), cfg)
     assert_close(kg.reshape(1), og.reshape(1), 2e-5, "BCE generator loss")
+
+
+@pytest.mark.gpu
+def test_fused_critic_loss_matches_torch():
+    """bg_gp_mix / bg_critic_loss_fwd / _bwd against the reference's torch spelling (trainer.py:298-301, 314, 323)."""
+    from building_gan_b200 import lib, step as bstep
+
+    torch.manual_seed(0)
+    n, k, lam = 5003, 7, 10.0
+    dev = "cuda"
+    e = torch.rand(n, 1, device=dev)
+    onehot = torch.nn.functional.one_hot(torch.randint(0, k, (n,), device=dev), k)  # int64, as the reference holds it
+    soft = torch.softmax(torch.randn(n, k, device=dev), dim=1)
+    mixed = lib.gp_mix(e, onehot, soft)
+    assert torch.equal(mixed, e * onehot + (1 - e) * soft)
+    d_fake = torch.randn(n, 1, device=dev, requires_grad=True)
+    d_real = torch.randn(n, 1, device=dev, requires_grad=True)
+    grad = (torch.randn(n, k, device=dev) * 0.3)
+    grad[7] = 0.0  # a zero row: torch's norm backward gives a zero subgradient there
+    grad.requires_grad_(True)
+    ref = d_fake.double().mean() - d_real.double().mean() + ((grad.double().norm(dim=1) - 1) ** 2).mean() * lam
+    gref = torch.autograd.grad(ref, (d_fake, d_real, grad))
+    got = bstep._CriticLossFn.apply(d_fake, d_real, grad, lam)
+    ggot = torch.autograd.grad(got, (d_fake, d_real, grad))
+    assert abs(got.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    for a, b in zip(ggot, gref):
+        assert_close(a, b, 1e-6)
+    # deterministic
+    got2 = bstep._CriticLossFn.apply(d_fake, d_real, grad, lam)
+    assert got2.item() == got.item()
