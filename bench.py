@@ -300,6 +300,18 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     ms = timed(step_resident, args.steps)
     launches = lib.LAUNCHES - launches0
     clock_info = clocks.stop()
+    # the same step with the trainer's per-step metrics call (trainer.py:497 -> step.compute_metrics: one
+    # confusion-matrix kernel + macro scores on the device, no sklearn, no D2H) included
+    metric_sink = []
+
+    def step_with_metrics(i):
+        out = step_resident(i)
+        metric_sink.append(step.compute_metrics(resident[i % len(resident)][1], out[2], cfg))
+        if len(metric_sink) > 4:
+            metric_sink.pop(0)
+
+    step_with_metrics(0)
+    ms_metrics = timed(step_with_metrics, args.steps)
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
     drain(0)
@@ -350,6 +362,10 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "steps/s",
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * (cfg.N_CRITIC + 1),
                         "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "with_metrics": {"value": round(world * args.steps / (ms_metrics * 1e-3), 3), "unit": "steps/s",
+                                 "ms_per_step": round(ms_metrics / args.steps, 3),
+                                 "note": "resident batches, trainer.py:497 metrics call included (device-side macro F1 / precision / "
+                                         "recall / accuracy, step.compute_metrics)"},
                 "gpu_launches": (ops["libbgb200_launches_per_step"] * args.steps
                                  if isinstance(ops, dict) and "libbgb200_launches_per_step" in ops else launches),
                 "gpu_launches_source": "kernels of libbgb200.so counted by CUPTI over one step x steps (torch's own kernels "
