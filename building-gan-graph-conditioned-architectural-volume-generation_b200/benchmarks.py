@@ -75,38 +75,67 @@ def run_c4(args, dev):
     print(json.dumps(out), flush=True)
 
 
-def run_sample(args, dev):
+def run_sample(args, dev, rank=0, world=1):
+    """BASELINE config 3 / metric 2: generator-only sampling (eval forward + argmax, trainer.py:769-770 + :73), batch 512
+    buildings per GPU (the reference's BATCH_SIZE, config.py:63, used by Trainer.test).  Independent batches: every rank samples
+    its own buildings (no collective on the data path; weak scaling), and on one GPU consecutive batches alternate between
+    ``BG_SAMPLE_STREAMS`` streams (default 2) so that the latency-bound narrow layers of one pass overlap the wide layers of
+    the other.  value = buildings of all ranks / max-over-ranks device time."""
+    import os
+    import torch.distributed as dist
     from .models import VoxelGNNGenerator
     cfg = Configuration()
     torch.manual_seed(777)
     G = VoxelGNNGenerator(cfg, 17, 12).to(dev).eval()
-    batch = 512  # the reference default BATCH_SIZE (config.py:63) used by Trainer.test
-    pairs = [synth.building_pair_fast(4001 + i) for i in range(batch)]
+    batch = 512
+    pairs = [synth.building_pair_fast(4001 + rank * batch + i) for i in range(batch)]
     lb, vb = graph.collate_fn(pairs)
     lb, vb = lb.to(dev), vb.to(dev)
-    for _ in range(max(args.warmup, 3)):
-        step.sample(G, lb, vb, cfg)
+    ns = max(1, int(os.environ.get("BG_SAMPLE_STREAMS", "2")))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(ns)] if ns > 1 else [torch.cuda.current_stream()]
+    cur = torch.cuda.current_stream()
+    labels = [None] * len(streams)
+
+    def run_steps(k):
+        for s in streams:
+            s.wait_stream(cur)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                labels[i % len(streams)] = step.sample(G, lb, vb, cfg)
+        for s in streams:
+            cur.wait_stream(s)
+
+    run_steps(max(args.warmup, 3) * len(streams))
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        labels = step.sample(G, lb, vb, cfg)
+    run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3
-    print(json.dumps({"metric": "generated buildings/sec", "value": round(batch * args.steps / sec, 1), "unit": "buildings/s",
-                      "n_gpus": 1, "steps": args.steps, "ms_per_step": round(1e3 * sec / args.steps, 3),
-                      "config": {"workload": "generator-only sampling (eval forward + argmax), batch 512 buildings",
-                                 "voxels_per_batch": vb.num_nodes}, "labels_checksum": int(labels.sum())}), flush=True)
+    ms = e0.elapsed_time(e1)
+    voxels = vb.num_nodes
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return
+    sec = ms * 1e-3
+    print(json.dumps({"metric": "generated buildings/sec", "value": round(world * batch * args.steps / sec, 1), "unit": "buildings/s",
+                      "n_gpus": world, "steps": args.steps, "ms_per_step": round(1e3 * sec / args.steps, 3), "scaling": "weak",
+                      "config": {"workload": "generator-only sampling (eval forward + argmax), batch 512 buildings per GPU",
+                                 "voxels_per_batch": voxels, "streams": len(streams)},
+                      "labels_checksum": int(labels[0].sum())}), flush=True)
 
 
 def run(args, rank, local_rank, world):
-    if rank != 0:
-        return
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib.load()
     if args.workload == "c4":
-        run_c4(args, dev)
+        if rank == 0:
+            run_c4(args, dev)  # a single-GPU kernel sweep
     else:
-        run_sample(args, dev)
+        run_sample(args, dev, rank, world)
