@@ -164,3 +164,38 @@ def test_capturable_counter_and_training_step():
         for (name, p), q in zip(m1.named_parameters(), m2.parameters()):
             # Adam's first steps move every parameter by ~lr regardless of gradient scale: compare against lr
             assert (p - q).abs().max().item() <= 0.05 * 2e-4 * 6, name
+
+
+def test_state_dict_round_trip_cpu():
+    """Host logic of the state_dict interchange without a GPU: torch.optim.Adam state (as `states.pt` holds it,
+    trainer.py:715-736) loads into optim.Adam - moments become views of the flat buffers laid out like the gradient bucket,
+    the step count is kept - and comes back out in torch's format, loadable by torch.optim.Adam again."""
+    cfg, A, B = _pair(VoxelGNNDiscriminator, "cpu")
+    ref = torch.optim.Adam(B.parameters(), lr=1e-3, betas=cfg.BETAS)
+    gen = torch.Generator().manual_seed(3)
+    for _ in range(2):
+        for p in B.parameters():
+            p.grad = torch.randn(p.shape, generator=gen)
+        ref.step()
+    ours = Adam(A.parameters(), lr=5e-4, betas=(0.9, 0.99))
+    buf = io.BytesIO()
+    torch.save(ref.state_dict(), buf)
+    buf.seek(0)
+    ours.load_state_dict(torch.load(buf, weights_only=False))
+    assert ours.param_groups[0]["lr"] == 1e-3 and tuple(ours.param_groups[0]["betas"]) == tuple(cfg.BETAS)
+    st, lay = A._native, A._native.layout
+    for (name, p), q in zip(A.named_parameters(), B.parameters()):
+        for key in ("exp_avg", "exp_avg_sq"):
+            assert torch.equal(ours.state[p][key], ref.state[q][key]), (name, key)
+        # views of the flat moment buffers, at the gradient bucket's offsets; parameters re-homed the same way
+        assert ours.state[p]["exp_avg"].data_ptr() == ours._m.data_ptr() + 4 * lay.offsets[name]
+        assert p.data_ptr() == st.pflat.data_ptr() + 4 * lay.offsets[name]
+    out = ours.state_dict()
+    assert all(float(s["step"]) == 2.0 for s in out["state"].values()) and len(out["state"]) == len(list(A.parameters()))
+    back = torch.optim.Adam(B.parameters(), lr=1.0)
+    back.load_state_dict(copy.deepcopy(out))
+    for q in B.parameters():
+        assert torch.equal(back.state[q]["exp_avg"], ref.state[q]["exp_avg"]) and float(back.state[q]["step"]) == 2.0
+    # the parameters themselves were not touched by re-homing them into the flat buffer
+    for (k, v), (_, w) in zip(A.state_dict().items(), B.state_dict().items()):
+        assert v.shape == w.shape
