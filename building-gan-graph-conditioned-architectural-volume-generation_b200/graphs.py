@@ -24,8 +24,6 @@ non-native conv types.
 from __future__ import annotations
 
 import collections
-import os
-from typing import Optional
 
 import torch
 
