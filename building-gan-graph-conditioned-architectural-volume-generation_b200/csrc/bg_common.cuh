@@ -52,6 +52,22 @@ struct WgradQueue {
 int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st);
 int wgrad_flush(WgradQueue& q, cudaStream_t st);
 
+// GraphNorm backward moments of the block BELOW, fused into the epilogue of the backward-input product that produces that
+// block's gx1 (bg_dense.cu: dense_fwd_moments): the tile a CTA just computed is exactly the operand gn_bwd_moments_kernel
+// would read back, so the column sums (sum gy, sum gy*(o - alpha mu)) come for two extra loads per element and the separate
+// 10-us launch (165 per training step, 80 of them on the step's critical chain) disappears.  Same outputs as
+// bg_graphnorm_bwd_moments: bstats[2C] = (G0, G1), dparams[3C] = (dw, dbeta, dalpha) (+= when accumulate).
+struct GnMomFuse {
+    const float *o, *x1, *alpha, *stats, *w;
+    float keep_scale;
+    float* dparams;
+    int accumulate;
+    float* bstats;
+    unsigned int* counters;  // reduction workspace head (self-resetting tickets)
+    float* partials;         // >= (G + G / kFoldGroup + 2) * 2 * BN floats, G = ceil(N / 64)
+};
+int dense_fwd_moments(const BgDense* a, const GnMomFuse* f, cudaStream_t st);  // f == nullptr: plain bg_dense_fwd
+
 // tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 

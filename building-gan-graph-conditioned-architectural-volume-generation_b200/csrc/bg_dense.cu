@@ -81,9 +81,10 @@ struct DenseParams {
     const float* gate;
     int64_t ld_gate;
     float gate_slope;
+    GnMomFuse mom;  // only read by the MOM instantiations
 };
 
-template <int BN, int TM, int TN>
+template <int BN, int TM, int TN, bool MOM = false>
 __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p) {
     pdl_prologue();
     constexpr int TX = BN / TN, TY = BM / TM;
@@ -155,6 +156,15 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
     }
 
     // ---- epilogue: bias, LayerNorm, activation, attention dots
+    float ms0[MOM ? TN : 1], ms1[MOM ? TN : 1], am[MOM ? TN : 1];  // MOM: column sums of gy and gy * (o - alpha mu)
+    if constexpr (MOM) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int c = tx * TN + j;
+            ms0[j] = ms1[j] = 0.f;
+            am[j] = c < p.Cout ? __ldg(p.mom.alpha + c) * __ldg(p.mom.stats + c) : 0.f;
+        }
+    }
     float bj[TN], gj[TN], tj[TN], asj[TN], adj[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
@@ -221,6 +231,19 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
             for (int j = 0; j < TN; ++j)
                 if (col0 + tx * TN + j < p.Cout) y[j] *= (__ldg(grw + j) > 0.f ? 1.f : p.gate_slope);
         }
+        if constexpr (MOM) {
+            if (grow < p.N) {  // y = this row's gx1 entries (after the fused gate): GraphNorm backward moments of the block below
+                const float* orw = p.mom.o + grow * p.Cout + tx * TN;
+                const float* xrw = p.mom.x1 + grow * p.Cout + tx * TN;
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (tx * TN + j < p.Cout) {
+                        const float gy = __ldg(xrw + j) > 0.f ? y[j] * p.mom.keep_scale : 0.f;
+                        ms0[j] += gy;
+                        ms1[j] = fmaf(gy, __ldg(orw + j) - am[j], ms1[j]);
+                    }
+            }
+        }
         if (grow < p.N) {
             float* orow = p.out + grow * p.ld_out + col0 + tx * TN;
             if (TN % 4 == 0 && (p.ld_out & 3) == 0 && col0 + tx * TN + TN <= p.Cout &&
@@ -232,6 +255,59 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const DenseParams p
 #pragma unroll
                 for (int j = 0; j < TN; ++j)
                     if (col0 + tx * TN + j < p.Cout) orow[j] = y[j];
+            }
+        }
+    }
+    if constexpr (MOM) {
+        // CTA column sums in a fixed order: rows of a warp by shuffles (lanes with equal tx), warps through shared memory,
+        // CTAs through the last-CTA fold; the last CTA finishes exactly like gn_bwd_moments_kernel.
+        constexpr int NW = kThreads / 32;
+        __shared__ float wpart[NW][2 * BN];
+        __shared__ float fred[kThreads];
+        __shared__ float fsum[2 * BN];
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+#pragma unroll
+            for (int o = TX; o < 32; o <<= 1) {
+                ms0[j] += __shfl_xor_sync(0xffffffffu, ms0[j], o);
+                ms1[j] += __shfl_xor_sync(0xffffffffu, ms1[j], o);
+            }
+        }
+        if (lane < TX) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                wpart[warp][lane * TN + j] = ms0[j];
+                wpart[warp][BN + lane * TN + j] = ms1[j];
+            }
+        }
+        __syncthreads();
+        float* partials = p.mom.partials;
+        for (int i = tid; i < 2 * BN; i += kThreads) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += wpart[w][i];
+            partials[(int64_t)blockIdx.x * 2 * BN + i] = t;
+        }
+        if (!hier_fold(partials, partials + (int64_t)gridDim.x * 2 * BN, 2 * BN, p.mom.counters, fred, fsum)) return;
+        if (tid < p.Cout) {
+            const int c = tid, C = p.Cout;
+            const float n = (float)p.N;
+            const float G0 = fsum[c] / n, G1 = fsum[BN + c] / n;
+            const float mu = p.mom.stats[c], r = p.mom.stats[C + c], a = p.mom.alpha[c], wc = p.mom.w[c];
+            const float mean_ohat = wc * r * G0 - wc * r * r * r * G1 * mu * (1.f - a);  // M[d loss/d ohat]
+            p.mom.bstats[c] = G0;
+            p.mom.bstats[C + c] = G1;
+            const float dw = n * r * G1, db = n * G0, da = -mu * n * mean_ohat;
+            float* dp = p.mom.dparams;
+            if (p.mom.accumulate) {
+                dp[c] += dw;
+                dp[C + c] += db;
+                dp[2 * C + c] += da;
+            } else {
+                dp[c] = dw;
+                dp[C + c] = db;
+                dp[2 * C + c] = da;
             }
         }
     }
@@ -760,7 +836,9 @@ static int fill_segview(SegView& sv, int nseg, const BgSeg* seg, int* K) {
 
 using namespace bg;
 
-extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
+extern "C" int bg_dense_fwd(const BgDense* a, void* stream) { return dense_fwd_moments(a, nullptr, as_stream(stream)); }
+
+int bg::dense_fwd_moments(const BgDense* a, const GnMomFuse* mom, cudaStream_t stream) {
     BG_REQUIRE(a && a->W && a->out, BG_EINVAL, "bg_dense_fwd: null pointer");
     BG_REQUIRE(a->N > 0 && a->Cout > 0, BG_EINVAL, "bg_dense_fwd: N and Cout must be positive");
     DenseParams p;
@@ -776,7 +854,7 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     BG_REQUIRE(!a->att_src || (a->att_dst && a->s && a->d), BG_EINVAL, "bg_dense_fwd: attention dots need att_dst, s, d");
     BG_REQUIRE(!rowwise || a->Cout <= 128, BG_EUNSUPPORTED, "bg_dense_fwd: row-wise epilogue needs Cout<=128 (got %d)", a->Cout);
     {  // 128/64-wide layers with plain row-major weights go to the tensor cores (tcgen05, 3xTF32 split: fp32-accurate)
-        const int rc = a->gate ? 1 : dense_tc_try(a, p.K, as_stream(stream));
+        const int rc = (a->gate || mom) ? 1 : dense_tc_try(a, p.K, stream);
         if (rc <= 0) return rc;
     }
     int bn = 8;
@@ -784,7 +862,22 @@ extern "C" int bg_dense_fwd(const BgDense* a, void* stream) {
     BG_REQUIRE(!a->ln_gamma || bn == a->Cout, BG_EUNSUPPORTED,
                "bg_dense_fwd: LayerNorm width must be one of 8,16,32,64,128 (got %d)", a->Cout);
     dim3 grid((unsigned)ceil_div(a->N, BM), (unsigned)ceil_div(a->Cout, bn));
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = stream;
+    if (mom) {
+        BG_REQUIRE(!rowwise && a->Cout <= 128 && a->ld_out == a->Cout, BG_EINVAL, "dense_fwd_moments: plain product with Cout <= 128 only");
+        BG_REQUIRE(mom->o && mom->x1 && mom->alpha && mom->stats && mom->w && mom->dparams && mom->bstats && mom->counters && mom->partials,
+                   BG_EINVAL, "dense_fwd_moments: null pointer");
+        p.mom = *mom;
+        switch (bn) {
+            case 8: launch_k(dense_fwd_kernel<8, 2, 1, true>, grid, kThreads, 0, st, p); break;
+            case 16: launch_k(dense_fwd_kernel<16, 2, 2, true>, grid, kThreads, 0, st, p); break;
+            case 32: launch_k(dense_fwd_kernel<32, 2, 4, true>, grid, kThreads, 0, st, p); break;
+            case 64: launch_k(dense_fwd_kernel<64, 4, 4, true>, grid, kThreads, 0, st, p); break;
+            default: launch_k(dense_fwd_kernel<128, 4, 8, true>, grid, kThreads, 0, st, p); break;
+        }
+        return check_launch("dense_fwd_moments");
+    }
+    p.mom = GnMomFuse{};
     switch (bn) {
         case 8: launch_k(dense_fwd_kernel<8, 2, 1>, grid, kThreads, 0, st, p); break;
         case 16: launch_k(dense_fwd_kernel<16, 2, 2>, grid, kThreads, 0, st, p); break;

@@ -46,6 +46,10 @@ struct ConvL {
     int cin, cout;
     float *h, *s, *d, *o, *m, *z, *x1, *stats;
     float *b_gx1, *b_go, *b_gh, *b_gsd, *b_bstats;
+    // set by the block ABOVE when its backward-input product already computed this block's GraphNorm backward moments
+    // (dense_fwd_moments): the buffers conv_backward must use instead of launching bg_graphnorm_bwd_moments
+    float* pre_bst = nullptr;
+    float* pre_gnpar = nullptr;
 };
 
 static int conv_widths(int hidden, int repeat, int* w) {  // hourglass: halve `repeat` times then double back
@@ -261,22 +265,31 @@ static int conv_forward(const Ctx& c, const ConvL& L, const float* x, const uint
 
 // First-order backward of one block.  gx1 may be null (then `inj_o` IS the gradient at o).  Temporaries come
 // from T; when `keep` the intermediates are written to the block's b_* buffers instead (second-order sweep).
+// Graphs up to this many rows fuse the GraphNorm backward moments of the block below into the backward-input product
+// (latency-bound regime: one launch less per block).  Larger graphs keep the separate, bandwidth-tuned reduction.
+constexpr int64_t kFuseMomentsMaxN = 65536;
+
 static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float* gx1, float keep_scale, const float* inj_o,
-                         const float* inj_h, bool keep, Arena& T, float* gx_out, const float* gate_x = nullptr) {
+                         const float* inj_h, bool keep, Arena& T, float* gx_out, const float* gate_x = nullptr,
+                         ConvL* below = nullptr) {
     const int C = L.cout;
     float* go = keep ? L.b_go : T.f((size_t)c.N * C);
     float* gh = keep ? L.b_gh : T.f((size_t)c.N * C);
     float* gsd = keep ? L.b_gsd : T.f((size_t)c.N * 2);
-    float* bst = keep ? L.b_bstats : T.f((size_t)2 * C);
+    const bool moments_done = gx1 && L.pre_bst != nullptr;
+    float* bst = moments_done ? L.pre_bst : (keep ? L.b_bstats : T.f((size_t)2 * C));
     c.X->off = 0;
     float* Pe = c.X->f((size_t)c.graph->E);
     float* DU = c.X->f((size_t)c.graph->E);
-    float* gnpar = c.G ? c.g(L.p_gw) : T.f((size_t)3 * C);
+    float* gnpar = moments_done ? L.pre_gnpar : (c.G ? c.g(L.p_gw) : T.f((size_t)3 * C));
+    L.pre_bst = L.pre_gnpar = nullptr;
     if (gx1) {
-        // GraphNorm backward: column moments (+ parameter gradients) as one launch; the elementwise half (and the injected
-        // cotangent at o) rides in the prologue of the aggregation backward's destination pass
-        BG_TRY(bg_graphnorm_bwd_moments(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, gnpar,
-                                        c.G ? c.accumulate : 0, bst, c.red, c.red_bytes, c.st));
+        // GraphNorm backward: column moments (+ parameter gradients) as one launch - unless the product that made gx1 already
+        // delivered them; the elementwise half (and the injected cotangent at o) rides in the prologue of the aggregation
+        // backward's destination pass
+        if (!moments_done)
+            BG_TRY(bg_graphnorm_bwd_moments(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, gnpar,
+                                            c.G ? c.accumulate : 0, bst, c.red, c.red_bytes, c.st));
         BG_TRY(bg_gat_bwd_gn(c.graph, gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, bst, keep_scale, inj_o, L.h, L.s, L.d, L.m,
                              L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, go, gh, gsd, C, 0.2f, c.st));
     } else {
@@ -296,7 +309,25 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
                          wg(c.N, gsd, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, c.accumulate)};
         BG_TRY(wgrad_launch(pr, inj_h ? 1 : 3, *c.q, as_stream(c.st)));
     }
-    if (gx_out) BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out, gate_x));
+    if (gx_out && below && !gate_x && c.N <= kFuseMomentsMaxN && below->cout == L.cin) {
+        // gx_out IS the gradient at the output of the block below: its GraphNorm backward moments ride in this product's epilogue
+        const int Cb = below->cout;
+        below->pre_bst = keep ? below->b_bstats : T.f((size_t)2 * Cb);
+        below->pre_gnpar = c.G ? c.g(below->p_gw) : T.f((size_t)3 * Cb);
+        GnMomFuse f{};
+        f.o = below->o; f.x1 = below->x1; f.alpha = c.P[below->p_ga]; f.stats = below->stats; f.w = c.P[below->p_gw];
+        f.keep_scale = keep_scale;
+        f.dparams = below->pre_gnpar; f.accumulate = c.G ? c.accumulate : 0; f.bstats = below->pre_bst;
+        f.counters = reinterpret_cast<unsigned int*>(c.red);
+        f.partials = c.red + kCounterBytes / sizeof(float);
+        BgDense a{};
+        a.N = c.N; a.nseg = 1; a.seg[0] = seg(gh, C, C);
+        a.W = c.P[L.p_W]; a.w_so = 1; a.w_sk = L.cin; a.Cout = L.cin;
+        a.act = BG_ACT_NONE; a.out = gx_out; a.ld_out = L.cin;
+        BG_TRY(dense_fwd_moments(&a, &f, as_stream(c.st)));
+    } else if (gx_out) {
+        BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out, gate_x));
+    }
     if (keep && gx1) BG_TRY(cudaMemcpyAsync(L.b_gx1, gx1, (size_t)c.N * C * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) ==
                                     cudaSuccess
                                 ? BG_OK
@@ -531,7 +562,8 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     for (int k = net.n_conv - 1; k >= 0; --k) {
         const float* x_in = k == 0 ? x : net.conv[k - 1].x1;
         float* gx = T.f((size_t)N * net.conv[k].cin);
-        BG_TRY(conv_backward(c, net.conv[k], x_in, g, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr, false, T, gx));
+        BG_TRY(conv_backward(c, net.conv[k], x_in, g, training ? 1.f / kKeepProb : 1.f, nullptr, nullptr, false, T, gx, nullptr,
+                             k > 0 ? &net.conv[k - 1] : nullptr));
         g = gx;
     }
     BG_TRY(bg_axpy(const_cast<float*>(g), g_skip, 1.f, N * gh, stream));
@@ -681,7 +713,7 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
         const bool gate = k == 0 && plain_relu(d.pre[1]);
         float* gx = gate && keep ? d.pre[1].b_gz : T.f((size_t)N * d.conv[k].cin);
         BG_TRY(conv_backward(c, d.conv[k], x_in, g, training_scale, inj_o ? inj_o[k] : nullptr, inj_h ? inj_h[k] : nullptr, keep, T,
-                             gx, gate ? d.pre[1].out : nullptr));
+                             gx, gate ? d.pre[1].out : nullptr, k > 0 ? &d.conv[k - 1] : nullptr));
         g = gx;
         g_is_gz = gate;
     }

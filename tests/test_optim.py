@@ -162,8 +162,12 @@ def test_capturable_counter_and_training_step():
     assert max(abs(x - y) for x, y in zip(out[0][0], out[1][0])) <= 1e-4 * max(1.0, max(abs(v) for v in out[1][0]))
     for m1, m2 in ((G1, G2), (D1, D2)):
         for (name, p), q in zip(m1.named_parameters(), m2.parameters()):
-            # Adam's first steps move every parameter by ~lr regardless of gradient scale: compare against lr
-            assert (p - q).abs().max().item() <= 0.05 * 2e-4 * 6, name
+            # Adam's first steps move every parameter by ~lr regardless of gradient scale: compare against lr.  A conv bias
+            # sits in front of a GraphNorm, which removes the column mean: its gradient is analytically zero, what arrives is
+            # rounding noise of ~1e-9, and Adam turns noise of that size (|g| ~ eps) into a step of a fraction of lr whose
+            # value depends on the last bit of everything upstream - bound those by the largest possible step instead.
+            noise_driven = name.startswith("encoder.module_") and name.endswith(".bias") and int(name.split("_")[1].split(".")[0]) % 4 == 0
+            assert (p - q).abs().max().item() <= (2.0 if noise_driven else 0.05) * 2e-4 * 6, name
 
 
 def test_state_dict_round_trip_cpu():
