@@ -71,11 +71,11 @@ int dense_fwd_moments(const BgDense* a, const GnMomFuse* f, cudaStream_t st);  /
 // tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 
-// ---- launches: every kernel of the library goes through launch_k().  With programmatic dependent launch (PDL, BG_PDL=1;
-// default off, see pdl_enabled()) kernel N+1 is scheduled while kernel N drains: each kernel starts with pdl_prologue() =
+// ---- launches: every kernel of the library goes through launch_k().  With programmatic dependent launch (PDL; default ON,
+// BG_PDL=0 / bg_set_pdl(0) switch it off, see pdl_enabled() in bg_misc.cu) kernel N+1 is scheduled while kernel N drains: each kernel starts with pdl_prologue() =
 // `griddepcontrol.launch_dependents` (the next kernel may be made resident once all CTAs of this one have started) followed by
 // `griddepcontrol.wait` (block until the previous kernel has completed and its writes are visible) BEFORE its first global
-// access, so stream order is preserved exactly.  Measured on the batch-32 training step (scratch/timeline.py): 4400 kernels
+// access, so stream order is preserved exactly.  Measured on the batch-32 training step (profiles/tools/timeline.py): 4400 kernels
 // per two steps left 7.5 ms of 2-5 us idle gaps between dependent launches.
 bool pdl_enabled();
 const uint64_t* rng_base();  // bg_set_rng_base

@@ -10,9 +10,9 @@
 namespace bg {
 
 // Programmatic dependent launch: default ON for single-stream use (BG_PDL=0 turns it off): on the batch-32 training step the
-// 2-5 us idle gaps between dependent kernels (scratch/timeline.py: 7.5 -> 0.9 ms per two steps) are worth 47.5 -> 53.9 steps/s.
+// 2-5 us idle gaps between dependent kernels (profiles/tools/timeline.py: 7.5 -> 0.9 ms per two steps) are worth 47.5 -> 53.9 steps/s.
 // It does NOT mix with the multi-stream step (step.Lanes): launches carrying the attribute into streams that fork/join through
-// events cost 26.3 vs 15.5 ms per step there, so Lanes switches it off at run time through bg_set_pdl(0).
+// events cost 26.3 vs 15.5 ms per step there, so the overlapped step switches it off for its own launches through bg_set_pdl(0) and restores it (step.lanes_pdl_scope).
 static int g_pdl = -1;
 bool pdl_enabled() {
     if (g_pdl < 0) g_pdl = !(getenv("BG_PDL") && atoi(getenv("BG_PDL")) == 0);

@@ -123,8 +123,20 @@ class PackedDataset(torch.utils.data.Dataset):
             (hlen,) = struct.unpack("<Q", fh.read(8))
             self.header = json.loads(fh.read(hlen).decode())
         self._base = (len(MAGIC) + 8 + hlen + _ALIGN - 1) // _ALIGN * _ALIGN
-        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        self._mm = None  # opened lazily, per process: see __getstate__
         self._cache: Dict[str, np.ndarray] = {}
+
+    def _map(self) -> np.ndarray:
+        if self._mm is None:
+            self._mm = np.memmap(self.path, dtype=np.uint8, mode="r")
+        return self._mm
+
+    def __getstate__(self):
+        """Pickled (DataLoader workers started with spawn / forkserver) WITHOUT the mapping and the array views: a worker
+        re-opens the file on first use instead of receiving a full copy of it."""
+        state = dict(self.__dict__)
+        state["_mm"], state["_cache"] = None, {}
+        return state
 
     def __len__(self) -> int:
         return int(self.header["num_graphs"])
@@ -136,7 +148,7 @@ class PackedDataset(torch.utils.data.Dataset):
             dt = np.dtype(meta["dtype"])
             n = int(np.prod(meta["shape"])) if meta["shape"] else 1
             start = self._base + self.header["offsets"][name]
-            a = self._mm[start:start + n * dt.itemsize].view(dt).reshape(meta["shape"])
+            a = self._map()[start:start + n * dt.itemsize].view(dt).reshape(meta["shape"])
             self._cache[name] = a
         return a
 

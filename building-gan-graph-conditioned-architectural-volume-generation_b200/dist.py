@@ -55,16 +55,21 @@ def shard_ids(ids: Sequence[int], rank: int, world: int) -> List[int]:
 
 def shard_by_nodes(sizes: Sequence[int], world: int) -> List[List[int]]:
     """Contiguous partition of a batch's graphs into ``world`` shards balanced by voxel count (greedy prefix split):
-    returns the graph indices of every shard."""
+    returns the graph indices of every shard.  Every shard holds at least one graph (a rank with an empty shard could not
+    build a batch and would miss the gradient all-reduce); fewer graphs than ranks is an error."""
+    if world < 1:
+        raise ValueError(f"shard_by_nodes: world = {world}")
+    if len(sizes) < world:
+        raise ValueError(f"shard_by_nodes: {len(sizes)} graphs cannot be split over {world} ranks (every rank needs >= 1 graph)")
     total, out, acc, cur, r = sum(sizes), [], 0, [], 0
     for i, s in enumerate(sizes):
         cur.append(i)
         acc += s
         remaining_graphs = len(sizes) - i - 1
-        if r < world - 1 and (acc >= total * (r + 1) / world or remaining_graphs == world - r - 1):
+        shards_after = world - r - 1  # shards still to be opened after the current one
+        if r < world - 1 and (acc >= total * (r + 1) / world or remaining_graphs == shards_after):
             out.append(cur)
             cur, r = [], r + 1
     out.append(cur)
-    while len(out) < world:
-        out.append([])
+    assert len(out) == world and all(out), (sizes, world, out)
     return out

@@ -70,7 +70,7 @@ class GraphedStep:
         device tensors for False)."""
         caller = torch.cuda.current_stream()
         self.main.wait_stream(caller)
-        with torch.cuda.stream(self.main):
+        with torch.cuda.stream(self.main), _step.lanes_pdl_scope():
             if not self._warm:
                 # first call: the eager overlapped step on the same streams creates every lazily cached buffer (per-stream
                 # workspaces, gradient / lane buckets, flat parameters, Adam state) outside any graph pool

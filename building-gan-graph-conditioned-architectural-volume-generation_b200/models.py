@@ -37,11 +37,40 @@ def _glorot(t: Tensor) -> None:
         t.uniform_(-bound, bound)
 
 
-class _PygLinearParams(nn.Module):
-    def __init__(self, cin: int, cout: int):
+def _kaiming(t: Tensor) -> None:
+    """torch_geometric.nn.inits.kaiming_uniform(value, fan=in_channels, a=sqrt(5)): U(+-1/sqrt(fan_in)), one draw."""
+    bound = 1.0 / math.sqrt(t.size(-1))
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
+
+
+def _uniform_fan(bias: Tensor, fan: int) -> None:
+    """torch_geometric.nn.inits.uniform(size=in_channels, bias): U(+-1/sqrt(in_channels))."""
+    bound = 1.0 / math.sqrt(fan)
+    with torch.no_grad():
+        bias.uniform_(-bound, bound)
+
+
+class _PygLinear(nn.Module):
+    """Parameters of torch_geometric.nn.dense.Linear(in, out, bias, weight_initializer): ``weight`` [out, in] drawn by
+    ``glorot`` or (weight_initializer=None) kaiming-uniform(a=sqrt 5); ``bias`` [out] drawn U(+-1/sqrt(in)) (PyG's
+    ``bias_initializer=None`` branch - NOT zeros).  ``reset_parameters()`` consumes the RNG exactly like PyG's: the convs
+    call it a second time from their own ``reset_parameters()`` (PyG 2.6.1 ``Linear.__init__`` already drew once)."""
+
+    def __init__(self, cin: int, cout: int, bias: bool = False, init: str = "glorot"):
         super().__init__()
+        self._init = init
         self.weight = nn.Parameter(torch.empty(cout, cin))
-        _glorot(self.weight)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(cout))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        (_glorot if self._init == "glorot" else _kaiming)(self.weight)
+        if self.bias is not None:
+            _uniform_fan(self.bias, self.weight.size(1))
 
 
 class GATConv(nn.Module):
@@ -51,11 +80,11 @@ class GATConv(nn.Module):
         super().__init__()
         _check_widths("GATConv", in_channels, out_channels)
         self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin = _PygLinearParams(in_channels, out_channels)
+        self.lin = _PygLinear(in_channels, out_channels)
         self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
         self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
         self.bias = nn.Parameter(torch.zeros(out_channels))
-        _glorot(self.lin.weight)  # PyG's reset_parameters() re-draws lin before the attention vectors
+        self.lin.reset_parameters()  # PyG's reset_parameters() re-draws lin before the attention vectors
         _glorot(self.att_src)
         _glorot(self.att_dst)
 
@@ -65,51 +94,45 @@ def _check_widths(name: str, in_channels: int, out_channels: int) -> None:
         raise ValueError(f"{name}({in_channels}, {out_channels}): libbgb200 supports widths {lib.SUPPORTED_WIDTHS}")
 
 
-class _PygLinearBias(nn.Module):
-    """torch_geometric.nn.dense.Linear(in, out, bias=True): ``weight`` [out, in], ``bias`` [out] (zeros)."""
-
-    def __init__(self, cin: int, cout: int, init: str = "glorot"):
-        super().__init__()
-        self.weight = nn.Parameter(torch.empty(cout, cin))
-        self.bias = nn.Parameter(torch.zeros(cout))
-        if init == "glorot":
-            _glorot(self.weight)
-        else:
-            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
-
-
 class GCNConv(nn.Module):
-    """Parameters of tgnn.GCNConv(in, out): bias[C], lin.weight[C, Cin] (glorot, no bias)."""
+    """Parameters of tgnn.GCNConv(in, out): bias[C] (zeros), lin.weight[C, Cin] (glorot, no bias; drawn by Linear.__init__
+    and again by GCNConv.reset_parameters())."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         _check_widths("GCNConv", in_channels, out_channels)
-        self.lin = _PygLinearParams(in_channels, out_channels)
+        self.lin = _PygLinear(in_channels, out_channels)
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin.reset_parameters()
 
 
 class GraphConv(nn.Module):
-    """Parameters of tgnn.GraphConv(in, out): lin_rel.{weight,bias}, lin_root.weight (kaiming-uniform Linears)."""
+    """Parameters of tgnn.GraphConv(in, out): lin_rel.{weight,bias}, lin_root.weight - PyG Linears with the default
+    initialisers (kaiming-uniform weight, U(+-1/sqrt(in)) bias), each drawn at construction and again by
+    GraphConv.reset_parameters()."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         _check_widths("GraphConv", in_channels, out_channels)
-        self.lin_rel = _PygLinearBias(in_channels, out_channels, init="kaiming")
-        self.lin_root = _PygLinearParams(in_channels, out_channels)
-        nn.init.kaiming_uniform_(self.lin_root.weight, a=math.sqrt(5))
+        self.lin_rel = _PygLinear(in_channels, out_channels, bias=True, init="kaiming")
+        self.lin_root = _PygLinear(in_channels, out_channels, init="kaiming")
+        self.lin_rel.reset_parameters()
+        self.lin_root.reset_parameters()
 
 
 class GATv2Conv(nn.Module):
-    """Parameters of tgnn.GATv2Conv(in, out) (heads=1, share_weights=False): att[1,1,C], bias[C],
-    lin_l.{weight,bias}, lin_r.{weight,bias}."""
+    """Parameters of tgnn.GATv2Conv(in, out) (heads=1, share_weights=False): att[1,1,C], bias[C] (zeros),
+    lin_l.{weight,bias}, lin_r.{weight,bias} (glorot weights, U(+-1/sqrt(in)) biases; drawn twice like PyG)."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         _check_widths("GATv2Conv", in_channels, out_channels)
-        self.lin_l = _PygLinearBias(in_channels, out_channels)
-        self.lin_r = _PygLinearBias(in_channels, out_channels)
+        self.lin_l = _PygLinear(in_channels, out_channels, bias=True)
+        self.lin_r = _PygLinear(in_channels, out_channels, bias=True)
         self.att = nn.Parameter(torch.empty(1, 1, out_channels))
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
         _glorot(self.att)
 
 
@@ -326,7 +349,28 @@ def _batch_in(bc) -> "lib.BgBatchIn":
 # per-batch cache of data-only quantities (hoisted out of every forward call)
 # ------------------------------------------------------------------------------------------------
 class _BatchCtx:
-    __slots__ = ("csr", "type32", "vx", "table", "local_id", "n", "real_onehot", "c_in")
+    __slots__ = ("csr", "type32", "vx", "table", "key", "local_ref", "n", "real_onehot", "c_in")
+
+
+def _tkey(t: Tensor):
+    """Identity of a tensor's CONTENT as far as it can be known without reading it: storage address, in-place version
+    counter, shape.  A cache entry also keeps a reference to the keyed tensor, so the address cannot be recycled."""
+    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+
+def _ctx_key(local_graph, voxel_graph):
+    return (id(local_graph), _tkey(local_graph.x), _tkey(local_graph.type), _tkey(voxel_graph.x), _tkey(voxel_graph.type))
+
+
+def _real_onehot(bc, label: Tensor) -> Tensor:
+    """Float copy of an integer one-hot label tensor (the real sample is int64, trainer.py:319), cached per batch and keyed by
+    the tensor's address, version and shape (a fresh tensor at a recycled address, or an in-place edit, misses)."""
+    key = _tkey(label)
+    hit = bc.real_onehot
+    if hit is None or hit[0] != key:
+        hit = (key, label.to(bc.vx.device, torch.float32).contiguous(), label)  # [2]: keeps the keyed tensor alive
+        bc.real_onehot = hit
+    return hit[1]
 
 
 def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
@@ -334,13 +378,14 @@ def _batch_ctx(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
     dev = voxel_graph.x.device
     if dev.type != "cuda":
         raise RuntimeError("building_gan_b200 models run on CUDA only (no CPU fallback): move the batch with .to('cuda')")
-    if ctx is None or ctx.local_id != id(local_graph) or ctx.vx.device != dev:
+    key = _ctx_key(local_graph, voxel_graph)
+    if ctx is None or ctx.key != key or ctx.vx.device != dev:
         ctx = _BatchCtx()
         ctx.csr = csr_of(voxel_graph)
         ctx.type32 = voxel_graph.type.to(torch.int32).contiguous()
         ctx.vx = voxel_graph.x.to(torch.float32).contiguous()
         ctx.table = lib.type_table(local_graph.x.to(torch.float32).contiguous(), local_graph.type, num_types)
-        ctx.local_id = id(local_graph)
+        ctx.key, ctx.local_ref = key, local_graph  # the reference keeps id(local_graph) from being recycled
         ctx.n = int(ctx.vx.shape[0])
         ctx.real_onehot = None
         ctx.c_in = None
@@ -356,8 +401,8 @@ def prepare_batch(local_graph, voxel_graph, num_types: int) -> _BatchCtx:
     nothing is allocated-and-cached during the model calls afterwards (required before CUDA-graph capture, graphs.py)."""
     bc = _batch_ctx(local_graph, voxel_graph, num_types)
     label = voxel_graph.types_onehot
-    if label.dtype != torch.float32 and (bc.real_onehot is None or bc.real_onehot[0] != label.data_ptr()):
-        bc.real_onehot = (label.data_ptr(), label.to(bc.vx.device, torch.float32).contiguous())
+    if label.dtype != torch.float32:
+        _real_onehot(bc, label)
     _batch_in(bc)
     bc.csr.c_struct()
     return bc
@@ -663,9 +708,7 @@ class VoxelGNNDiscriminator(nn.Module):
         bc = _batch_ctx(local_graph, voxel_graph, self.configuration.NUM_CLASSES)
         label = label_hard.squeeze(0)
         if label.dtype != torch.float32:  # the real sample is an int64 one-hot (trainer.py:319); torch.cat promotes it
-            if bc.real_onehot is None or bc.real_onehot[0] != label.data_ptr():
-                bc.real_onehot = (label.data_ptr(), label.to(bc.vx.device, torch.float32).contiguous())
-            label = bc.real_onehot[1]
+            label = _real_onehot(bc, label)
         label = label.to(bc.vx.device).contiguous()
         seed, offset = _philox_ticket()
         EXECUTOR = _executor_for(self._kind)
@@ -837,6 +880,13 @@ class _DiscNativeFn(torch.autograd.Function):
         label, score, *tensors = ctx.saved_tensors
         if ctx.lane is not None:  # runs on the lane's stream (autograd: the forward's stream); g_score came from another one
             g_score.record_stream(torch.cuda.current_stream())
+        if ctx.bucket_mode and torch.is_grad_enabled() and ctx.needs_input_grad[6]:
+            # create_graph=True AND the parameters' anchor needs a gradient: this is loss.backward(create_graph=True), not the
+            # WGAN-GP autograd.grad(..., inputs=[interpolated]) (whose anchor needs none).  Bucket mode would silently drop every
+            # parameter gradient of this pass.
+            raise RuntimeError("building_gan_b200: backward(create_graph=True) w.r.t. the parameters is not supported with "
+                               "BG_GRADS=bucket (only input gradients are differentiable a second time, trainer.py:306-312); "
+                               "set BG_GRADS=autograd")
         outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training,
                                       (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score,
                                       g_score.contiguous(), label, *tensors)

@@ -8,7 +8,7 @@ parameter tensors, ~14 launches each).  This class is the same optimiser behind 
 ``exp_avg_sq`` of a model live in four index-aligned flat fp32 buffers (the gradient one is the bucket the backward kernels
 accumulate into and the NCCL all-reduce payload), and ``step()`` is one ``bg_adam_flat`` launch.
 
-* Same update as torch (``_multi_tensor_adam``, amsgrad / maximize off): tests/test_optim_gpu.py compares it against
+* Same update as torch (``_multi_tensor_adam``, amsgrad / maximize off): tests/test_optim.py compares it against
   ``torch.optim.Adam`` over many steps.
 * ``state_dict()`` / ``load_state_dict()`` use torch.optim.Adam's format in both directions (``states.pt``,
   trainer.py:715-736): per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` entries are views of the flat buffers.

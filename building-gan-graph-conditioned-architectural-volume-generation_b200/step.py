@@ -14,6 +14,7 @@ GPU (same distributions, no host round trip) - the fast default of the benchmark
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import List, Optional, Tuple
 
@@ -56,8 +57,6 @@ class Lanes:
 
     def __init__(self, device):
         self.real, self.fake, self.gen = (torch.cuda.Stream(device=device, priority=-1) for _ in range(3))
-        if os.environ.get("BG_PDL") is None:
-            lib.set_pdl(False)  # programmatic dependent launch and event-forked streams do not mix (csrc/bg_misc.cu)
 
     @classmethod
     def get(cls, device) -> "Lanes":
@@ -65,6 +64,21 @@ class Lanes:
         if key not in cls._per_device:
             cls._per_device[key] = cls(device)
         return cls._per_device[key]
+
+
+@contextlib.contextmanager
+def lanes_pdl_scope():
+    """Programmatic dependent launch and event-forked streams do not mix (csrc/bg_misc.cu: 26.3 vs 15.5 ms per step), so
+    the overlapped step switches PDL off for ITS launches only and restores the previous setting on exit (an explicit
+    ``BG_PDL`` in the environment is left alone)."""
+    if os.environ.get("BG_PDL") is not None:
+        yield
+        return
+    prev = lib.set_pdl(False)
+    try:
+        yield
+    finally:
+        lib.set_pdl(prev)
 
 
 class _CriticLossFn(torch.autograd.Function):
@@ -190,6 +204,14 @@ def compute_metrics(voxel_graph, label_hard: Tensor, cfg):
 
 def train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng: str = "cpu",
                grad_sync=None, sync_losses="each", overlap=False):
+    """trainer.py:467-495 for one device-resident batch (see ``_train_step``); the multi-stream variant runs with
+    programmatic dependent launch scoped off."""
+    with (lanes_pdl_scope() if overlap is True else contextlib.nullcontext()):
+        return _train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng, grad_sync, sync_losses,
+                           overlap)
+
+
+def _train_step(generator, discriminator, opt_g, opt_d, local_graph, voxel_graph, cfg, rng, grad_sync, sync_losses, overlap):
     """trainer.py:467-495 for one device-resident batch.  ``grad_sync(model)`` (optional) is called after each
     backward, before the optimiser step - the data-parallel gradient all-reduce hooks in here.
     Returns (critic losses, generator loss, label_hard[1,N,7]).  ``sync_losses``: "each" = ``.item()`` right after every

@@ -79,15 +79,28 @@ def glorot_(t: Tensor) -> Tensor:
 # conv layers
 # --------------------------------------------------------------------------------------
 class PygLinear(nn.Module):
-    """torch_geometric.nn.dense.Linear with glorot weight init, zero bias."""
+    """torch_geometric.nn.dense.Linear(in, out, bias, weight_initializer=..., bias_initializer=None) of PyG 2.6.1:
+    ``Linear.__init__`` ends with ``reset_parameters()``: weight by ``glorot`` or (weight_initializer=None)
+    ``inits.kaiming_uniform(fan=in, a=sqrt 5)`` = U(+-1/sqrt(in)); bias by ``inits.uniform(in, bias)`` = U(+-1/sqrt(in))
+    (NOT zeros).  The convs' own ``reset_parameters()`` call it a second time, so every Linear of a conv consumes the RNG
+    twice - restated here so a seeded construction matches PyG draw for draw."""
 
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, weight_initializer: Optional[str] = "glorot"):
         super().__init__()
+        self.in_channels, self.weight_initializer = in_channels, weight_initializer
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
-        glorot_(self.weight)
-        if self.bias is not None:
-            nn.init.zeros_(self.bias)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        bound = 1.0 / math.sqrt(self.in_channels)
+        with torch.no_grad():
+            if self.weight_initializer == "glorot":
+                glorot_(self.weight)
+            else:  # None / 'kaiming_uniform': sqrt(6 / ((1 + a^2) fan)) with a = sqrt(5)
+                self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.uniform_(-bound, bound)
 
     def forward(self, x: Tensor) -> Tensor:
         return F.linear(x, self.weight, self.bias)
@@ -121,7 +134,7 @@ class GATConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channels))
         # PyG's constructor ends with reset_parameters(), which re-draws lin.weight (already
         # drawn once by Linear.__init__) before att_src / att_dst: keep the same RNG consumption.
-        glorot_(self.lin.weight)
+        self.lin.reset_parameters()
         glorot_(self.att_src)
         glorot_(self.att_dst)
 
@@ -144,6 +157,8 @@ class GATv2Conv(nn.Module):
         self.lin_r = PygLinear(in_channels, out_channels, bias=True)
         self.att = nn.Parameter(torch.empty(1, 1, out_channels))
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin_l.reset_parameters()  # GATv2Conv.reset_parameters(): lin_l, lin_r, att, zeros(bias)
+        self.lin_r.reset_parameters()
         glorot_(self.att)
 
     def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
@@ -166,6 +181,7 @@ class GCNConv(nn.Module):
         super().__init__()
         self.lin = PygLinear(in_channels, out_channels, bias=False)
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin.reset_parameters()  # GCNConv.reset_parameters() draws lin a second time
 
     def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
         n = x.size(0)
@@ -189,11 +205,12 @@ class GraphConv(nn.Module):
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
-        self.lin_rel = PygLinear(in_channels, out_channels, bias=True)
-        self.lin_root = PygLinear(in_channels, out_channels, bias=False)
-        # PyG's GraphConv builds its Linears with the default (kaiming-uniform) initialiser
-        nn.init.kaiming_uniform_(self.lin_rel.weight, a=math.sqrt(5))
-        nn.init.kaiming_uniform_(self.lin_root.weight, a=math.sqrt(5))
+        # PyG's GraphConv builds its Linears with the default initialisers (kaiming-uniform weight, uniform bias) and
+        # GraphConv.reset_parameters() draws both again
+        self.lin_rel = PygLinear(in_channels, out_channels, bias=True, weight_initializer=None)
+        self.lin_root = PygLinear(in_channels, out_channels, bias=False, weight_initializer=None)
+        self.lin_rel.reset_parameters()
+        self.lin_root.reset_parameters()
 
     def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
         n = x.size(0)

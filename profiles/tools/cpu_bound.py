@@ -1,6 +1,6 @@
 """Is the training step CPU- or GPU-bound?  Enqueue time vs completion time, plus a per-phase CPU breakdown."""
 import sys, os, time
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, lib, step

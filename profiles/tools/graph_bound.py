@@ -1,6 +1,6 @@
 """Host vs GPU time of the graphed training step, with a host-side breakdown of one step."""
 import sys, os, time
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, lib, step, graphs, models

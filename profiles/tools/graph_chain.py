@@ -1,6 +1,6 @@
 """Kernel sequence of one captured critic update on the stream that carries the gradient-penalty chain (diagnostic)."""
 import sys, os, json, collections, tempfile
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, graphs

@@ -1,6 +1,6 @@
 """Per-step wall times of the graphed step over the bench's 6 cycling batches (diagnostic)."""
 import sys, os, time
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, graphs

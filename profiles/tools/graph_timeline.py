@@ -1,6 +1,6 @@
 """Per-stream GPU timeline of graphed training steps (chrome trace of torch.profiler, kernels grouped by stream)."""
 import sys, os, json, collections, tempfile
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, graphs

@@ -1,6 +1,6 @@
 """One training step under cudaProfilerStart/Stop for ncu (--profile-from-start off)."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, lib, step

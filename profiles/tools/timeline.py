@@ -1,6 +1,6 @@
 """GPU timeline of one training step: busy time (union of kernel intervals), idle gaps and what they wait for."""
 import sys, os, collections
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import bench
 from building_gan_b200 import Configuration, lib, step

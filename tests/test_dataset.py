@@ -77,3 +77,16 @@ def test_on_disk_size_is_ragged_not_dense(pack):
     pairs, ds = pack
     n2 = sum(4 * v.num_nodes ** 2 for _, v in pairs)
     assert os.path.getsize(ds.path) < n2
+
+
+def test_pickling_does_not_copy_the_mapping(pack):
+    """DataLoader workers started with spawn pickle the dataset: the memory map must not travel (it would be copied in
+    full); the worker re-opens the file lazily."""
+    import pickle
+    pairs, ds = pack
+    _ = ds[0]  # opens the mapping and fills the view cache
+    blob = pickle.dumps(ds)
+    assert len(blob) < 64 * 1024 + len(pickle.dumps(ds.header)), len(blob)
+    ds2 = pickle.loads(blob)
+    assert ds2._mm is None and ds2._cache == {}
+    _same_data(ds2[1][1], pairs[1][1])

@@ -72,3 +72,23 @@ def test_shard_by_nodes_is_contiguous_and_balanced():
         assert sum(shards, []) == list(range(len(sizes))) and len(shards) == world
         loads = [sum(sizes[i] for i in s) for s in shards]
         assert max(loads) <= sum(sizes) / world + max(sizes)
+
+
+@pytest.mark.parametrize("sizes,world", [([1, 1, 100], 3), ([100, 1, 1], 3), ([1, 1, 100], 2), ([5] * 8, 4), ([400, 10, 10, 10, 10, 400], 4),
+                                         ([180, 378, 450, 504] * 8, 8), ([7], 1), ([3, 900, 2, 2], 4)])
+def test_shard_by_nodes_never_leaves_a_rank_without_graphs(sizes, world):
+    shards = bdist.shard_by_nodes(sizes, world)
+    assert len(shards) == world and all(len(s) >= 1 for s in shards)
+    assert [i for s in shards for i in s] == list(range(len(sizes)))  # contiguous, order kept, every graph exactly once
+
+
+def test_shard_by_nodes_balances_by_voxel_count():
+    sizes = [180, 378, 450, 504] * 64  # a batch-256 worth of buildings
+    shards = bdist.shard_by_nodes(sizes, 8)
+    load = [sum(sizes[i] for i in s) for s in shards]
+    assert max(load) - min(load) <= max(sizes)
+
+
+def test_shard_by_nodes_refuses_fewer_graphs_than_ranks():
+    with pytest.raises(ValueError, match="cannot be split"):
+        bdist.shard_by_nodes([10, 20], 4)
