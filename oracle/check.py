@@ -1,0 +1,133 @@
+"""ORACLE-side parity checker (test infrastructure, see oracle/__init__.py): runs the drop-in models of the product and
+the oracle models (fp64, CPU) on the SAME buildings, weights and random draws and reports how far apart they are.
+
+Used as the checker by ``tests/`` (benchmark-size parity), ``__graft_entry__.smoke()`` and the ``parity`` block of
+``bench.py``'s line - never as the thing measured.  Error norm everywhere: max |a - ref| / max |ref| per tensor (the
+"rel 1e-5 of the tensor's magnitude" of BASELINE.json's north star); ``*_elementwise`` adds the stricter per-element
+relative error over the elements that are not tiny (|ref| > 1e-3 max|ref|).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import models as omodels
+from . import pyg as opyg
+from . import trainer as otrainer
+
+
+def rel(a: Tensor, ref: Tensor) -> float:
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def rel_elementwise(a: Tensor, ref: Tensor, floor: float = 1e-3) -> float:
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    big = ref.abs() > floor * ref.abs().max()
+    if not bool(big.any()):
+        return 0.0
+    return float(((a - ref).abs()[big] / ref.abs()[big]).max())
+
+
+def to_oracle_batch(batch, dtype=torch.float64) -> "opyg.Batch":
+    """Product ``Batch`` (any device) -> oracle ``Batch`` on the CPU, floating-point fields in ``dtype``."""
+    graphs = []
+    for i in range(batch.num_graphs):
+        g = batch[i]
+        fields = {}
+        for k, v in g._fields.items():
+            if isinstance(v, Tensor):
+                v = v.detach().cpu()
+                if v.is_floating_point():
+                    v = v.to(dtype)
+            fields[k] = v
+        graphs.append(opyg.Data(**fields))
+    return opyg.Batch.from_data_list(graphs)
+
+
+def oracle_twins(G, D, cfg, dtype=torch.float64):
+    oG, oD = omodels.OracleGenerator(cfg, G.local_graph_dim, G.voxel_graph_dim), omodels.OracleDiscriminator(cfg, D.local_graph_dim, D.voxel_graph_dim)
+    oG.load_state_dict({k: v.detach().cpu() for k, v in G.state_dict().items()})
+    oD.load_state_dict({k: v.detach().cpu() for k, v in D.state_dict().items()})
+    return oG.to(dtype), oD.to(dtype)
+
+
+def _worst_grad(model, omodel) -> Dict[str, float]:
+    """Worst parameter-gradient error of a model: per tensor max|err| / max|ref grad|, tensors whose reference gradient is
+    below 1e-6 of the model's largest gradient are judged against that scale (exact-cancellation gradients)."""
+    gmax = max(float(p.grad.abs().max()) for p in omodel.parameters() if p.grad is not None)
+    worst, name = 0.0, ""
+    for (k, p), (_, op) in zip(model.named_parameters(), omodel.named_parameters()):
+        if op.grad is None:
+            continue
+        if p.grad is None:
+            return {"worst_grad_rel": float("inf"), "worst_grad_param": k}
+        err = float((p.grad.detach().double().cpu() - op.grad).abs().max())
+        e = err / max(float(op.grad.abs().max()), 1e-6 * gmax)
+        if e > worst:
+            worst, name = e, k
+    return {"worst_grad_rel": worst, "worst_grad_param": name}
+
+
+def parity_report(G, D, local_graph, voxel_graph, cfg, step_module, seed: int = 2024, gradients: bool = True,
+                  envelope: bool = True) -> Dict[str, object]:
+    """Eval-mode (no dropout) generator forward, critic loss with its gradient penalty (second-order backward) and generator
+    loss, product vs fp64 oracle with shared z / Gumbel noise / mixing factor.  ``step_module`` = the product's ``step``
+    (passed in: oracle/ never imports the product).  ``envelope``: also runs the oracle in fp32 - the reference's own
+    arithmetic - and reports ITS distance from fp64 (the rounding envelope of a correct fp32 implementation)."""
+    dev = voxel_graph.x.device
+    was = G.training, D.training
+    G.eval(), D.eval()
+    oG, oD = oracle_twins(G, D, cfg)
+    oG.eval(), oD.eval()
+    olb, ovb = to_oracle_batch(local_graph), to_oracle_batch(voxel_graph)
+    n, k = voxel_graph.num_nodes, cfg.NUM_CLASSES
+    gen = torch.Generator().manual_seed(seed)
+    z = torch.randn(1, n, cfg.Z_DIM, generator=gen)
+    noise = -torch.empty(n, k).exponential_(generator=gen).log()
+    out: Dict[str, object] = {"N": int(n), "graphs": int(voxel_graph.num_graphs), "oracle": "fp64 CPU restatement (oracle/models.py)"}
+    with torch.no_grad():
+        ol, oh, os_ = oG(olb, ovb, z.double(), noise.double())
+        kl, kh, ks = G(local_graph, voxel_graph, z.to(dev), noise.to(dev))
+    out["logits_rel"], out["logits_rel_elementwise"] = rel(kl, ol), rel_elementwise(kl, ol)
+    out["label_soft_rel"] = rel(ks, os_)
+    top2 = os_.topk(2, dim=1).values
+    tie = (top2[:, 0] - top2[:, 1]) <= 1e-4
+    differ = kh.argmax(1).cpu() != oh.argmax(1)
+    out["labels_differ_outside_ties"] = int((differ & ~tie).sum())
+    out["labels_differ_at_ties"], out["near_ties"] = int((differ & tie).sum()), int(tie.sum())
+    if envelope:
+        oG32 = omodels.OracleGenerator(cfg, G.local_graph_dim, G.voxel_graph_dim).eval()
+        oG32.load_state_dict({k_: v.detach().cpu() for k_, v in G.state_dict().items()})
+        with torch.no_grad():
+            l32, _, _ = oG32(to_oracle_batch(local_graph, torch.float32), to_oracle_batch(voxel_graph, torch.float32), z, noise)
+        out["fp32_oracle_logits_rel"] = rel(l32, ol)
+    # critic loss: both sides draw the mixing factor from the CPU generator under the same seed (trainer.py:298)
+    hard_in, soft_in = oh.detach().unsqueeze(0), os_.detach().unsqueeze(0)
+    D.zero_grad(set_to_none=True), oD.zero_grad(set_to_none=True)
+    torch.manual_seed(seed + 1)
+    o_d = otrainer.discriminator_loss(oD, olb, ovb, hard_in, soft_in, cfg)
+    torch.manual_seed(seed + 1)
+    k_d = step_module.discriminator_loss(D, local_graph, voxel_graph, hard_in.float().to(dev), soft_in.float().to(dev), cfg, rng="cpu")
+    out["d_loss_rel"] = rel(k_d.reshape(1), o_d.reshape(1))
+    if gradients:
+        o_d.backward(), k_d.backward()
+        g = _worst_grad(D, oD)
+        out["d_worst_grad_rel"], out["d_worst_grad_param"] = g["worst_grad_rel"], g["worst_grad_param"]
+    # generator loss through the (updated-gradient-free) critic
+    G.zero_grad(set_to_none=True), oG.zero_grad(set_to_none=True)
+    ol2, oh2, _ = oG(olb, ovb, z.double(), noise.double())
+    kl2, kh2, _ = G(local_graph, voxel_graph, z.to(dev), noise.to(dev))
+    o_g = otrainer.generator_loss(oD, olb, ovb, ol2, oh2.unsqueeze(0), cfg)
+    k_g = step_module.generator_loss(D, local_graph, voxel_graph, kl2, kh2.unsqueeze(0), cfg)
+    out["g_loss_rel"] = rel(k_g.reshape(1), o_g.reshape(1))
+    if gradients:
+        o_g.backward(), k_g.backward()
+        g = _worst_grad(G, oG)
+        out["g_worst_grad_rel"], out["g_worst_grad_param"] = g["worst_grad_rel"], g["worst_grad_param"]
+        out["worst_grad_rel"] = max(out["d_worst_grad_rel"], out["g_worst_grad_rel"])
+    G.zero_grad(set_to_none=True), D.zero_grad(set_to_none=True)
+    G.train(was[0]), D.train(was[1])
+    return {k_: (round(v, 10) if isinstance(v, float) else v) for k_, v in out.items()}

@@ -51,7 +51,7 @@ def _tensor_fields(batch):
 
 def main() -> None:
     config, data, models, trainer = _import_reference()
-    from building_gan_b200 import synth  # synthetic raw JSON (the real dataset is an LFS pointer)
+    from workloads import synth  # synthetic raw JSON (the real dataset is an LFS pointer); neutral code, no product import
 
     os.makedirs(OUT, exist_ok=True)
     ids = [4001, 4002, 4003]
