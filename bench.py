@@ -574,7 +574,9 @@ def _parity_block(G, D, resident0, cfg, lib):
         from oracle import check
         lb, vb = resident0
         r = check.parity_report(G, D, lb, vb, cfg, step, gradients=True, envelope=True)
-        r["dense_mode"] = "tcgen05 3xTF32 (128-wide layers) + FFMA" if int(os.environ.get("BG_DENSE_TC", "1")) else "FFMA"
+        mode = lib.set_dense_tc(1)
+        lib.set_dense_tc(mode)
+        r["dense_mode"] = {0: "FFMA", 1: "tcgen05 3xTF32, 4 TMEM accumulators (128-wide layers) + FFMA", 2: "tcgen05 bf16 operands (128-wide layers) + FFMA"}[mode]
         r["norm"] = "max|a - ref| / max|ref| per tensor; gradients: worst parameter tensor"
         return r
     except Exception as exc:

@@ -1,4 +1,5 @@
-// Dense layers on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via the 3xTF32 split.
+// Dense layers on the 5th-generation tensor cores (tcgen05 + TMEM): fp32-accurate via the 3xTF32 split (default), or
+// bf16 operands with fp32 accumulation (BG_DENSE_TC=bf16 / bg_set_dense_tc(2): the stated reduced-precision mode).
 //
 // y[128 rows, BN] = epilogue(X[128, K] W[BN, K]^T): the 128/64-wide Linear(+LayerNorm+LeakyReLU/ReLU)(+attention dots)
 // layers of the generator / discriminator (reference models.py:49-66,92-113 and the conv `lin`s).
@@ -10,16 +11,26 @@
 // (one 128-byte row = 32 fp32 = 4 UMMA k-steps), accumulators live in TMEM (128 lanes x BN columns fp32), the epilogue
 // reads them back with tcgen05.ld, one thread per row (bias, LayerNorm, activation, attention dots, store).
 //
+// Accumulation accuracy (3xTF32 mode).  The tensor core adds every k-step into the fp32 TMEM accumulator with truncation
+// (round toward zero): one chain over K = 128..524 is 16..66 one-sided roundings on the hi*hi products alone, and the bias
+// does not average out (measured round 1: logits 5e-5 of max through 33 layers against 2.4e-5 for fp32 FFMA arithmetic).  The
+// kernel therefore keeps FOUR accumulators in TMEM (4 x BN columns): the hi*hi products go round-robin by k-step into three
+// of them (a third of the roundings each, on a third of the magnitude), all lo*hi / hi*lo correction products into the
+// fourth (they are 2^-11 of the result: their roundings vanish), and the epilogue adds the four in fp32 round-to-nearest.
+//
+// bf16 mode: operands rounded to bf16 (RN) in the stage loader, ONE kind::f16 MMA per 16-wide k-step, same SWIZZLE_128B
+// staging (a 128-byte row then holds 64 k), single accumulator.  Tolerance stated in tests/test_models_gpu.py.
+//
 // Pipeline per CTA: 2 shared-memory stages.  All 256 threads load / split / store the next stage while the tensor core
 // consumes the previous one; one thread issues the 12 MMAs of a stage and a tcgen05.commit that frees it.
 #include <stdlib.h>
+#include <string.h>
 
 #include "bg_common.cuh"
 
 namespace bg {
 
 constexpr int TC_M = 128;        // rows per CTA = UMMA M
-constexpr int TC_K = 32;         // fp32 per 128-byte swizzle row
 constexpr int TC_STAGES = 2;
 
 struct SegViewTc {
@@ -97,6 +108,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, SWIZZLE_128B operand descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -110,12 +129,52 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // byte offset of element (row, k) inside a [rows][32 fp32] SWIZZLE_128B tile (Swizzle<3,4,3>: 16-byte chunk ^= row & 7)
 __device__ __forceinline__ int swz(int row, int k) { return row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)); }
 
-template <int BN>
+#define BG_TMEM_LD32(v, addr)                                                                                                      \
+    asm volatile(                                                                                                                 \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22," \
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                                             \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),   \
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),     \
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),     \
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                       \
+        : "r"(addr))
+
+// 32 accumulator columns [c0, c0+32) of this thread's row: the NACC partial accumulators (BN columns apart) summed in fp32
+// round-to-nearest, in a fixed order
+template <int NACC, int BN>
+__device__ __forceinline__ void tmem_row32(uint32_t taddr, int c0, float (&out)[32]) {
+    uint32_t v[32];
+    BG_TMEM_LD32(v, taddr + c0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = __uint_as_float(v[j]);
+#pragma unroll
+    for (int a = 1; a < NACC; ++a) {
+        BG_TMEM_LD32(v, taddr + a * BN + c0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[j] += __uint_as_float(v[j]);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // d = {hi -> upper half, lo -> lower half}
+    return r;
+}
+
+// MODE 0: 3xTF32 (fp32-accurate), MODE 1: bf16 operands / fp32 accumulate
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcParams p) {
     pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int SK = MODE ? 64 : 32;          // k per shared-memory stage (one 128-byte swizzle row of the operand type)
+    constexpr int NV = MODE ? 2 : 1;            // float4 loads per (thread, row): 16 bytes of the staged operand type
+    constexpr int NACC = MODE ? 1 : 4;          // TMEM accumulators (see the header comment)
+    constexpr int NSPLIT = MODE ? 1 : 2;        // hi / lo copies of every operand tile
     constexpr int A_BYTES = TC_M * 128, B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
+    constexpr int TMEM_COLS = NACC * BN;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);  // [TC_STAGES]
     uint64_t* accum_bar = empty_bar + TC_STAGES;
@@ -129,8 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    if (warp == 0) {  // TMEM: NACC x BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -138,73 +197,93 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // instruction descriptor: D=F32, A=B=TF32 (kind::tf32) or BF16 (kind::f16), both K-major, N=BN, M=128
+    constexpr uint32_t FMT = MODE ? 1u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-    const int nkb = (p.K + TC_K - 1) / TC_K;
-    // Loader mapping: a thread owns one 16-byte chunk (4 consecutive k) of the 128-byte row, rows tid/8 + 32 i: 128-bit global
-    // loads (coalesced: 8 threads = one row), 128-bit swizzled shared stores (8 distinct chunks per row: conflict-free).
-    // Needs every segment width / row stride / pointer to be a multiple of 4 floats (checked on the host).
+    const int nkb = (p.K + SK - 1) / SK;
+    // Loader mapping: a thread owns one 16-byte chunk of the staged 128-byte row (4 consecutive k in fp32 / tf32, 8 in bf16),
+    // rows tid/8 + 32 i: 128-bit global loads (coalesced: 8 threads = one row), 128-bit swizzled shared stores (8 distinct
+    // chunks per row: conflict-free).  Needs every segment width / row stride / pointer to be a multiple of 4 floats
+    // (checked on the host), so a float4 never straddles two segments.
     const int chunk = tid & 7;
     const int rbase = tid >> 3;  // 0..31
     struct Regs {
-        float4 a[TC_M / 32], b[BN / 32];
+        float4 a[TC_M / 32][NV], b[BN / 32][NV];
     };
     auto fetch = [&](int kb, Regs& R) {  // global -> registers for k-block kb, issued TWO iterations ahead of its use
-        const int kg = kb * TC_K + chunk * 4;
-        const SegColTc xc = seg_resolve_tc(p.x, kg, p.K);
 #pragma unroll
-        for (int i = 0; i < TC_M / 32; ++i) {
-            const int64_t r = row0 + rbase + 32 * i;
-            R.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < p.N && xc.base) {
-                const int64_t rr = xc.gather ? (int64_t)__ldg(xc.gather + r) : r;
-                R.a[i] = __ldg(reinterpret_cast<const float4*>(xc.base + rr * xc.ld));
+        for (int v = 0; v < NV; ++v) {
+            const int kg = kb * SK + chunk * (4 * NV) + 4 * v;
+            const SegColTc xc = seg_resolve_tc(p.x, kg, p.K);
+#pragma unroll
+            for (int i = 0; i < TC_M / 32; ++i) {
+                const int64_t r = row0 + rbase + 32 * i;
+                R.a[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < p.N && xc.base) {
+                    const int64_t rr = xc.gather ? (int64_t)__ldg(xc.gather + r) : r;
+                    R.a[i][v] = __ldg(reinterpret_cast<const float4*>(xc.base + rr * xc.ld));
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i)
-            R.b[i] = kg < p.K ? __ldg(reinterpret_cast<const float4*>(p.W + (int64_t)(rbase + 32 * i) * p.K + kg))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < BN / 32; ++i)
+                R.b[i][v] = kg < p.K ? __ldg(reinterpret_cast<const float4*>(p.W + (int64_t)(rbase + 32 * i) * p.K + kg))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     };
-    auto split_store = [&](const float4& v, uint8_t* hi_tile, uint8_t* lo_tile, int row) {
-        const float in[4] = {v.x, v.y, v.z, v.w};
-        float hi[4], lo[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {  // round-to-nearest TF32 split: hi + lo == a up to 2^-22 |a|, both unbiased
-            uint32_t hb, lb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[u]));
-            hi[u] = __uint_as_float(hb);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(in[u] - hi[u]));
-            lo[u] = __uint_as_float(lb);
-        }
+    auto stage_store = [&](const float4 (&v)[NV], uint8_t* tile, int tile_bytes, int row) {
         const int o = row * 128 + ((chunk ^ (row & 7)) << 4);
-        *reinterpret_cast<float4*>(hi_tile + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(lo_tile + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        if constexpr (MODE == 0) {
+            const float in[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+            float hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // round-to-nearest TF32 split: hi + lo == a up to 2^-22 |a|, both unbiased
+                uint32_t hb, lb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[u]));
+                hi[u] = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(in[u] - hi[u]));
+                lo[u] = __uint_as_float(lb);
+            }
+            *reinterpret_cast<float4*>(tile + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(tile + tile_bytes + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+            uint4 q;
+            q.x = pack_bf16(v[0].x, v[0].y);
+            q.y = pack_bf16(v[0].z, v[0].w);
+            q.z = pack_bf16(v[NV - 1].x, v[NV - 1].y);
+            q.w = pack_bf16(v[NV - 1].z, v[NV - 1].w);
+            *reinterpret_cast<uint4*>(tile + o) = q;
+        }
     };
     auto process = [&](int kb, Regs& R) {
         const int s = kb % TC_STAGES;
         uint8_t* st = smem + s * STAGE_BYTES;
         if (kb >= TC_STAGES) mbar_wait(empty_bar + s, ((kb / TC_STAGES) - 1) & 1);  // MMAs that read this stage retired
 #pragma unroll
-        for (int i = 0; i < TC_M / 32; ++i) split_store(R.a[i], st, st + A_BYTES, rbase + 32 * i);
+        for (int i = 0; i < TC_M / 32; ++i) stage_store(R.a[i], st, A_BYTES, rbase + 32 * i);
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) split_store(R.b[i], st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, rbase + 32 * i);
+        for (int i = 0; i < BN / 32; ++i) stage_store(R.b[i], st + NSPLIT * A_BYTES, B_BYTES, rbase + 32 * i);
         if (kb + 2 < nkb) fetch(kb + 2, R);  // refill this register set: in flight for two full iterations
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+            const uint32_t a_hi = smem_u32(st), b_hi = a_hi + NSPLIT * A_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < TC_K / 8; ++ks) {  // UMMA K = 8 tf32 = 32 bytes
+            for (int ks = 0; ks < 4; ++ks) {  // one UMMA k-step = 32 bytes of the K-major row (8 tf32 / 16 bf16)
                 const uint32_t adv = ks * 32;
-                tc_mma_tf32(tmem_base, make_desc(a_hi + adv), make_desc(b_hi + adv), IDESC, (kb | ks) != 0);
-                tc_mma_tf32(tmem_base, make_desc(a_lo + adv), make_desc(b_hi + adv), IDESC, 1);
-                tc_mma_tf32(tmem_base, make_desc(a_hi + adv), make_desc(b_lo + adv), IDESC, 1);
+                if constexpr (MODE == 0) {
+                    const uint32_t a_lo = a_hi + A_BYTES, b_lo = b_hi + B_BYTES;
+                    const int g = kb * 4 + ks;  // global k-step: hi*hi round-robin over accumulators 0..2, corrections into 3
+                    tc_mma_tf32(tmem_base + (uint32_t)((g % 3) * BN), make_desc(a_hi + adv), make_desc(b_hi + adv), IDESC, g >= 3);
+                    tc_mma_tf32(tmem_base + 3u * BN, make_desc(a_lo + adv), make_desc(b_hi + adv), IDESC, g != 0);
+                    tc_mma_tf32(tmem_base + 3u * BN, make_desc(a_hi + adv), make_desc(b_lo + adv), IDESC, 1);
+                } else {
+                    tc_mma_bf16(tmem_base, make_desc(a_hi + adv), make_desc(b_hi + adv), IDESC, (kb | ks) != 0);
+                }
             }
             tc_commit(empty_bar + s);               // frees the stage when these MMAs have read it
-            if (kb == nkb - 1) tc_commit(accum_bar);  // accumulator complete
+            if (kb == nkb - 1) tc_commit(accum_bar);  // accumulators complete
         }
     };
     Regs R0, R1;
@@ -223,38 +302,21 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
         const int64_t grow = row0 + r_local;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
         float mean = 0.f, rs = 1.f;
+        float v[32];
         if (p.gamma) {
             float sm = 0.f;
             for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-                    "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_row32<NACC, BN>(taddr, c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sm += __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                for (int j = 0; j < 32; ++j) sm += v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
             }
             mean = sm / (float)BN;
             float vs = 0.f;
             for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-                    "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_row32<NACC, BN>(taddr, c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float dlt = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - mean;
+                    const float dlt = v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - mean;
                     vs = fmaf(dlt, dlt, vs);
                 }
             }
@@ -263,16 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
         }
         float ss = 0.f, dd = 0.f;
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-                "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr + c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_row32<NACC, BN>(taddr, c0, v);
             float y[32];
             if (p.gamma && p.xhat && grow < p.N) {  // normalised value saved for the backward, 128-bit stores
                 float4* x4 = reinterpret_cast<float4*>(p.xhat + grow * BN + c0);
@@ -280,14 +333,14 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
                 for (int j = 0; j < 32; j += 4) {
                     float q[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) q[u] = (__uint_as_float(v[j + u]) + (p.bias ? __ldg(p.bias + c0 + j + u) : 0.f) - mean) * rs;
+                    for (int u = 0; u < 4; ++u) q[u] = (v[j + u] + (p.bias ? __ldg(p.bias + c0 + j + u) : 0.f) - mean) * rs;
                     x4[j >> 2] = make_float4(q[0], q[1], q[2], q[3]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
-                float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                float t = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
                 if (p.gamma) {
                     const float xh = (t - mean) * rs;
                     t = fmaf(xh, __ldg(p.gamma + c), __ldg(p.beta + c));
@@ -313,16 +366,32 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
 }
 
-static int g_dense_tc = -1;  // -1: read BG_DENSE_TC on first use (default on)
+// 0: off (FFMA kernels only), 1: 3xTF32 (default), 2: bf16 operands.  -1: read BG_DENSE_TC on first use.
+static int g_dense_tc = -1;
+static int dense_tc_mode() {
+    if (g_dense_tc < 0) {
+        const char* e = getenv("BG_DENSE_TC");
+        g_dense_tc = !e ? 1 : (!strcmp(e, "bf16") || !strcmp(e, "2")) ? 2 : (atoi(e) ? 1 : 0);
+    }
+    return g_dense_tc;
+}
+
+template <int BN, int MODE>
+static void launch_dense_tc(const DenseTcParams& p, unsigned grid, cudaStream_t st) {
+    constexpr int smem = TC_STAGES * (MODE ? 1 : 2) * (TC_M * 128 + BN * 128) + 1024 + 64;
+    static bool once = (cudaFuncSetAttribute(dense_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
+    (void)once;
+    launch_k(dense_tc_kernel<BN, MODE>, grid, kThreads, smem, st, p);
+}
 
 // Returns BG_OK if the layer was launched on the tensor-core path, 1 if the shape is not eligible (caller falls back to
 // the FFMA kernel), negative on error.
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st) {
-    if (g_dense_tc < 0) g_dense_tc = getenv("BG_DENSE_TC") ? atoi(getenv("BG_DENSE_TC")) : 1;
-    if (!g_dense_tc) return 1;
+    const int mode = dense_tc_mode();
+    if (!mode) return 1;
     if (a->w_sk != 1 || a->w_so != K) return 1;                 // plain [Cout, K] row-major weights only
     // measured crossover against the FFMA kernel: 128-wide layers from K=128, 64-wide layers from K=256
     if (!((a->Cout == 128 && K >= 128) || (a->Cout == 64 && K >= 256)) || a->N < 128) return 1;
@@ -347,23 +416,21 @@ int dense_tc_try(const BgDense* a, int K, cudaStream_t st) {
     p.out = a->out; p.ld_out = a->ld_out; p.xhat = a->xhat; p.rstd = a->rstd; p.s = a->s; p.d = a->d;
     const unsigned grid = (unsigned)ceil_div(a->N, TC_M);
     if (a->Cout == 128) {
-        constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 128 * 128) + 1024 + 64;
-        static bool once = (cudaFuncSetAttribute(dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
-        (void)once;
-        launch_k(dense_tc_kernel<128>, grid, kThreads, smem, st, p);
+        if (mode == 2) launch_dense_tc<128, 1>(p, grid, st);
+        else launch_dense_tc<128, 0>(p, grid, st);
     } else {
-        constexpr int smem = TC_STAGES * (2 * TC_M * 128 + 2 * 64 * 128) + 1024 + 64;
-        static bool once = (cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
-        (void)once;
-        launch_k(dense_tc_kernel<64>, grid, kThreads, smem, st, p);
+        if (mode == 2) launch_dense_tc<64, 1>(p, grid, st);
+        else launch_dense_tc<64, 0>(p, grid, st);
     }
     return check_launch("bg_dense_fwd(tcgen05)");
 }
 
 }  // namespace bg
 
-extern "C" int bg_set_dense_tc(int32_t on) {
-    const int prev = bg::g_dense_tc;
-    bg::g_dense_tc = on ? 1 : 0;
+// 0 = FFMA kernels only, 1 = tcgen05 3xTF32 (fp32-accurate, default), 2 = tcgen05 bf16 operands (reduced precision).
+// Returns the previous mode.
+extern "C" int bg_set_dense_tc(int32_t mode) {
+    const int prev = bg::dense_tc_mode();
+    bg::g_dense_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
     return prev;
 }

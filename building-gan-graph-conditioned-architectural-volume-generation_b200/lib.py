@@ -196,9 +196,17 @@ def load() -> C.CDLL:
     return _lib
 
 
-def set_dense_tc(on: bool) -> int:
-    """Switch the tcgen05 3xTF32 dense path on/off at run time (default on; BG_DENSE_TC=0 in the environment disables it)."""
-    return load().bg_set_dense_tc(int(bool(on)))
+DENSE_MODES = {"ffma": 0, "tcgen05": 1, "3xtf32": 1, "bf16": 2}
+
+
+def set_dense_tc(mode) -> int:
+    """Dense-layer mode of the 128/64-wide layers, returns the previous one (0/1/2).  False / 0 / "ffma": FP32 FFMA kernels only
+    (strict parity mode, env BG_DENSE_TC=0); True / 1 / "tcgen05": tcgen05 3xTF32, fp32-accurate (default); 2 / "bf16": tcgen05
+    with bf16 operands and fp32 accumulation (reduced precision, env BG_DENSE_TC=bf16; tolerance stated in
+    tests/test_models_gpu.py::test_bf16_dense_mode)."""
+    if isinstance(mode, str):
+        mode = DENSE_MODES[mode.lower()]
+    return load().bg_set_dense_tc(int(mode))
 
 
 def last_error() -> str:

@@ -880,13 +880,12 @@ class _DiscNativeFn(torch.autograd.Function):
         label, score, *tensors = ctx.saved_tensors
         if ctx.lane is not None:  # runs on the lane's stream (autograd: the forward's stream); g_score came from another one
             g_score.record_stream(torch.cuda.current_stream())
-        if ctx.bucket_mode and torch.is_grad_enabled() and ctx.needs_input_grad[6]:
-            # create_graph=True AND the parameters' anchor needs a gradient: this is loss.backward(create_graph=True), not the
-            # WGAN-GP autograd.grad(..., inputs=[interpolated]) (whose anchor needs none).  Bucket mode would silently drop every
-            # parameter gradient of this pass.
-            raise RuntimeError("building_gan_b200: backward(create_graph=True) w.r.t. the parameters is not supported with "
-                               "BG_GRADS=bucket (only input gradients are differentiable a second time, trainer.py:306-312); "
-                               "set BG_GRADS=autograd")
+        # NOTE (BG_GRADS=bucket): a backward that runs under create_graph=True delivers INPUT gradients only - that is the
+        # WGAN-GP ``autograd.grad(score, inputs=[interpolated], create_graph=True)`` of trainer.py:306-312.  It cannot be told
+        # apart here from ``loss.backward(create_graph=True)`` (``ctx.needs_input_grad`` is fixed at forward time and says True
+        # for the parameters' anchor in both cases; a custom Function does not see the engine's pruning), so the latter is
+        # documented as unsupported in this mode (module docstring) instead of being detected: use
+        # BG_GRADS=autograd for it.
         outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training,
                                       (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score,
                                       g_score.contiguous(), label, *tensors)

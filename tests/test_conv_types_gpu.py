@@ -143,7 +143,11 @@ def test_generator_with_conv_type(kind, train):
     ql, qh, qs = oG32b(lb32b, vb32b, z, noise)
     ((ql * w1.float()).sum() + (qh * w2.float()).sum() + (qs * w3.float()).sum()).backward()
     ((logits * w1.float().to(DEV)).sum() + (hard * w2.float().to(DEV)).sum() + (soft * w3.float().to(DEV)).sum()).backward()
-    _grads_close(G, oG, 1e-3, f"generator {kind}", oG32b)
+    # The 1- and 2-channel bottleneck blocks are ill-conditioned: with PyG's U(+-1/sqrt(in)) Linear biases (in = 1, 2 there) the
+    # reference's OWN fp32 arithmetic is 1e-2 of the gradient scale away from fp64 on the GATv2 / GraphConv stacks
+    # (profiles/tools/diag_conv_grads.py prints both), and two correct fp32 implementations differ from each other by a
+    # small multiple of that.  Criterion: 1e-3 of the tensor's scale, or within 8x the fp32 oracle's own error.
+    _grads_close(G, oG, 1e-3, f"generator {kind}", oG32b, env=8.0 if kind != "GATCONV" else 3.0)
 
 
 @pytest.mark.parametrize("kind", KINDS)

@@ -300,6 +300,31 @@ def test_dense_fwd(cin, cout, ln, act):
     assert_close(res["out"], y, 1e-5, f"dense_fwd {cin}->{cout}")
 
 
+@pytest.mark.parametrize("cin,cout", [(128, 128), (268, 128), (524, 128), (256, 64)])
+def test_dense_tensor_core_modes(cin, cout):
+    """The three dense modes of the 128/64-wide layers on the same problem (Linear + LayerNorm + LeakyReLU), against fp64:
+    FFMA and tcgen05 3xTF32 (four TMEM accumulators, fp32 round-to-nearest combine) both hold rel 1e-5 with the tensor-core
+    path within 4x of the FFMA error; bf16 operands / fp32 accumulation: stated tolerance 1e-2 of max magnitude (operands
+    carry 8 mantissa bits: 2^-9 relative rounding each, K random-sign terms)."""
+    n = 1500
+    x, W, b = _rand(n, cin, seed=1), _rand(cout, cin, seed=2, scale=0.2), _rand(cout, seed=3)
+    gamma, beta = _rand(cout, seed=4) * 0.2 + 1, _rand(cout, seed=5) * 0.2
+    y = F.leaky_relu(F.layer_norm(x @ W.t() + b, (cout,), gamma, beta, 1e-5), 0.2)
+    f = lambda t: t.float().to(DEV).contiguous()
+    errs = {}
+    try:
+        for mode in ("ffma", "tcgen05", "bf16"):
+            lib.set_dense_tc(mode)
+            out = lib.dense_fwd([f(x)], f(W), f(b), (f(gamma), f(beta)), 2, save_ln=True)["out"]
+            errs[mode] = float((out.double().cpu() - y).abs().max() / y.abs().max())
+    finally:
+        lib.set_dense_tc("tcgen05")
+    print(f"dense {cin}->{cout}: rel err", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["ffma"] <= 1e-5 and errs["tcgen05"] <= 1e-5
+    assert errs["tcgen05"] <= 4 * errs["ffma"] + 2e-7, errs
+    assert 1e-5 < errs["bf16"] <= 1e-2, errs      # a real reduced-precision mode, inside its stated tolerance
+
+
 def test_dense_segments_gather_att():
     """cat[table[type] | vx | z] @ W^T with attention dots, as the generator's encoder input and a conv `lin`."""
     n = 500

@@ -131,7 +131,7 @@ G_WIDTHS = [64, 32, 16, 8, 4, 2, 1, 2, 4, 8, 16, 32, 64, 128]
 D_WIDTHS = [32, 16, 8, 16, 32, 64]
 
 
-def _grads_close(model, omodel, tol, what, omodel32=None):
+def _grads_close(model, omodel, tol, what, omodel32=None, env=3.0):
     """Every parameter gradient within tol of its own max magnitude; gradients that are ~0 by exact
     cancellation in exact arithmetic (e.g. att_dst when all logits of a row share a sign) are judged
     against the fp32 oracle's own rounding noise / the largest gradient of the model instead."""
@@ -147,7 +147,7 @@ def _grads_close(model, omodel, tol, what, omodel32=None):
         err = float((p.grad.double().cpu() - op.grad).abs().max())
         scale = float(op.grad.abs().max())
         err32 = float((o32[k].grad.double() - op.grad).abs().max()) if k in o32 and o32[k].grad is not None else 0.0
-        if not (err <= tol * scale or err <= 3.0 * err32 or err <= 1e-6 * gmax):
+        if not (err <= tol * scale or err <= env * err32 or err <= 1e-6 * gmax):
             bad.append(f"{k}: abs err {err:.2e}, scale {scale:.2e}, fp32-oracle err {err32:.2e}")
     assert not bad, f"{what}: " + "; ".join(bad)
 
@@ -164,6 +164,34 @@ def test_generator_forward_backward(train, dense):
         _generator_forward_backward(train, 1e-4 if dense == "tcgen05" else 1e-5)
     finally:
         lib.set_dense_tc(True)
+
+
+def test_bf16_dense_mode():
+    """BG_DENSE_TC=bf16 (bg_set_dense_tc(2)): the generator's 128-wide Linear layers with bf16 operands and fp32 accumulation.
+    STATED TOLERANCE of the mode: logits / label_soft within 3e-2 of max magnitude of the fp64 oracle through the 33-layer
+    generator (every other kernel stays fp32); labels agree wherever the oracle's top-2 soft gap exceeds 0.1."""
+    from building_gan_b200 import lib
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
+    n = vb.num_nodes
+    z = torch.randn(1, n, cfg.Z_DIM, generator=torch.Generator().manual_seed(5))
+    noise = -torch.empty(n, 7).exponential_(generator=torch.Generator().manual_seed(6)).log()
+    G.eval(), oG.eval()
+    ologits, ohard, osoft = oG(olb, ovb, z.double(), noise.double())
+    lib.set_dense_tc("bf16")
+    try:
+        with torch.no_grad():
+            logits, hard, soft = G(lb, vb, z.to(DEV), noise.to(DEV))
+    finally:
+        lib.set_dense_tc("tcgen05")
+    with torch.no_grad():
+        l1, _, _ = G(lb, vb, z.to(DEV), noise.to(DEV))
+    e_bf16, e_tc = rel_err(logits, ologits), rel_err(l1, ologits)
+    print(f"generator logits rel err: bf16 mode {e_bf16:.2e}, 3xTF32 mode {e_tc:.2e}")
+    assert e_tc < 1e-4 < e_bf16 <= 3e-2
+    assert rel_err(soft, osoft) <= 3e-2
+    top2 = osoft.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 0.1
+    assert torch.equal(hard.argmax(1).cpu()[safe], ohard.argmax(1)[safe])
 
 
 def _generator_forward_backward(train, fwd_tol):
