@@ -104,13 +104,13 @@ def parity_report(G, D, local_graph, voxel_graph, cfg, step_module, seed: int = 
         with torch.no_grad():
             l32, _, _ = oG32(to_oracle_batch(local_graph, torch.float32), to_oracle_batch(voxel_graph, torch.float32), z, noise)
         out["fp32_oracle_logits_rel"] = rel(l32, ol)
-    # critic loss: both sides draw the mixing factor from the CPU generator under the same seed (trainer.py:298)
+    # critic loss: one float32 draw of the mixing factor from the CPU generator (trainer.py:298), handed to both sides
     hard_in, soft_in = oh.detach().unsqueeze(0), os_.detach().unsqueeze(0)
     D.zero_grad(set_to_none=True), oD.zero_grad(set_to_none=True)
-    torch.manual_seed(seed + 1)
-    o_d = otrainer.discriminator_loss(oD, olb, ovb, hard_in, soft_in, cfg)
-    torch.manual_seed(seed + 1)
-    k_d = step_module.discriminator_loss(D, local_graph, voxel_graph, hard_in.float().to(dev), soft_in.float().to(dev), cfg, rng="cpu")
+    e = torch.rand(n, 1, generator=gen)
+    o_d = otrainer.discriminator_loss(oD, olb, ovb, hard_in, soft_in, cfg, e=e.double())
+    k_d = step_module.discriminator_loss(D, local_graph, voxel_graph, hard_in.float().to(dev), soft_in.float().to(dev), cfg,
+                                         rng="cpu", e=e.to(dev))
     out["d_loss_rel"] = rel(k_d.reshape(1), o_d.reshape(1))
     if gradients:
         o_d.backward(), k_d.backward()
@@ -120,7 +120,12 @@ def parity_report(G, D, local_graph, voxel_graph, cfg, step_module, seed: int = 
     G.zero_grad(set_to_none=True), oG.zero_grad(set_to_none=True)
     ol2, oh2, _ = oG(olb, ovb, z.double(), noise.double())
     kl2, kh2, _ = G(local_graph, voxel_graph, z.to(dev), noise.to(dev))
-    o_g = otrainer.generator_loss(oD, olb, ovb, ol2, oh2.unsqueeze(0), cfg)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)  # int64 one-hot counts / N must come out in the oracle's precision
+    try:
+        o_g = otrainer.generator_loss(oD, olb, ovb, ol2, oh2.unsqueeze(0), cfg)
+    finally:
+        torch.set_default_dtype(prev)
     k_g = step_module.generator_loss(D, local_graph, voxel_graph, kl2, kh2.unsqueeze(0), cfg)
     out["g_loss_rel"] = rel(k_g.reshape(1), o_g.reshape(1))
     if gradients:

@@ -9,29 +9,33 @@ trainer.py:298,470,484).
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
 from torch import Tensor
 
 
-def gradient_penalty(discriminator, local_graph, voxel_graph, label_soft: Tensor, cfg) -> Tensor:
-    """trainer.py:291-316."""
-    e = torch.rand(voxel_graph.types_onehot.shape[0], 1).to(label_soft.device)
+def gradient_penalty(discriminator, local_graph, voxel_graph, label_soft: Tensor, cfg, e: Optional[Tensor] = None) -> Tensor:
+    """trainer.py:291-316.  ``e`` (optional): the mixing factor, injected by parity checks that run this restatement in
+    fp64 (the reference always draws it: ``torch.rand(N, 1)`` on the CPU generator, float32)."""
+    if e is None:
+        e = torch.rand(voxel_graph.types_onehot.shape[0], 1)
+    e = e.to(label_soft.device)
     mixed = (e * voxel_graph.types_onehot + (1 - e) * label_soft.squeeze(0)).requires_grad_(True)
     score = discriminator(local_graph, voxel_graph, mixed.unsqueeze(0))
     (grad,) = torch.autograd.grad(score, mixed, torch.ones_like(score), create_graph=True, only_inputs=True)
     return ((grad.norm(dim=1) - 1) ** 2).mean() * cfg.LAMBDA_GP
 
 
-def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tensor, label_soft: Tensor, cfg) -> Tensor:
+def discriminator_loss(discriminator, local_graph, voxel_graph, label_hard: Tensor, label_soft: Tensor, cfg,
+                       e: Optional[Tensor] = None) -> Tensor:
     """trainer.py:318-332 (label_* carry the leading unsqueeze(0) the trainer adds)."""
     d_real = discriminator(local_graph, voxel_graph, voxel_graph.types_onehot.unsqueeze(0))
     d_fake = discriminator(local_graph, voxel_graph, label_hard)
     if cfg.USE_WGANGP:
         loss = d_fake.mean() - d_real.mean()
-        loss = loss + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg)
+        loss = loss + gradient_penalty(discriminator, local_graph, voxel_graph, label_soft, cfg, e)
         return loss
     return F.binary_cross_entropy(d_fake, torch.zeros_like(d_fake)) + F.binary_cross_entropy(
         d_real, torch.ones_like(d_real)

@@ -149,11 +149,12 @@ def test_aggregation_kernels_large_graphs_natural_dispatch(ngraphs, C):
     assert_close(go, go_ref, 1e-6, "fused go")
     assert_close(gh2, gh_ref, 1e-5, "fused gh")
     assert_close(gsd2, gsd_ref, 1e-5, "fused gsd")
-    # and the GraphNorm backward itself against autograd of the definition in fp64 (per-channel moments over N rows)
+    # and the GraphNorm backward itself against autograd of the definition in fp64 (per-channel moments over N rows), on the
+    # ReLU pattern the kernel took (among 1e7 elements a few pre-activations sit within fp32 rounding of 0 and flip)
     o_r = o.double().requires_grad_()
     mu_r = o_r.mean(0)
     oh_r = o_r - f(alpha).double() * mu_r
-    y = torch.relu(f(w).double() * oh_r / (oh_r.pow(2).mean(0) + 1e-5).sqrt() + f(beta).double())
+    y = (f(w).double() * oh_r / (oh_r.pow(2).mean(0) + 1e-5).sqrt() + f(beta).double()) * (x1 > 0)
     (go64,) = torch.autograd.grad(y, o_r, gx1.double())
     assert_close(go_ref, go64, 2e-5, "graphnorm_bwd go")
 
