@@ -68,6 +68,10 @@ struct GnMomFuse {
 };
 int dense_fwd_moments(const BgDense* a, const GnMomFuse* f, cudaStream_t st);  // f == nullptr: plain bg_dense_fwd
 
+// row-per-thread kernel for the small layers of the latency-bound regime (bg_rowdense.cu): BG_OK when launched, 1 when
+// the shape is not eligible, <0 on error.  seg_off = the BG_MAX_SEG + 1 column offsets of the segmented input.
+int rowdense_try(const BgDense* a, const int* seg_off, int K, const GnMomFuse* mom, cudaStream_t st);
+
 // tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 

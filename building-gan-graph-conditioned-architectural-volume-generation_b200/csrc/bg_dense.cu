@@ -857,6 +857,15 @@ int bg::dense_fwd_moments(const BgDense* a, const GnMomFuse* mom, cudaStream_t s
         const int rc = (a->gate || mom) ? 1 : dense_tc_try(a, p.K, stream);
         if (rc <= 0) return rc;
     }
+    if (mom) {
+        BG_REQUIRE(!rowwise && a->Cout <= 128 && a->ld_out == a->Cout, BG_EINVAL, "dense_fwd_moments: plain product with Cout <= 128 only");
+        BG_REQUIRE(mom->o && mom->x1 && mom->alpha && mom->stats && mom->w && mom->dparams && mom->bstats && mom->counters && mom->partials,
+                   BG_EINVAL, "dense_fwd_moments: null pointer");
+    }
+    {  // small layers in the latency-bound regime: one thread per row (bg_rowdense.cu)
+        const int rc = rowdense_try(a, p.x.off, p.K, mom, stream);
+        if (rc <= 0) return rc;
+    }
     int bn = 8;
     while (bn < a->Cout && bn < 128) bn <<= 1;
     BG_REQUIRE(!a->ln_gamma || bn == a->Cout, BG_EUNSUPPORTED,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "bg_type_scatter_sum_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_fwd": (C.c_int, [C.POINTER(BgDense), _P]),
     "bg_set_dense_tc": (C.c_int, [_I32]),
+    "bg_set_rowdense": (C.c_int, [_I32]),
     "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
     "bg_wgrad_multi_ws": (_SZ, [_I64, _I32, _P, _P]),
@@ -207,6 +208,12 @@ def set_dense_tc(mode) -> int:
     if isinstance(mode, str):
         mode = DENSE_MODES[mode.lower()]
     return load().bg_set_dense_tc(int(mode))
+
+
+def set_rowdense(on: bool) -> bool:
+    """Row-per-thread kernel for the small dense layers of the latency-bound regime on/off (default on, env BG_ROWDENSE);
+    returns the previous setting."""
+    return bool(load().bg_set_rowdense(int(bool(on))))
 
 
 def last_error() -> str:

@@ -124,12 +124,17 @@ typedef struct BgDense {
     float gate_slope;
 } BgDense;
 int bg_dense_fwd(const BgDense* a, void* stream);
-/* 128-wide (K >= 128) and 64-wide (K >= 256) layers with plain row-major weights run on the tensor cores: tcgen05.mma
- * kind::tf32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo), accumulators in TMEM (csrc/bg_dense_tc.cu).  Per-layer error
- * <= 1e-5 of max|y| (the tensor core accumulates with round-toward-zero: ~4e-6 at K=524 against ~1.4e-6 for the FFMA
- * kernel).  bg_set_dense_tc(0) (or BG_DENSE_TC=0) forces the FP32 FFMA kernel everywhere; returns the previous setting
- * (-1 = not yet initialised from the environment). */
-int bg_set_dense_tc(int32_t on);
+/* 128-wide (K >= 128) and 64-wide (K >= 256) layers with plain row-major weights run on the tensor cores: tcgen05.mma with
+ * accumulators in TMEM (csrc/bg_dense_tc.cu).  mode 1 (default): kind::tf32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo) into
+ * four TMEM accumulators combined in fp32 round-to-nearest - fp32-accurate, per-layer error <= 1e-5 of max|y| (measured
+ * 2.4e-7 .. 3.4e-7 for K = 128 .. 524, FFMA kernel: 3.4e-7 .. 7.6e-7).  mode 2 (BG_DENSE_TC=bf16): kind::f16 with bf16
+ * operands, fp32 accumulation - the stated reduced-precision mode, per-layer error <= 1e-2 (measured 2.2e-3 .. 2.5e-3).
+ * mode 0 (BG_DENSE_TC=0): FP32 FFMA kernels everywhere (strict parity mode).  Returns the previous mode. */
+int bg_set_dense_tc(int32_t mode);
+/* Small layers (K <= 128, Cout <= 64) of graphs up to 131072 rows - the latency-bound regime of the training step - run on
+ * a row-per-thread FFMA kernel (csrc/bg_rowdense.cu); 0 (or BG_ROWDENSE=0) keeps them on the tiled kernel.  Same results up
+ * to fp32 summation order inside LayerNorm / the attention dots.  Returns the previous setting. */
+int bg_set_rowdense(int32_t on);
 
 /* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
  * yields the bias gradient as an extra column); deterministic split-N reduction.

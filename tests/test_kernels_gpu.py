@@ -325,6 +325,53 @@ def test_dense_tensor_core_modes(cin, cout):
     assert 1e-5 < errs["bf16"] <= 1e-2, errs      # a real reduced-precision mode, inside its stated tolerance
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1500, 15145])
+def test_rowdense_matches_tiled_kernel_and_oracle(n):
+    """The row-per-thread kernel of the latency-bound regime (csrc/bg_rowdense.cu) against fp64 and against the tiled kernel
+    it replaces there: the discriminator's first layer (cat[table[type] 17 | vx 12 | label 7] -> 64, ReLU: a gathered segment
+    and widths that are not multiples of 4), a LayerNorm layer with saved xhat / rstd, a conv `lin` with attention dots, a
+    gated backward-input product through a column window of W, and 1- / 2-wide layers."""
+    g = torch.Generator().manual_seed(n)
+    f = lambda t: t.float().to(DEV).contiguous()
+    table, typ = _rand(7, 17, seed=1), torch.randint(0, 7, (n,), generator=g)
+    vx, lab = _rand(n, 12, seed=3), _rand(n, 7, seed=4)
+    W0, b0 = _rand(64, 36, seed=5, scale=0.2), _rand(64, seed=6)
+    x64 = _rand(n, 64, seed=7)
+    Wl, bl, gam, bet = _rand(32, 64, seed=8, scale=0.2), _rand(32, seed=9), _rand(32, seed=10) * 0.2 + 1, _rand(32, seed=11) * 0.2
+    Wc, a_s, a_d = _rand(16, 64, seed=12, scale=0.2), _rand(16, seed=13), _rand(16, seed=14)
+    gz, Wt, gate = _rand(n, 32, seed=15), _rand(32, 100, seed=16, scale=0.2), _rand(n, 48, seed=17)
+    x2, W21 = _rand(n, 2, seed=18), _rand(1, 2, seed=19)
+    ref = {
+        "first": torch.relu(torch.cat([table[typ], vx, lab], 1) @ W0.t() + b0),
+        "ln": F.leaky_relu(F.layer_norm(x64 @ Wl.t() + bl, (32,), gam, bet, 1e-5), 0.2),
+        "lin": x64 @ Wc.t(),
+        "dgrad": (gz @ Wt[:, 20:68]) * (gate > 0),
+        "narrow": x2 @ W21.t(),
+    }
+    got = {}
+    try:
+        for mode in (True, False):
+            lib.set_rowdense(mode)
+            r = {}
+            r["first"] = lib.dense_fwd([(f(table), typ.to(torch.int32).to(DEV)), f(vx), f(lab)], f(W0), f(b0), None, 1)["out"]
+            res = lib.dense_fwd([f(x64)], f(Wl), f(bl), (f(gam), f(bet)), 2, save_ln=True)
+            r["ln"], r["xhat"], r["rstd"] = res["out"], res["xhat"], res["rstd"]
+            res = lib.dense_fwd([f(x64)], f(Wc), att=(f(a_s), f(a_d)))
+            r["lin"], r["s"], r["d"] = res["out"], res["s"], res["d"]
+            r["dgrad"] = lib.dense_fwd([f(gz)], f(Wt), transposed=True, cols=(20, 68), gate=f(gate))["out"]
+            r["narrow"] = lib.dense_fwd([f(x2)], f(W21))["out"]
+            got[mode] = r
+    finally:
+        lib.set_rowdense(True)
+    for mode in (True, False):
+        for k in ref:
+            assert_close(got[mode][k], ref[k], 1e-5, f"{k} (rowdense={mode}, n={n})")
+        assert_close(got[mode]["s"], ref["lin"] @ a_s, 1e-5, "s")
+        assert_close(got[mode]["d"], ref["lin"] @ a_d, 1e-5, "d")
+    for k in ("xhat", "rstd"):
+        assert_close(got[True][k], got[False][k].double(), 1e-5, k)
+
+
 def test_dense_segments_gather_att():
     """cat[table[type] | vx | z] @ W^T with attention dots, as the generator's encoder input and a conv `lin`."""
     n = 500
