@@ -72,6 +72,9 @@ int dense_fwd_moments(const BgDense* a, const GnMomFuse* f, cudaStream_t st);  /
 // the shape is not eligible, <0 on error.  seg_off = the BG_MAX_SEG + 1 column offsets of the segmented input.
 int rowdense_try(const BgDense* a, const int* seg_off, int K, const GnMomFuse* mom, cudaStream_t st);
 
+// warp-MMA 3xTF32 kernel for small single-segment layers (bg_dense_mma.cu); same return convention
+int dense_mma_try(const BgDense* a, int K, const GnMomFuse* mom, cudaStream_t st);
+
 // tcgen05 3xTF32 dense path (bg_dense_tc.cu): BG_OK when launched, 1 when the shape is not eligible, <0 on error
 int dense_tc_try(const BgDense* a, int K, cudaStream_t st);
 

@@ -862,8 +862,10 @@ int bg::dense_fwd_moments(const BgDense* a, const GnMomFuse* mom, cudaStream_t s
         BG_REQUIRE(mom->o && mom->x1 && mom->alpha && mom->stats && mom->w && mom->dparams && mom->bstats && mom->counters && mom->partials,
                    BG_EINVAL, "dense_fwd_moments: null pointer");
     }
-    {  // small layers in the latency-bound regime: one thread per row (bg_rowdense.cu)
-        const int rc = rowdense_try(a, p.x.off, p.K, mom, stream);
+    {  // small layers in the latency-bound regime: warp-MMA 3xTF32 (bg_dense_mma.cu), very narrow ones row-per-thread (bg_rowdense.cu)
+        int rc = dense_mma_try(a, p.K, mom, stream);
+        if (rc <= 0) return rc;
+        rc = rowdense_try(a, p.x.off, p.K, mom, stream);
         if (rc <= 0) return rc;
     }
     int bn = 8;

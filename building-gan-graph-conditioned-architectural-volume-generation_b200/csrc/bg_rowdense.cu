@@ -57,56 +57,121 @@ __global__ void __launch_bounds__(RD_T) rowdense_kernel(const RdParams p) {
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * RD_T;
 
-    // ---- stage W: Ws[k][c] = W[c * w_so + k * w_sk] (zero beyond Cout)
-    if (p.w_sk == 1) {
-        for (int idx = tid; idx < COUT * K; idx += RD_T) {
-            const int c = idx / K, k = idx - c * K;
-            Ws[k * WSTR + c] = c < p.Cout ? __ldg(p.W + (int64_t)c * p.w_so + k) : 0.f;
-        }
-    } else {
-        for (int idx = tid; idx < COUT * K; idx += RD_T) {
-            const int k = idx / COUT, c = idx - k * COUT;
-            Ws[k * WSTR + c] = c < p.Cout ? __ldg(p.W + (int64_t)c * p.w_so + (int64_t)k * p.w_sk) : 0.f;
-        }
-    }
-    // ---- stage X: thread -> fixed column kc = tid % KP (KP = K rounded up to a power of two <= RD_T), rows tid / KP + i * RPI
+    // ---- stage W: Ws[k][c] = W[c * w_so + k * w_sk] (zero beyond Cout).  Loads are issued in register batches (all of a
+    // batch in flight before the first shared store) so the staging costs one or two L2 round trips, not one per element.
     {
-        int KP = 1;
-        while (KP < K) KP <<= 1;
-        const int kc = tid % KP, RPI = RD_T / KP, r0 = tid / KP;
-        const float* base = nullptr;
-        const int32_t* gather = nullptr;
-        int ld = 0;
-        bool ones = false;
-        if (kc < K) {
+        const bool rowmajor = p.w_sk == 1;
+        const int inner = rowmajor ? K : p.Cout;        // contiguous run length in W
+        const int outer = rowmajor ? p.Cout : K;        // number of runs
+        const int64_t run_ld = rowmajor ? p.w_so : p.w_sk;
+        const bool vec = (inner & 3) == 0 && (run_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0;
+        if (vec) {
+            const int i4 = inner >> 2, total = outer * i4;
+            for (int base = 0; base < total; base += 8 * RD_T) {
+                float4 v[8];
 #pragma unroll
-            for (int q = 0; q < BG_MAX_SEG; ++q)
-                if (q < p.nseg && kc >= p.off[q] && kc < p.off[q + 1]) {
-                    ones = p.seg[q].ptr == nullptr;
-                    base = p.seg[q].ptr ? p.seg[q].ptr + (kc - p.off[q]) : nullptr;
-                    gather = p.seg[q].gather;
-                    ld = p.seg[q].ld;
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < total) v[u] = __ldg(reinterpret_cast<const float4*>(p.W + (int64_t)(idx / i4) * run_ld) + (idx % i4));
                 }
-            if (gather) {  // two dependent loads per element: issue all index loads first, then all value loads
-                for (int i0 = 0; i0 < KP; i0 += 8) {
-                    int gi[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    if (idx < total) {
+                        const int o = idx / i4, i = (idx % i4) * 4;
+                        if (rowmajor) {  // o = output column c, i = k
+                            Ws[(i + 0) * WSTR + o] = v[u].x;
+                            Ws[(i + 1) * WSTR + o] = v[u].y;
+                            Ws[(i + 2) * WSTR + o] = v[u].z;
+                            Ws[(i + 3) * WSTR + o] = v[u].w;
+                        } else {         // o = k, i = output column c
+                            *reinterpret_cast<float4*>(Ws + o * WSTR + i) = v[u];
+                        }
+                    }
+                }
+            }
+        } else {
+            const int total = outer * inner;
+            for (int base = 0; base < total; base += 16 * RD_T) {
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    v[u] = idx < total ? __ldg(p.W + (int64_t)(idx / inner) * run_ld + (idx % inner)) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    if (idx < total) {
+                        const int o = idx / inner, i = idx % inner;
+                        Ws[rowmajor ? i * WSTR + o : o * WSTR + i] = v[u];
+                    }
+                }
+            }
+        }
+        // zero the padded output columns [Cout, COUT)
+        if (p.Cout < COUT)
+            for (int idx = tid; idx < K * (COUT - p.Cout); idx += RD_T) {
+                const int k = idx / (COUT - p.Cout), c = p.Cout + idx % (COUT - p.Cout);
+                Ws[k * WSTR + c] = 0.f;
+            }
+    }
+    // ---- stage X
+    {
+        const BgSeg& s0 = p.seg[0];
+        const bool flat = p.nseg == 1 && s0.ptr && !s0.gather && (K & 3) == 0 && (s0.ld & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(s0.ptr) & 15) == 0;
+        if (flat) {  // one plain segment: the tile is RD_T rows of K/4 float4, up to 16 per thread in flight at once
+            const int k4 = K >> 2, total = RD_T * k4;
+            for (int base = 0; base < total; base += 16 * RD_T) {
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    const int r = idx / k4;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < total && row0 + r < p.N) v[u] = __ldg(reinterpret_cast<const float4*>(s0.ptr + (row0 + r) * s0.ld) + (idx % k4));
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * RD_T + tid;
+                    if (idx < total) {
+                        float* dst = Xs + (idx / k4) * KS + (idx % k4) * 4;
+                        dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+                    }
+                }
+            }
+        } else {  // general: thread -> fixed column kc = tid % KP (segment / gather resolved once), rows r0 + i * RPI
+            int KP = 1;
+            while (KP < K) KP <<= 1;
+            const int kc = tid % KP, RPI = RD_T / KP, r0 = tid / KP;
+            const float* base = nullptr;
+            const int32_t* gather = nullptr;
+            int ld = 0;
+            bool ones = false;
+            if (kc < K) {
+#pragma unroll
+                for (int q = 0; q < BG_MAX_SEG; ++q)
+                    if (q < p.nseg && kc >= p.off[q] && kc < p.off[q + 1]) {
+                        ones = p.seg[q].ptr == nullptr;
+                        base = p.seg[q].ptr ? p.seg[q].ptr + (kc - p.off[q]) : nullptr;
+                        gather = p.seg[q].gather;
+                        ld = p.seg[q].ld;
+                    }
+                for (int i0 = 0; i0 < KP; i0 += 16) {
+                    int64_t gi[16];
+                    float v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
                         const int64_t gr = row0 + r0 + (int64_t)(i0 + u) * RPI;
-                        gi[u] = (i0 + u < KP && gr < p.N) ? __ldg(gather + gr) : -1;
+                        gi[u] = (i0 + u < KP && gr < p.N) ? (gather ? (int64_t)__ldg(gather + gr) : gr) : -1;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (i0 + u < KP) Xs[(r0 + (i0 + u) * RPI) * KS + kc] = gi[u] >= 0 ? __ldg(base + (int64_t)gi[u] * ld) : 0.f;
-                }
-            } else {
-#pragma unroll 8
-                for (int i = 0; i < KP; ++i) {
-                    const int r = r0 + i * RPI;
-                    const int64_t gr = row0 + r;
-                    float v = 0.f;
-                    if (gr < p.N) v = base ? __ldg(base + gr * ld) : (ones ? 1.f : 0.f);
-                    Xs[r * KS + kc] = v;
+                    for (int u = 0; u < 16; ++u) v[u] = gi[u] < 0 ? 0.f : (base ? __ldg(base + gi[u] * ld) : (ones ? 1.f : 0.f));
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (i0 + u < KP) Xs[(r0 + (i0 + u) * RPI) * KS + kc] = v[u];
                 }
             }
         }
@@ -292,7 +357,9 @@ static void rd_launch(const RdParams& p, bool mom, unsigned grid, size_t smem, c
 int rowdense_try(const BgDense* a, const int* seg_off, int K, const GnMomFuse* mom, cudaStream_t st) {
     if (g_rowdense < 0) g_rowdense = getenv("BG_ROWDENSE") ? atoi(getenv("BG_ROWDENSE")) : 1;
     if (!g_rowdense) return 1;
-    if (a->N > RD_MAX_N || K > 128 || K < 1 || a->Cout > 64) return 1;
+    // measured against the tiled kernel on the dependency chain (profiles/r02_summary.md): ahead only for very narrow layers
+    // (the 1/2/4-channel bottleneck blocks, the critic's 8 -> 1 score layer); BG_ROWDENSE=2 lifts the limit (K <= 128, Cout <= 64)
+    if (a->N > RD_MAX_N || K < 1 || (g_rowdense == 2 ? (K > 128 || a->Cout > 64) : (K > 16 || a->Cout > 8))) return 1;
     int cp = 4;
     while (cp < a->Cout) cp <<= 1;
     if (a->ln_gamma && cp != a->Cout) return 1;
@@ -331,6 +398,6 @@ int rowdense_try(const BgDense* a, const int* seg_off, int K, const GnMomFuse* m
 extern "C" int bg_set_rowdense(int32_t on) {
     if (bg::g_rowdense < 0) bg::g_rowdense = getenv("BG_ROWDENSE") ? atoi(getenv("BG_ROWDENSE")) : 1;
     const int prev = bg::g_rowdense;
-    bg::g_rowdense = on ? 1 : 0;
+    bg::g_rowdense = on < 0 ? 0 : (on > 2 ? 2 : on);
     return prev;
 }

@@ -78,6 +78,7 @@ SIGNATURES = {
     "bg_dense_fwd": (C.c_int, [C.POINTER(BgDense), _P]),
     "bg_set_dense_tc": (C.c_int, [_I32]),
     "bg_set_rowdense": (C.c_int, [_I32]),
+    "bg_set_dense_mma": (C.c_int, [_I32]),
     "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
     "bg_wgrad_multi_ws": (_SZ, [_I64, _I32, _P, _P]),
@@ -210,10 +211,15 @@ def set_dense_tc(mode) -> int:
     return load().bg_set_dense_tc(int(mode))
 
 
-def set_rowdense(on: bool) -> bool:
-    """Row-per-thread kernel for the small dense layers of the latency-bound regime on/off (default on, env BG_ROWDENSE);
-    returns the previous setting."""
-    return bool(load().bg_set_rowdense(int(bool(on))))
+def set_rowdense(on) -> int:
+    """Row-per-thread kernel for the very narrow dense layers of the latency-bound regime: 0 off, 1 on (default, env
+    BG_ROWDENSE), 2 = also for every layer up to K 128 / Cout 64; returns the previous setting."""
+    return load().bg_set_rowdense(int(on))
+
+
+def set_dense_mma(on: bool) -> bool:
+    """Warp-MMA 3xTF32 kernel for the small single-segment dense layers on/off (default on, env BG_DENSE_MMA)."""
+    return bool(load().bg_set_dense_mma(int(bool(on))))
 
 
 def last_error() -> str:

@@ -132,9 +132,15 @@ int bg_dense_fwd(const BgDense* a, void* stream);
  * mode 0 (BG_DENSE_TC=0): FP32 FFMA kernels everywhere (strict parity mode).  Returns the previous mode. */
 int bg_set_dense_tc(int32_t mode);
 /* Small layers (K <= 128, Cout <= 64) of graphs up to 131072 rows - the latency-bound regime of the training step - run on
- * a row-per-thread FFMA kernel (csrc/bg_rowdense.cu); 0 (or BG_ROWDENSE=0) keeps them on the tiled kernel.  Same results up
+ * a row-per-thread FFMA kernel (csrc/bg_rowdense.cu) - by default only the very narrow ones (K <= 16, Cout <= 8: the 1/2/4-channel
+ * bottleneck blocks, the critic's 8 -> 1 score layer), 2 lifts that limit; 0 (or BG_ROWDENSE=0) keeps them on the tiled kernel.  Same results up
  * to fp32 summation order inside LayerNorm / the attention dots.  Returns the previous setting. */
 int bg_set_rowdense(int32_t on);
+/* Single-segment layers with K in {8,16,...,128}, Cout in {8,16,32,64} of graphs up to 131072 rows run on a warp-level
+ * tensor-core kernel (mma.sync m16n8k8, 3xTF32 split with separate main / correction accumulators: fp32-accurate,
+ * csrc/bg_dense_mma.cu): these launches are instruction-issue bound, one MMA replaces 32 warp-FFMAs.  0 (or BG_DENSE_MMA=0)
+ * switches it off.  Returns the previous setting. */
+int bg_set_dense_mma(int32_t on);
 
 /* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
  * yields the bias gradient as an extra column); deterministic split-N reduction.

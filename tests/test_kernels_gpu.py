@@ -350,8 +350,9 @@ def test_rowdense_matches_tiled_kernel_and_oracle(n):
     }
     got = {}
     try:
+        lib.set_dense_mma(False)  # this test compares the row-per-thread kernel (mode 2: every eligible shape) with the tiled one
         for mode in (True, False):
-            lib.set_rowdense(mode)
+            lib.set_rowdense(2 if mode else 0)
             r = {}
             r["first"] = lib.dense_fwd([(f(table), typ.to(torch.int32).to(DEV)), f(vx), f(lab)], f(W0), f(b0), None, 1)["out"]
             res = lib.dense_fwd([f(x64)], f(Wl), f(bl), (f(gam), f(bet)), 2, save_ln=True)
@@ -362,7 +363,8 @@ def test_rowdense_matches_tiled_kernel_and_oracle(n):
             r["narrow"] = lib.dense_fwd([f(x2)], f(W21))["out"]
             got[mode] = r
     finally:
-        lib.set_rowdense(True)
+        lib.set_rowdense(1)
+        lib.set_dense_mma(True)
     for mode in (True, False):
         for k in ref:
             assert_close(got[mode][k], ref[k], 1e-5, f"{k} (rowdense={mode}, n={n})")
@@ -370,6 +372,41 @@ def test_rowdense_matches_tiled_kernel_and_oracle(n):
         assert_close(got[mode]["d"], ref["lin"] @ a_d, 1e-5, "d")
     for k in ("xhat", "rstd"):
         assert_close(got[True][k], got[False][k].double(), 1e-5, k)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 129, 1500, 15145])
+@pytest.mark.parametrize("k,c", [(8, 8), (16, 8), (8, 16), (32, 16), (64, 32), (64, 64), (128, 64), (24, 32)])
+def test_dense_mma_kernel(n, k, c):
+    """The warp-MMA 3xTF32 kernel of the small single-segment layers (csrc/bg_dense_mma.cu) against fp64, rel 1e-5: plain
+    product with attention dots (a conv `lin`), bias + LayerNorm + LeakyReLU with the saved xhat / rstd, bias + ReLU, and the
+    gated backward-input product through transposed weights; and against the tiled FFMA kernel with the MMA path off."""
+    f = lambda t: t.float().to(DEV).contiguous()
+    x, W, b = _rand(n, k, seed=1), _rand(c, k, seed=2, scale=0.3), _rand(c, seed=3)
+    gam, bet, a_s, a_d = _rand(c, seed=4) * 0.2 + 1, _rand(c, seed=5) * 0.2, _rand(c, seed=6), _rand(c, seed=7)
+    gz, gate = _rand(n, c, seed=8), _rand(n, k, seed=9)
+    lin = x @ W.t()
+    pre = lin + b
+    ln = F.layer_norm(pre, (c,), gam, bet, 1e-5)
+    ref = {"lin": lin, "s": lin @ a_s, "d": lin @ a_d, "ln": F.leaky_relu(ln, 0.2), "relu": torch.relu(pre),
+           "xhat": (pre - pre.mean(1, keepdim=True)) / (pre.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt(),
+           "dgrad": (gz @ W) * torch.where(gate > 0, 1.0, 0.2)}
+    got = {}
+    try:
+        for on in (True, False):
+            lib.set_dense_mma(on)
+            r = {}
+            res = lib.dense_fwd([f(x)], f(W), att=(f(a_s), f(a_d)))
+            r["lin"], r["s"], r["d"] = res["out"], res["s"], res["d"]
+            res = lib.dense_fwd([f(x)], f(W), f(b), (f(gam), f(bet)), 2, save_ln=True)
+            r["ln"], r["xhat"] = res["out"], res["xhat"]
+            r["relu"] = lib.dense_fwd([f(x)], f(W), f(b), None, 1)["out"]
+            r["dgrad"] = lib.dense_fwd([f(gz)], f(W), transposed=True, gate=f(gate), gate_slope=0.2)["out"]
+            got[on] = r
+    finally:
+        lib.set_dense_mma(True)
+    for on in (True, False):
+        for key, want in ref.items():
+            assert_close(got[on][key], want, 1e-5, f"{key} {k}->{c} n={n} mma={on}")
 
 
 def test_dense_segments_gather_att():
