@@ -18,9 +18,11 @@
 //     t+4, i.e. the k index inside a k-step is permuted (logical t <-> physical 2t, logical t+4 <-> physical 2t+1);
 //   B (8 x 8 per k-step and n-tile) is staged once per CTA in shared memory IN FRAGMENT ORDER with the same permutation
 //     and already split into (hi, lo) TF32 halves: one conflict-free LDS.64 per fragment register;
-//   3xTF32: a = a_hi + a_lo (cvt.rna), acc_main += a_hi b_hi, acc_corr += a_lo b_hi + a_hi b_lo; the correction terms get
-//     their own accumulator (they are 2^-11 of the result, their roundings vanish) and K <= 128 keeps the main chain at
-//     <= 16 accumulations; out = acc_main + acc_corr in fp32.
+//   3xTF32: a = a_hi + a_lo (cvt.rna: |a_lo| <= 2^-12 |a|, and rounding a_lo itself to TF32 loses <= 2^-24 |a| - fp32-level),
+//     acc_main += a_hi b_hi, acc_corr += a_lo b_hi + a_hi b_lo.  The tensor core accumulates with truncation, one rounding per
+//     k-step, biased toward zero: the hi*hi products alternate between TWO main accumulators (even / odd k-steps: <= 8
+//     roundings each at K = 128, on half the magnitude) and the correction terms get their own (they are 2^-12 of the result,
+//     their roundings vanish); out = (main0 + main1) + corr in fp32 round-to-nearest.
 //   Epilogue on the C fragment (rows g, g+8; columns 8 nt + 2t, +1): bias, LayerNorm (row sums over the quad: two
 //     shuffles), activation, attention dots, the fused activation-backward gate, saved xhat / rstd, float2 stores (a quad
 //     writes one 32-byte sector per row and n-tile), and the optional GraphNorm-backward column moments of the block below
@@ -125,11 +127,11 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     }
     __syncthreads();
 
-    float cm[NT][4], cc[NT][4];
+    float cm[NT][4], cn[NT][4], cc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cm[nt][i] = cc[nt][i] = 0.f;
+        for (int i = 0; i < 4; ++i) cm[nt][i] = cn[nt][i] = cc[nt][i] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < KSM; ++ks) {
         if (ks < KS) {
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
                 const float2 b0 = wf[nt * 64], b1 = wf[nt * 64 + 32];
                 const uint32_t b0h = __float_as_uint(b0.x), b0l = __float_as_uint(b0.y);
                 const uint32_t b1h = __float_as_uint(b1.x), b1l = __float_as_uint(b1.y);
-                mma_tf32(cm[nt], ah, b0h, b1h);
+                if (ks & 1) mma_tf32(cn[nt], ah, b0h, b1h);
+                else mma_tf32(cm[nt], ah, b0h, b1h);
                 mma_tf32(cc[nt], al, b0h, b1h);
                 mma_tf32(cc[nt], ah, b0l, b1l);
             }
@@ -165,10 +168,10 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
             b0 = bv.x;
             b1 = bv.y;
         }
-        y[nt][0] = cm[nt][0] + cc[nt][0] + b0;
-        y[nt][1] = cm[nt][1] + cc[nt][1] + b1;
-        y[nt][2] = cm[nt][2] + cc[nt][2] + b0;
-        y[nt][3] = cm[nt][3] + cc[nt][3] + b1;
+        y[nt][0] = (cm[nt][0] + cn[nt][0]) + cc[nt][0] + b0;
+        y[nt][1] = (cm[nt][1] + cn[nt][1]) + cc[nt][1] + b1;
+        y[nt][2] = (cm[nt][2] + cn[nt][2]) + cc[nt][2] + b0;
+        y[nt][3] = (cm[nt][3] + cn[nt][3]) + cc[nt][3] + b1;
     }
     if (p.gamma) {  // LayerNorm over the COUT columns of each row (eps = 1e-5): row sums over the quad
         float sa = 0.f, sb = 0.f;

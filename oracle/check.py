@@ -55,31 +55,36 @@ def oracle_twins(G, D, cfg, dtype=torch.float64):
 
 
 def _worst_grad(model, omodel, omodel32=None) -> Dict[str, object]:
-    """Worst parameter-gradient error of a model.  Per tensor: max|err| / max(max|ref grad|, 1e-3 gmax), gmax = the model's
-    largest reference gradient - the absolute error of ANY fp32 evaluation scales with the magnitudes upstream, so tensors
-    whose own gradient is three orders below gmax (exact-cancellation gradients: a conv bias in front of a GraphNorm with
-    mean_scale = 1, weight columns that only ever see zero inputs) are judged on that absolute scale.  With ``omodel32`` (the
-    same oracle evaluated in fp32 = the reference's own arithmetic) also the error as a multiple of ITS error."""
+    """Parameter-gradient error of a model against the fp64 oracle.
+    ``grad_rel_l2``  || g - g_ref ||_2 / || g_ref ||_2 over ALL parameters concatenated (the error of the update direction).
+    ``worst_grad_rel``  worst tensor: max|err| / max(max|ref grad|, 1e-2 gmax), gmax = the model's largest reference gradient:
+        the absolute error of any fp32 evaluation scales with the magnitudes upstream, so tensors whose own gradient is two
+        orders below gmax (exact-cancellation gradients: a conv bias in front of a GraphNorm, weight columns that only ever
+        multiply zero inputs) are judged on that absolute scale.
+    With ``omodel32`` (the same oracle in fp32 = the reference's own arithmetic) also the fp32 oracle's own figures."""
     gmax = max(float(p.grad.abs().max()) for p in omodel.parameters() if p.grad is not None)
     o32 = dict(omodel32.named_parameters()) if omodel32 is not None else {}
-    worst, name, over, over_name = 0.0, "", 0.0, ""
+    worst, name, w32 = 0.0, "", 0.0
+    num = den = num32 = 0.0
     for (k, p), (_, op) in zip(model.named_parameters(), omodel.named_parameters()):
         if op.grad is None:
             continue
         if p.grad is None:
-            return {"worst_grad_rel": float("inf"), "worst_grad_param": k}
-        err = float((p.grad.detach().double().cpu() - op.grad).abs().max())
-        e = err / max(float(op.grad.abs().max()), 1e-3 * gmax)
+            return {"worst_grad_rel": float("inf"), "worst_grad_param": k, "grad_rel_l2": float("inf")}
+        diff = p.grad.detach().double().cpu() - op.grad
+        num += float(diff.pow(2).sum())
+        den += float(op.grad.pow(2).sum())
+        scale = max(float(op.grad.abs().max()), 1e-2 * gmax)
+        e = float(diff.abs().max()) / scale
         if e > worst:
             worst, name = e, k
         if k in o32 and o32[k].grad is not None:
-            e32 = float((o32[k].grad.double() - op.grad).abs().max())
-            r = err / max(e32, 1e-7 * gmax)
-            if r > over:
-                over, over_name = r, k
-    out = {"worst_grad_rel": worst, "worst_grad_param": name}
+            d32 = o32[k].grad.double() - op.grad
+            num32 += float(d32.pow(2).sum())
+            w32 = max(w32, float(d32.abs().max()) / scale)
+    out = {"worst_grad_rel": worst, "worst_grad_param": name, "grad_rel_l2": (num / max(den, 1e-300)) ** 0.5}
     if o32:
-        out["over_fp32_oracle"], out["over_fp32_oracle_param"] = over, over_name
+        out["fp32_oracle_worst_grad_rel"], out["fp32_oracle_grad_rel_l2"] = w32, (num32 / max(den, 1e-300)) ** 0.5
     return out
 
 
@@ -131,9 +136,9 @@ def parity_report(G, D, local_graph, voxel_graph, cfg, step_module, seed: int = 
         if envelope:  # the same loss in the reference's own fp32 arithmetic
             otrainer.discriminator_loss(oD32, olb32, ovb32, hard_in.float(), soft_in.float(), cfg, e=e).backward()
         g = _worst_grad(D, oD, oD32)
-        out["d_worst_grad_rel"], out["d_worst_grad_param"] = g["worst_grad_rel"], g["worst_grad_param"]
+        out["d_worst_grad_rel"], out["d_worst_grad_param"], out["d_grad_rel_l2"] = g["worst_grad_rel"], g["worst_grad_param"], g["grad_rel_l2"]
         if envelope:
-            out["d_grad_err_over_fp32_oracle_err"] = g["over_fp32_oracle"]
+            out["fp32_oracle_d_worst_grad_rel"], out["fp32_oracle_d_grad_rel_l2"] = g["fp32_oracle_worst_grad_rel"], g["fp32_oracle_grad_rel_l2"]
     # generator loss through the (updated-gradient-free) critic
     G.zero_grad(set_to_none=True), oG.zero_grad(set_to_none=True)
     ol2, oh2, _ = oG(olb, ovb, z.double(), noise.double())
@@ -153,12 +158,13 @@ def parity_report(G, D, local_graph, voxel_graph, cfg, step_module, seed: int = 
             l32b, h32b, _ = oG32(olb32, ovb32, z, noise)
             otrainer.generator_loss(oD32, olb32, ovb32, l32b, h32b.unsqueeze(0), cfg).backward()
         g = _worst_grad(G, oG, oG32)
-        out["g_worst_grad_rel"], out["g_worst_grad_param"] = g["worst_grad_rel"], g["worst_grad_param"]
+        out["g_worst_grad_rel"], out["g_worst_grad_param"], out["g_grad_rel_l2"] = g["worst_grad_rel"], g["worst_grad_param"], g["grad_rel_l2"]
         if envelope:
-            out["g_grad_err_over_fp32_oracle_err"] = g["over_fp32_oracle"]
+            out["fp32_oracle_g_worst_grad_rel"], out["fp32_oracle_g_grad_rel_l2"] = g["fp32_oracle_worst_grad_rel"], g["fp32_oracle_grad_rel_l2"]
         out["worst_grad_rel"] = max(out["d_worst_grad_rel"], out["g_worst_grad_rel"])
     G.zero_grad(set_to_none=True), D.zero_grad(set_to_none=True)
     G.train(was[0]), D.train(was[1])
-    out["grad_norm"] = ("per tensor max|err| / max(max|ref grad|, 1e-3 x the model's largest gradient); *_over_fp32_oracle_err: "
-                        "worst ratio to the error of the reference's own fp32 arithmetic")
+    out["grad_norm"] = ("*_grad_rel_l2: ||g - ref||_2 / ||ref||_2 over all parameters; *_worst_grad_rel: worst tensor, max|err| / "
+                        "max(max|ref grad|, 1e-2 x the model's largest gradient); fp32_oracle_*: the reference's own fp32 arithmetic "
+                        "measured the same way")
     return {k_: (round(v, 10) if isinstance(v, float) else v) for k_, v in out.items()}

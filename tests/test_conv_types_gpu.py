@@ -149,7 +149,10 @@ def test_generator_with_conv_type(kind, train):
     ql, qh, qs = oG32b(lb32b, vb32b, z, noise)
     ((ql * w1.float()).sum() + (qh * w2.float()).sum() + (qs * w3.float()).sum()).backward()
     ((logits * w1.float().to(DEV)).sum() + (hard * w2.float().to(DEV)).sum() + (soft * w3.float().to(DEV)).sum()).backward()
-    _grads_close(G, oG, 1e-3, f"generator {kind}", oG32b)
+    # GATv2 applies a LeakyReLU to x_l[j] + x_r[i] per EDGE inside the attention; that pattern is not synced with the oracle, and
+    # one site within rounding distance of the kink landing on the other side moves a gradient sum by O(1/N) of the largest
+    # gradient - lin_r / att only receive gradient through those sites - hence the absolute floor for that conv type.
+    _grads_close(G, oG, 1e-3, f"generator {kind}", oG32b, floor=3e-5 if kind == "GATV2CONV" else 1e-6)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -199,7 +202,7 @@ def test_discriminator_and_gradient_penalty_with_conv_type(kind, train):
     ogp.backward()
     ogp32.backward()
     kgp.backward()
-    _grads_close(D, oD, 2e-4, f"gradient-penalty param grads {kind}", oD32b)
+    _grads_close(D, oD, 2e-4, f"gradient-penalty param grads {kind}", oD32b, floor=3e-5 if kind == "GATV2CONV" else 1e-6)
 
 
 def test_graphconv_refuses_input_self_loops():

@@ -66,7 +66,13 @@ def test_batch32_model_parity(dense):
         assert r["label_soft_rel"] <= fwd_tol, r
         assert r["labels_differ_outside_ties"] == 0, r
         assert r["d_loss_rel"] <= fwd_tol and r["g_loss_rel"] <= max(fwd_tol, 2e-4 * (r["labels_differ_at_ties"] > 0)), r
-        assert r["d_worst_grad_rel"] <= 1e-3 and r["g_worst_grad_rel"] <= 2e-3, r
+        # gradients: error of the whole update direction (l2 over all parameters) and the worst single tensor; next to the
+        # tolerance the reference's OWN fp32 arithmetic is measured the same way (fp32_oracle_*): a correct fp32
+        # implementation cannot be asked to sit far inside that envelope
+        assert r["d_grad_rel_l2"] <= max(2e-4, 4 * r["fp32_oracle_d_grad_rel_l2"]), r
+        assert r["g_grad_rel_l2"] <= max(1e-3, 4 * r["fp32_oracle_g_grad_rel_l2"]), r
+        assert r["d_worst_grad_rel"] <= max(1e-3, 4 * r["fp32_oracle_d_worst_grad_rel"]), r
+        assert r["g_worst_grad_rel"] <= max(2e-3, 4 * r["fp32_oracle_g_worst_grad_rel"]), r
     finally:
         lib.set_dense_tc(True)
 
