@@ -118,7 +118,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline int reduce_splits(int64_t N, int rows_per_cta_iter) {
     int64_t want = ceil_div(N, (int64_t)rows_per_cta_iter * 4);
     if (want < 1) want = 1;
-    if (want > 2 * kSMs) want = 2 * kSMs;
+    // latency-bound sizes: at most one CTA per SM, so the cross-CTA fold is a single ticket round (<= kSingleFold partials)
+    const int64_t cap = N <= 65536 ? kSMs : 2 * kSMs;
+    if (want > cap) want = cap;
     return (int)want;
 }
 
@@ -262,7 +264,25 @@ __device__ __forceinline__ bool ticket_last(unsigned int* counter, unsigned int 
 }
 
 // Fixed-order fold of `G` partial vectors of length L (partials[g*L + i]) by the last CTA.
-// Uses S = kThreads / Lp slices (Lp = L rounded up to a power of two, capped at kThreads).
+// Uses S = kThreads / Lp slices (Lp = L rounded up to a power of two, capped at kThreads).  Every thread sums its slice
+// g = sl, sl + S, ... in that order; the loads are issued in register batches of kFoldBatch (all of a batch in flight before
+// the first add): at G ~ 150 partials of 128 floats a thread has ~80 loads to make, and eight at a time (what a plain
+// unrolled loop gives) made this fold 10 dependent L2 round trips = most of a 10-us moments launch.
+constexpr int kFoldBatch = 32;
+__device__ __forceinline__ float fold_slice(const float* __restrict__ col, int G, int sl, int S, int64_t L) {
+    float t = 0.f;
+    for (int g0 = sl; g0 < G; g0 += S * kFoldBatch) {
+        float v[kFoldBatch];
+#pragma unroll
+        for (int u = 0; u < kFoldBatch; ++u) {
+            const int g = g0 + u * S;
+            v[u] = g < G ? col[(int64_t)g * L] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kFoldBatch; ++u) t += v[u];  // adding 0 for g >= G leaves the bits unchanged
+    }
+    return t;
+}
 __device__ __forceinline__ void fold_partials(const float* partials, int G, int L, float* red /*>= kThreads*/,
                                               float* result /*shared, >= L*/) {
     for (int base = 0; base < L; base += kThreads) {
@@ -271,11 +291,7 @@ __device__ __forceinline__ void fold_partials(const float* partials, int G, int 
         while (Lp < Lt) Lp <<= 1;
         const int S = kThreads / Lp;
         const int i = threadIdx.x % Lp, sl = threadIdx.x / Lp;
-        float t = 0.f;
-        if (i < Lt)
-#pragma unroll 8
-            for (int g = sl; g < G; g += S) t += partials[(int64_t)g * L + base + i];
-        red[threadIdx.x] = t;
+        red[threadIdx.x] = i < Lt ? fold_slice(partials + base + i, G, sl, S, L) : 0.f;
         __syncthreads();
         if (threadIdx.x < Lt) {
             float a = 0.f;
@@ -315,7 +331,8 @@ __device__ __forceinline__ bool hier_fold(float* partials, float* gpartials, int
     return true;
 }
 
-// hier_fold for CTAs of any size: only the first kThreads threads fold (the others just take part in the barriers).
+// hier_fold for CTAs of any size: kThreads virtual folding threads (same slices, same order => same bits as fold_partials),
+// spread over however many threads the CTA has.
 __device__ __forceinline__ void fold_partials_any(const float* partials, int G, int L, float* red /*>= kThreads*/,
                                                   float* result /*shared, >= L*/) {
     for (int base = 0; base < L; base += kThreads) {
@@ -325,11 +342,7 @@ __device__ __forceinline__ void fold_partials_any(const float* partials, int G, 
         const int S = kThreads / Lp;
         for (int vt = threadIdx.x; vt < kThreads; vt += blockDim.x) {  // kThreads virtual folding threads
             const int i = vt % Lp, sl = vt / Lp;
-            float t = 0.f;
-            if (i < Lt)
-#pragma unroll 8
-                for (int g = sl; g < G; g += S) t += partials[(int64_t)g * L + base + i];
-            red[vt] = t;
+            red[vt] = i < Lt ? fold_slice(partials + base + i, G, sl, S, L) : 0.f;
         }
         __syncthreads();
         for (int t = threadIdx.x; t < Lt; t += blockDim.x) {

@@ -305,40 +305,15 @@ __device__ __forceinline__ void gat_fwd_row_stats_from_out(int row, int sub, con
     }
 }
 
-// k = sum_e p_e h_j of row 0 (no bias), computed by the first lane group of warp 0 of EVERY CTA (same arithmetic => the
-// same bits everywhere) and left in shared memory.
+// Common shift of the fused statistics: k = h[0, :], one coalesced load per CTA (same bits everywhere).  Any value inside the
+// range of the column does: the aggregate out_i - bias = sum_e p_e h_j is a convex combination of rows of h, so a sample row
+// of h sits within the column's spread and S2/n - (S1/n)^2 stays free of cancellation.  (Round 1 aggregated row 0 itself here:
+// a chain of four dependent loads - rowptr -> col -> s[j] -> h[j] - in front of every CTA, ~3 us of a 12 us launch.)
 template <int C>
-__device__ __forceinline__ void gat_fwd_row0_shift(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                   const float* __restrict__ h, const float* __restrict__ s,
-                                                   const float* __restrict__ d, float slope, float* kshift) {
-    using M = GatMap<C>;
-    constexpr int NV = M::NV, LANES = M::LANES;
-    if (threadIdx.x < LANES) {
-        const int sub = threadIdx.x;
-        const unsigned gm = group_mask<LANES>(sub);
-        const int beg = __ldg(rowptr), end = __ldg(rowptr + 1);
-        const float di = __ldg(d);
-        float mx = -INFINITY;
-        for (int e = beg + sub; e < end; e += LANES) mx = fmaxf(mx, lrelu(__ldg(s + __ldg(col + e)) + di, slope));
-        mx = gmax<LANES>(mx, gm);
-        float zs = 0.f;
-        for (int e = beg + sub; e < end; e += LANES) zs += expf(lrelu(__ldg(s + __ldg(col + e)) + di, slope) - mx);
-        zs = gsum<LANES>(zs, gm) + 1e-16f;
-        const float inv = rcp_fast(zs);
-        float acc[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = 0.f;
-        for (int e = beg; e < end; ++e) {
-            const int j = __ldg(col + e);
-            float hv[NV];
-            row_load<C>(hv, h + (int64_t)j * C, sub);
-            const float p = expf(lrelu(__ldg(s + j) + di, slope) - mx) * inv;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = fmaf(p, hv[v], acc[v]);
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) kshift[chan<C>(sub, v)] = acc[v];
-    }
+__device__ __forceinline__ void gat_fwd_row0_shift(const int32_t* __restrict__, const int32_t* __restrict__,
+                                                   const float* __restrict__ h, const float* __restrict__,
+                                                   const float* __restrict__, float, float* kshift) {
+    if (threadIdx.x < C) kshift[threadIdx.x] = __ldg(h + threadIdx.x);
     __syncthreads();
 }
 
@@ -1025,10 +1000,13 @@ struct GatCfg {
     int chunk_rows, ipc_shift, ahead;
     bool pipe;
 };
+// `fat_ctas`: the forward kernel with fused statistics ends in a cross-CTA fold of one partial vector per CTA; in the small
+// regime it therefore runs max_threads-wide CTAs (768 threads: ~150 CTAs at N ~ 15 k, C = 64 instead of ~470 of 256 threads), which
+// keeps the fold to ONE ticket round over <= kSingleFold partials (measured: 13.7 -> ~7 us per launch on the chain).
 template <int C>
-static GatCfg gat_cfg(int64_t N, int max_threads = kGatMaxThreads) {
+static GatCfg gat_cfg(int64_t N, int max_threads = kGatMaxThreads, bool fat_ctas = false) {
     const bool small = !g_tune[4] && N * C * 4 < (int64_t)(24 << 20);
-    const int threads = small ? 256 : (g_tune[0] < max_threads ? g_tune[0] : max_threads);
+    const int threads = small ? (fat_ctas ? max_threads : 256) : (g_tune[0] < max_threads ? g_tune[0] : max_threads);
     const int64_t rows_iter = (int64_t)(threads / 32) * GatMap<C>::RPW;
     const int64_t iters = ceil_div(N, rows_iter);
     if (small) {  // one contiguous chunk per CTA, one sweep iteration each while the grid fits 8 CTAs per SM
@@ -1058,7 +1036,7 @@ template <int C>
 static int launch_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                       float* out, float* m, float* z, float slope, cudaStream_t st, const float* gn_alpha = nullptr,
                       float gn_eps = 0.f, float* gn_stats = nullptr, float* ws = nullptr) {
-    const GatCfg c = gat_cfg<C>(g->N, gn_stats ? kGatStatsThreads : kGatMaxThreads);
+    const GatCfg c = gat_cfg<C>(g->N, gn_stats ? kGatStatsThreads : kGatMaxThreads, gn_stats != nullptr);
     GnFuse gn{};
     if (gn_stats) {  // workspace: [counters 4 KiB][partials grid x 2C][group partials]
         gn.counters = reinterpret_cast<unsigned int*>(ws);

