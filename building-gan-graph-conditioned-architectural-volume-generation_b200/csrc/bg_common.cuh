@@ -72,6 +72,11 @@ int dense_fwd_moments(const BgDense* a, const GnMomFuse* f, cudaStream_t st);  /
 // the shape is not eligible, <0 on error.  seg_off = the BG_MAX_SEG + 1 column offsets of the segmented input.
 int rowdense_try(const BgDense* a, const int* seg_off, int K, const GnMomFuse* mom, cudaStream_t st);
 
+// TMA-gather variant of the aggregation forward (bg_gat_tma.cu); same return convention
+int gat_tma_enabled();
+int gat_fwd_tma_try(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias, float* out, float* m,
+                    float* z, int C, float slope, cudaStream_t st);
+
 // warp-MMA 3xTF32 kernel for small single-segment layers (bg_dense_mma.cu); same return convention
 int dense_mma_try(const BgDense* a, int K, const GnMomFuse* mom, cudaStream_t st);
 

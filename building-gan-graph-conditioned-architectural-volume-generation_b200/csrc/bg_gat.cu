@@ -1140,6 +1140,10 @@ extern "C" int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, cons
                           float* out, float* m, float* z, int32_t C, float slope, void* stream) {
     if (int rc = check_graph(g)) return rc;
     BG_REQUIRE(h && s && d && out && m && z, BG_EINVAL, "bg_gat_fwd: null pointer");
+    if (gat_tma_enabled() && g->N * C * 4 >= (int64_t)(24 << 20)) {  // HBM-sized graphs: TMA-gather kernel where eligible
+        const int rc = gat_fwd_tma_try(g, h, s, d, bias, out, m, z, C, slope, as_stream(stream));
+        if (rc <= 0) return rc;
+    }
 #define CALL(CC) launch_fwd<CC>(g, h, s, d, bias, out, m, z, slope, as_stream(stream))
     BG_DISPATCH_C(C, CALL)
 #undef CALL

@@ -87,6 +87,8 @@ SIGNATURES = {
     "bg_ln_act_bwd_ws": (_SZ, [_I64, _I32]),
     "bg_tune": (C.c_int, [_I32, _I32]),
     "bg_gat_fwd": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
+    "bg_gat_fwd_tma": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P]),
+    "bg_set_gat_tma": (C.c_int, [_I32]),
     "bg_gat_fwd_gn_ws": (_SZ, [_I64, _I32]),
     "bg_gat_fwd_gn": (C.c_int, [C.POINTER(BgGraph), _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P, _F, _P, _P, _SZ, _P]),
     "bg_graphnorm_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, C.c_uint64, C.c_uint64, _I64, _I32, _P, _P]),
@@ -488,6 +490,25 @@ def gat_fwd(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope:
     _check(lib.bg_gat_fwd(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
                           m.data_ptr(), z.data_ptr(), c, slope, _stream()))
     return out, m, z
+
+
+@_op("gat_fwd_tma", 1)
+def gat_fwd_tma(csr, h: Tensor, s: Tensor, d: Tensor, bias: Optional[Tensor], slope: float = 0.2):
+    """bg_gat_fwd with the neighbour rows gathered by TMA (tile::gather4); C in {64, 128}, max in-degree <= 8."""
+    lib = load()
+    _cf32(h, "h")
+    n, c = h.shape
+    out = torch.empty_like(h)
+    m = torch.empty(n, dtype=torch.float32, device=h.device)
+    z = torch.empty(n, dtype=torch.float32, device=h.device)
+    _check(lib.bg_gat_fwd_tma(C.byref(csr.c_struct()), h.data_ptr(), s.data_ptr(), d.data_ptr(), _p(bias), out.data_ptr(),
+                              m.data_ptr(), z.data_ptr(), c, slope, _stream()))
+    return out, m, z
+
+
+def set_gat_tma(on: bool) -> bool:
+    """Route bg_gat_fwd through the TMA-gather kernel for HBM-sized eligible graphs (env BG_GAT_TMA); returns the previous setting."""
+    return bool(load().bg_set_gat_tma(int(bool(on))))
 
 
 @_op("gat_fwd_gn", 2)

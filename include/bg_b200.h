@@ -204,6 +204,13 @@ int bg_gatv2_bwd2(const BgGraph* g, const float* Hl, const float* Hr, const floa
  * Saves the per-row softmax max `m` and denominator `z` (incl. PyG's +1e-16). */
 int bg_gat_fwd(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
                float* out, float* m, float* z, int32_t C, float slope, void* stream);
+/* bg_gat_fwd with the neighbour rows gathered by the TMA: cp.async.bulk.tensor.2d tile::gather4 into an mbarrier-pipelined
+ * shared-memory ring, consumer warps doing softmax + weighted sum out of shared memory (csrc/bg_gat_tma.cu).  Same
+ * arguments and results.  Eligible: C in {64, 128}, max in-degree (incl. the self loop) <= 8, 16-byte aligned h / out;
+ * otherwise BG_EUNSUPPORTED.  bg_gat_fwd itself takes this path for HBM-sized graphs when bg_set_gat_tma(1) / BG_GAT_TMA=1. */
+int bg_gat_fwd_tma(const BgGraph* g, const float* h, const float* s, const float* d, const float* bias,
+                   float* out, float* m, float* z, int32_t C, float slope, void* stream);
+int bg_set_gat_tma(int32_t on);
 /* The same aggregation with the statistics of the GraphNorm that follows it (models.py:72-73) fused into its epilogue:
  * gn_stats[3C] = (mean, rstd, var of out - mean_scale*mean) over all N rows, as bg_graphnorm_fwd computes them, so that
  * the normalisation is one elementwise pass (bg_graphnorm_apply) and `out` is not re-read for its moments.  The moment
