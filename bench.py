@@ -48,11 +48,22 @@ def _env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def _make_batches(rank: int, num_batches: int, batch: int, pin: bool):
+def _shard_ids(rank: int, world: int, b: int, batch: int):
+    """Data-parallel batches: global batch b = batch x world consecutive buildings, cut into `world` contiguous shards balanced by
+    voxel count (dist.shard_by_nodes) - BASELINE config 5 at 8 GPUs (global batch 256), its scaled-down versions at 2 / 4."""
+    from building_gan_b200.dist import shard_by_nodes
+    from workloads import synth as wsynth
+    ids = [4001 + b * batch * world + i for i in range(batch * world)]
+    shards = shard_by_nodes([wsynth.voxel_count(i) for i in ids], world)
+    return [ids[k] for k in shards[rank]]
+
+
+def _make_batches(rank: int, num_batches: int, batch: int, pin: bool, world: int = 1):
     from building_gan_b200 import graph, synth
     out = []
     for b in range(num_batches):
-        pairs = [synth.building_pair_fast(i) for i in _building_ids(rank, b, batch)]
+        ids = _building_ids(rank, b, batch) if world == 1 else _shard_ids(rank, world, b, batch)
+        pairs = [synth.building_pair_fast(i) for i in ids]
         lb, vb = graph.collate_fn(pairs)
         if pin:
             lb, vb = lb.pin_memory(), vb.pin_memory()
@@ -240,11 +251,21 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     og = Adam(G.parameters(), lr=cfg.LEARNING_RATE_GENERATOR, betas=cfg.BETAS)
     od = Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
     OVERLAP = not args.no_overlap
-    grad_sync = None
+    grad_sync, sync_kind = None, "none"
     if world > 1:
-        from building_gan_b200.dist import GradSync
+        from building_gan_b200.dist import GradSync, PeerSync
+        sync_kind = "nccl all-reduce (AVG) of the flat gradient bucket, then one-launch Adam"
         grad_sync = GradSync(world)
-    host = _make_batches(rank, NUM_BATCHES, BATCH, pin=True)
+        if args.adam == "flat" and not args.nccl_sync:
+            try:  # one-shot peer-memory all-reduce fused with the Adam step (csrc/bg_p2p.cu)
+                peer = PeerSync()
+                peer.attach(D, od)
+                peer.attach(G, og)
+                grad_sync = peer
+                sync_kind = "bg_p2p_allreduce_adam: one-shot NVLink peer-memory all-reduce fused with the Adam step (one launch per update)"
+            except Exception as exc:  # symmetric memory not available on this box: NCCL path
+                sync_kind += f" (peer-memory path unavailable: {repr(exc)[:120]})"
+    host = _make_batches(rank, NUM_BATCHES, BATCH, pin=True, world=world)
     resident = [_clone_to(lb, vb, dev) for lb, vb in host]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     h2d = sum(_batch_bytes(lb, vb) for lb, vb in host) / len(host)
@@ -391,6 +412,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                                            "(graphs.GraphedStep)" if gstep is not None else "none"),
                            "pdl": _pdl_state(lib),
                            "grads": os.environ.get("BG_GRADS", "bucket"), "executor": os.environ.get("BG_EXECUTOR", "native"),
+                           "gradient_exchange": sync_kind,
+                           "sharding": ("global batch of 32 x world buildings per step, contiguous shards balanced by voxel count "
+                                        "(dist.shard_by_nodes)" if world > 1 else "none"),
                            "parallelism": f"dp{world}" if world > 1 else "single"},
                 "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "steps/s",
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * (cfg.N_CRITIC + 1),
@@ -803,6 +827,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "sample", "c4"])
     ap.add_argument("--adam", default="flat", choices=["flat", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="no CUDA-graph replay of the critic updates")
+    ap.add_argument("--nccl-sync", action="store_true", help="gradient exchange through ncclAllReduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-overlap", action="store_true", help="every pass on one stream in the reference's call order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-roofline", action="store_true")

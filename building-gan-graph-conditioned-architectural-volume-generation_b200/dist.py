@@ -29,8 +29,7 @@ class GradSync:
         if not params:
             return
         if bucket is not None and params[0].grad.data_ptr() == native.views[0].data_ptr():
-            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)  # grads already live in one flat bucket
-            bucket.mul_(1.0 / self.world)
+            dist.all_reduce(bucket, op=dist.ReduceOp.AVG)  # grads already live in one flat bucket; 1/world folded into the reduction
             return
         total = sum(p.numel() for p in params)
         flat = self._buckets.get(id(model))
@@ -42,9 +41,59 @@ class GradSync:
             views.append(flat[off: off + p.numel()].view_as(p))
             off += p.numel()
         torch._foreach_copy_(views, [p.grad for p in params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.mul_(1.0 / self.world)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM)
+        if dist.get_backend() != "nccl":  # gloo has no AVG
+            flat.mul_(1.0 / self.world)
         torch._foreach_copy_([p.grad for p in params], views)
+
+
+class PeerSync:
+    """Gradient exchange FUSED with the optimiser step over NVLink peer memory (``bg_p2p_allreduce_adam``, csrc/bg_p2p.cu):
+    ``attach(model, optimizer)`` moves the model's flat gradient bucket into symmetric memory
+    (torch.distributed._symmetric_memory) and tells the flat Adam (``optim.Adam``) to run the one-launch
+    "read every rank's bucket, average, Adam" kernel instead of ncclAllReduce + scale + Adam.  Calling the object like a
+    ``GradSync`` (``sync(model)``) is then a no-op for attached models - the exchange happens inside ``optimizer.step()`` -
+    and falls back to the NCCL all-reduce for anything else."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self._attached: Dict[int, object] = {}
+        self._nccl = GradSync(self.world)
+        self._keep = []  # symmetric-memory handles must outlive the tensors' use
+
+    def attach(self, model, optimizer) -> None:
+        import torch.distributed._symmetric_memory as symm
+        from . import lib
+        from .models import _param_list
+        from .optim import Adam
+        if not isinstance(optimizer, Adam):
+            raise TypeError("PeerSync.attach: the fused exchange needs building_gan_b200.optim.Adam (flat buffers)")
+        if self.world > lib.MAX_PEERS:
+            raise ValueError(f"PeerSync: at most {lib.MAX_PEERS} ranks (one NVSwitch domain), got {self.world}")
+        st, params = model._native, _param_list(model)
+        dev = params[0].device
+        name = self.group.group_name
+        bucket = symm.empty(st.layout.total, dtype=torch.float32, device=dev)
+        bucket.zero_()
+        flags = symm.empty(2 * lib.MAX_PEERS, dtype=torch.int32, device=dev)
+        flags.zero_()
+        hb, hf = symm.rendezvous(bucket, name), symm.rendezvous(flags, name)
+        torch.cuda.synchronize(dev)
+        hb.barrier()  # every rank's zeroing is complete before anybody signals
+        peers = lib.BgPeers()
+        peers.rank, peers.world = self.rank, self.world
+        for r in range(self.world):
+            peers.grad[r], peers.flags[r] = hb.buffer_ptrs[r], hf.buffer_ptrs[r]
+        st.install_bucket(bucket, params)
+        optimizer._peer = (peers, torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+        self._attached[id(model)] = optimizer
+        self._keep += [bucket, flags, hb, hf]
+
+    def __call__(self, model) -> None:
+        if id(model) in self._attached:
+            return  # exchanged inside optimizer.step()
+        self._nccl(model)
 
 
 def shard_ids(ids: Sequence[int], rank: int, world: int) -> List[int]:

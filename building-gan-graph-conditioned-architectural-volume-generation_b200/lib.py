@@ -58,6 +58,13 @@ class BgBatchIn(C.Structure):
     _fields_ = [("table", C.c_void_p), ("type32", C.c_void_p), ("vx", C.c_void_p)]
 
 
+MAX_PEERS = 8
+
+
+class BgPeers(C.Structure):
+    _fields_ = [("grad", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class BgWgrad(C.Structure):
     _fields_ = [("N", C.c_int64), ("gz", C.c_void_p), ("ld_gz", C.c_int64), ("Cout", C.c_int32), ("nseg", C.c_int32),
                 ("seg", BgSeg * MAX_SEG), ("dW", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),
@@ -133,6 +140,8 @@ SIGNATURES = {
     "bg_set_pdl": (C.c_int, [_I32]),
     "bg_set_rng_base": (C.c_int, [_P]),
     "bg_adam_flat": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I64, _P, _P]),
+    "bg_p2p_allreduce_adam": (C.c_int, [C.POINTER(BgPeers), _P, _P, _P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, _I64, _P, _P]),
 }
 
 _lib = None
@@ -870,6 +879,23 @@ def adam_flat_(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, beta1: flo
         sd = step_dev.data_ptr()
     _check(lib.bg_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
                             weight_decay, int(step), sd, _stream()))
+
+
+@_op("p2p_allreduce_adam", 1)
+def p2p_allreduce_adam_(peers: BgPeers, epoch: Tensor, ticket: Tensor, n: int, p: Optional[Tensor] = None, m: Optional[Tensor] = None,
+                        v: Optional[Tensor] = None, gavg: Optional[Tensor] = None, lr: float = 0.0, beta1: float = 0.9,
+                        beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1,
+                        step_dev: Optional[Tensor] = None) -> None:
+    """bg_p2p_allreduce_adam: one-shot peer-memory all-reduce (average) of the ranks' flat gradient buckets fused with the Adam
+    step over the local flat buffers; with p = m = v = None only the averaged gradient is written to ``gavg``."""
+    lib = load()
+    assert epoch.dtype == torch.int32 and ticket.dtype == torch.int32 and epoch.is_cuda and ticket.is_cuda
+    for t in (p, m, v, gavg):
+        if t is not None:
+            _cf32(t, "flat buffer")
+            assert t.numel() == n
+    _check(lib.bg_p2p_allreduce_adam(C.byref(peers), epoch.data_ptr(), ticket.data_ptr(), _p(p), _p(m), _p(v), _p(gavg), n, lr, beta1, beta2,
+                                     eps, weight_decay, int(step), _p(step_dev), _stream()))
 
 
 # ------------------------------------------------------------------------------------------------

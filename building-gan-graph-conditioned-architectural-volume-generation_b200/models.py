@@ -304,6 +304,17 @@ class _NativeState:
             self.anchor = torch.zeros(1, device=device, requires_grad=True)
         return self.anchor
 
+    def install_bucket(self, bucket: Tensor, params) -> Tensor:
+        """Use an externally allocated flat buffer (symmetric memory: dist.PeerSync) as the gradient bucket."""
+        assert bucket.numel() == self.layout.total and bucket.dtype == torch.float32
+        self.bucket = bucket
+        self.views = [self.layout.view(bucket, n) for n in self.layout.names]
+        for p, v in zip(params, self.views):
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+        return bucket
+
     def bind_grads(self, params) -> Tensor:
         """Make every ``p.grad`` a view of the flat bucket (zeroing what ``zero_grad(set_to_none=True)`` dropped)."""
         dev = params[0].device

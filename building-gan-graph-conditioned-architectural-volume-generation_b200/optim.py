@@ -61,6 +61,7 @@ class Adam(torch.optim.Optimizer):
         self._m: Optional[Tensor] = None
         self._v: Optional[Tensor] = None
         self._t_dev: Optional[Tensor] = None
+        self._peer = None  # (BgPeers, epoch, ticket) once dist.PeerSync.attach() fused the gradient exchange into step()
 
     # -- flat state ---------------------------------------------------------------------------------
     def _flats(self):
@@ -104,6 +105,11 @@ class Adam(torch.optim.Optimizer):
         b1, b2 = g["betas"]
         if g["capturable"]:
             self._t_dev.add_(1)
+        if self._peer is not None:  # data parallel: all ranks' buckets are averaged inside the same launch (csrc/bg_p2p.cu)
+            peers, epoch, ticket = self._peer
+            lib.p2p_allreduce_adam_(peers, epoch, ticket, pflat.numel(), pflat, m, v, None, float(g["lr"]), float(b1), float(b2),
+                                    float(g["eps"]), float(g["weight_decay"]), self._t, self._t_dev if g["capturable"] else None)
+            return loss
         lib.adam_flat_(pflat, st.bucket, m, v, float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
                        self._t, self._t_dev if g["capturable"] else None)
         return loss

@@ -384,6 +384,27 @@ int bg_fill(float* y, float v, int64_t n, void* stream);
 int bg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
                  double weight_decay, int64_t step, const int64_t* step_dev, void* stream);
 
+/* Data-parallel gradient exchange fused with the optimiser step (replaces the flat-bucket ncclAllReduce +
+ * scale + bg_adam_flat sequence, i.e. what DistributedDataParallel + torch.optim.Adam.step would run around the reference's
+ * train.py:36-37 / trainer.py:481,495).  One launch: waits until every rank's gradient bucket is complete, reads all `world`
+ * buckets out of the peers' memory over NVLink / NVSwitch (one-shot all-reduce, summed in rank order => bit-identical on every
+ * rank), averages, and applies Adam to the LOCAL flat p / m / v (same arithmetic as bg_adam_flat); with p = m = v = NULL it only
+ * writes the averaged gradient to `gavg` (optional otherwise).  grad[r] / flags[r]: rank r's gradient bucket (n floats, 16-byte
+ * aligned) and its flag array (2 * world uint32, zero before the first call), both in memory every rank can address (symmetric
+ * memory / CUDA IPC; the host side uses torch.distributed._symmetric_memory).  epoch, ticket: LOCAL device words, zero before
+ * the first call; the kernel advances them itself, so the launch is CUDA-graph capturable.  Every rank must make the same
+ * sequence of calls (like a collective).  No NCCL types: this replaces the `bg_allreduce_flat(ncclComm_t, ...)` entry the
+ * survey sketched - the host keeps torch.distributed / NCCL for everything else (barriers, the max-over-ranks timing). */
+#define BG_MAX_PEERS 8
+typedef struct {
+    const float* grad[BG_MAX_PEERS];
+    uint32_t* flags[BG_MAX_PEERS];
+    int32_t rank, world;
+} BgPeers;
+int bg_p2p_allreduce_adam(const BgPeers* peers, uint32_t* epoch, uint32_t* ticket, float* p, float* m, float* v, float* gavg,
+                          int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                          const int64_t* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

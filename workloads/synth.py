@@ -97,6 +97,12 @@ def grid_arrays(building_id: int, floors: int = 0, ny: int = 0, nx: int = 0, shu
     )
 
 
+def voxel_count(building_id: int) -> int:
+    """Number of voxels of ``grid_arrays(building_id)`` without building it (the first three draws of its generator)."""
+    rng = np.random.default_rng(777 + int(building_id))
+    return int(rng.integers(2, 12)) * int(rng.integers(4, 13)) * int(rng.integers(4, 13))
+
+
 def _neighbour_pairs(loc: np.ndarray, F: int, Y: int, X: int) -> Tuple[np.ndarray, np.ndarray]:
     """Directed face-adjacency (src, dst) pairs in node-id space, sorted src-major then dst - the
     order ``adjacency.nonzero().t()`` produces (data.py:326-335)."""
