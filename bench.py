@@ -372,12 +372,12 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             roofline, agg = _hbm_roofline(dev, flush)
         if roofline is None:
             roofline = roof_step
-        # local step (no gradient all-reduce: the other ranks do not take part in this extra step)
-        if gstep is not None and world == 1:
-            ops = _kernel_shares(lambda: gstep(*resident[0], sync_losses=False))
-        else:
-            ops = _kernel_shares(lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=None,
-                                                         sync_losses=False, overlap=OVERLAP))
+    # one extra step under the CUPTI profiler (kernel shares).  With several ranks the step contains collectives (the fused
+    # peer-memory exchange sits inside optimizer.step()), so EVERY rank runs it; rank 0 reports.
+    if world > 1 or rank == 0:
+        run_one = (lambda: gstep(*resident[0], sync_losses=False)) if gstep is not None else \
+            (lambda: step.train_step(G, D, og, od, *resident[0], cfg, rng="device", grad_sync=grad_sync, sync_losses=False, overlap=OVERLAP))
+        ops = _kernel_shares(run_one)
     cpu_baseline, torch_gpu, dropin, parity, extra = None, None, None, None, {}
     if rank == 0:
         roof_dense = _dense_rooflines(resident[0][1], G, D, flush)

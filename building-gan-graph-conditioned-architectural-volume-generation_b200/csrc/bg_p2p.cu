@@ -36,6 +36,17 @@ __device__ __forceinline__ float4 ld_peer4(const float4* p) {
     return v;
 }
 
+// Bounded spin: a peer that never makes the matching call (a rank that died, a call sequence that differs between ranks)
+// must end in a loud launch failure, not in a silent hang of every rank.  ~2e7 polls of a system-scope load: tens of seconds.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t want) {
+    for (unsigned int polls = 0; (int32_t)(ld_acquire_sys(flag) - want) < 0; ++polls)
+        if (polls > 20000000u) {
+            printf("bg_p2p_allreduce_adam: timed out waiting for a peer (flag %p = %u, want %u): ranks out of step\n", (const void*)flag,
+                   ld_acquire_sys(flag), want);
+            __trap();
+        }
+}
+
 struct AdamConsts {
     double lr, b1, b2d;
     float b2, w1, w2, eps, wd, step_size, bc2_sqrt;
@@ -55,8 +66,7 @@ __global__ void __launch_bounds__(kThreads) p2p_allreduce_adam_kernel(const BgPe
         __threadfence_system();
         st_release_sys(P.flags[threadIdx.x] + me, e + 1);
     }
-    if (threadIdx.x < W)
-        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - (e + 1)) < 0) {}
+    if (threadIdx.x < W) wait_flag(my_flags + threadIdx.x, e + 1);
     __syncthreads();
     if (step_dev) {
         const double t = (double)*step_dev;
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) p2p_allreduce_adam_kernel(const BgPe
     if (!last) return;
     if (threadIdx.x < W) {
         st_release_sys(P.flags[threadIdx.x] + W + me, e + 2);
-        while ((int32_t)(ld_acquire_sys(my_flags + W + threadIdx.x) - (e + 2)) < 0) {}
+        wait_flag(my_flags + W + threadIdx.x, e + 2);
     }
     __syncthreads();
     if (threadIdx.x == 0) *epoch = e + 2;

@@ -18,8 +18,8 @@ What makes the replays differ (a graph freezes every kernel argument):
   same call sequence would have used;
 * Adam's step count lives in a device counter (optim.Adam(capturable=True) semantics, switched on for the captured step).
 
-Not supported here (use step.train_step): rng="cpu" (host draws cannot be captured), torch.optim.Adam for the critic, the
-non-native conv types.
+Not supported here (use step.train_step): rng="cpu" (host draws cannot be captured), torch.optim.Adam for the critic.
+All four conv types are covered (the non-default ones through the op-by-op executor).
 """
 from __future__ import annotations
 
@@ -48,9 +48,11 @@ class GraphedStep:
         self.grad_sync = grad_sync
         if not isinstance(opt_d, Adam):
             raise TypeError("GraphedStep: the critic optimiser must be building_gan_b200.optim.Adam (its step is captured)")
-        if models._executor_for(discriminator._kind) == "python" or models._executor_for(generator._kind) == "python" \
-                or models.GRAD_MODE != "bucket" or models.RNG_MODE != "philox" or not cfg.USE_WGANGP:
-            raise NotImplementedError("GraphedStep covers the default configuration (GATCONV, WGAN-GP, BG_GRADS=bucket, BG_RNG=philox)")
+        if models.GRAD_MODE != "bucket" or models.RNG_MODE != "philox" or not cfg.USE_WGANGP:
+            raise NotImplementedError("GraphedStep covers WGAN-GP with BG_GRADS=bucket and BG_RNG=philox")
+        # GCNCONV / GRAPHCONV / GATV2CONV models run the op-by-op executor (models._executor_for): its launches (library kernels +
+        # torch's dropout / Gumbel draws from the graph-registered generator + autograd's gradient accumulation) are all
+        # stream-ordered and allocation-pool safe, so the same capture / replay scheme applies to them.
         self.G, self.D, self.opt_g, self.opt_d, self.cfg = generator, discriminator, opt_g, opt_d, cfg
         self.dev = next(discriminator.parameters()).device
         # the stream of the gradient-penalty chain (the step's critical path) outranks the lanes (-1) and the weight-gradient

@@ -130,14 +130,17 @@ def test_graphed_step_runs_and_trains():
     assert abs(ref_real) < 1e4
 
 
-def test_graphed_step_matches_eager_statistics():
+@pytest.mark.parametrize("kind", ["GATCONV", "GCNCONV", "GRAPHCONV", "GATV2CONV"])
+def test_graphed_step_matches_eager_statistics(kind):
     """Train the same initial state for a few steps with the eager overlapped step and with GraphedStep: different random
-    draws (so no element-wise equality), but the critic losses must stay in the same range and all parameters finite."""
+    draws (so no element-wise equality), but the critic losses must stay in the same range and all parameters finite.  For
+    every conv type of models.py:22-31 (the non-default ones run the op-by-op executor inside the captured graphs)."""
     from building_gan_b200.graphs import GraphedStep
 
     out = {}
     for mode in ("eager", "graph"):
         cfg = Configuration()
+        cfg.GENERATOR_CONV_TYPE = cfg.DISCRIMINATOR_CONV_TYPE = kind
         cfg.DEVICE = "cuda"
         torch.manual_seed(1)
         torch.cuda.manual_seed(1)
