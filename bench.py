@@ -740,6 +740,33 @@ def _extra_workloads(cfg, dev, flush):
                                  "ms_per_step": round(1e3 * sec / k, 3),
                                  "config": {"workload": "BASELINE config 1: sanity.py single-datum overfit step (one building)",
                                             "voxels": int(vb1.num_nodes), "path": "graphs.GraphedStep"}}
+        # ---- the three non-default conv types (models.py:22-31) through the same graphed step, batch 32
+        from building_gan_b200 import Configuration
+        lb32, vb32 = graph.collate_fn([synth.building_pair_fast(i) for i in _building_ids(0, 0, BATCH)])
+        lb32, vb32 = lb32.to(dev), vb32.to(dev)
+        conv = {}
+        for kind in ("GCNCONV", "GRAPHCONV", "GATV2CONV"):
+            c2 = Configuration()
+            c2.GENERATOR_CONV_TYPE = c2.DISCRIMINATOR_CONV_TYPE = kind
+            torch.manual_seed(777)
+            G2, D2 = VoxelGNNGenerator(c2, 17, 12).to(dev), VoxelGNNDiscriminator(c2, 17, 12).to(dev)
+            og2 = Adam(G2.parameters(), lr=c2.LEARNING_RATE_GENERATOR, betas=c2.BETAS)
+            od2 = Adam(D2.parameters(), lr=c2.LEARNING_RATE_DISCRIMINATOR, betas=c2.BETAS)
+            gs2 = GraphedStep(G2, D2, og2, od2, c2)
+            for _ in range(3):
+                gs2(lb32, vb32, sync_losses=False)
+            torch.cuda.synchronize()
+            k = 6
+            e0.record()
+            for _ in range(k):
+                gs2(lb32, vb32, sync_losses=False)
+            e1.record()
+            torch.cuda.synchronize()
+            conv[kind] = round(k / (e0.elapsed_time(e1) * 1e-3), 2)
+            del G2, D2, og2, od2, gs2
+        out["conv_types"] = {"metric": "G+D train steps/sec", "unit": "steps/s", "values": conv,
+                             "config": "batch 32, graphs.GraphedStep, GENERATOR_CONV_TYPE = DISCRIMINATOR_CONV_TYPE = the key "
+                                       "(op-by-op executor on the library kernels inside the captured graphs)"}
     except Exception as exc:
         out["extra_workloads_error"] = repr(exc)[:300]
     return out

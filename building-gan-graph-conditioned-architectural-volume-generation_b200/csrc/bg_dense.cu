@@ -489,6 +489,164 @@ __global__ void __launch_bounds__(kThreads) wgrad_multi_kernel(const WgBatch b) 
         }
 }
 
+// The same partial sums on the warp-level tensor cores (3xTF32 mma.sync.m16n8k8, fp32-accurate): D[o, k] = sum_rows gz[row, o] X[row, k]
+// is an M = Cout, N = K, "K" = rows product.  Same tiles, same splits, same slab loader (coalesced, segment / gather aware, software
+// pipelined) and the same partial layout as wgrad_multi_kernel - only the inner product differs: the slab's operands are read
+// from shared memory as MMA fragments (A[m][kk] = Gs[kk][m], B[kk][n] = Xs[kk][n]; row stride 72 floats: conflict-free), split
+// into TF32 hi / lo on the fly, hi*hi into a main accumulator, the two correction products into a second one.  Warp w of the 8
+// owns the 16 x 32 sub-tile (m-tile w % MT', k-half ...) of the 64 x 64 tile; tiles with fewer than 8 sub-tiles split the slab's
+// four 8-row k-steps over R row groups of warps, folded in group order at the end (deterministic).  Why: the FFMA kernel
+// was the second-largest consumer of SM time in the training step (5.5 of 22.7 ms of kernel time per step, round 2), bound
+// by instruction issue; one MMA replaces 32 warp-FFMAs.
+__global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(const WgBatch b) {
+    pdl_prologue();
+    constexpr int T = 64, RB = 32, LD = T + 8;
+    __shared__ __align__(16) float smem[2][RB][LD];
+    float(*Gs)[LD] = smem[0];
+    float(*Xs)[LD] = smem[1];
+    int pi = 0;
+#pragma unroll 1
+    for (int q = 1; q < b.nprob; ++q)
+        if ((int)blockIdx.x >= b.p[q].tile_base) pi = q;
+    const WgProblem& p = b.p[pi];
+    const int lt = blockIdx.x - p.tile_base;
+    const int k0 = (lt % p.tiles_k) * T, o0 = (lt / p.tiles_k) * T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t rbeg = (int64_t)blockIdx.y * p.rows_per_split, rend = min(p.N, rbeg + p.rows_per_split);
+    const int no = min(T, p.Cout - o0), nk = min(T, p.K - k0);  // valid extent of this tile
+    // warp -> (sub-tile, row group): MT m-tiles of 16 outputs x NG groups of 32 k columns, units rounded up to a power of two
+    const int MT = (no + 15) >> 4, NG = (nk + 31) >> 5, units = MT * NG;
+    int U = 1;
+    while (U < units) U <<= 1;            // 1, 2, 4, 8
+    const int R = 8 / U;                   // row groups: k-steps rg, rg + R, ... of every slab (R in {1, 2, 4, 8}; 8 > 4 k-steps: some idle)
+    const int unit = warp % U, rg = warp / U;
+    const bool active = unit < units;
+    const int m0 = (unit % MT) * 16, n0 = (unit / MT) * 32;
+    float cm[4][4], cc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cm[j][i] = cc[j][i] = 0.f;
+    // ---- slab loader: identical to wgrad_multi_kernel
+    const int mycol = tid % T;
+    const SegCol xcol = seg_resolve(p.x, k0 + mycol, mycol < nk ? p.K : 0);
+    const float* gcol = mycol < no ? p.gz + o0 + mycol : nullptr;
+    constexpr int PER = RB * T / kThreads, RSTEP = kThreads / T;
+    float gv[PER], xv[PER];
+    const int rl = tid / T;
+    const float* gp = gcol ? gcol + (rbeg + rl) * p.ld_gz : nullptr;
+    const int64_t gstep = (int64_t)RSTEP * p.ld_gz;
+    const bool xdirect = xcol.base != nullptr && xcol.gather == nullptr;
+    const float* xp = xdirect ? xcol.base + (rbeg + rl) * (int64_t)xcol.ld : nullptr;
+    const int64_t xstep = (int64_t)RSTEP * xcol.ld;
+    const float xconst = (xcol.base == nullptr && xcol.ones) ? 1.f : 0.f;
+    auto fetch = [&](int64_t r0) {
+        if (r0 + RB <= rend) {
+            if (gp) {
+                const float* g0 = gp + (r0 - rbeg) * p.ld_gz;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) gv[q] = __ldg(g0 + q * gstep);
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) gv[q] = 0.f;
+            }
+            if (xdirect) {
+                const float* x0 = xp + (r0 - rbeg) * (int64_t)xcol.ld;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = __ldg(x0 + q * xstep);
+            } else if (xcol.base == nullptr) {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = xconst;
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) xv[q] = seg_load(xcol, r0 + rl + q * RSTEP);
+            }
+            return;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int64_t r = r0 + (tid + q * kThreads) / T;
+            gv[q] = (r < rend && gcol) ? __ldg(gcol + r * p.ld_gz) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int64_t r = r0 + (tid + q * kThreads) / T;
+            xv[q] = (r < rend) ? seg_load(xcol, r) : 0.f;
+        }
+    };
+    auto split = [](float v, uint32_t& hi, uint32_t& lo) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+    };
+    auto mma = [](float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    };
+    if (rbeg < rend) fetch(rbeg);
+    for (int64_t r0 = rbeg; r0 < rend; r0 += RB) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            Gs[rl + q * RSTEP][mycol] = gv[q];
+            Xs[rl + q * RSTEP][mycol] = xv[q];
+        }
+        __syncthreads();
+        if (r0 + RB < rend) fetch(r0 + RB);
+        if (active) {
+            for (int ks = rg; ks < RB / 8; ks += R) {  // the slab's 8-row k-steps of this row group, ascending
+                const int ra = 8 * ks + t, rb = ra + 4;
+                uint32_t ah[4], al[4];
+                split(Gs[ra][m0 + g], ah[0], al[0]);
+                split(Gs[ra][m0 + g + 8], ah[1], al[1]);
+                split(Gs[rb][m0 + g], ah[2], al[2]);
+                split(Gs[rb][m0 + g + 8], ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t b0h, b0l, b1h, b1l;
+                    split(Xs[ra][n0 + 8 * j + g], b0h, b0l);
+                    split(Xs[rb][n0 + 8 * j + g], b1h, b1l);
+                    mma(cm[j], ah, b0h, b1h);
+                    mma(cc[j], al, b0h, b1h);
+                    mma(cc[j], ah, b0l, b1l);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cm[j][i] += cc[j][i];
+    if (R > 1) {  // fold the row groups through shared memory in group order (Gs / Xs are free now)
+        float* red = &smem[0][0][0];
+        static_assert(sizeof(smem) >= kThreads * 16 * sizeof(float), "fold buffer");
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[(j * 4 + i) * kThreads + tid] = active ? cm[j][i] : 0.f;
+        __syncthreads();
+        if (rg == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s = 0.f;
+                    for (int q = 0; q < R; ++q) s += red[(j * 4 + i) * kThreads + (q * U + unit) * 32 + lane];
+                    cm[j][i] = s;
+                }
+        }
+    }
+    if (rg != 0 || !active) return;
+    float* mine = p.partial + (int64_t)blockIdx.y * p.Cout * p.K;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // C fragment: (row g | g + 8, column 2t | 2t + 1) of n-tile j
+            const int o = o0 + m0 + g + ((i & 2) ? 8 : 0), k = k0 + n0 + 8 * j + 2 * t + (i & 1);
+            if (o < p.Cout && k < p.K) mine[(int64_t)o * p.K + k] = cm[j][i];
+        }
+}
+
 __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb) {
     pdl_prologue();
     int e = 0;
@@ -575,7 +733,12 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
         q.phase[phase].push_back(f);
     }
     dim3 grid((unsigned)tiles, (unsigned)b.S);
-    launch_k(wgrad_multi_kernel, grid, kThreads, 0, st, b);
+    static const bool skip = getenv("BG_DEBUG_SKIP_WGRAD") && atoi(getenv("BG_DEBUG_SKIP_WGRAD"));  // timing experiments only: WRONG gradients
+    static const bool use_mma = !(getenv("BG_WGRAD_MMA") && atoi(getenv("BG_WGRAD_MMA")) == 0);  // default: tensor-core partial sums
+    if (!skip) {
+        if (use_mma) launch_k(wgrad_mma_kernel, grid, kThreads, 0, st, b);
+        else launch_k(wgrad_multi_kernel, grid, kThreads, 0, st, b);
+    }
     return check_launch("wgrad");
 }
 
