@@ -335,7 +335,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     # the eager first step, so that the graph memory pools reach their steady-state size before the clock starts (a first
     # capture at a new, larger N grows the pool with cudaMalloc: 30-700 ms once per pool, profiles/tools/graph_steps.py)
     # (round 2: TWO passes - the first timed block of a full run once came out 13 % slower than the blocks after it)
-    n_warm = max(args.warmup, 2 * NUM_BATCHES + 2) if gstep is not None else args.warmup
+    # and at least as many steps as the timed block itself, so that clocks / power state / pools are where the timed block keeps them)
+    n_warm = max(args.warmup, 2 * NUM_BATCHES + 2, args.steps) if gstep is not None else args.warmup
     for i in range(n_warm):
         step_resident(i)
     clocks = _Clocks(local_rank)
