@@ -49,6 +49,14 @@ struct WgradQueue {
     float* buf = nullptr;
     size_t cap = 0, used = 0;  // floats
 };
+// bg_gat_bwd / bg_gat_bwd_gn with the second-order sweep's cotangent at h added in the source pass's epilogue (bg_gat.cu)
+int gat_bwd_inj(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d, const float* m, const float* z,
+                const float* a_src, const float* a_dst, float* P, float* DU, float* gh_tot, float* gsd, int32_t C, float slope,
+                const float* inj_h, void* stream);
+int gat_bwd_gn_inj(const BgGraph* g, const float* gx1, const float* o, const float* x1, const float* gn_w, const float* gn_alpha,
+                   const float* gn_stats, const float* gn_bstats, float keep_scale, const float* inj_o, const float* h, const float* s,
+                   const float* d, const float* m, const float* z, const float* a_src, const float* a_dst, float* P, float* DU,
+                   float* go, float* gh_tot, float* gsd, int32_t C, float slope, const float* inj_h, void* stream);
 int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st);
 int wgrad_flush(WgradQueue& q, cudaStream_t st);
 

@@ -331,6 +331,7 @@ struct WgProblem {
 };
 constexpr int kWgMax = 16;  // problems per launch (keeps the parameter block under 4 KiB)
 constexpr int kWgKick = 8;  // deferred mode: a batch leaves for the side stream as soon as this many problems are queued
+constexpr double kWgKickWork = 1.2e8;  // ... or as soon as the queued multiply-adds reach this (N x Cout x K; one 128 x 128 layer at N = 8 k)
 struct WgBatch {
     int nprob, S;
     WgProblem p[kWgMax];
@@ -678,7 +679,7 @@ static inline int wgrad_splits(int64_t N, int total_tiles) {
     // one parallel launch, so more partials are cheap); large outputs keep the partial traffic bounded
     int64_t ns = ceil_div(4 * kSMs, total_tiles);
     const int64_t maxs = ceil_div(N, 64);
-    const int64_t cap = total_tiles <= 4 ? 128 : 64;
+    const int64_t cap = total_tiles <= 2 ? 128 : 64;
     if (ns > maxs) ns = maxs;
     if (ns > cap) ns = cap;
     if (ns < 1) ns = 1;
@@ -705,6 +706,12 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
         if (a.N > nmax) nmax = a.N;
     }
     b.S = wgrad_splits(nmax, tiles);
+    {   // the partial sums of every batch of a pass live side by side until the fold: shorten the splits rather than fail
+        size_t per_split = 0;
+        for (int i = 0; i < nprob; ++i) per_split += ((size_t)b.p[i].Cout * b.p[i].K + 63) / 64 * 64 + 64;
+        const size_t room = q.cap > q.used ? q.cap - q.used : 0;
+        if ((size_t)b.S * per_split > room && room / per_split >= 1) b.S = (int)(room / per_split);
+    }
     for (int i = 0; i < nprob; ++i) {
         WgProblem& p = b.p[i];
         p.rows_per_split = ceil_div(ceil_div(p.N, b.S), 32) * 32;
@@ -803,6 +810,17 @@ int wgrad_launch(const BgWgrad* probs, int nprob, WgradQueue& q, cudaStream_t st
         q.pending.insert(q.pending.end(), probs, probs + nprob);
         while (q.pending.size() >= (size_t)kWgKick)
             if (int rc = wgrad_kick(q, kWgKick, st)) return rc;
+        // a LARGE problem does not wait for seven more: the generator's 128-wide layers are ~25 us of side-stream work each,
+        // and batched by count the last five of a backward pass left together AFTER the dgrad chain had ended (141 us batch,
+        // ~100 us of it exposed at the end of the step: profiles/r02b_summary.md); kicked as they arrive only the last one is
+        double work = 0.0;
+        for (const BgWgrad& a : q.pending) {
+            int64_t k = 0;
+            for (int i = 0; i < a.nseg; ++i) k += a.seg[i].width;
+            work += (double)a.N * (double)a.Cout * (double)k;
+        }
+        if (work >= kWgKickWork && !q.pending.empty())
+            if (int rc = wgrad_kick(q, q.pending.size(), st)) return rc;
         return BG_OK;
     }
     for (int i = 0; i < nprob; i += kWgMax)

@@ -759,13 +759,14 @@ __device__ __noinline__ void gat_bwd_src_row_generic(int row, int sub, const int
                                                      const float* __restrict__ P, const float* __restrict__ DU,
                                                      const float* __restrict__ G, const float* __restrict__ a_src,
                                                      const float* __restrict__ a_dst, float* __restrict__ out_tot,
-                                                     float* __restrict__ gsd) {
+                                                     float* __restrict__ gsd, const float* __restrict__ add) {
     using M = GatMap<C>;
     constexpr int NV = M::NV;
     const int beg = __ldg(cscptr + row), end = __ldg(cscptr + row + 1);
-    float acc[NV];
+    float acc[NV], inj[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+    for (int v = 0; v < NV; ++v) acc[v] = inj[v] = 0.f;
+    if (add) row_load<C>(inj, add + (int64_t)row * C, sub);
     float gs = 0.f;
     for (int k = beg; k < end; ++k) {
         const int i = __ldg(cscrow + k), e = __ldg(perm + k);
@@ -779,6 +780,10 @@ __device__ __noinline__ void gat_bwd_src_row_generic(int row, int sub, const int
     const float gd = gsd[2 * (int64_t)row + 1];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] += gs * __ldg(a_src + chan<C>(sub, v)) + gd * __ldg(a_dst + chan<C>(sub, v));
+    if (add) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] += inj[v];
+    }
     row_store<C>(acc, out_tot + (int64_t)row * C, sub);
     if (sub == 0) gsd[2 * (int64_t)row] = gs;
 }
@@ -789,21 +794,28 @@ __device__ __forceinline__ void gat_bwd_src_row_fast(int row, bool valid, int ma
                                                      const float (&du)[GatMap<C>::EPL], float gd,
                                                      const float* __restrict__ gb, const float* __restrict__ a_src,
                                                      const float* __restrict__ a_dst, float* __restrict__ out_tot,
-                                                     float* __restrict__ gsd) {
+                                                     float* __restrict__ gsd, const float* __restrict__ add) {
     using M = GatMap<C>;
     constexpr int NV = M::NV, LANES = M::LANES, EPL = M::EPL;
     float gs = 0.f;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) gs += du[k];
     gs = group_sum<LANES>(gs);
-    float acc[NV];
+    float acc[NV], inj[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+    for (int v = 0; v < NV; ++v) acc[v] = inj[v] = 0.f;
+    // injected cotangent at this row (second-order sweep): issued with the gather, added last - the same single rounding as
+    // the separate axpy it replaces (out + 1.0 * add)
+    if (add && valid) row_load<C>(inj, add + (int64_t)row * C, sub);
     gather_fma4<C, EPL>(gb, i, p, 0, acc);
     if (maxdeg > 4) gather_fma4<C, EPL>(gb, i, p, 4, acc);
     if (valid) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] += gs * __ldg(a_src + chan<C>(sub, v)) + gd * __ldg(a_dst + chan<C>(sub, v));
+        if (add) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] += inj[v];
+        }
         row_store<C>(acc, out_tot + (int64_t)row * C, sub);
         if (sub == 0) gsd[2 * (int64_t)row] = gs;
     }
@@ -814,7 +826,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
     const int32_t* __restrict__ cscptr, const int32_t* __restrict__ cscrow, const int32_t* __restrict__ perm,
     const float* __restrict__ P, const float* __restrict__ DU, const float* __restrict__ G,
     const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out_tot,
-    float* __restrict__ gsd, int N, int chunk_rows, int ipc_shift, int ahead) {
+    float* __restrict__ gsd, const float* __restrict__ add, int N, int chunk_rows, int ipc_shift, int ahead) {
     pdl_prologue();
     using M = GatMap<C>;
     constexpr int VEC = M::VEC, LANES = M::LANES, EPL = M::EPL, CAP = M::CAP, RPW = M::RPW;
@@ -831,7 +843,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
             const int deg = __ldg(cscptr + rr + 1) - beg;
             const int maxdeg = __reduce_max_sync(kFull, deg);
             if (maxdeg > CAP) {
-                if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd);
+                if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd, add);
                 continue;
             }
             int i[EPL];
@@ -844,7 +856,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
                 p[k] = ok ? P[e] : 0.f;
                 du[k] = ok ? DU[e] : 0.f;
             }
-            gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i, p, du, gsd[2 * (int64_t)rr + 1], gb, a_src, a_dst, out_tot, gsd);
+            gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i, p, du, gsd[2 * (int64_t)rr + 1], gb, a_src, a_dst, out_tot, gsd, add);
         }
     } else {
         if (sw.niter == 0) return;
@@ -885,9 +897,9 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
                 const bool valid = row < N;
                 const int maxdeg = __reduce_max_sync(kFull, deg0);
                 if (maxdeg > CAP) {
-                    if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd);
+                    if (valid) gat_bwd_src_row_generic<C>(row, sub, cscptr, cscrow, perm, P, DU, G, a_src, a_dst, out_tot, gsd, add);
                 } else {
-                    gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i0, p0, du0, gd0, gb, a_src, a_dst, out_tot, gsd);
+                    gat_bwd_src_row_fast<C>(row, valid, maxdeg, sub, i0, p0, du0, gd0, gb, a_src, a_dst, out_tot, gsd, add);
                 }
             }
             deg0 = deg1, gd0 = gd1;
@@ -1058,7 +1070,7 @@ static int launch_fwd(const BgGraph* g, const float* h, const float* s, const fl
 template <int C>
 static int launch_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
                       const float* m, const float* z, const float* a_src, const float* a_dst, float* P,
-                      float* DU, float* gh_tot, float* gsd, float slope, cudaStream_t st) {
+                      float* DU, float* gh_tot, float* gsd, float slope, cudaStream_t st, const float* inj_h = nullptr) {
     const GatCfg c = gat_cfg<C>(g->N);
     const GnBwdFuse nofuse{};
     if (kPipeOK<C> && c.pipe)
@@ -1067,14 +1079,14 @@ static int launch_bwd(const BgGraph* g, const float* gout, const float* h, const
     else
         launch_k(gat_bwd_dst_kernel<C, false, false>, c.grid, c.threads, 0, st, g->rowptr, g->col, gout, h, s, d, m, z, P, DU, gsd,
                                                                          (int)g->N, slope, c.chunk_rows, c.ipc_shift, c.ahead, nofuse);
-    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src, a_dst, gh_tot, gsd, (int)g->N);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, gout, a_src, a_dst, gh_tot, gsd, inj_h, (int)g->N);
     return check_launch("bg_gat_bwd");
 }
 // destination pass with the GraphNorm backward fused in (go is produced here), then the source pass on that go
 template <int C>
 static int launch_bwd_gn(const BgGraph* g, const GnBwdFuse& f, const float* h, const float* s, const float* d, const float* m,
                          const float* z, const float* a_src, const float* a_dst, float* P, float* DU, float* gh_tot, float* gsd,
-                         float slope, cudaStream_t st) {
+                         float slope, cudaStream_t st, const float* inj_h = nullptr) {
     const GatCfg cd = gat_cfg<C>(g->N, kGatStatsThreads);
     if (kPipeOK<C> && cd.pipe)
         launch_k(gat_bwd_dst_kernel<C, kPipeOK<C>, true>, cd.grid, cd.threads, 0, st, g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
@@ -1083,7 +1095,7 @@ static int launch_bwd_gn(const BgGraph* g, const GnBwdFuse& f, const float* h, c
         launch_k(gat_bwd_dst_kernel<C, false, true>, cd.grid, cd.threads, 0, st, g->rowptr, g->col, nullptr, h, s, d, m, z, P, DU, gsd,
                                                                           (int)g->N, slope, cd.chunk_rows, cd.ipc_shift, cd.ahead, f);
     const GatCfg c = gat_cfg<C>(g->N);
-    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, f.go_out, a_src, a_dst, gh_tot, gsd, (int)g->N);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, P, DU, f.go_out, a_src, a_dst, gh_tot, gsd, inj_h, (int)g->N);
     return check_launch("bg_gat_bwd_gn");
 }
 template <int C>
@@ -1096,7 +1108,7 @@ static int launch_bwd2(const BgGraph* g, const float* Ht, const float* St, const
     launch_k(gat_bwd2_dst_kernel<C>, (unsigned)grid, kThreads, 0, st, g->rowptr, g->col, Ht, St, Dt, gout, h, s, d, m, z,
                                                                A0, A1, A2, A3, gt, sdt, g->N, slope);
     const GatCfg c = gat_cfg<C>(g->N);
-    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, A1, A2, gout, a_src, a_dst, ht_tot, sdt, (int)g->N);
+    BG_GAT_LAUNCH(gat_bwd_src_kernel, g->cscptr, g->cscrow, g->perm, A1, A2, gout, a_src, a_dst, ht_tot, sdt, (const float*)nullptr, (int)g->N);
     return check_launch("bg_gat_bwd2");
 }
 
@@ -1168,30 +1180,50 @@ extern "C" int bg_gat_fwd_gn(const BgGraph* g, const float* h, const float* s, c
 #undef CALL
 }
 
-extern "C" int bg_gat_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
-                          const float* m, const float* z, const float* a_src, const float* a_dst, float* P,
-                          float* DU, float* gh_tot, float* gsd, int32_t C, float slope, void* stream) {
+// bg_gat_bwd / bg_gat_bwd_gn with a cotangent injected at h (second-order sweep, bg_passes.cu): gh_tot = (source pass) + inj_h,
+// added in the source pass's epilogue instead of by a separate axpy launch on the critic update's critical chain
+namespace bg {
+int gat_bwd_inj(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d, const float* m, const float* z,
+                const float* a_src, const float* a_dst, float* P, float* DU, float* gh_tot, float* gsd, int32_t C, float slope,
+                const float* inj_h, void* stream) {
     if (int rc = check_graph(g)) return rc;
     BG_REQUIRE(gout && h && s && d && m && z && a_src && a_dst && P && DU && gh_tot && gsd, BG_EINVAL,
                "bg_gat_bwd: null pointer");
-#define CALL(CC) launch_bwd<CC>(g, gout, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream))
+#define CALL(CC) launch_bwd<CC>(g, gout, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream), inj_h)
     BG_DISPATCH_C(C, CALL)
 #undef CALL
 }
+}  // namespace bg
+
+extern "C" int bg_gat_bwd(const BgGraph* g, const float* gout, const float* h, const float* s, const float* d,
+                          const float* m, const float* z, const float* a_src, const float* a_dst, float* P,
+                          float* DU, float* gh_tot, float* gsd, int32_t C, float slope, void* stream) {
+    return bg::gat_bwd_inj(g, gout, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, C, slope, nullptr, stream);
+}
+
+namespace bg {
+int gat_bwd_gn_inj(const BgGraph* g, const float* gx1, const float* o, const float* x1, const float* gn_w, const float* gn_alpha,
+                   const float* gn_stats, const float* gn_bstats, float keep_scale, const float* inj_o, const float* h, const float* s,
+                   const float* d, const float* m, const float* z, const float* a_src, const float* a_dst, float* P, float* DU,
+                   float* go, float* gh_tot, float* gsd, int32_t C, float slope, const float* inj_h, void* stream) {
+    if (int rc = check_graph(g)) return rc;
+    BG_REQUIRE(gx1 && o && x1 && gn_w && gn_alpha && gn_stats && gn_bstats && h && s && d && m && z && a_src && a_dst && P && DU &&
+                   go && gh_tot && gsd,
+               BG_EINVAL, "bg_gat_bwd_gn: null pointer");
+    const GnBwdFuse f{gx1, o, x1, inj_o, gn_w, gn_alpha, gn_stats, gn_bstats, go, keep_scale};
+#define CALL(CC) launch_bwd_gn<CC>(g, f, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream), inj_h)
+    BG_DISPATCH_C(C, CALL)
+#undef CALL
+}
+}  // namespace bg
 
 extern "C" int bg_gat_bwd_gn(const BgGraph* g, const float* gx1, const float* o, const float* x1, const float* gn_w,
                              const float* gn_alpha, const float* gn_stats, const float* gn_bstats, float keep_scale,
                              const float* inj_o, const float* h, const float* s, const float* d, const float* m, const float* z,
                              const float* a_src, const float* a_dst, float* P, float* DU, float* go, float* gh_tot, float* gsd,
                              int32_t C, float slope, void* stream) {
-    if (int rc = check_graph(g)) return rc;
-    BG_REQUIRE(gx1 && o && x1 && gn_w && gn_alpha && gn_stats && gn_bstats && h && s && d && m && z && a_src && a_dst && P && DU &&
-                   go && gh_tot && gsd,
-               BG_EINVAL, "bg_gat_bwd_gn: null pointer");
-    const GnBwdFuse f{gx1, o, x1, inj_o, gn_w, gn_alpha, gn_stats, gn_bstats, go, keep_scale};
-#define CALL(CC) launch_bwd_gn<CC>(g, f, h, s, d, m, z, a_src, a_dst, P, DU, gh_tot, gsd, slope, as_stream(stream))
-    BG_DISPATCH_C(C, CALL)
-#undef CALL
+    return bg::gat_bwd_gn_inj(g, gx1, o, x1, gn_w, gn_alpha, gn_stats, gn_bstats, keep_scale, inj_o, h, s, d, m, z, a_src, a_dst, P, DU,
+                              go, gh_tot, gsd, C, slope, nullptr, stream);
 }
 
 extern "C" int bg_gat_bwd2(const BgGraph* g, const float* Ht, const float* St, const float* Dt, const float* gout,

@@ -86,6 +86,58 @@ __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __r
     for (int i = threadIdx.x; i < K * C; i += kThreads) out[i] = acc[i];
 }
 
+// The same for K <= 8 types (the models' 7): per-type sums in REGISTERS.  The kernel above walks its rows one at a time through a
+// shared-memory read-modify-write (a dependent chain with the global load inside: 37-49 us at N = 15 k on the generator's
+// backward chain, profiles/r02b_summary.md); here thread (slot, c) owns column c of every (kThreads / C)-th row of the CTA's
+// chunk, keeps 8 accumulators, and has four independent row loads in flight.  Slots, then CTAs, are folded in a fixed order.
+__global__ void __launch_bounds__(kThreads) type_scatter8_kernel(const float* __restrict__ g, int64_t ld, const int32_t* __restrict__ type,
+                                                                 int64_t N, int C, int K, int G, float* out,
+                                                                 unsigned int* counter, float* partials) {
+    pdl_prologue();
+    extern __shared__ float acc[];  // [nslot][K*C]; the head doubles as the fold result
+    const int nslot = kThreads / C, c = threadIdx.x % C, slot = threadIdx.x / C;
+    const int64_t chunk = ceil_div(N, G);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    if (slot < nslot) {
+        int64_t r = r0 + slot;
+        for (; r + 3 * nslot < r1; r += 4 * nslot) {
+            int t[4];
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                t[q] = __ldg(type + r + q * nslot);
+                v[q] = __ldg(g + (r + q * nslot) * ld + c);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += t[q] == k ? v[q] : 0.f;
+        }
+        for (; r < r1; r += nslot) {
+            const int t = __ldg(type + r);
+            const float v = __ldg(g + r * ld + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += t == k ? v : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < K) acc[(slot * K + k) * C + c] = a[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * C; i += kThreads) {
+        float t = 0.f;
+        for (int sl = 0; sl < nslot; ++sl) t += acc[sl * K * C + i];
+        partials[(int64_t)blockIdx.x * K * C + i] = t;
+    }
+    __shared__ float red[kThreads];
+    __syncthreads();
+    if (!hier_fold(partials, partials + (int64_t)G * K * C, K * C, counter, red, acc)) return;
+    for (int i = threadIdx.x; i < K * C; i += kThreads) out[i] = acc[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // H7: Gumbel-softmax + straight-through, one thread per row (K <= 16)
 // ---------------------------------------------------------------------------------------------
@@ -366,8 +418,12 @@ extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* ty
     BG_REQUIRE(ws_bytes >= bg_type_scatter_sum_ws(N, C, K), BG_EINVAL, "bg_type_scatter_sum: workspace too small");
     BG_REQUIRE((size_t)K * C * sizeof(float) <= 48 * 1024, BG_EUNSUPPORTED, "bg_type_scatter_sum: K*C too large");
     const int G = scatter_splits(N);
-    launch_k(type_scatter_kernel, G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream), 
-        g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
+    if (K <= 8 && C <= kThreads)
+        launch_k(type_scatter8_kernel, G, kThreads, (size_t)(kThreads / C) * K * C * sizeof(float), as_stream(stream),
+            g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
+    else
+        launch_k(type_scatter_kernel, G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream),
+            g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
     return check_launch("bg_type_scatter_sum");
 }
 

@@ -50,6 +50,13 @@ __device__ __forceinline__ void cta_colsum(float (&val)[K * ColMap<C>::VEC], flo
     __syncthreads();
 }
 
+// Column of flat element i in an [N, C] row-major tensor.  Every width the models use is a power of two: a mask instead of
+// a 64-bit modulo (ncu r01h: gn_apply_kernel spent ~210 instructions per 128-bit element group, issue-bound at 48 % of the copy
+// bandwidth at N = 1e6 - four runtime `% C` per group were a third of that).
+__device__ __forceinline__ int col_of(int64_t i, int C) {
+    return (C & (C - 1)) == 0 ? (int)(i & (int64_t)(C - 1)) : (int)(i % C);
+}
+
 // y = w*(o - alpha*mu)*rstd + beta ; x1 = relu(y) * keep / keep_prob      (flat elementwise)
 // keep: explicit uint8 mask, or (keep == NULL && keep_prob < 1) a Philox Bernoulli(keep_prob) mask.
 __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restrict__ o, const float* __restrict__ w,
@@ -73,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
 #pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(o) + i);
-        const int c0 = (int)((i * 4) % C);
+        const int c0 = col_of(i * 4, C);
         float xv[4] = {x.x, x.y, x.z, x.w}, y[4];
         bool kp[4] = {true, true, true, true};
         if (keep) {
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int c = (c0 + k) % C;
+            const int c = (C & 3) == 0 ? c0 + k : col_of(c0 + k, C);  // C % 4 == 0: the group never straddles a row
             float t = fmaf(xv[k], sc[c], sh[c]);
             t = t > 0.f ? t : 0.f;
             y[k] = kp[k] ? t * keep_scale : 0.f;
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const float* __restr
     }
     if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
         const int64_t i = n4 * 4 + threadIdx.x;
-        const int c = (int)(i % C);
+        const int c = col_of(i, C);
         float t = fmaf(o[i], sc[c], sh[c]);
         t = t > 0.f ? t : 0.f;
         bool kp = true;
@@ -298,12 +305,12 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(BwdMoments p, co
     const int64_t n4 = total / 4;  // 128-bit loads/stores (C >= 4: a float4 never straddles a row)
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     auto one4 = [&](int64_t i, const float4& xa, const float4& ga, const float4& oa) {
-        const int c0 = (int)((i * 4) % C);
+        const int c0 = col_of(i * 4, C);
         const float xv[4] = {xa.x, xa.y, xa.z, xa.w}, gv[4] = {ga.x, ga.y, ga.z, ga.w}, ov[4] = {oa.x, oa.y, oa.z, oa.w};
         float r[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int c = (c0 + k) % C;
+            const int c = (C & 3) == 0 ? c0 + k : col_of(c0 + k, C);
             const float gy = xv[k] > 0.f ? gv[k] * p.keep_scale : 0.f;
             r[k] = gy * k1[c] - (ov[k] - sh[c]) * k2[c] - k3[c];
         }
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(BwdMoments p, co
              __ldg(reinterpret_cast<const float4*>(p.o) + i));
     if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
         const int64_t t = n4 * 4 + threadIdx.x;
-        const int c = (int)(t % C);
+        const int c = col_of(t, C);
         const float gy = p.x1[t] > 0.f ? p.gx1[t] * p.keep_scale : 0.f;
         go[t] = gy * k1[c] - (p.o[t] - sh[c]) * k2[c] - k3[c];
     }
@@ -426,7 +433,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd2_apply_kernel(Bwd2Moments p, 
     }
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
-        const int c = (int)(i % C);
+        const int c = col_of(i, C);
         const bool on = p.x1[i] > 0.f;
         const float gy = on ? p.gx1[i] * p.keep_scale : 0.f;
         const float oh = p.o[i] - sh[c];

@@ -8,6 +8,7 @@
 // Parameter order = torch's named_parameters() order of the reference modules:
 //   Linear+LayerNorm layer: W, b, gamma, beta        bare Linear: W, b
 //   conv block: att_src, att_dst, bias, lin.weight, gn.weight, gn.bias, gn.mean_scale
+#include <stdlib.h>
 #include <vector>
 
 #include "bg_common.cuh"
@@ -201,6 +202,33 @@ static int init_queue(WgradQueue& q, float* red, size_t red_bytes) {
 
 static inline BgSeg seg(const float* p, int width, int ld, const int32_t* gather = nullptr) { return BgSeg{p, gather, width, ld}; }
 
+// The type-matched encoder runs on the K table rows: K <= 8 => the whole chain is one single-CTA launch per direction
+// (bg_smallmlp.cu) instead of a launch (backward: three) per layer.  BG_SMALL_MLP=0 keeps the per-layer launches (A/B switch).
+static bool small_chain_ok(const DenseL* l, int n, int rows) {
+    static const bool on = !(getenv("BG_SMALL_MLP") && atoi(getenv("BG_SMALL_MLP")) == 0);
+    if (!on || n < 1 || n > BG_SMALL_MAX_LAYERS || rows < 1 || rows > BG_SMALL_MAX_ROWS) return false;
+    for (int i = 0; i < n; ++i)
+        if (l[i].cin > 128 || l[i].cout > 128 || (i > 0 && l[i].cin != l[i - 1].cout)) return false;
+    return true;
+}
+static void small_chain_fill(const Ctx& c, const DenseL* l, int n, BgSmallLayer* out, bool grads) {
+    for (int i = 0; i < n; ++i) {
+        BgSmallLayer& a = out[i];
+        a = BgSmallLayer{};
+        a.W = c.P[l[i].pW];
+        a.bias = l[i].pb >= 0 ? c.P[l[i].pb] : nullptr;
+        if (l[i].pg >= 0) { a.gamma = c.P[l[i].pg]; a.beta = c.P[l[i].pbeta]; a.xhat = l[i].xhat; a.rstd = l[i].rstd; }
+        a.cin = l[i].cin; a.cout = l[i].cout; a.act = l[i].act;
+        a.out = l[i].out;
+        if (grads && c.G) {
+            a.dW = c.g(l[i].pW);
+            a.dbias = c.g(l[i].pb);
+            a.dgamma = c.g(l[i].pg);
+            a.dbeta = c.g(l[i].pbeta);
+        }
+    }
+}
+
 static int dense_fwd_call(const Ctx& c, const DenseL& l, int64_t rows, const BgSeg* segs, int nseg, bool save_ln) {
     BgDense a{};
     a.N = rows; a.nseg = nseg;
@@ -290,11 +318,11 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
         if (!moments_done)
             BG_TRY(bg_graphnorm_bwd_moments(gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, keep_scale, c.N, C, gnpar,
                                             c.G ? c.accumulate : 0, bst, c.red, c.red_bytes, c.st));
-        BG_TRY(bg_gat_bwd_gn(c.graph, gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, bst, keep_scale, inj_o, L.h, L.s, L.d, L.m,
-                             L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, go, gh, gsd, C, 0.2f, c.st));
+        BG_TRY(gat_bwd_gn_inj(c.graph, gx1, L.o, L.x1, c.P[L.p_gw], c.P[L.p_ga], L.stats, bst, keep_scale, inj_o, L.h, L.s, L.d, L.m,
+                              L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, go, gh, gsd, C, 0.2f, inj_h, c.st));
     } else {
         go = const_cast<float*>(inj_o);
-        BG_TRY(bg_gat_bwd(c.graph, go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, gh, gsd, C, 0.2f, c.st));
+        BG_TRY(gat_bwd_inj(c.graph, go, L.h, L.s, L.d, L.m, L.z, c.P[L.p_as], c.P[L.p_ad], Pe, DU, gh, gsd, C, 0.2f, inj_h, c.st));
     }
     BgSeg ones = seg(nullptr, 1, 0), hseg = seg(L.h, C, C), xseg = seg(x_in, L.cin, L.cin);
     if (c.G && inj_h) {  // bias, [att_src; att_dst] see gh BEFORE the injection at h (those cotangents are h-path only)
@@ -302,7 +330,7 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
                          wg(c.N, gsd, 2, 2, &hseg, 1, c.g(L.p_as), C, nullptr, c.accumulate)};
         BG_TRY(wgrad_launch(pr, 2, *c.q, as_stream(c.st)));
     }
-    if (inj_h) BG_TRY(bg_axpy(gh, inj_h, 1.f, c.N * C, c.st));
+    // the injection at h (gh += inj_h) rides in the source pass's epilogue (gat_bwd_*_inj above)
     if (c.G) {
         BgWgrad pr[3] = {wg(c.N, gh, C, C, &xseg, 1, c.g(L.p_W), L.cin, nullptr, c.accumulate),
                          wg(c.N, go, C, C, &ones, 1, c.g(L.p_bias), 1, nullptr, c.accumulate),
@@ -328,10 +356,11 @@ static int conv_backward(const Ctx& c, ConvL& L, const float* x_in, const float*
     } else if (gx_out) {
         BG_TRY(matmul_nn(c, gh, c.N, C, c.P[L.p_W], L.cin, 0, L.cin, gx_out, gate_x));
     }
-    if (keep && gx1) BG_TRY(cudaMemcpyAsync(L.b_gx1, gx1, (size_t)c.N * C * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) ==
-                                    cudaSuccess
-                                ? BG_OK
-                                : BG_ECUDA);
+    // second-order sweep needs gx1: the callers let the producer write it straight into the saved slot (no copy on the chain)
+    if (keep && gx1 && gx1 != L.b_gx1)
+        BG_TRY(cudaMemcpyAsync(L.b_gx1, gx1, (size_t)c.N * C * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(c.st)) == cudaSuccess
+                   ? BG_OK
+                   : BG_ECUDA);
     return BG_OK;
 }
 
@@ -439,11 +468,19 @@ extern "C" int bg_gen_forward(const BgModelDesc* md, const float* const* params,
     // type-matched encoder on the K table rows (row-wise ops commute with the per-voxel gather)
     const float* e = in->table;
     int ew = md->local_dim;
-    for (int i = 0; i < g.n_menc; ++i) {
-        BgSeg s = seg(e, ew, ew);
-        BG_TRY(dense_fwd_call(c, g.menc[i], K, &s, 1, true));
-        e = g.menc[i].out;
-        ew = g.menc[i].cout;
+    if (small_chain_ok(g.menc, g.n_menc, K)) {
+        BgSmallLayer sl[BG_SMALL_MAX_LAYERS];
+        small_chain_fill(c, g.menc, g.n_menc, sl, false);
+        BG_TRY(bg_small_mlp_fwd(sl, g.n_menc, e, K, stream));
+        e = g.menc[g.n_menc - 1].out;
+        ew = g.menc[g.n_menc - 1].cout;
+    } else {
+        for (int i = 0; i < g.n_menc; ++i) {
+            BgSeg s = seg(e, ew, ew);
+            BG_TRY(dense_fwd_call(c, g.menc[i], K, &s, 1, true));
+            e = g.menc[i].out;
+            ew = g.menc[i].cout;
+        }
     }
     const BgSeg enc = seg(e, md->le_dim, md->le_dim, in->type32);
     const BgSeg vx = seg(in->vx, md->voxel_dim, md->voxel_dim), zz = seg(z, md->z_dim, md->z_dim);
@@ -585,6 +622,11 @@ extern "C" int bg_gen_backward(const BgModelDesc* md, const float* const* params
     BG_TRY(bg_type_scatter_sum(g_e2, le, in->type32, N, le, K, ge2, red, red_bytes, stream));
     BG_TRY(bg_axpy(ge, ge2, 1.f, (int64_t)K * le, stream));
     const float* gcur = ge;
+    if (small_chain_ok(net.menc, net.n_menc, K)) {
+        BgSmallLayer sl[BG_SMALL_MAX_LAYERS];
+        small_chain_fill(c, net.menc, net.n_menc, sl, true);
+        BG_TRY(bg_small_mlp_bwd(sl, net.n_menc, in->table, K, ge, nullptr, c.accumulate, stream));
+    } else
     for (int i = net.n_menc - 1; i >= 0; --i) {
         const float* xin = i == 0 ? in->table : net.menc[i - 1].out;
         BgSeg s = seg(xin, net.menc[i].cin, net.menc[i].cin);
@@ -695,7 +737,8 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
             if (i == 3) l.out = const_cast<float*>(score);
             int win[1][2] = {{0, l.cin}};
             const bool gate = i > 0 && plain_relu(d.dec[i - 1]);  // dec[i-1]'s ReLU backward rides on this dgrad
-            float* gin[1] = {gate && keep ? d.dec[i - 1].b_gz : T.f((size_t)N * l.cin)};
+            // i == 0: the product's output is gx1 of the top block - written into its saved slot when the sweep is kept
+            float* gin[1] = {gate && keep ? d.dec[i - 1].b_gz : (i == 0 && keep ? d.conv[d.n_conv - 1].b_gx1 : T.f((size_t)N * l.cin))};
             float* gzbuf = g_is_gz ? nullptr : (keep ? l.b_gz : T.f((size_t)N * l.cout));
             const float* gz_used = nullptr;
             BG_TRY(dense_backward(c, l, N, &s, 1, g, gzbuf, win, gin, 1, &gz_used, g_is_gz, gate ? d.dec[i - 1].out : nullptr));
@@ -711,7 +754,7 @@ static int disc_backward_impl(const BgModelDesc* md, DiscNet& d, Ctx& c, const B
     for (int k = d.n_conv - 1; k >= 0; --k) {
         const float* x_in = k == 0 ? d.pre[1].out : d.conv[k - 1].x1;
         const bool gate = k == 0 && plain_relu(d.pre[1]);
-        float* gx = gate && keep ? d.pre[1].b_gz : T.f((size_t)N * d.conv[k].cin);
+        float* gx = gate && keep ? d.pre[1].b_gz : (k > 0 && keep ? d.conv[k - 1].b_gx1 : T.f((size_t)N * d.conv[k].cin));
         BG_TRY(conv_backward(c, d.conv[k], x_in, g, training_scale, inj_o ? inj_o[k] : nullptr, inj_h ? inj_h[k] : nullptr, keep, T,
                              gx, gate ? d.pre[1].out : nullptr, k > 0 ? &d.conv[k - 1] : nullptr));
         g = gx;

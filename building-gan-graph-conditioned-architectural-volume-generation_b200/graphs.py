@@ -57,7 +57,7 @@ class GraphedStep:
         self.dev = next(discriminator.parameters()).device
         # the stream of the gradient-penalty chain (the step's critical path) outranks the lanes (-1) and the weight-gradient
         # side streams (0): 12.8 -> 12.1 ms per step (the batched weight-gradient launches fill every SM for ~40 us)
-        self.main = torch.cuda.Stream(device=self.dev, priority=-2)
+        self.main = torch.cuda.Stream(device=self.dev, priority=_step.stream_priorities()[0])
         self.lanes = _step.Lanes.get(self.dev)
         self.pool_s, self.pool_c = torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle()
         self.base_s = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -151,7 +151,7 @@ class GraphedStep:
         models._philox_calls = t0 + R * S.calls  # S's replays use tickets t0+1 .. t0+R*S.calls; C's start after them
         c0 = models._philox_calls
         C = self._capture_critic(lb, vb, sample)
-        taken, gen_out = None, None
+        taken, gen_out, side = None, None, None
         for k in range(R):
             with torch.cuda.stream(gen):
                 if taken is not None:
@@ -165,7 +165,10 @@ class GraphedStep:
                     models._philox_calls = c0 + R * C.calls  # the tickets an eager run of the same calls would have consumed
                     z = torch.randn(1, n, cfg.Z_DIM, device=dev)
                     gen_out = self.G(lb, vb, z)
-                    for t in gen_out:
+                    # the critic-independent loss terms and their gradients: here, beside the critic updates (step.SideLoss)
+                    side = _step.SideLoss(vb, gen_out[0], gen_out[1].unsqueeze(0), cfg)
+                    for t in tuple(gen_out) + (side.r_main, side.ce, side.r_void, side.far, side.g_logits, side.g_hard_main,
+                                        side.g_hard_void):
                         t.record_stream(main)
                     gen_ready = gen.record_event()
             main.wait_event(ready)
@@ -182,7 +185,7 @@ class GraphedStep:
         logits, hard, soft = gen_out
         hard = hard.unsqueeze(0)
         self.opt_g.zero_grad()
-        g_loss = _step.generator_loss(self.D, lb, vb, logits, hard, cfg)
+        g_loss = _step.generator_loss(self.D, lb, vb, logits, hard, cfg, side=side)
         g_loss.backward()  # the generator's backward pass runs on the stream of its forward (autograd's stream affinity)
         main.wait_stream(gen)
         if self.grad_sync is not None:

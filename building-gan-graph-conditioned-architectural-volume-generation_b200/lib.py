@@ -72,6 +72,16 @@ class BgWgrad(C.Structure):
                 ("workspace", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+SMALL_MAX_LAYERS, SMALL_MAX_ROWS = 8, 8
+
+
+class BgSmallLayer(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("act", C.c_int32),
+                ("out", C.c_void_p), ("xhat", C.c_void_p), ("rstd", C.c_void_p),
+                ("dW", C.c_void_p), ("dbias", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _P, _I64, _I32, _F, _SZ, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_uint64
 _MD, _BI, _GR = C.POINTER(BgModelDesc), C.POINTER(BgBatchIn), C.POINTER(BgGraph)
@@ -86,6 +96,8 @@ SIGNATURES = {
     "bg_set_dense_tc": (C.c_int, [_I32]),
     "bg_set_rowdense": (C.c_int, [_I32]),
     "bg_set_dense_mma": (C.c_int, [_I32]),
+    "bg_small_mlp_fwd": (C.c_int, [C.POINTER(BgSmallLayer), _I32, _P, _I32, _P]),
+    "bg_small_mlp_bwd": (C.c_int, [C.POINTER(BgSmallLayer), _I32, _P, _I32, _P, _P, _I32, _P]),
     "bg_dense_wgrad_ws": (_SZ, [_I64, _I32, _I32]),
     "bg_dense_wgrad": (C.c_int, [C.POINTER(BgWgrad), _P]),
     "bg_wgrad_multi_ws": (_SZ, [_I64, _I32, _P, _P]),
@@ -386,6 +398,66 @@ def _fill_segs(arr, segs: Sequence[Seg]) -> Tuple[int, int]:
 
 
 @_op("dense_fwd", 1)
+def _small_chain(x: Tensor, layers):
+    """layers: list of dicts {W, bias?, ln? = (gamma, beta), act?}; returns (ctypes array, per-layer tensor dicts)."""
+    _cf32(x, "x")
+    if not 1 <= len(layers) <= SMALL_MAX_LAYERS:
+        raise RuntimeError(f"small_mlp: {len(layers)} layers (1..{SMALL_MAX_LAYERS})")
+    arr = (BgSmallLayer * len(layers))()
+    for a, l in zip(arr, layers):
+        W = _cf32(l["W"], "W")
+        a.W, a.cout, a.cin = W.data_ptr(), W.shape[0], W.shape[1]
+        a.bias = _p(l.get("bias"))
+        if l.get("ln") is not None:
+            a.gamma, a.beta = l["ln"][0].data_ptr(), l["ln"][1].data_ptr()
+        a.act = l.get("act", ACT_NONE)
+    return arr
+
+
+def small_mlp_fwd(x: Tensor, layers):
+    """bg_small_mlp_fwd: the whole chain of Linear (+LayerNorm) (+activation) layers on <= 8 rows in one launch.
+    Returns a list of {"out", "xhat"?, "rstd"?} per layer."""
+    arr = _small_chain(x, layers)
+    rows, dev, res = x.shape[0], x.device, []
+    for a, l in zip(arr, layers):
+        r = {"out": torch.empty(rows, a.cout, dtype=torch.float32, device=dev)}
+        a.out = r["out"].data_ptr()
+        if l.get("ln") is not None:
+            r["xhat"] = torch.empty(rows, a.cout, dtype=torch.float32, device=dev)
+            r["rstd"] = torch.empty(rows, dtype=torch.float32, device=dev)
+            a.xhat, a.rstd = r["xhat"].data_ptr(), r["rstd"].data_ptr()
+        res.append(r)
+    _check(load().bg_small_mlp_fwd(arr, len(layers), x.data_ptr(), rows, _stream()))
+    return res
+
+
+def small_mlp_bwd(x: Tensor, layers, saved, gout: Tensor, need_gin: bool = True, grads=None):
+    """bg_small_mlp_bwd.  ``saved`` = small_mlp_fwd's result.  ``grads`` (optional): per-layer dicts of existing
+    {"dW", "dbias", "dgamma", "dbeta"} tensors to ACCUMULATE into; otherwise fresh tensors are written.
+    Returns (gin or None, list of per-layer gradient dicts)."""
+    arr = _small_chain(x, layers)
+    _cf32(gout, "gout")
+    rows, dev = x.shape[0], x.device
+    out = []
+    for i, (a, l, sv) in enumerate(zip(arr, layers, saved)):
+        a.out = sv["out"].data_ptr()
+        if l.get("ln") is not None:
+            a.xhat, a.rstd = sv["xhat"].data_ptr(), sv["rstd"].data_ptr()
+        g = dict(grads[i]) if grads is not None else {}
+        if grads is None:
+            g["dW"] = torch.empty(a.cout, a.cin, dtype=torch.float32, device=dev)
+            if l.get("bias") is not None:
+                g["dbias"] = torch.empty(a.cout, dtype=torch.float32, device=dev)
+            if l.get("ln") is not None:
+                g["dgamma"] = torch.empty(a.cout, dtype=torch.float32, device=dev)
+                g["dbeta"] = torch.empty(a.cout, dtype=torch.float32, device=dev)
+        a.dW, a.dbias, a.dgamma, a.dbeta = _p(g.get("dW")), _p(g.get("dbias")), _p(g.get("dgamma")), _p(g.get("dbeta"))
+        out.append(g)
+    gin = torch.empty(rows, arr[0].cin, dtype=torch.float32, device=dev) if need_gin else None
+    _check(load().bg_small_mlp_bwd(arr, len(layers), x.data_ptr(), rows, gout.data_ptr(), _p(gin), int(grads is not None), _stream()))
+    return gin, out
+
+
 def dense_fwd(segs: Sequence[Seg], W: Tensor, bias: Optional[Tensor] = None, ln: Optional[Tuple[Tensor, Tensor]] = None,
               act: int = ACT_NONE, att: Optional[Tuple[Tensor, Tensor]] = None, transposed: bool = False,
               save_ln: bool = False, out: Optional[Tensor] = None, cols: Optional[Tuple[int, int]] = None,

@@ -879,6 +879,9 @@ class _DiscNativeFn(torch.autograd.Function):
         if getattr(model, "debug_keep_saved", False):
             model.debug_saved = _saved_views(model, ws, n, score, False)
         ctx.need, ctx.bucket_mode, ctx.lane = need, ticket[2], st.lane
+        # an undefined output gradient stays None (see backward): autograd would otherwise hand this node a zero-filled g_score
+        ctx.set_materialize_grads(False)
+        ctx.n_inputs = 6 + len(tensors)
         if need:
             ctx.model, ctx.bc, ctx.ws, ctx.training = model, bc, ws, model.training
             ctx.save_for_backward(label, score, *tensors)
@@ -886,6 +889,8 @@ class _DiscNativeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_score):
+        if g_score is None:  # nothing flows into the score (e.g. the gradient-penalty pass inside d_loss.backward())
+            return (None,) * ctx.n_inputs
         if not ctx.need:
             raise RuntimeError("discriminator backward called but the forward ran without grad")
         label, score, *tensors = ctx.saved_tensors
@@ -897,8 +902,13 @@ class _DiscNativeFn(torch.autograd.Function):
         # for the parameters' anchor in both cases; a custom Function does not see the engine's pruning), so the latter is
         # documented as unsupported in this mode (module docstring) instead of being detected: use
         # BG_GRADS=autograd for it.
+        # `score` enters detached: the first-order backward reads it as a saved value only.  Passed as this node's own output
+        # it would (under create_graph=True) put an edge from the differentiable backward op back to this forward node, and
+        # d_loss.backward() of the WGAN-GP critic loss would then run a second, full first-order backward of the gradient-
+        # penalty pass with an all-zero g_score (one whole sweep + its weight gradients on the step's critical path,
+        # profiles/r02b_summary.md)
         outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training,
-                                      (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score,
+                                      (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score.detach(),
                                       g_score.contiguous(), label, *tensors)
         return (None, None, None, None, None) + tuple(outs)
 

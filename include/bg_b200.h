@@ -142,6 +142,32 @@ int bg_set_rowdense(int32_t on);
  * switches it off.  Returns the previous setting. */
 int bg_set_dense_mma(int32_t on);
 
+/* A chain of n <= BG_SMALL_MAX_LAYERS Linear (+LayerNorm eps 1e-5) (+activation) layers on rows <= BG_SMALL_MAX_ROWS rows as ONE
+ * single-CTA launch per direction (csrc/bg_smallmlp.cu): the generator's matched_features_encoder on the K = 7 rows of the
+ * type-matched program table (reference models.py:36-47,131-133), where a launch per layer is pure latency.  Widths 1..128,
+ * layer i+1 reads layer i's `out`.  Forward saves out / xhat / rstd like bg_dense_fwd.  Backward takes gout[rows, cout_last],
+ * writes (accumulate != 0: adds into) dW / dbias / dgamma / dbeta of every layer whose pointers are non-null and, when gin is
+ * non-null, the input gradient gin[rows, cin_0].  Deterministic (fixed summation order). */
+#define BG_SMALL_MAX_LAYERS 8
+#define BG_SMALL_MAX_ROWS 8
+typedef struct BgSmallLayer {
+    const float* W;       /* [cout, cin] row-major */
+    const float* bias;    /* [cout] or NULL */
+    const float* gamma;   /* LayerNorm weight [cout] or NULL => no LayerNorm */
+    const float* beta;
+    int32_t cin, cout, act;
+    float* out;           /* [rows, cout] */
+    float* xhat;          /* [rows, cout], LayerNorm layers (forward: optional; backward: required) */
+    float* rstd;          /* [rows] */
+    float* dW;            /* backward outputs, each optional */
+    float* dbias;
+    float* dgamma;
+    float* dbeta;
+} BgSmallLayer;
+int bg_small_mlp_fwd(const BgSmallLayer* layers, int32_t n, const float* x, int32_t rows, void* stream);
+int bg_small_mlp_bwd(const BgSmallLayer* layers, int32_t n, const float* x, int32_t rows, const float* gout, float* gin,
+                     int32_t accumulate, void* stream);
+
 /* Weight gradient: dW[o,k] = sum_n gz[n,o] * X[n,k] over the segment list X (a ones segment
  * yields the bias gradient as an extra column); deterministic split-N reduction.
  * dW is written with leading dimension ld_dw; accumulate!=0 adds into dW (and dbias).

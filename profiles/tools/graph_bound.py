@@ -11,7 +11,7 @@ cfg = Configuration()
 torch.manual_seed(777)
 G, D = VoxelGNNGenerator(cfg, 17, 12).to(dev), VoxelGNNDiscriminator(cfg, 17, 12).to(dev)
 og, od = Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS), Adam(D.parameters(), lr=2e-4, betas=cfg.BETAS)
-host = bench._make_batches(0, 1, 32, pin=False)
+host = bench._make_batches(0, 1, int(os.environ.get("BATCH", "32")), pin=False)
 lb, vb = bench._clone_to(*host[0], dev)
 gs = graphs.GraphedStep(G, D, og, od, cfg)
 for _ in range(4):

@@ -35,7 +35,7 @@ win = [e for e in ks if w0 <= e["ts"] < w1]
 print(f"critic update window {(w1-w0)/1e3:.3f} ms, {len(win)} GPU ops")
 step0 = adams[5]["ts"] + adams[5]["dur"]
 json.dump([[round(e["ts"] - step0, 2), e["dur"], e["args"].get("stream"), e["name"][:70]] for e in ks if e["ts"] >= step0],
-          open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "s3_step_ops.json"), "w"))
+          open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "gpurun_out", "s4_step_ops.json"), "w"))
 st = collections.Counter(e["args"].get("stream") for e in win if "bwd2" in e["name"])
 chain_stream = st.most_common(1)[0][0]
 print("per stream in window:", {s: (len(v := [e for e in win if e['args'].get('stream') == s]), round(sum(e['dur'] for e in v) / 1e3, 3)) for s in set(e['args'].get('stream') for e in win)})

@@ -119,3 +119,55 @@ def test_fused_critic_loss_matches_torch():
     # deterministic
     got2 = bstep._CriticLossFn.apply(d_fake, d_real, grad, lam)
     assert got2.item() == got.item()
+
+
+def test_precomputed_side_loss_matches_the_spelled_generator_loss():
+    """step.SideLoss (critic-independent generator-loss terms + their gradients, evaluated ahead of the critic pass) gives the
+    same loss value bit for bit and the same parameter gradients as the reference spelling (trainer.py:334-385)."""
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
+    G.eval(), D.eval()
+    n = vb.num_nodes
+    z = torch.randn(1, n, cfg.Z_DIM, generator=torch.Generator().manual_seed(5)).to(DEV)
+    noise = (-torch.empty(n, 7).exponential_(generator=torch.Generator().manual_seed(6)).log()).to(DEV)
+    res = []
+    for use_side in (False, True):
+        G.zero_grad(), D.zero_grad()
+        logits, hard, _ = G(lb, vb, z, noise)
+        side = step.SideLoss(vb, logits, hard.unsqueeze(0), cfg) if use_side else None
+        loss = step.generator_loss(D, lb, vb, logits, hard.unsqueeze(0), cfg, side=side)
+        loss.backward()
+        res.append((loss.detach().clone(), [p.grad.detach().clone() for p in G.parameters()]))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert_close(b, a, 1e-6, "generator gradient with the precomputed side terms")
+
+
+def test_gradient_penalty_backward_runs_no_zero_gradient_sweep():
+    """d_loss.backward() of the WGAN-GP critic loss must not visit the gradient-penalty pass's forward node: nothing flows into
+    its score (only into its input gradient), and a materialised all-zero g_score would cost one full first-order backward per
+    critic update on the step's critical path.  Counted by the library's launch counter; gradients checked against a run whose
+    forward node IS visited (a zero-weighted score term added to the loss)."""
+    cfg, G, D, oG, oD, lb, vb, olb, ovb = _setup()
+    D.eval()
+    n = vb.num_nodes
+    g = torch.Generator().manual_seed(11)
+    soft = torch.softmax(torch.randn(n, 7, generator=g), dim=1).to(DEV)
+    e = torch.rand(n, 1, generator=g).to(DEV)
+
+    def run(visit_forward_node: bool):
+        D.zero_grad()
+        mixed = lib.gp_mix(e, vb.types_onehot.contiguous(), soft).requires_grad_(True)
+        score = D(lb, vb, mixed.unsqueeze(0))
+        (grad,) = torch.autograd.grad(score, mixed, torch.ones_like(score), create_graph=True, only_inputs=True)
+        loss = ((grad.norm(dim=1) - 1) ** 2).mean() * cfg.LAMBDA_GP
+        if visit_forward_node:
+            loss = loss + 0.0 * score.sum()
+        l0 = lib.LAUNCHES
+        loss.backward()
+        return lib.LAUNCHES - l0, [p.grad.detach().clone() for p in D.parameters()]
+
+    n_skip, g_skip = run(False)
+    n_visit, g_visit = run(True)
+    assert n_skip < n_visit, (n_skip, n_visit)
+    for a, b in zip(g_skip, g_visit):
+        assert_close(a, b, 1e-6, "gradient-penalty parameter gradients")
