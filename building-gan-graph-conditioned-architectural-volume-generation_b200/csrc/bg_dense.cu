@@ -884,31 +884,62 @@ __global__ void __launch_bounds__(kThreads) ln_act_bwd_kernel(const float* __res
         dg[v] = 0.f;
         db[v] = 0.f;
     }
-    for (int64_t r = r0 + slot; r < r1; r += RPC) {
-        Vec<VEC> g, o, xh;
-        const int64_t off = r * C + sub * VEC;
-        g.load(gout + off);
-        o.load(out + off);
-        xh.load(xhat + off);
-        const float rs = __ldg(rstd + r);
-        float gx[VEC], s1 = 0.f, s2 = 0.f;
+    // four rows of a lane group in flight per trip (a warp walks ~13 rows of a 128-wide layer at N = 15 k: one row at a time
+    // was 13 dependent load -> shuffle-reduce -> store chains, 18-25 us per launch on the generator's backward chain); the
+    // per-thread dgamma / dbeta sums still add the rows in ascending order: same bits as the one-row loop
+    constexpr int U = 4;
+    for (int64_t r = r0 + slot; r < r1; r += U * RPC) {
+        Vec<VEC> g[U], o[U], xh[U];
+        float rs[U];
+        bool ok[U];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            float gy = g.v[v];
-            if (act == BG_ACT_LRELU) gy = o.v[v] > 0.f ? gy : 0.2f * gy;
-            else if (act == BG_ACT_RELU) gy = o.v[v] > 0.f ? gy : 0.f;
-            dg[v] = fmaf(gy, xh.v[v], dg[v]);
-            db[v] += gy;
-            gx[v] = gy * gam[v];
-            s1 += gx[v];
-            s2 = fmaf(gx[v], xh.v[v], s2);
+        for (int q = 0; q < U; ++q) {
+            const int64_t rq = r + (int64_t)q * RPC;
+            ok[q] = rq < r1;
+            if (ok[q]) {
+                const int64_t off = rq * C + sub * VEC;
+                g[q].load(gout + off);
+                o[q].load(out + off);
+                xh[q].load(xhat + off);
+                rs[q] = __ldg(rstd + rq);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) g[q].v[v] = o[q].v[v] = xh[q].v[v] = 0.f;
+                rs[q] = 0.f;
+            }
         }
-        s1 = gsum<LANES>(s1, gm) / (float)C;
-        s2 = gsum<LANES>(s2, gm) / (float)C;
-        Vec<VEC> z;
+        float gx[U][VEC], s1[U], s2[U];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) z.v[v] = rs * (gx[v] - s1 - xh.v[v] * s2);
-        z.store(gz + off);
+        for (int q = 0; q < U; ++q) {
+            s1[q] = s2[q] = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float gy = g[q].v[v];
+                if (act == BG_ACT_LRELU) gy = o[q].v[v] > 0.f ? gy : 0.2f * gy;
+                else if (act == BG_ACT_RELU) gy = o[q].v[v] > 0.f ? gy : 0.f;
+                if (ok[q]) {
+                    dg[v] = fmaf(gy, xh[q].v[v], dg[v]);
+                    db[v] += gy;
+                }
+                gx[q][v] = gy * gam[v];
+                s1[q] += gx[q][v];
+                s2[q] = fmaf(gx[q][v], xh[q].v[v], s2[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            s1[q] = gsum<LANES>(s1[q], gm) / (float)C;
+            s2[q] = gsum<LANES>(s2[q], gm) / (float)C;
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (ok[q]) {
+                Vec<VEC> z;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) z.v[v] = rs[q] * (gx[q][v] - s1[q] - xh[q].v[v] * s2[q]);
+                z.store(gz + (r + (int64_t)q * RPC) * C + sub * VEC);
+            }
+        }
     }
     // column sums over the CTA's row slots: fixed order
 #pragma unroll

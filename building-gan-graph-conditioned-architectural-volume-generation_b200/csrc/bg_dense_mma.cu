@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     extern __shared__ __align__(16) float2 mm_wf[];  // [K/8][NT][2][32] (hi, lo) B fragments
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int K = p.K, KS = K >> 3;
+    // column half of a 128-wide plain product (grid.y = 2: the generator's 128 -> 128 backward-input products; LayerNorm /
+    // attention dots / moments need the whole row in one warp and never come with grid.y > 1)
+    const int col0 = blockIdx.y * COUT;
     const int64_t row_a = (int64_t)blockIdx.x * MM_ROWS + warp * 16 + g, row_b = row_a + 8;
     const bool live_a = row_a < p.N, live_b = row_b < p.N;
 
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
                 const int e = base + u * MM_T + tid;
                 const int l = e & 31, r = (e >> 5) & 1, q = e >> 6;  // q = ks * NT + nt
                 const int nt = q % NT, ks = q / NT;
-                const int n = 8 * nt + (l >> 2), k = 8 * ks + 2 * (l & 3) + r;
+                const int n = col0 + 8 * nt + (l >> 2), k = 8 * ks + 2 * (l & 3) + r;
                 v[u] = (e < total && n < p.Cout) ? __ldg(p.W + (int64_t)n * p.w_so + (int64_t)k * p.w_sk) : 0.f;
             }
 #pragma unroll
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     float y[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int c = 8 * nt + 2 * t;
+        const int c = col0 + 8 * nt + 2 * t;
         float b0 = 0.f, b1 = 0.f;
         if (p.bias) {
             const float2 bv = __ldg(reinterpret_cast<const float2*>(p.bias + c));
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     if (p.gate) {  // fused activation backward of the layer below
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            const int c = 8 * nt + 2 * t;
+            const int c = col0 + 8 * nt + 2 * t;
             if (live_a) {
                 const float2 gv = __ldg(reinterpret_cast<const float2*>(p.gate + row_a * p.ld_gate + c));
                 y[nt][0] *= gv.x > 0.f ? 1.f : p.gate_slope;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int c = 8 * nt + 2 * t;
+        const int c = col0 + 8 * nt + 2 * t;
         if (live_a) *reinterpret_cast<float2*>(p.out + row_a * p.ld_out + c) = make_float2(y[nt][0], y[nt][1]);
         if (live_b) *reinterpret_cast<float2*>(p.out + row_b * p.ld_out + c) = make_float2(y[nt][2], y[nt][3]);
     }
@@ -320,6 +323,7 @@ __global__ void __launch_bounds__(MM_T) dense_mma_kernel(const MmParams p) {
     }
 }
 
+static const bool g_dense_mma128 = !(getenv("BG_DENSE_MMA128") && atoi(getenv("BG_DENSE_MMA128")) == 0);  // A/B switch of the column-half mode
 static int g_dense_mma = -1;  // BG_DENSE_MMA=0: off (A/B switch)
 static int dense_mma_on() {
     if (g_dense_mma < 0) g_dense_mma = getenv("BG_DENSE_MMA") ? atoi(getenv("BG_DENSE_MMA")) : 1;
@@ -327,13 +331,13 @@ static int dense_mma_on() {
 }
 
 template <int COUT, int KSM, bool MOM>
-static void mm_launch2(const MmParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+static void mm_launch2(const MmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     static bool once = (cudaFuncSetAttribute(dense_mma_kernel<COUT, KSM, MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
     (void)once;
     launch_k(dense_mma_kernel<COUT, KSM, MOM>, grid, MM_T, smem, st, p);
 }
 template <int COUT>
-static void mm_launch(const MmParams& p, bool mom, unsigned grid, size_t smem, cudaStream_t st) {
+static void mm_launch(const MmParams& p, bool mom, dim3 grid, size_t smem, cudaStream_t st) {
     const int ks = p.K >> 3;
     if (mom) {
         if (ks <= 4) mm_launch2<COUT, 4, true>(p, grid, smem, st);
@@ -350,7 +354,9 @@ static void mm_launch(const MmParams& p, bool mom, unsigned grid, size_t smem, c
 int dense_mma_try(const BgDense* a, int K, const GnMomFuse* mom, cudaStream_t st) {
     if (!dense_mma_on()) return 1;
     const int C = a->Cout;
-    if (a->N > MM_MAX_N || K > MM_MAX_K || (K & 7) || !(C == 8 || C == 16 || C == 32 || C == 64)) return 1;
+    // 128 columns: two column halves per row tile (grid.y = 2), plain epilogue only (bias / activation / gate)
+    const bool halves = C == 128 && !a->ln_gamma && !a->att_src && !a->xhat && !mom && g_dense_mma128;
+    if (a->N > MM_MAX_N || K > MM_MAX_K || (K & 7) || !(C == 8 || C == 16 || C == 32 || C == 64 || halves)) return 1;
     if (a->nseg != 1 || !a->seg[0].ptr || a->seg[0].gather || a->seg[0].width != K) return 1;
     const auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
     if ((a->seg[0].ld & 1) || !al8(a->seg[0].ptr) || (a->ld_out & 1) || !al8(a->out)) return 1;
@@ -367,9 +373,10 @@ int dense_mma_try(const BgDense* a, int K, const GnMomFuse* mom, cudaStream_t st
     p.out = a->out; p.ld_out = a->ld_out; p.xhat = a->xhat; p.rstd = a->rstd; p.s = a->s; p.d = a->d;
     p.gate = a->gate; p.ld_gate = a->ld_gate; p.gate_slope = a->gate_slope;
     p.mom = mom ? *mom : GnMomFuse{};
-    const size_t smem = (size_t)K * C * sizeof(float2);
-    const unsigned grid = (unsigned)ceil_div(a->N, MM_ROWS);
-    switch (C) {
+    const int Ct = halves ? 64 : C;  // columns per CTA
+    const size_t smem = (size_t)K * Ct * sizeof(float2);
+    const dim3 grid((unsigned)ceil_div(a->N, MM_ROWS), halves ? 2u : 1u);
+    switch (Ct) {
         case 8: mm_launch<8>(p, mom != nullptr, grid, smem, st); break;
         case 16: mm_launch<16>(p, mom != nullptr, grid, smem, st); break;
         case 32: mm_launch<32>(p, mom != nullptr, grid, smem, st); break;

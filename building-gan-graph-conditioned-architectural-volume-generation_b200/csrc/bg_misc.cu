@@ -86,56 +86,74 @@ __global__ void __launch_bounds__(kThreads) type_scatter_kernel(const float* __r
     for (int i = threadIdx.x; i < K * C; i += kThreads) out[i] = acc[i];
 }
 
-// The same for K <= 8 types (the models' 7): per-type sums in REGISTERS.  The kernel above walks its rows one at a time through a
-// shared-memory read-modify-write (a dependent chain with the global load inside: 37-49 us at N = 15 k on the generator's
-// backward chain, profiles/r02b_summary.md); here thread (slot, c) owns column c of every (kThreads / C)-th row of the CTA's
-// chunk, keeps 8 accumulators, and has four independent row loads in flight.  Slots, then CTAs, are folded in a fixed order.
+// The same for K <= 8 types (the models' 7) and C a multiple of 32: per-type sums in REGISTERS, grid = row chunks x 32-column
+// groups.  The kernel above walks its rows one at a time through a shared-memory read-modify-write (a dependent chain with the
+// global load inside) and ends in a last-CTA fold of ~120 partial vectors of K*C = 896 floats by ONE CTA: 37-49 us at N = 15 k
+// on the generator's backward chain (profiles/r02b_summary.md).  Here warp `slot` of a CTA owns every 8th row of the chunk and
+// lane l one column: 8 accumulators per thread, eight independent row loads in flight; the 8 slots fold through shared
+// memory, the <= 64 row chunks of a column group through one ticket round by the group's last CTA (224 floats x <= 64 partials,
+// 32 loads in flight per thread).  Fixed order everywhere: bitwise reproducible.
+constexpr int kTsSlots = kThreads / 32;
+static inline int ts_row_chunks(int64_t N) {
+    int64_t rc = ceil_div(N, 256);
+    return (int)(rc < 1 ? 1 : rc > 64 ? 64 : rc);
+}
 __global__ void __launch_bounds__(kThreads) type_scatter8_kernel(const float* __restrict__ g, int64_t ld, const int32_t* __restrict__ type,
-                                                                 int64_t N, int C, int K, int G, float* out,
-                                                                 unsigned int* counter, float* partials) {
+                                                                 int64_t N, int C, int K, float* out, unsigned int* counters,
+                                                                 float* partials) {
     pdl_prologue();
-    extern __shared__ float acc[];  // [nslot][K*C]; the head doubles as the fold result
-    const int nslot = kThreads / C, c = threadIdx.x % C, slot = threadIdx.x / C;
-    const int64_t chunk = ceil_div(N, G);
-    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    __shared__ float sacc[kTsSlots][8 * 32];
+    const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const int RC = gridDim.x, rc = blockIdx.x, cg = blockIdx.y, c = cg * 32 + lane;
+    const int64_t chunk = ceil_div(N, RC);
+    const int64_t r0 = (int64_t)rc * chunk, r1 = min(N, r0 + chunk);
     float a[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] = 0.f;
-    if (slot < nslot) {
-        int64_t r = r0 + slot;
-        for (; r + 3 * nslot < r1; r += 4 * nslot) {
-            int t[4];
-            float v[4];
+    int64_t r = r0 + slot;
+    for (; r + 7 * kTsSlots < r1; r += 8 * kTsSlots) {
+        int t[8];
+        float v[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                t[q] = __ldg(type + r + q * nslot);
-                v[q] = __ldg(g + (r + q * nslot) * ld + c);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += t[q] == k ? v[q] : 0.f;
-        }
-        for (; r < r1; r += nslot) {
-            const int t = __ldg(type + r);
-            const float v = __ldg(g + r * ld + c);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += t == k ? v : 0.f;
+        for (int q = 0; q < 8; ++q) {
+            t[q] = __ldg(type + r + q * kTsSlots);
+            v[q] = __ldg(g + (r + q * kTsSlots) * ld + c);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < K) acc[(slot * K + k) * C + c] = a[k];
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += t[q] == k ? v[q] : 0.f;
     }
+    for (; r < r1; r += kTsSlots) {
+        const int t = __ldg(type + r);
+        const float v = __ldg(g + r * ld + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += t == k ? v : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc[slot][k * 32 + lane] = a[k];
     __syncthreads();
-    for (int i = threadIdx.x; i < K * C; i += kThreads) {
+    const int L = K * 32;
+    float* mine = partials + ((int64_t)cg * RC + rc) * L;
+    if (threadIdx.x < L) {
         float t = 0.f;
-        for (int sl = 0; sl < nslot; ++sl) t += acc[sl * K * C + i];
-        partials[(int64_t)blockIdx.x * K * C + i] = t;
+#pragma unroll
+        for (int sl = 0; sl < kTsSlots; ++sl) t += sacc[sl][threadIdx.x];
+        mine[threadIdx.x] = t;
     }
-    __shared__ float red[kThreads];
-    __syncthreads();
-    if (!hier_fold(partials, partials + (int64_t)G * K * C, K * C, counter, red, acc)) return;
-    for (int i = threadIdx.x; i < K * C; i += kThreads) out[i] = acc[i];
+    if (!ticket_last(counters + 1 + cg, RC)) return;
+    if (threadIdx.x < L) {
+        const float* col = partials + (int64_t)cg * RC * L + threadIdx.x;
+        float t = 0.f;
+        for (int g0 = 0; g0 < RC; g0 += 32) {
+            float v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = g0 + u < RC ? col[(int64_t)(g0 + u) * L] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) t += v[u];
+        }
+        out[(threadIdx.x >> 5) * C + c] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,9 +436,11 @@ extern "C" int bg_type_scatter_sum(const float* g, int64_t ld, const int32_t* ty
     BG_REQUIRE(ws_bytes >= bg_type_scatter_sum_ws(N, C, K), BG_EINVAL, "bg_type_scatter_sum: workspace too small");
     BG_REQUIRE((size_t)K * C * sizeof(float) <= 48 * 1024, BG_EUNSUPPORTED, "bg_type_scatter_sum: K*C too large");
     const int G = scatter_splits(N);
-    if (K <= 8 && C <= kThreads)
-        launch_k(type_scatter8_kernel, G, kThreads, (size_t)(kThreads / C) * K * C * sizeof(float), as_stream(stream),
-            g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
+    if (K <= 8 && (C & 31) == 0) {
+        const int RC = ts_row_chunks(N);  // partials: RC x K x C floats <= the (scatter_splits(N) + 2) x K x C the caller provides
+        launch_k(type_scatter8_kernel, dim3((unsigned)RC, (unsigned)(C / 32)), kThreads, 0, as_stream(stream), g, ld, type, N, C, K, out,
+                 reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));
+    }
     else
         launch_k(type_scatter_kernel, G, kThreads, (size_t)K * C * sizeof(float), as_stream(stream),
             g, ld, type, N, C, K, G, out, reinterpret_cast<unsigned int*>(workspace), workspace + kCounterBytes / sizeof(float));

@@ -43,11 +43,52 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// W[cout * cin] -> 32 registers per thread (element i = tid + 512 j, or float4 i = tid + 512 j when the buffer allows 128-bit
+// loads): every load of a layer's weights is in flight at once - a single CTA streaming 64 KB through a loop of dependent
+// round trips was the whole cost of the first version (6 us per layer).
+struct WRegs {
+    float v[32];
+};
+__device__ __forceinline__ bool w_vec4(const float* W, int total) { return (total & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0; }
+__device__ __forceinline__ void w_fetch(WRegs& r, const float* __restrict__ W, int total, int tid) {
+    if (w_vec4(W, total)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + SM_T * j;
+            const float4 q = i < total / 4 ? __ldg(reinterpret_cast<const float4*>(W) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r.v[4 * j] = q.x; r.v[4 * j + 1] = q.y; r.v[4 * j + 2] = q.z; r.v[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int i = tid + SM_T * j;
+            r.v[j] = i < total ? __ldg(W + i) : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void w_store(const WRegs& r, float* sm, const float* W, int total, int tid) {
+    if (w_vec4(W, total)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + SM_T * j;
+            if (i < total / 4) reinterpret_cast<float4*>(sm)[i] = make_float4(r.v[4 * j], r.v[4 * j + 1], r.v[4 * j + 2], r.v[4 * j + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int i = tid + SM_T * j;
+            if (i < total) sm[i] = r.v[j];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain p) {
     pdl_prologue();
     extern __shared__ __align__(16) float sm_w[];  // [cout * cin] of the current layer
     __shared__ float xs[SM_R][SM_C], ys[SM_R][SM_C];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WRegs wr;
+    w_fetch(wr, p.l[0].W, p.l[0].cin * p.l[0].cout, tid);
     {
         const int cin0 = p.l[0].cin;
         for (int i = tid; i < SM_R * SM_C; i += SM_T) {
@@ -57,11 +98,22 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain
     }
     for (int li = 0; li < p.n; ++li) {
         const BgSmallLayer& L = p.l[li];
-        const int cin = L.cin, cout = L.cout, total = cin * cout;
-        if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(L.W) & 15) == 0) {
-            for (int i = tid; i < total / 4; i += SM_T) reinterpret_cast<float4*>(sm_w)[i] = __ldg(reinterpret_cast<const float4*>(L.W) + i);
-        } else {
-            for (int i = tid; i < total; i += SM_T) sm_w[i] = __ldg(L.W + i);
+        const int cin = L.cin, cout = L.cout;
+        w_store(wr, sm_w, L.W, cin * cout, tid);
+        if (li + 1 < p.n) w_fetch(wr, p.l[li + 1].W, p.l[li + 1].cin * p.l[li + 1].cout, tid);  // in flight during this layer's work
+        // per-column constants of this layer's epilogue, fetched before the barrier
+        float bias_c[SM_C / SM_W];
+#pragma unroll
+        for (int q = 0; q < SM_C / SM_W; ++q) {
+            const int c = warp + SM_W * q;
+            bias_c[q] = (L.bias && c < cout) ? __ldg(L.bias + c) : 0.f;
+        }
+        float gam[4], bet[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = lane + 32 * j;
+            gam[j] = (L.gamma && c < cout) ? __ldg(L.gamma + c) : 1.f;
+            bet[j] = (L.gamma && c < cout) ? __ldg(L.beta + c) : 0.f;
         }
         __syncthreads();  // W staged, xs of this layer complete
         float xr[SM_R][4];
@@ -69,7 +121,10 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain
         for (int r = 0; r < SM_R; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) xr[r][j] = (lane + 32 * j < cin) ? xs[r][lane + 32 * j] : 0.f;
-        for (int c = warp; c < cout; c += SM_W) {
+#pragma unroll
+        for (int q = 0; q < SM_C / SM_W; ++q) {
+            const int c = warp + SM_W * q;
+            if (c >= cout) break;
             float wv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) wv[j] = (lane + 32 * j < cin) ? sm_w[c * cin + lane + 32 * j] : 0.f;
@@ -99,10 +154,10 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain
             d += __shfl_xor_sync(0xffffffffu, d, 1);
             if ((lane & 3) == 0) {
                 const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                ys[r][c] = d + (L.bias ? __ldg(L.bias + c) : 0.f);
+                ys[r][c] = d + bias_c[q];
             }
         }
-        __syncthreads();  // ys complete; every warp is done with xs
+        __syncthreads();  // ys complete; every warp is done with xs and sm_w
         if (warp < SM_R) {
             const int r = warp;
             float v[4];
@@ -122,7 +177,7 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain
                     if (c < cout) {
                         const float xh = (v[j] - mean) * rs;
                         if (L.xhat && r < p.rows) L.xhat[(int64_t)r * cout + c] = xh;
-                        v[j] = fmaf(xh, __ldg(L.gamma + c), __ldg(L.beta + c));
+                        v[j] = fmaf(xh, gam[j], bet[j]);
                     }
                 }
             }
@@ -136,7 +191,8 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_fwd_kernel(const SmallChain
                 }
             }
         }
-        // the next layer's W staging overwrites sm_w: every warp left the product loop before the barrier above
+        // the next iteration's w_store overwrites sm_w: every warp left the product loop before the barrier above; its
+        // barrier orders the xs writes of this epilogue before the next product
     }
 }
 
@@ -158,33 +214,67 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_bwd_kernel(const SmallChain
     }
     for (int li = p.n - 1; li >= 0; --li) {
         const BgSmallLayer& L = p.l[li];
-        const int cin = L.cin, cout = L.cout;
+        const int cin = L.cin, cout = L.cout, total = cin * cout;
         const float* xsrc = li == 0 ? p.x : p.l[li - 1].out;
-        for (int i = tid; i < SM_R * SM_C; i += SM_T) {
-            const int r = i / SM_C, k = i % SM_C;
-            xin[r][k] = (r < p.rows && k < cin) ? __ldg(xsrc + (int64_t)r * cin + k) : 0.f;
+        const bool need_gin = li > 0 || p.gin != nullptr;
+        // ---- every global read of the layer is issued here, before the first barrier: one round trip per layer
+        float xv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + SM_T * j, r = i / SM_C, k = i % SM_C;
+            xv[j] = (r < p.rows && k < cin) ? __ldg(xsrc + (int64_t)r * cin + k) : 0.f;
+        }
+        // this thread's quarter-column of W for the backward-input product: W[c0 + u][k], u < 32
+        const int kq = tid & (SM_C - 1), cq = tid >> 7;
+        const int per = (cout + 3) / 4, c0 = cq * per, c1 = min(cout, c0 + per);
+        float wq[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) wq[u] = (need_gin && kq < cin && c0 + u < c1) ? __ldg(L.W + (int64_t)(c0 + u) * cin + kq) : 0.f;
+        // existing parameter gradients (accumulate mode): element i = tid + 512 j
+        float dwv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int i = tid + SM_T * j;
+            dwv[j] = (p.accumulate && L.dW && i < total) ? L.dW[i] : 0.f;
+        }
+        // row r = warp: saved output, normalised value, LayerNorm constants
+        float o4[4], h4[4], gm4[4], rs = 0.f;
+        {
+            const int r = warp;
+            const bool live = r < SM_R && r < p.rows;
+            if (live && L.gamma) rs = __ldg(L.rstd + r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * j;
+                const bool ok = live && c < cout;
+                o4[j] = ok ? __ldg(L.out + (int64_t)r * cout + c) : 0.f;
+                h4[j] = (ok && L.gamma) ? __ldg(L.xhat + (int64_t)r * cout + c) : 0.f;
+                gm4[j] = (ok && L.gamma) ? __ldg(L.gamma + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + SM_T * j;
+            xin[i / SM_C][i % SM_C] = xv[j];
         }
         __syncthreads();  // gs of this layer complete (written by the previous iteration), xin staged
         if (warp < SM_R) {  // row r: activation backward, LayerNorm backward
             const int r = warp;
             const bool live = r < p.rows;
-            const float rs = (L.gamma && live) ? __ldg(L.rstd + r) : 0.f;
-            float g[4], h[4], gx[4], s1 = 0.f, s2 = 0.f;
+            float g[4], gx[4], s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = lane + 32 * j;
-                g[j] = h[j] = gx[j] = 0.f;
+                g[j] = gx[j] = 0.f;
                 if (c < cout && live) {
-                    const float o = __ldg(L.out + (int64_t)r * cout + c);
                     float t = gs[r][c];
-                    if (L.act == BG_ACT_LRELU) t = o > 0.f ? t : 0.2f * t;
-                    else if (L.act == BG_ACT_RELU) t = o > 0.f ? t : 0.f;
+                    if (L.act == BG_ACT_LRELU) t = o4[j] > 0.f ? t : 0.2f * t;
+                    else if (L.act == BG_ACT_RELU) t = o4[j] > 0.f ? t : 0.f;
                     g[j] = t;
                     if (L.gamma) {
-                        h[j] = __ldg(L.xhat + (int64_t)r * cout + c);
-                        gx[j] = t * __ldg(L.gamma + c);
+                        gx[j] = t * gm4[j];
                         s1 += gx[j];
-                        s2 = fmaf(gx[j], h[j], s2);
+                        s2 = fmaf(gx[j], h4[j], s2);
                     }
                 }
             }
@@ -195,11 +285,9 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_bwd_kernel(const SmallChain
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = lane + 32 * j;
-                if (c < SM_C) {
-                    gy[r][c] = g[j];
-                    xh[r][c] = h[j];
-                    gz[r][c] = (c < cout && live) ? (L.gamma ? rs * (gx[j] - s1 - h[j] * s2) : g[j]) : 0.f;
-                }
+                gy[r][c] = g[j];
+                xh[r][c] = h4[j];
+                gz[r][c] = (c < cout && live) ? (L.gamma ? rs * (gx[j] - s1 - h4[j] * s2) : g[j]) : 0.f;
             }
         }
         __syncthreads();  // gy, xh, gz complete
@@ -219,41 +307,33 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_bwd_kernel(const SmallChain
             if (L.dbias) L.dbias[c] = p.accumulate ? L.dbias[c] + dbias : dbias;
         }
         if (L.dW) {
-            const int total = cin * cout;
-            for (int i = tid; i < total; i += SM_T) {
-                const int c = i / cin, k = i - c * cin;
-                float t = 0.f;
 #pragma unroll
-                for (int r = 0; r < SM_R; ++r) t = fmaf(gz[r][c], xin[r][k], t);
-                L.dW[i] = p.accumulate ? L.dW[i] + t : t;
+            for (int j = 0; j < 32; ++j) {
+                const int i = tid + SM_T * j;
+                if (i < total) {
+                    const int c = i / cin, k = i - c * cin;
+                    float t = 0.f;
+#pragma unroll
+                    for (int r = 0; r < SM_R; ++r) t = fmaf(gz[r][c], xin[r][k], t);
+                    L.dW[i] = dwv[j] + t;  // dwv = 0 unless accumulating
+                }
             }
         }
-        const bool need_gin = li > 0 || p.gin != nullptr;
-        if (need_gin) {  // gin[r][k] = sum_c gz[r][c] W[c][k]: thread = (column quarter, k), W rows read coalesced
-            const int k = tid & (SM_C - 1), cq = tid >> 7;  // SM_T / SM_C = 4 quarters
+        if (need_gin) {  // gin[r][k] = sum_c gz[r][c] W[c][k]: thread = (column quarter, k)
             float acc[SM_R];
 #pragma unroll
             for (int r = 0; r < SM_R; ++r) acc[r] = 0.f;
-            if (k < cin) {
-                const int per = (cout + 3) / 4, c0 = cq * per, c1 = min(cout, c0 + per);
-                int c = c0;
-                for (; c + 8 <= c1; c += 8) {
-                    float w[8];
+            if (kq < cin) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) w[u] = __ldg(L.W + (int64_t)(c + u) * cin + k);
+                for (int u = 0; u < 32; ++u) {
+                    if (c0 + u < c1) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-#pragma unroll
-                        for (int r = 0; r < SM_R; ++r) acc[r] = fmaf(gz[r][c + u], w[u], acc[r]);
-                }
-                for (; c < c1; ++c) {
-                    const float w = __ldg(L.W + (int64_t)c * cin + k);
-#pragma unroll
-                    for (int r = 0; r < SM_R; ++r) acc[r] = fmaf(gz[r][c], w, acc[r]);
+                        for (int r = 0; r < SM_R; ++r) acc[r] = fmaf(gz[r][c0 + u], wq[u], acc[r]);
+                    }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < SM_R; ++r) part[cq][r][k] = acc[r];
+            for (int r = 0; r < SM_R; ++r) part[cq][r][kq] = acc[r];
         }
         __syncthreads();  // part complete; gs free to be overwritten
         if (need_gin) {
@@ -265,7 +345,6 @@ __global__ void __launch_bounds__(SM_T, 1) small_mlp_bwd_kernel(const SmallChain
             }
         }
         // the next iteration's first barrier orders these writes (and the xin restaging) before any read
-        __syncthreads();
     }
 }
 

@@ -172,19 +172,39 @@ class SideLoss:
     terms, the detached FAR term) evaluated AHEAD of the critic pass together with their gradients w.r.t. (logits, label_hard).
     They depend on the generator's outputs only, so the overlapped step computes them on the sampling stream right after the
     generator's forward - beside the last critic updates - instead of as ~75 small torch launches (0.3 ms) between D(fake)'s
-    forward and backward on the step's critical path."""
+    forward and backward on the step's critical path.  The gradients are written out in closed form (no autograd pass):
+    d ce / d logits = (softmax - onehot) * LAMBDA_LABEL / N;  the ratio terms are means of squared column-mean differences, so
+    their gradient w.r.t. label_hard is one [K] vector broadcast over the rows: 2 * diff_k * LAMBDA / (cols * N)."""
     __slots__ = ("r_main", "ce", "r_void", "far", "g_logits", "g_hard_main", "g_hard_void")
 
     def __init__(self, voxel_graph, logits: Tensor, label_hard: Tensor, cfg):
-        with torch.enable_grad():
-            lg = logits.detach().requires_grad_(True)
-            hd = label_hard.detach().requires_grad_(True)
-            ce, r_main, r_void = _label_terms(voxel_graph, lg, hd, cfg)
-            (self.g_logits,) = torch.autograd.grad(ce, lg)
-            (self.g_hard_main,) = torch.autograd.grad(r_main, hd, retain_graph=True)
-            (self.g_hard_void,) = torch.autograd.grad(r_void, hd)
-        self.r_main, self.ce, self.r_void = r_main.detach(), ce.detach(), r_void.detach()
-        self.far = far_loss(voxel_graph, label_hard, cfg)
+        with torch.no_grad():
+            n, k = voxel_graph.num_nodes, logits.shape[1]
+            logp = F.log_softmax(logits, dim=1)
+            self.ce = F.nll_loss(logp, voxel_graph.type) * cfg.LAMBDA_LABEL  # == F.cross_entropy(logits, type) * LAMBDA_LABEL
+            self.g_logits = torch.sub(logp.exp(), voxel_graph.types_onehot) * (cfg.LAMBDA_LABEL / n)
+            ratio_g = label_hard.squeeze(0).sum(dim=0) / n
+            ratio = voxel_graph.types_onehot.sum(dim=0) / n
+            self.r_main = F.mse_loss(ratio_g[:-2], ratio[:-2]) * cfg.LAMBDA_RATIO
+            self.r_void = F.mse_loss(ratio_g[-2:], ratio[-2:]) * cfg.LAMBDA_RATIO_VOID
+            diff = (ratio_g - ratio) / n
+            w = _ratio_weights(k, cfg.LAMBDA_RATIO, cfg.LAMBDA_RATIO_VOID, diff.device)
+            self.g_hard_main, self.g_hard_void = diff * w[0], diff * w[1]  # [K] each: the same row for every voxel
+            self.far = far_loss(voxel_graph, label_hard, cfg)
+
+
+_RATIO_W = {}
+
+
+def _ratio_weights(k: int, lam_main: float, lam_void: float, device):
+    """[2, K] constants of the ratio terms' gradients: 2 * LAMBDA / (number of columns of the term) on the term's columns."""
+    key = (k, float(lam_main), float(lam_void), str(device))
+    if key not in _RATIO_W:
+        w = torch.zeros(2, k, dtype=torch.float32)
+        w[0, :-2] = 2.0 * lam_main / (k - 2)
+        w[1, -2:] = 2.0 * lam_void / 2
+        _RATIO_W[key] = w.to(device)
+    return _RATIO_W[key]
 
 
 class _SideLossFn(torch.autograd.Function):
@@ -196,13 +216,15 @@ class _SideLossFn(torch.autograd.Function):
         # cycle tensor -> grad_fn -> ctx -> side -> tensor through the C++ node, invisible to Python's collector - and with it the
         # generator's whole forward workspace would leak every step
         ctx.save_for_backward(side.g_logits, side.g_hard_main, side.g_hard_void)
+        ctx.hard_shape = label_hard.shape
         ctx.mark_non_differentiable(side.far)
         return side.r_main, side.ce, side.r_void, side.far
 
     @staticmethod
     def backward(ctx, g_main, g_ce, g_void, _g_far):
         g_logits, g_hard_main, g_hard_void = ctx.saved_tensors
-        return g_logits * g_ce, torch.addcmul(g_hard_main * g_main, g_hard_void, g_void), None
+        row = torch.addcmul(g_hard_main * g_main, g_hard_void, g_void)  # [K]
+        return g_logits * g_ce, row.expand(ctx.hard_shape), None
 
 
 def _label_terms(voxel_graph, logits: Tensor, label_hard: Tensor, cfg):

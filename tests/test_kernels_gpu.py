@@ -374,6 +374,32 @@ def test_rowdense_matches_tiled_kernel_and_oracle(n):
         assert_close(got[True][k], got[False][k].double(), 1e-5, k)
 
 
+@pytest.mark.parametrize("n", [1, 129, 15145])
+@pytest.mark.parametrize("k", [64, 128])
+def test_dense_mma_kernel_128_columns_in_two_halves(n, k):
+    """128 output columns on the warp-MMA kernel as two column halves per row tile (grid.y = 2): the generator's 128-wide
+    backward-input products (plain epilogue: bias / activation / gate) against fp64, rel 1e-5, and against the tiled FFMA kernel."""
+    f = lambda t: t.float().to(DEV).contiguous()
+    c = 128
+    x, W, b = _rand(n, k, seed=1), _rand(c, k, seed=2, scale=0.3), _rand(c, seed=3)
+    Wt, gz, gate = _rand(k, c, seed=4, scale=0.3), _rand(n, k, seed=8), _rand(n, c, seed=9)
+    ref = {"relu": torch.relu(x @ W.t() + b), "dgrad": (gz @ Wt) * torch.where(gate > 0, 1.0, 0.2), "plain": gz @ Wt}
+    got = {}
+    try:
+        for on in (True, False):
+            lib.set_dense_mma(on)
+            lib.set_dense_tc(0)  # keep the tcgen05 kernel out of the way: this compares the warp-MMA path with the FFMA path
+            got[on] = {"relu": lib.dense_fwd([f(x)], f(W), f(b), None, 1)["out"],
+                       "dgrad": lib.dense_fwd([f(gz)], f(Wt), transposed=True, gate=f(gate), gate_slope=0.2)["out"],
+                       "plain": lib.dense_fwd([f(gz)], f(Wt), transposed=True)["out"]}
+    finally:
+        lib.set_dense_mma(True)
+        lib.set_dense_tc(1)
+    for on in (True, False):
+        for key, want in ref.items():
+            assert_close(got[on][key], want, 1e-5, f"{key} {k}->128 n={n} mma={on}")
+
+
 @pytest.mark.parametrize("n", [1, 15, 16, 17, 129, 1500, 15145])
 @pytest.mark.parametrize("k,c", [(8, 8), (16, 8), (8, 16), (32, 16), (64, 32), (64, 64), (128, 64), (24, 32)])
 def test_dense_mma_kernel(n, k, c):

@@ -129,5 +129,9 @@ def test_generator_pass_with_the_fused_encoder_chain_matches_the_per_layer_launc
     # the encoder's own 20 parameter tensors come out of the fused backward; the rest of the generator sees the encoder only through
     # its (1e-7-different) forward values, amplified by the 1- / 2-channel bottleneck blocks like any fp32 reordering
     # (tests/test_models_gpu.py states 2e-3 for those against fp64)
+    # Error norm: max |a - b| over max(|b|_max, 1e-2 x the largest gradient of the model) - some tensors (every att_dst: the
+    # edge softmax is invariant to a per-destination shift) have an exactly-zero true gradient and hold rounding noise only.
+    gmax = max(float(b.abs().max()) for b in res[1]["grads"])
     for i, (a, b) in enumerate(zip(res[0]["grads"], res[1]["grads"])):
-        assert_close(a, b, 1e-3 if i < 20 else 1e-2, f"parameter gradient {i}")
+        err = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-2 * gmax)
+        assert err <= (1e-3 if i < 20 else 1e-2), f"parameter gradient {i}: {err:.3e}"
