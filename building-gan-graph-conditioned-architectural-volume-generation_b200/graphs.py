@@ -186,7 +186,8 @@ class GraphedStep:
         hard = hard.unsqueeze(0)
         self.opt_g.zero_grad()
         g_loss = _step.generator_loss(self.D, lb, vb, logits, hard, cfg, side=side)
-        g_loss.backward()  # the generator's backward pass runs on the stream of its forward (autograd's stream affinity)
+        with self.D.input_grads_only():  # the critic's own .grad from this backward would be zeroed unread (next zero_grad)
+            g_loss.backward()  # the generator's backward pass runs on the stream of its forward (autograd's stream affinity)
         main.wait_stream(gen)
         if self.grad_sync is not None:
             self.grad_sync(self.G)

@@ -709,6 +709,22 @@ class VoxelGNNDiscriminator(nn.Module):
         finally:
             self._native.lane = prev
 
+    @contextlib.contextmanager
+    def input_grads_only(self):
+        """Backward passes of this model that START inside this context deliver the input gradient only (native executor,
+        BG_GRADS=bucket): no weight-gradient launches, ``p.grad`` untouched.  For the generator update (trainer.py:486-491):
+        the reference's ``g_loss.backward()`` also fills the critic's ``.grad``, which the next ``optimizer_d.zero_grad()``
+        discards unread - the fast path (graphs.GraphedStep) skips producing them."""
+        st = getattr(self, "_native", None)
+        if st is None or _executor_for(self._kind) != "native":  # op-by-op executor: parameter gradients go through autograd
+            yield self
+            return
+        prev, st.skip_param_grads = getattr(st, "skip_param_grads", False), True
+        try:
+            yield self
+        finally:
+            st.skip_param_grads = prev
+
     def merge_lanes(self) -> None:
         """Add the lane buckets into ``p.grad`` (call on the main stream after the lane streams were joined)."""
         self._native.merge_lanes(_param_list(self))
@@ -924,7 +940,7 @@ class _DiscNativeBwdFn(torch.autograd.Function):
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         accumulate = bucket_mode
         if bucket_mode:  # under create_graph only the input gradient is wanted (autograd.grad(..., only_inputs=True))
-            if second_order:
+            if second_order or getattr(st, "skip_param_grads", False):
                 flat = None
             elif lane is None:
                 flat = st.bind_grads(params)
