@@ -176,7 +176,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
     constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
     constexpr int TMEM_COLS = NACC * BN;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);  // [TC_STAGES]
+    // the epilogue re-uses the operand stages as its staging area (parameters, row partials, padded output tile): the mbarriers
+    // sit behind whichever of the two is larger
+    constexpr int EPI_BYTES = (5 * BN + 4 * TC_M + TC_M * (BN + 1)) * 4;
+    constexpr int BAR_OFF = ((TC_STAGES * STAGE_BYTES > EPI_BYTES ? TC_STAGES * STAGE_BYTES : EPI_BYTES) + 15) & ~15;
+    uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [TC_STAGES]
     uint64_t* accum_bar = empty_bar + TC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
@@ -294,75 +298,103 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseTcPara
         if (kb + 1 < nkb) process(kb + 1, R1);
     }
 
-    // ---- epilogue: warps 0..3, one thread per row (TMEM lane = row), columns in chunks of 32
+    // ---- epilogue: all 8 warps.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (the hardware's lane quarter of a warp) = rows, and the
+    // column half w / 4: each thread pulls its BN / 2 accumulator columns out of TMEM ONCE (summing the NACC partial
+    // accumulators), the LayerNorm row statistics and the attention dots are completed across the two halves through shared
+    // memory, and results leave through a padded shared-memory tile so that global stores are coalesced (a warp writes 128
+    // consecutive bytes of one row).  Round 1/2a: warps 0..3 only, three TMEM sweeps per row (mean, variance, output) and
+    // 16-byte stores 512 bytes apart - the epilogue was ~20 of the kernel's ~35 us at N = 15 k (profiles/r02b_summary.md).
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    if (warp < 4) {
-        const int r_local = warp * 32 + lane;
-        const int64_t grow = row0 + r_local;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float mean = 0.f, rs = 1.f;
-        float v[32];
+    {
+        constexpr int HB = BN / 2, TLD = BN + 1;
+        float* sbias = reinterpret_cast<float*>(smem);          // operand stages are free: every MMA has completed
+        float* sgam = sbias + BN;
+        float* sbet = sgam + BN;
+        float* sas = sbet + BN;
+        float* sad = sas + BN;
+        float* red = sad + BN;                                    // [2][2][TC_M]
+        float* tile = red + 4 * TC_M;                             // [TC_M][TLD]
+        for (int c = tid; c < BN; c += kThreads) {
+            sbias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+            sgam[c] = p.gamma ? __ldg(p.gamma + c) : 1.f;
+            sbet[c] = p.gamma ? __ldg(p.beta + c) : 0.f;
+            sas[c] = p.att_src ? __ldg(p.att_src + c) : 0.f;
+            sad[c] = p.att_src ? __ldg(p.att_dst + c) : 0.f;
+        }
+        const int q4 = warp & 3, half = warp >> 2;
+        const int r_local = q4 * 32 + lane, c0 = half * HB;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float v[HB];
+#pragma unroll
+        for (int ch = 0; ch < HB / 32; ++ch) {
+            float t32[32];
+            tmem_row32<NACC, BN>(taddr, c0 + 32 * ch, t32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[32 * ch + j] = t32[j];
+        }
+        __syncthreads();  // parameters staged
+#pragma unroll
+        for (int j = 0; j < HB; ++j) v[j] += sbias[c0 + j];
+        // coalesced copy of the staged tile to a row-major global tensor
+        auto flush_tile = [&](float* dst, int64_t ld) {
+            __syncthreads();
+            for (int idx = tid; idx < TC_M * BN; idx += kThreads) {
+                const int r = idx / BN, c = idx % BN;
+                if (row0 + r < p.N) dst[(row0 + r) * ld + c] = tile[r * TLD + c];
+            }
+            __syncthreads();
+        };
         if (p.gamma) {
             float sm = 0.f;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                tmem_row32<NACC, BN>(taddr, c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sm += v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-            }
-            mean = sm / (float)BN;
+            for (int j = 0; j < HB; ++j) sm += v[j];
+            red[half * TC_M + r_local] = sm;
+            __syncthreads();
+            const float mean = (red[r_local] + red[TC_M + r_local]) / (float)BN;
             float vs = 0.f;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                tmem_row32<NACC, BN>(taddr, c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float dlt = v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - mean;
-                    vs = fmaf(dlt, dlt, vs);
-                }
+            for (int j = 0; j < HB; ++j) vs = fmaf(v[j] - mean, v[j] - mean, vs);
+            red[(2 + half) * TC_M + r_local] = vs;
+            __syncthreads();
+            const float rs = 1.f / sqrtf((red[2 * TC_M + r_local] + red[3 * TC_M + r_local]) / (float)BN + 1e-5f);
+            if (p.rstd && half == 0 && row0 + r_local < p.N) p.rstd[row0 + r_local] = rs;
+#pragma unroll
+            for (int j = 0; j < HB; ++j) v[j] = (v[j] - mean) * rs;
+            if (p.xhat) {  // normalised value saved for the backward
+#pragma unroll
+                for (int j = 0; j < HB; ++j) tile[r_local * TLD + c0 + j] = v[j];
+                flush_tile(p.xhat, BN);
             }
-            rs = 1.f / sqrtf(vs / (float)BN + 1e-5f);
-            if (p.rstd && grow < p.N) p.rstd[grow] = rs;
+#pragma unroll
+            for (int j = 0; j < HB; ++j) v[j] = fmaf(v[j], sgam[c0 + j], sbet[c0 + j]);
         }
-        float ss = 0.f, dd = 0.f;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            tmem_row32<NACC, BN>(taddr, c0, v);
-            float y[32];
-            if (p.gamma && p.xhat && grow < p.N) {  // normalised value saved for the backward, 128-bit stores
-                float4* x4 = reinterpret_cast<float4*>(p.xhat + grow * BN + c0);
+        if (p.act == BG_ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float q[4];
+            for (int j = 0; j < HB; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+        } else if (p.act == BG_ACT_LRELU) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) q[u] = (v[j + u] + (p.bias ? __ldg(p.bias + c0 + j + u) : 0.f) - mean) * rs;
-                    x4[j >> 2] = make_float4(q[0], q[1], q[2], q[3]);
-                }
+            for (int j = 0; j < HB; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+        }
+        if (p.att_src) {
+            float ss = 0.f, dd = 0.f;
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                ss = fmaf(v[j], sas[c0 + j], ss);
+                dd = fmaf(v[j], sad[c0 + j], dd);
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                float t = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
-                if (p.gamma) {
-                    const float xh = (t - mean) * rs;
-                    t = fmaf(xh, __ldg(p.gamma + c), __ldg(p.beta + c));
-                }
-                if (p.act == BG_ACT_RELU) t = t > 0.f ? t : 0.f;
-                else if (p.act == BG_ACT_LRELU) t = t > 0.f ? t : 0.2f * t;
-                if (p.att_src) {
-                    ss = fmaf(t, __ldg(p.att_src + c), ss);
-                    dd = fmaf(t, __ldg(p.att_dst + c), dd);
-                }
-                y[j] = t;
-            }
-            if (grow < p.N) {
-                float4* o4 = reinterpret_cast<float4*>(p.out + grow * p.ld_out + c0);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) o4[j >> 2] = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            __syncthreads();  // red is reused
+            red[half * TC_M + r_local] = ss;
+            red[(2 + half) * TC_M + r_local] = dd;
+            __syncthreads();
+            if (half == 0 && row0 + r_local < p.N) {
+                p.s[row0 + r_local] = red[r_local] + red[TC_M + r_local];
+                p.d[row0 + r_local] = red[2 * TC_M + r_local] + red[3 * TC_M + r_local];
             }
         }
-        if (p.att_src && grow < p.N) {
-            p.s[grow] = ss;
-            p.d[grow] = dd;
-        }
+#pragma unroll
+        for (int j = 0; j < HB; ++j) tile[r_local * TLD + c0 + j] = v[j];
+        flush_tile(p.out, p.ld_out);
     }
     tc_fence_before();
     __syncthreads();
@@ -381,7 +413,9 @@ static int dense_tc_mode() {
 
 template <int BN, int MODE>
 static void launch_dense_tc(const DenseTcParams& p, unsigned grid, cudaStream_t st) {
-    constexpr int smem = TC_STAGES * (MODE ? 1 : 2) * (TC_M * 128 + BN * 128) + 1024 + 64;
+    constexpr int stage_bytes = TC_STAGES * (MODE ? 1 : 2) * (TC_M * 128 + BN * 128);
+    constexpr int epi_bytes = (5 * BN + 4 * TC_M + TC_M * (BN + 1)) * 4;  // epilogue: parameters, row partials, padded output tile
+    constexpr int smem = (stage_bytes > epi_bytes ? stage_bytes : epi_bytes) + 16 + 1024 + 64;
     static bool once = (cudaFuncSetAttribute(dense_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), true);
     (void)once;
     launch_k(dense_tc_kernel<BN, MODE>, grid, kThreads, smem, st, p);
