@@ -301,7 +301,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     def step_resident(i):
         lb, vb = resident[i % len(resident)]
         if gstep is not None:
-            return gstep(lb, vb, sync_losses=False)
+            # next_batch: the following step's graphs are captured during this one (a prefetching loader knows the next batch)
+            return gstep(lb, vb, sync_losses=False, next_batch=resident[(i + 1) % len(resident)])
         return step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses=False, overlap=OVERLAP)
 
     result_sink = []
@@ -314,13 +315,19 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             vals = buf.tolist()
             result_sink.append((vals[:-1], vals[-1]))  # the step's 6 losses (trainer.py:479,493) as floats
 
+    ahead = {}  # step index -> its batch, already on its way to the device (one step of prefetch, like a data loader's)
+
     def step_e2e(i):
-        lb, vb = _clone_to(*host[i % len(host)], dev)  # pinned host -> device, every step
         if gstep is not None:
+            # pinned host -> device, one batch per step: step i+1's copy is enqueued during step i (prefetch depth 1), so that
+            # its graphs can be captured during step i as well; the first batch of a timed block is copied here
+            lb, vb = ahead.pop(i) if i in ahead else _clone_to(*host[i % len(host)], dev)
+            ahead.clear()
+            ahead[i + 1] = _clone_to(*host[(i + 1) % len(host)], dev)
             # the 6 losses of EVERY step are read back (one async D2H into pinned memory per step); the host looks at step i's
             # floats while step i+1 is being captured, so capture and execution overlap.  fin_e2e() collects the last one
             # inside the timed region.
-            gstep(lb, vb, sync_losses=False)
+            gstep(lb, vb, sync_losses=False, next_batch=ahead[i + 1])
             buf = torch.empty(cfg.N_CRITIC + 1, dtype=torch.float32, pin_memory=True)
             buf.copy_(gstep.last_losses, non_blocking=True)
             ev = torch.cuda.Event()
@@ -328,6 +335,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             pending.append((buf, ev))
             drain(1)
             return
+        lb, vb = _clone_to(*host[i % len(host)], dev)  # pinned host -> device, every step
         d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step", overlap=OVERLAP)
         result_sink.append((d_losses, g_loss))  # the step's 6 losses (trainer.py:479,493) read back as floats, one D2H
 
@@ -411,7 +419,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                            "overlap": ("independent passes on 4 streams (step.Lanes): sampling passes up front, D(real)/D(fake) beside "
                                        "the gradient-penalty pass" if OVERLAP else "single stream"),
                            "cuda_graphs": ("critic update and sampling pass captured once per step, replayed N_CRITIC times "
-                                           "(graphs.GraphedStep)" if gstep is not None else "none"),
+                                           "(graphs.GraphedStep); the next step's graphs are captured during the current step "
+                                           "(next_batch=: prefetch depth 1; e2e: the next batch's H2D copy is enqueued one step ahead, "
+                                           "inside the timed region)" if gstep is not None else "none"),
                            "pdl": _pdl_state(lib),
                            "grads": os.environ.get("BG_GRADS", "bucket"), "executor": os.environ.get("BG_EXECUTOR", "native"),
                            "gradient_exchange": sync_kind,

@@ -40,6 +40,11 @@ class _Captured:
         self.graph, self.out, self.calls, self.done = torch.cuda.CUDAGraph(), None, 0, None
 
 
+class _Prepared:
+    """The captures and static buffers of one step (GraphedStep._prepare)."""
+    __slots__ = ("lb", "vb", "sample", "losses", "S", "C")
+
+
 class GraphedStep:
     def __init__(self, generator, discriminator, opt_g, opt_d, cfg, grad_sync=None):
         """``grad_sync(model)``: the data-parallel gradient all-reduce (dist.GradSync), called after each backward and before
@@ -64,12 +69,14 @@ class GraphedStep:
         self.base_c = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._alive = collections.deque()  # captured graphs of the last steps (their replays may still be queued)
         self._warm = False
+        self._prepared = None  # the next step, prepared ahead of its call (see _prepare)
         self.last_losses = None  # [N_CRITIC + 1] device tensor of the last step's losses (critic updates, generator update)
 
     # ------------------------------------------------------------------------------------------------------------
-    def __call__(self, local_graph, voxel_graph, sync_losses="step"):
+    def __call__(self, local_graph, voxel_graph, sync_losses="step", next_batch=None):
         """One training step; same return value as step.train_step (losses as floats for sync_losses="step", as 0-dim
-        device tensors for False)."""
+        device tensors for False).  ``next_batch`` = (local_graph, voxel_graph) of the FOLLOWING call, when the caller knows it (a
+        prefetching data loader does): its graphs are then captured during this step, off the critical path."""
         caller = torch.cuda.current_stream()
         self.main.wait_stream(caller)
         with torch.cuda.stream(self.main), _step.lanes_pdl_scope():
@@ -81,7 +88,7 @@ class GraphedStep:
                                        overlap=True)
                 self._warm = True
             else:
-                out = self._run(local_graph, voxel_graph, sync_losses)
+                out = self._run(local_graph, voxel_graph, sync_losses, next_batch)
         caller.wait_stream(self.main)
         return out
 
@@ -135,22 +142,37 @@ class GraphedStep:
         cap.calls = models._philox_calls - c0
         return cap
 
-    def _run(self, lb, vb, sync_losses):
+    def _prepare(self, lb, vb) -> "_Prepared":
+        """Everything of a step that can be done before its first launch: per-batch constants, the two captures, the static
+        buffers.  Nothing here executes on the GPU (captures only record), so the step AFTER the current one can be prepared
+        while the current one's critic updates are still running (``__call__(..., next_batch=...)``)."""
+        cfg, dev = self.cfg, self.dev
+        n, R = vb.num_nodes, cfg.N_CRITIC
+        models.prepare_batch(lb, vb, cfg.NUM_CLASSES)
+        if self.D._native.bucket is None or next(self.D.parameters()).grad is None:
+            self.D._native.bind_grads(models._param_list(self.D))
+        P = _Prepared()
+        P.lb, P.vb = lb, vb
+        P.sample = torch.empty(2, n, cfg.NUM_CLASSES, dtype=torch.float32, device=dev)  # the critic graph's static input
+        P.losses = torch.empty(R + 1, dtype=torch.float32, device=dev)
+        t0 = models._philox_calls
+        P.S = self._capture_sampling(lb, vb, n)
+        models._philox_calls = t0 + R * P.S.calls  # S's replays use tickets t0+1 .. t0+R*S.calls; C's start after them
+        c0 = models._philox_calls
+        P.C = self._capture_critic(lb, vb, P.sample)
+        models._philox_calls = c0 + R * P.C.calls  # the tickets an eager run of the R critic updates would have consumed
+        return P
+
+    def _run(self, lb, vb, sync_losses, next_batch=None):
         cfg, main, gen, dev = self.cfg, self.main, self.lanes.gen, self.dev
         n, R = vb.num_nodes, cfg.N_CRITIC
         while len(self._alive) > 4:  # graphs older than two steps: wait until their last replay has finished, then drop them
             old = self._alive.popleft()
             old.done.synchronize()
-        models.prepare_batch(lb, vb, cfg.NUM_CLASSES)
-        if self.D._native.bucket is None or next(self.D.parameters()).grad is None:
-            self.D._native.bind_grads(models._param_list(self.D))
-        sample = torch.empty(2, n, cfg.NUM_CLASSES, dtype=torch.float32, device=dev)  # the critic graph's static input
-        losses = torch.empty(R + 1, dtype=torch.float32, device=dev)
-        t0 = models._philox_calls
-        S = self._capture_sampling(lb, vb, n)
-        models._philox_calls = t0 + R * S.calls  # S's replays use tickets t0+1 .. t0+R*S.calls; C's start after them
-        c0 = models._philox_calls
-        C = self._capture_critic(lb, vb, sample)
+        P, self._prepared = self._prepared, None
+        if P is None or P.lb is not lb or P.vb is not vb:  # nothing prepared ahead (or for another batch): prepare now
+            P = self._prepare(lb, vb)
+        S, C, sample, losses = P.S, P.C, P.sample, P.losses
         taken, gen_out, side = None, None, None
         for k in range(R):
             with torch.cuda.stream(gen):
@@ -162,7 +184,6 @@ class GraphedStep:
                 if k == R - 1:
                     # the generator update's forward pass (trainer.py:483-485) depends on nothing the critic updates change:
                     # it runs on the sampling stream beside the last critic updates (eager: once per step, needs autograd)
-                    models._philox_calls = c0 + R * C.calls  # the tickets an eager run of the same calls would have consumed
                     z = torch.randn(1, n, cfg.Z_DIM, device=dev)
                     gen_out = self.G(lb, vb, z)
                     # the critic-independent loss terms and their gradients: here, beside the critic updates (step.SideLoss)
@@ -180,6 +201,12 @@ class GraphedStep:
         self.opt_d._t += R
         S.done, C.done = gen.record_event(), main.record_event()
         self._alive.extend((S, C))
+        if next_batch is not None:
+            # The host is ~5 critic updates ahead of the GPU here.  Capturing the NEXT step's graphs now, before the generator
+            # update's tail is enqueued, takes the two captures (~2.4 ms of host time) out of the window between this step's
+            # last launch and the next step's first one, where the GPU had only the ~1.5 ms tail left to run
+            # (profiles/r02b_summary.md: ~0.9 ms of idle GPU per step).
+            self._prepared = self._prepare(*next_batch)
         # generator update, the part that needs the updated critic: D(fake), backward, Adam (trainer.py:486-495)
         main.wait_event(gen_ready)
         logits, hard, soft = gen_out

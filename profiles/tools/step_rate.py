@@ -15,6 +15,7 @@ og, od = Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS), Adam(D.parameters(), lr
 host = bench._make_batches(0, 6, int(os.environ.get("BATCH", "32")), pin=False)
 res = [bench._clone_to(*h, dev) for h in host]
 gs = graphs.GraphedStep(G, D, og, od, cfg)
+AHEAD = os.environ.get("AHEAD", "1") == "1"
 STEPS, BLOCKS = int(os.environ.get("STEPS", "30")), int(os.environ.get("BLOCKS", "3"))
 for i in range(24):
     gs(*res[i % 6], sync_losses=False)
@@ -25,7 +26,7 @@ for b in range(BLOCKS):
     t0 = time.perf_counter()
     e0.record()
     for i in range(STEPS):
-        gs(*res[i % 6], sync_losses=False)
+        gs(*res[i % 6], sync_losses=False, next_batch=res[(i + 1) % 6] if AHEAD else None)
     e1.record()
     th = time.perf_counter() - t0
     torch.cuda.synchronize()

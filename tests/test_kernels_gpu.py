@@ -374,6 +374,22 @@ def test_rowdense_matches_tiled_kernel_and_oracle(n):
         assert_close(got[True][k], got[False][k].double(), 1e-5, k)
 
 
+def test_dense_kernels_are_deterministic():
+    """Every dense path twice on the same inputs: bitwise equal (fixed reduction trees; the tcgen05 epilogue completes its
+    LayerNorm statistics across two column halves in a fixed order)."""
+    f = lambda t: t.float().to(DEV).contiguous()
+    n = 15145
+    for k, c in ((128, 128), (268, 128), (64, 64), (64, 32)):
+        x, W, b = f(_rand(n, k, seed=1)), f(_rand(c, k, seed=2, scale=0.3)), f(_rand(c, seed=3))
+        gam, bet = f(_rand(c, seed=4) * 0.2 + 1), f(_rand(c, seed=5) * 0.2)
+        a = lib.dense_fwd([x], W, b, (gam, bet), 2, save_ln=True)
+        bb = lib.dense_fwd([x], W, b, (gam, bet), 2, save_ln=True)
+        for key in ("out", "xhat", "rstd"):
+            assert torch.equal(a[key], bb[key]), (k, c, key)
+    gz, Wt = f(_rand(n, 128, seed=6)), f(_rand(128, 128, seed=7, scale=0.3))
+    assert torch.equal(lib.dense_fwd([gz], Wt, transposed=True)["out"], lib.dense_fwd([gz], Wt, transposed=True)["out"])
+
+
 @pytest.mark.parametrize("n", [1, 129, 15145])
 @pytest.mark.parametrize("k", [64, 128])
 def test_dense_mma_kernel_128_columns_in_two_halves(n, k):
