@@ -620,10 +620,12 @@ def _parity_block(G, D, resident0, cfg, lib):
 
 
 def _dense_rooflines(vb, G, D, flush):
-    """Rooflines of the two kernels that dominate the step's GPU time (dense_fwd_kernel ~29 %, wgrad_multi_kernel ~14 % of
-    the launch list): the step's own dense shapes, CUDA-graph replayed, cold L2, CUDA events; flops = 2 N K Cout against
-    the FP32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz) and algorithmic bytes against the measured HBM peak.  At
-    N ~ 15 k both are latency-bound: the honest figure is the average launch time against a ~3 us launch floor."""
+    """Rooflines of the dense work that dominates the step's GPU time (launch list profiles/r02b_*: dense_mma_kernel 23 %,
+    wgrad_mma_kernel 13.5 %, dense_tc_kernel 8 %): the step's own dense shapes through the public entry points (bg_dense_fwd /
+    bg_dense_wgrad dispatch them exactly as inside the step), CUDA-graph replayed, cold L2, CUDA events; logical flops =
+    2 N K Cout against the FP32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz) - the warp-MMA kernels issue 3 TF32 MMAs per
+    logical product - and algorithmic bytes against the measured HBM peak.  At N ~ 15 k all of them are latency-bound: the
+    honest figure is the average launch time against a ~1 us launch floor and ~3 us for an elementwise pass over the same rows."""
     try:
         from building_gan_b200 import lib
         n, dev = vb.num_nodes, vb.x.device
@@ -633,7 +635,8 @@ def _dense_rooflines(vb, G, D, flush):
         shapes = [(c.cin, c.cout) for c in D._convs] + [(36, 64), (64, 64), (64, 32), (32, 16), (16, 8), (8, 1)]
         shapes += [(c.cin, c.cout) for c in G._convs] + [(64, 32), (32, 16), (16, 7)]
         out = {}
-        for label, mode in (("dense_fwd_kernel (FFMA)", "fwd"), ("wgrad_multi_kernel", "wgrad")):
+        for label, mode in (("bg_dense_fwd (dense_mma_kernel: mma.sync 3xTF32 for K % 8 == 0 and Cout in 8..64; rowdense / tiled FFMA for the rest)", "fwd"),
+                            ("bg_dense_wgrad (wgrad_mma_kernel: mma.sync 3xTF32 partial sums + fold)", "wgrad")):
             bufs = []
             for k, c in shapes:
                 x, w, g = torch.randn(n, k, device=dev), torch.randn(c, k, device=dev), torch.randn(n, c, device=dev)
@@ -668,6 +671,37 @@ def _dense_rooflines(vb, G, D, flush):
                           "algorithmic_GBs": round(byts / (ms * 1e-3) / 1e9, 1), "frac_hbm_peak": round(byts / (ms * 1e-3) / 1e9 / hbm, 4),
                           "bound": "latency (L2-resident operands, tens of CTAs per launch)"}
         out["shapes"] = f"N={n}; (K, Cout) of the narrow / plain dense layers of one G + one D pass: {shapes}"
+        # the 128-wide Linear + LayerNorm + LeakyReLU layers of the generator: tcgen05 3xTF32 (dense_tc_kernel<128>)
+        tensor_peak = peaks.get("bf16_tflops", peaks.get("dense_bf16_tflops", 0.0)) or None
+        x, w, b = torch.randn(n, 128, device=dev), torch.randn(128, 128, device=dev) * 0.1, torch.zeros(128, device=dev)
+        gam, bet = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+        run = lambda: lib.dense_fwd([x], w, b, (gam, bet), 2, save_ln=True)
+        reps = 4
+        stream, graph = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            run()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=stream):
+                for _ in range(reps):
+                    run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2] / reps
+        tf = 2.0 * n * 128 * 128 / (ms * 1e-3) / 1e12
+        out["dense_tc_kernel<128> (tcgen05 3xTF32, Linear 128 -> 128 + LayerNorm + LeakyReLU, xhat / rstd saved)"] = {
+            "launches": reps, "avg_launch_us": round(1e3 * ms, 2), "logical_tflops": round(tf, 2), "tensor_pipe_tflops": round(3 * tf, 2),
+            "measured_bf16_peak_tflops": tensor_peak,
+            "frac_tensor_peak": (round(3 * tf / (tensor_peak / 2), 4) if tensor_peak else None),
+            "algorithmic_GBs": round(4.0 * (3 * n * 128 + 128 * 128) / (ms * 1e-3) / 1e9, 1),
+            "bound": "latency (119 tiles on 148 SMs: one wave; TF32 peak taken as half the measured bf16 peak; 4 launches back to back in one CUDA graph)"}
         return out
     except Exception as exc:
         return {"error": repr(exc)[:300]}
