@@ -674,12 +674,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_fold_kernel(const FoldBatch fb
     *dst = f.accumulate ? *dst + t : t;
 }
 
-static inline int wgrad_splits(int64_t N, int total_tiles) {
+static inline int wgrad_splits(int64_t N, int total_tiles, int64_t max_ck = 0) {
     // small outputs (a handful of tiles) are pure latency: use many short row ranges (the folds of a whole pass run as
     // one parallel launch, so more partials are cheap); large outputs keep the partial traffic bounded
     int64_t ns = ceil_div(4 * kSMs, total_tiles);
     const int64_t maxs = ceil_div(N, 64);
-    const int64_t cap = total_tiles <= 2 ? 128 : 64;
+    // a handful of SMALL outputs (the last batch of a pass: its launch sits between the end of the dgrad chain and the fold):
+    // 128 short row ranges; wide outputs (a 128 x 128 layer alone is 4 tiles too) keep the partial-sum traffic at 64
+    const int64_t cap = (total_tiles <= 2 || (total_tiles <= 4 && max_ck <= 64 * 65)) ? 128 : 64;
     if (ns > maxs) ns = maxs;
     if (ns > cap) ns = cap;
     if (ns < 1) ns = 1;
@@ -705,7 +707,9 @@ static int wgrad_launch_batch(const BgWgrad* probs, int nprob, WgradQueue& q, cu
         tiles += p.ntiles;
         if (a.N > nmax) nmax = a.N;
     }
-    b.S = wgrad_splits(nmax, tiles);
+    int64_t max_ck = 0;
+    for (int i = 0; i < nprob; ++i) max_ck = std::max<int64_t>(max_ck, (int64_t)b.p[i].Cout * b.p[i].K);
+    b.S = wgrad_splits(nmax, tiles, max_ck);
     {   // the partial sums of every batch of a pass live side by side until the fold: shorten the splits rather than fail
         size_t per_split = 0;
         for (int i = 0; i < nprob; ++i) per_split += ((size_t)b.p[i].Cout * b.p[i].K + 63) / 64 * 64 + 64;

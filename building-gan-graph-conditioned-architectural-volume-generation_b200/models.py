@@ -924,7 +924,7 @@ class _DiscNativeFn(torch.autograd.Function):
         # penalty pass with an all-zero g_score (one whole sweep + its weight gradients on the step's critical path,
         # profiles/r02b_summary.md)
         outs = _DiscNativeBwdFn.apply(ctx.model, ctx.bc, ctx.ws, ctx.training,
-                                      (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane), score.detach(),
+                                      (torch.is_grad_enabled(), ctx.bucket_mode, ctx.lane, ctx.needs_input_grad[5]), score.detach(),
                                       g_score.contiguous(), label, *tensors)
         return (None, None, None, None, None) + tuple(outs)
 
@@ -936,7 +936,7 @@ class _DiscNativeBwdFn(torch.autograd.Function):
     def forward(ctx, model: VoxelGNNDiscriminator, bc, ws, training, flags, score, g_score, label, *tensors):
         L, st = lib.load(), model._native
         params = _param_list(model)
-        second_order, bucket_mode, lane = flags
+        second_order, bucket_mode, lane, want_g_label = flags  # want_g_label: the label input itself asks for a gradient
         dev, n, e = label.device, bc.n, bc.csr.num_edges
         accumulate = bucket_mode
         if bucket_mode:  # under create_graph only the input gradient is wanted (autograd.grad(..., only_inputs=True))
@@ -951,11 +951,12 @@ class _DiscNativeBwdFn(torch.autograd.Function):
         saved = lib.u8_buffer(L.bg_disc_bwd_saved_ws(C.byref(st.md), n, e), dev) if second_order else None
         tmp = lib.u8_buffer(L.bg_disc_tmp_ws(C.byref(st.md), n, e), dev)
         red = lib.workspace(lib.RED_BYTES, dev)
-        g_label = torch.empty_like(label)
+        # D(real) / D(fake) of a critic update score constant labels: no backward-input product of the first layer for them
+        g_label = torch.empty_like(label) if (want_g_label or second_order) else None
         lib._check(L.bg_disc_backward(C.byref(st.md), st.ptrs(params), C.byref(bc.csr.c_struct()), C.byref(_batch_in(bc)),
                                       label.data_ptr(), ws.data_ptr(), score.data_ptr(), g_score.data_ptr(), int(training),
                                       lib._p(flat), st.goff, int(accumulate), lib._p(saved), 0 if saved is None else saved.numel(),
-                                      tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4, g_label.data_ptr(),
+                                      tmp.data_ptr(), tmp.numel(), red.data_ptr(), red.numel() * 4, lib._p(g_label),
                                       lib._stream()))
         lib.pass_launches((3 * 4 + 6 * len(model._convs) + 3 * 2) if flat is not None else (2 * 4 + 5 * len(model._convs) + 4))
         ctx.model, ctx.bc, ctx.ws, ctx.saved, ctx.training, ctx.bucket_mode = model, bc, ws, saved, training, bucket_mode
