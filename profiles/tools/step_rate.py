@@ -31,5 +31,15 @@ for b in range(BLOCKS):
     th = time.perf_counter() - t0
     torch.cuda.synchronize()
     out.append((e0.elapsed_time(e1) / STEPS, 1e3 * th / STEPS))
+if os.environ.get("DRAIN") == "1":  # pure host cost per step: GPU drained before every step, host time of the call only
+    hs = []
+    for i in range(STEPS):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gs(*res[i % 6], sync_losses=False, next_batch=res[(i + 1) % 6] if AHEAD else None)
+        hs.append(1e3 * (time.perf_counter() - t0))
+    torch.cuda.synchronize()
+    hs.sort()
+    print("host ms per step with the GPU drained before each step: median %.3f, min %.3f" % (hs[len(hs) // 2], hs[0]))
 print("ms/step (device, host enqueue) per block:", [(round(a, 3), round(b, 3)) for a, b in out],
       "best %.3f ms = %.1f steps/s" % (min(a for a, _ in out), 1e3 / min(a for a, _ in out)))
