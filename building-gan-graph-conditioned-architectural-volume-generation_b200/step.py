@@ -217,8 +217,10 @@ class _SideLossFn(torch.autograd.Function):
         # generator's whole forward workspace would leak every step
         ctx.save_for_backward(side.g_logits, side.g_hard_main, side.g_hard_void)
         ctx.hard_shape = label_hard.shape
-        ctx.mark_non_differentiable(side.far)
-        return side.r_main, side.ce, side.r_void, side.far
+        # fresh views: the outputs get this node as their grad_fn, `side` keeps its own tensors untouched (and reusable)
+        far = side.far.view_as(side.far)
+        ctx.mark_non_differentiable(far)
+        return side.r_main.view_as(side.r_main), side.ce.view_as(side.ce), side.r_void.view_as(side.r_void), far
 
     @staticmethod
     def backward(ctx, g_main, g_ce, g_void, _g_far):

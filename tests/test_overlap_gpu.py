@@ -161,3 +161,32 @@ def test_graphed_step_matches_eager_statistics(kind):
     for mode in out:
         assert out[mode][-1] < out[mode][0], out
     assert abs(out["graph"][-1] - out["eager"][-1]) <= 0.25 * abs(out["eager"][0]), out
+
+
+def test_graphed_step_prepares_the_next_batch_ahead():
+    """GraphedStep(..., next_batch=): the following step's graphs are captured during the current step and used by the next call
+    when it is handed the same batch objects; a different batch falls back to capturing at the start of its own step.  Same
+    training behaviour either way (finite losses, Adam counters advance, the critic loss decreases)."""
+    from building_gan_b200.graphs import GraphedStep
+
+    cfg = Configuration()
+    cfg.DEVICE = "cuda"
+    torch.manual_seed(1)
+    G, D = VoxelGNNGenerator(cfg, 17, 12), VoxelGNNDiscriminator(cfg, 17, 12)
+    og, od = Adam(G.parameters(), lr=2e-4, betas=cfg.BETAS), Adam(D.parameters(), lr=2e-4, betas=cfg.BETAS)
+    batches = [tuple(b.to("cuda") for b in small_batch(ids)) for ids in ((21, 22, 23), (24, 25, 26, 27), (28, 29))]
+    gs = GraphedStep(G, D, og, od, cfg)
+    first = []
+    for s in range(7):
+        cur, nxt = batches[s % 3], batches[(s + 1) % 3]
+        d, g, hard = gs(*cur, sync_losses="step", next_batch=nxt)
+        assert all(v == v and abs(v) < 1e4 for v in d + [g]) and hard.shape[1] == cur[1].num_nodes
+        if s >= 1:  # (the very first call is the eager warm-up step: nothing is prepared there)
+            assert gs._prepared is not None and gs._prepared.lb is nxt[0] and gs._prepared.vb is nxt[1]
+        if s % 3 == 0:
+            first.append(d[0])
+    # hand the step a batch other than the prepared one: it must notice and capture for the batch it was given
+    d, g, hard = gs(*batches[2], sync_losses="step")
+    assert hard.shape[1] == batches[2][1].num_nodes and all(v == v for v in d + [g]) and gs._prepared is None
+    assert float(od.state_dict()["state"][0]["step"]) == 8 * cfg.N_CRITIC and float(og.state_dict()["state"][0]["step"]) == 8
+    assert first[-1] < first[0], first  # the critic loss on batch 0 decreases over the steps
