@@ -174,6 +174,27 @@ struct Vec<4> {
     }
 };
 
+// 256-bit global load / store (sm_100: LDG.E.256 / STG.E.256 - what nvcc emits for a 32-byte aligned aggregate; p must be
+// 32-byte aligned and, for load(), point to data that is read-only for the kernel's lifetime)
+struct alignas(32) Float8 {
+    float v[8];
+};
+template <>
+struct Vec<8> {
+    float v[8];
+    __device__ __forceinline__ void load(const float* __restrict__ p) {
+        const Float8 t = *reinterpret_cast<const Float8*>(p);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = t.v[q];
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        Float8 t;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t.v[q] = v[q];
+        *reinterpret_cast<Float8*>(p) = t;
+    }
+};
+
 // Butterfly sum over a group of LANES consecutive lanes (LANES power of two <= 32): every lane of
 // the group ends with the same, order-fixed result.
 template <int LANES>

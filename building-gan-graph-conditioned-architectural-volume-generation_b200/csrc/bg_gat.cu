@@ -53,6 +53,15 @@ template <int C>
 struct GatMap {
     static constexpr int HALVES = C >= 64 ? 2 : 1;
     static constexpr int VEC = C >= 4 ? 4 : C;
+#ifdef BG_GAT_V8
+    // experiment: a lane's two 128-bit pieces are CONTIGUOUS (channels [8 sub, 8 sub + 8)), so that a gathered row is ONE 256-bit
+    // load per lane (LDG.E.256) instead of two 128-bit loads half a row apart
+    static constexpr bool V8 = HALVES == 2;
+#else
+    static constexpr bool V8 = false;
+#endif
+    static constexpr int LOFF = V8 ? 2 * VEC : VEC;          // channel offset of lane `sub`'s first piece: sub * LOFF
+    static constexpr int HOFF = V8 ? VEC : C / 2;            // channel offset between a lane's pieces
     static constexpr int NV = VEC * HALVES;                  // floats per lane
     static constexpr int LANES = C / NV;
     static constexpr int RPW = 32 / LANES;                   // rows per warp
@@ -66,7 +75,7 @@ __device__ __forceinline__ void row_load(float (&v)[GatMap<C>::NV], const float*
 #pragma unroll
     for (int hh = 0; hh < M::HALVES; ++hh) {
         Vec<M::VEC> t;
-        t.load(xrow + hh * (C / 2) + sub * M::VEC);
+        t.load(xrow + hh * M::HOFF + sub * M::LOFF);
 #pragma unroll
         for (int q = 0; q < M::VEC; ++q) v[hh * M::VEC + q] = t.v[q];
     }
@@ -79,14 +88,14 @@ __device__ __forceinline__ void row_store(const float (&v)[GatMap<C>::NV], float
         Vec<M::VEC> t;
 #pragma unroll
         for (int q = 0; q < M::VEC; ++q) t.v[q] = v[hh * M::VEC + q];
-        t.store(xrow + hh * (C / 2) + sub * M::VEC);
+        t.store(xrow + hh * M::HOFF + sub * M::LOFF);
     }
 }
 // channel index of element q of a lane's row piece
 template <int C>
 __device__ __forceinline__ int chan(int sub, int q) {
     using M = GatMap<C>;
-    return (q / M::VEC) * (C / 2) + sub * M::VEC + q % M::VEC;
+    return (q / M::VEC) * M::HOFF + sub * M::LOFF + q % M::VEC;
 }
 
 __device__ __forceinline__ float rcp_fast(float x) {  // x >= 1 here (softmax denominators): MUFU.RCP, <= 1 ulp
@@ -105,6 +114,20 @@ __device__ __forceinline__ T slot_get(const T (&a)[EPL], int t) {
     }
 }
 
+// a lane's HALVES pieces of the row at `xlane` (= row base + the lane's channel offset): two 128-bit loads, or one 256-bit load
+template <int C>
+__device__ __forceinline__ void load_pieces(Vec<GatMap<C>::VEC> (&x)[GatMap<C>::HALVES], const float* __restrict__ xlane) {
+    using M = GatMap<C>;
+    if constexpr (M::V8) {
+        Vec<8> t;
+        t.load(xlane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[0].v[q] = t.v[q], x[1].v[q] = t.v[4 + q];
+    } else {
+#pragma unroll
+        for (int hh = 0; hh < M::HALVES; ++hh) x[hh].load(xlane + hh * M::HOFF);
+    }
+}
 // acc += sum_{q < 4} w[t0+q] * X[idx[t0+q], :]   (4 independent 128-bit gathers in flight)
 template <int C, int EPL>
 __device__ __forceinline__ void gather_fma4(const float* __restrict__ xb, const int (&idx)[EPL], const float (&w)[EPL],
@@ -119,9 +142,7 @@ __device__ __forceinline__ void gather_fma4(const float* __restrict__ xb, const 
 #pragma unroll
         for (int q = 0; q < NB; ++q) jj[q] = slot_get<LANES, EPL>(idx, t0 + b + q);
 #pragma unroll
-        for (int q = 0; q < NB; ++q)
-#pragma unroll
-            for (int hh = 0; hh < HALVES; ++hh) xv[q][hh].load(xb + (int64_t)jj[q] * C + hh * (C / 2));
+        for (int q = 0; q < NB; ++q) load_pieces<C>(xv[q], xb + (int64_t)jj[q] * C);
 #pragma unroll
         for (int q = 0; q < NB; ++q) pp[q] = slot_get<LANES, EPL>(w, t0 + b + q);
 #pragma unroll
@@ -181,7 +202,9 @@ __device__ __forceinline__ void prefetch_far_row(const float* __restrict__ x, in
 template <int C>
 __device__ __forceinline__ void prefetch_stream(const float* __restrict__ x, int row_ahead, int r1, int sub) {
     using M = GatMap<C>;
-    if (row_ahead < r1 && ((sub * M::VEC * 4) & 127) == 0) {
+    if constexpr (M::V8) {  // contiguous pieces: lanes whose 32 bytes start a 128-byte line prefetch that line
+        if (row_ahead < r1 && ((sub * M::LOFF * 4) & 127) == 0) prefetch_l2(x + (int64_t)row_ahead * C + sub * M::LOFF);
+    } else if (row_ahead < r1 && ((sub * M::VEC * 4) & 127) == 0) {
 #pragma unroll
         for (int hh = 0; hh < M::HALVES; ++hh) prefetch_l2(x + (int64_t)row_ahead * C + hh * (C / 2) + sub * M::VEC);
     }
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(STATS ? kGatStatsThreads : kGatMaxThreads, 1) 
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
     const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
-    const float* hb = h + sub * VEC;
+    const float* hb = h + sub * M::LOFF;
     constexpr bool stats = STATS;  // a compile-time switch: the 2*NV accumulators must not cost the plain kernel registers
     __shared__ float kshift[STATS ? C : 1];
     if constexpr (STATS) gat_fwd_row0_shift<C>(rowptr, col, h, s, d, slope, kshift);
@@ -580,9 +603,7 @@ __device__ __forceinline__ void gather_dot4(const float* __restrict__ hb, const 
 #pragma unroll
         for (int q = 0; q < NB; ++q) jj[q] = slot_get<LANES, EPL>(j, t0 + b + q);
 #pragma unroll
-        for (int q = 0; q < NB; ++q)
-#pragma unroll
-            for (int hh = 0; hh < HALVES; ++hh) hv[q][hh].load(hb + (int64_t)jj[q] * C + hh * (C / 2));
+        for (int q = 0; q < NB; ++q) load_pieces<C>(hv[q], hb + (int64_t)jj[q] * C);
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
             cc[q] = 0.f;
@@ -658,7 +679,7 @@ __global__ void __launch_bounds__(FUSE ? kGatStatsThreads : kGatMaxThreads, 1) g
     const int sub = lane % LANES, grow = lane / LANES;
     const unsigned gm = group_mask<LANES>(lane);
     const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
-    const float* hb = h + sub * VEC;
+    const float* hb = h + sub * M::LOFF;
     if constexpr (!PIPE) {
         for (int it = 0; it < sw.niter; ++it) {
             const int row = sw.raw(it);
@@ -833,7 +854,7 @@ __global__ void __launch_bounds__(kGatMaxThreads, 1) gat_bwd_src_kernel(
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES, grow = lane / LANES;
     const Sweep sw(N, chunk_rows, ipc_shift, RPW, grow);
-    const float* gb = G + sub * VEC;
+    const float* gb = G + sub * M::LOFF;
     if constexpr (!PIPE) {
         for (int it = 0; it < sw.niter; ++it) {
             const int row = sw.raw(it);
