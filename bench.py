@@ -110,7 +110,7 @@ class _Clocks(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self._stop_evt, self._smax = index, [], threading.Event(), None
         self.nvml, self.handle, self.source = None, None, "nvidia-smi"
         try:
             import pynvml
@@ -124,11 +124,12 @@ class _Clocks(threading.Thread):
 
     def _sample_nvml(self):
         n = self.nvml
+        if self._smax is None:  # constant: asked once (start() is called before the timed region begins)
+            self._smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
         sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-        smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
         get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         mask = int(get(self.handle))
-        self.rows.append([str(sm), str(smax)] + ["Active" if mask & bit else "Not Active" for _, bit in self.NVML_REASONS])
+        self.rows.append([str(sm), str(self._smax)] + ["Active" if mask & bit else "Not Active" for _, bit in self.NVML_REASONS])
 
     def run(self):
         while not self._stop_evt.is_set():
@@ -142,7 +143,10 @@ class _Clocks(threading.Thread):
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.05 if self.nvml is not None else 1.0)
+            # 10 samples a second: on some boxes an NVML query takes ~100 ms instead of microseconds and holds a driver lock that
+            # kernel launches wait for - the timed step is host-launch-sensitive (one run read 91 steps/s with the sampler's
+            # first block against 131 in the block after it, profiles/r02b_summary.md)
+            self._stop_evt.wait(float(os.environ.get("BG_CLOCK_PERIOD", "0.1")) if self.nvml is not None else 1.0)
 
     def stop(self):
         self._stop_evt.set()
@@ -316,6 +320,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             result_sink.append((vals[:-1], vals[-1]))  # the step's 6 losses (trainer.py:479,493) as floats
 
     ahead = {}  # step index -> its batch, already on its way to the device (one step of prefetch, like a data loader's)
+    ring = [(torch.empty(cfg.N_CRITIC + 1, dtype=torch.float32, pin_memory=True), torch.cuda.Event()) for _ in range(4)]
 
     def step_e2e(i):
         if gstep is not None:
@@ -328,9 +333,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             # floats while step i+1 is being captured, so capture and execution overlap.  fin_e2e() collects the last one
             # inside the timed region.
             gstep(lb, vb, sync_losses=False, next_batch=ahead[i + 1])
-            buf = torch.empty(cfg.N_CRITIC + 1, dtype=torch.float32, pin_memory=True)
+            buf, ev = ring[i % len(ring)]  # pinned result buffers allocated once (no cudaHostAlloc inside the timed region)
             buf.copy_(gstep.last_losses, non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record()
             pending.append((buf, ev))
             drain(1)
