@@ -144,7 +144,16 @@ def test_capturable_counter_and_training_step():
         assert (p - q).abs().max().item() <= 1e-6 * max(1e-2, q.abs().max().item())
     assert float(a.state_dict()["state"][0]["step"]) == 5.0
 
+    # A real training step through the kernels, optim.Adam against torch.optim.Adam, with ONE critic update per step: up to the
+    # first optimiser step the two arms run identical arithmetic (same kernels, same inputs: bitwise equal gradients), so the
+    # critic after its Adam step differs by the two implementations' rounding only, and the generator's gradient - computed
+    # through that critic - by a relative 1e-7.  (With the reference's five critic updates the arms drift apart at the noise
+    # level instead: parameters whose gradient is rounding noise - conv biases in front of a GraphNorm, sums with heavy
+    # cancellation such as the type-matched encoder's - move by a fraction of lr per step in a direction that depends on the
+    # last bit of everything upstream; which and how many elements do so changes with every kernel revision.  That says nothing
+    # about the optimiser; graphs.GraphedStep / step.train_step with five updates are covered by tests/test_overlap_gpu.py.)
     cfg, G1, G2 = _pair(VoxelGNNGenerator, "cuda")
+    cfg.N_CRITIC = 1
     _, D1, D2 = _pair(VoxelGNNDiscriminator, "cuda")
     for m in (G1, G2, D1, D2):
         m.eval()  # no dropout: the two runs see the same arithmetic
@@ -159,28 +168,24 @@ def test_capturable_counter_and_training_step():
         from building_gan_b200 import models as bm
         bm._philox_calls = 0
         out.append(bstep.train_step(G, D, og, od, lb, vb, cfg, rng="cpu"))
-    # the first critic loss is computed before any optimiser step: identical arithmetic, identical value.  Later losses see
-    # parameters after Adam steps; parameters whose gradient is rounding noise (see below) move by a fraction of lr in a
-    # direction that depends on the last bit of everything upstream, and the 1-channel bottleneck amplifies that: 2e-3.
-    scale = max(1.0, max(abs(v) for v in out[1][0]))
-    assert abs(out[0][0][0] - out[1][0][0]) <= 1e-6 * scale
-    assert max(abs(x - y) for x, y in zip(out[0][0], out[1][0])) <= 2e-3 * scale
-    for m1, m2 in ((G1, G2), (D1, D2)):
-        for (name, p), q in zip(m1.named_parameters(), m2.parameters()):
-            # Adam's first steps move every parameter by ~lr regardless of gradient scale: compare against lr.  A conv bias
-            # sits in front of a GraphNorm, which removes the column mean: its gradient is analytically zero, what arrives is
-            # rounding noise of ~1e-9, and Adam turns noise of that size (|g| ~ eps) into a step of a fraction of lr whose
-            # value depends on the last bit of everything upstream - bound those by the largest possible step instead.
-            # The same holds for isolated ELEMENTS of other tensors (weight columns that only ever multiply a zero input
-            # feature).  How many elements of a tensor sit at the noise level, and which, depends on the kernels' rounding
-            # pattern and changes with every kernel revision (0.1 % .. 3.4 % of a tensor seen): the bulk of every tensor - all
-            # but 5 % of its elements, or four of a small tensor - must agree within 5 % of lr per step, every element within
-            # the largest possible step.
-            noise_driven = name.startswith("encoder.module_") and name.endswith(".bias") and int(name.split("_")[1].split(".")[0]) % 4 == 0
-            diff = (p - q).abs()
-            assert diff.max().item() <= 2.0 * 2e-4 * 6, name
-            bad = int((diff > 0.05 * 2e-4 * 6).sum())
-            assert noise_driven or bad <= max(4, 5e-2 * diff.numel()), (name, bad, diff.numel())
+    assert out[0][0][0] == out[1][0][0]                       # the critic loss: before any optimiser step
+    assert abs(out[0][1] - out[1][1]) <= 1e-5 * max(1.0, abs(out[1][1]))  # the generator loss: after the critic's one step
+    lr = 2e-4
+    for (name, p), q in zip(D1.named_parameters(), D2.parameters()):
+        assert (p - q).abs().max().item() <= 1e-6 * max(1e-2, q.abs().max().item()), name   # one Adam step on equal gradients
+    failures = []
+    for (name, p), q in zip(G1.named_parameters(), G2.parameters()):
+        # gradients equal to ~1e-7 relative; Adam's first step moves an element by lr g / (|g| + eps): only elements whose
+        # gradient is of the size of eps = 1e-8 can feel that.  A conv bias sits in front of a GraphNorm, which removes the
+        # column mean: its gradient is analytically zero, what arrives is rounding noise of the size of eps, and the step Adam
+        # makes of it depends on the last bit of everything upstream - those are bounded by the largest possible step only.
+        # Every other tensor: all but 2 % of its elements (or four) within 5 % of lr, every element within the largest step.
+        noise_driven = name.startswith("encoder.module_") and name.endswith(".bias") and int(name.split("_")[1].split(".")[0]) % 4 == 0
+        diff = (p - q).abs()
+        bad = int((diff > 0.05 * lr).sum())
+        if diff.max().item() > 2.0 * lr or (not noise_driven and bad > max(4, 2e-2 * diff.numel())):
+            failures.append((name, diff.max().item(), bad, diff.numel()))
+    assert not failures, failures
 
 
 def test_state_dict_round_trip_cpu():
