@@ -67,3 +67,43 @@ def test_far_invariant_of_synthetic_buildings():
         gfa = sum(n["dimension"][1] * n["dimension"][2] for n in v["voxel_node"] if n["type"] >= 0)
         assert abs(g["far"] - gfa / g["site_area"]) < 1e-9
         assert abs(sum(x["proportion"] for x in g["global_node"]) - 1.0) < 1e-9
+
+
+def test_csr_random_ragged_graphs_property():
+    """Property test of bg_csr_build_host on random COO lists (ragged degrees, duplicate edges, input self loops, isolated
+    nodes, a single node, hubs with hundreds of in-edges): every structural invariant of _check_csr holds and building the same
+    list twice gives identical arrays (the counting sort is stable and has no data-dependent tie breaks)."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(n=st.integers(1, 40), e=st.integers(0, 400), hub=st.booleans(), seed=st.integers(0, 2**31 - 1))
+    def run(n, e, hub, seed):
+        rng = np.random.default_rng(seed)
+        src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+        if hub and e:
+            dst[rng.random(e) < 0.7] = rng.integers(0, n)  # most edges end in one node
+        ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+        a, b = graph.VoxelCSR.build(ei, n), graph.VoxelCSR.build(ei.clone(), n)
+        _check_csr(ei, n, a)
+        for name in ("rowptr", "col", "cscptr", "cscrow", "perm"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        assert a.num_edges == int((src != dst).sum()) + n  # input self loops stripped, one appended per node
+
+    run()
+
+
+def test_collate_single_graph_and_order_independence():
+    """A batch of one building collates to that building's own arrays (offsets 0), and the CSR of a batch equals the per-graph
+    CSRs shifted by the cumulative node counts (graphs are disjoint components: data.py:160-161)."""
+    pairs = [synth.building_pair(i) for i in (51, 52, 53)]
+    _, one = graph.collate_fn(pairs[:1])
+    assert one.ptr.tolist() == [0, one.num_nodes] and torch.equal(one.edge_index, pairs[0][1].edge_index)
+    _, vb = graph.collate_fn(pairs)
+    off, rp, col = 0, [0], []
+    for _, v in pairs:
+        c = graph.VoxelCSR.build(v.edge_index, v.num_nodes)
+        rp += (c.rowptr[1:] + rp[-1]).tolist()
+        col += (c.col + off).tolist()
+        off += v.num_nodes
+    assert vb.bg_csr.rowptr.tolist() == rp and vb.bg_csr.col.tolist() == col
