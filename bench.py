@@ -132,6 +132,15 @@ class _Clocks(threading.Thread):
         self.rows.append([str(sm), str(self._smax)] + ["Active" if mask & bit else "Not Active" for _, bit in self.NVML_REASONS])
 
     def run(self):
+        # The first NVML sample comes 60 ms into the timed region, not at its start: it then reads the clocks under load, and a
+        # slow query (see below) does not land on the first step's launches, where the host has no run-ahead yet and every
+        # stalled launch is idle GPU time.  A region shorter than that still gets its one sample (taken as it ends).
+        if self.nvml is not None and self._stop_evt.wait(float(os.environ.get("BG_CLOCK_DELAY", "0.06"))):
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            return
         while not self._stop_evt.is_set():
             try:
                 if self.nvml is not None:
