@@ -55,3 +55,30 @@ def test_reference_arm_does_not_load_the_product():
     import bench
     assert line["impl"] == "reference" and line["config"]["workload"] == bench.WORKLOAD
     assert line["product_package_loaded"] is False
+
+
+def test_committed_bench_lines_are_valid_json_with_the_contract_keys():
+    """Every bench line committed under profiles/ parses as ONE JSON object (a captured stdout once carried NCCL's version
+    banner in front of it) and the default-arm lines of this round carry the keys the bench contract names."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "*bench_line*.json")) + glob.glob(os.path.join(root, "profiles", "*reference_arm_line*.json")))
+    assert files
+    for f in files:
+        with open(f) as fh:
+            d = json.load(fh)
+        assert isinstance(d, dict), f
+    for name in ("r02c_bench_line.json", "r02c_bench_line_2gpu.json"):
+        with open(os.path.join(root, "profiles", name)) as fh:
+            d = json.load(fh)
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                    "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert key in d, (name, key)
+        assert d["config"]["workload"] and d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    with open(os.path.join(root, "profiles", "r02c_bench_line.json")) as fh:
+        d = json.load(fh)
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-3
