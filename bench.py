@@ -288,11 +288,14 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, fin=None):
+    def timed(fn, steps, fin=None, start=0):
+        """``start``: index of the block's first step = the number of untimed calls of ``fn`` before it, so that the batch sequence
+        simply continues: the last untimed step has then announced (next_batch=) exactly the batch the first timed step runs,
+        as a prefetching loader does at every step - otherwise each block would open with a capture on an idle GPU."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
+        for i in range(start, start + steps):
             flush.zero_()  # L2 flush between timed iterations (inside the timed region, ~40 us)
             fn(i)
         if fin is not None:
@@ -363,7 +366,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     clocks = _Clocks(local_rank)
     clocks.start()
     launches0 = lib.LAUNCHES
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps, start=n_warm)
     launches = lib.LAUNCHES - launches0
     clock_info = clocks.stop()
     # the same step with the trainer's per-step metrics call (trainer.py:497 -> step.compute_metrics: one
@@ -377,12 +380,13 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             metric_sink.pop(0)
 
     step_with_metrics(0)
-    ms_metrics = timed(step_with_metrics, args.steps)
-    for i in range(min(args.warmup, 2)):
+    ms_metrics = timed(step_with_metrics, args.steps, start=1)
+    n_e2e_warm = min(args.warmup, 2)
+    for i in range(n_e2e_warm):
         step_e2e(i)
     drain(0)
     n_before = len(result_sink)
-    ms_e2e = timed(step_e2e, args.steps, fin=lambda: drain(0))
+    ms_e2e = timed(step_e2e, args.steps, fin=lambda: drain(0), start=n_e2e_warm)
     assert len(result_sink) - n_before == args.steps, "every timed end-to-end step must have delivered its losses to the host"
 
     # ---- roofline of the aggregation kernel at the bench shapes (rank 0): the 46 gat_fwd launches of one step's layer
