@@ -342,14 +342,17 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             ahead.clear()
             ahead[i + 1] = _clone_to(*host[(i + 1) % len(host)], dev)
             # the 6 losses of EVERY step are read back (one async D2H into pinned memory per step); the host looks at step i's
-            # floats while step i+1 is being captured, so capture and execution overlap.  fin_e2e() collects the last one
+            # floats two steps later, so capture and execution overlap.  fin_e2e() collects the last one
             # inside the timed region.
             gstep(lb, vb, sync_losses=False, next_batch=ahead[i + 1])
             buf, ev = ring[i % len(ring)]  # pinned result buffers allocated once (no cudaHostAlloc inside the timed region)
             buf.copy_(gstep.last_losses, non_blocking=True)
             ev.record()
             pending.append((buf, ev))
-            drain(1)
+            # the host reads step i's floats once step i+2 is enqueued: two steps of run-ahead, the same depth GraphedStep itself
+            # allows (it waits for the graphs of step i-2 before it drops them); with one step the host stalled on step i-1's
+            # completion right after enqueueing step i and every bit of host jitter was idle GPU time
+            drain(int(os.environ.get("BG_E2E_DEPTH", "2")))
             return
         lb, vb = _clone_to(*host[i % len(host)], dev)  # pinned host -> device, every step
         d_losses, g_loss, _ = step.train_step(G, D, og, od, lb, vb, cfg, rng="device", grad_sync=grad_sync, sync_losses="step", overlap=OVERLAP)
