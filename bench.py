@@ -17,6 +17,7 @@ public API from pinned HOST buffers (H2D of the batch + CSR every step, the loss
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -97,6 +98,17 @@ def _clone_to(lb, vb, device):
         nb._fields.pop("_bg_cache", None)
         out.append(nb.to(device, non_blocking=True))
     return out
+
+
+def _settle_heap() -> None:
+    """Called (untimed) right before a timed block: collect the cyclic garbage of the setup / warm-up phase and move the
+    surviving heap - models, batches, the imported libraries: ~1e6 tracked objects - to the permanent generation (gc.freeze).
+    The collector stays ON; what it no longer does is re-traverse that static heap when a full collection falls into the
+    block: one such pass costs 50-150 ms of host time, and the step is ~1700 driver calls with the host barely ahead of
+    the GPU (single blocks of otherwise healthy runs read 91-106 steps/s instead of 130: profiles/r02b_summary.md)."""
+    if os.environ.get("BG_GC_FREEZE", "1") == "1":
+        gc.collect()
+        gc.freeze()
 
 
 class _Clocks(threading.Thread):
@@ -210,6 +222,7 @@ def run_reference(args, rank: int, world: int) -> None:
     od = torch.optim.Adam(D.parameters(), lr=cfg.LEARNING_RATE_DISCRIMINATOR, betas=cfg.BETAS)
     for i in range(args.warmup):
         otrainer.train_step(G, D, og, od, *batches[i % len(batches)], cfg)
+    _settle_heap()
     t0 = time.perf_counter()
     for i in range(args.steps):
         otrainer.train_step(G, D, og, od, *batches[(args.warmup + i) % len(batches)], cfg)
@@ -292,6 +305,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         """``start``: index of the block's first step = the number of untimed calls of ``fn`` before it, so that the batch sequence
         simply continues: the last untimed step has then announced (next_batch=) exactly the batch the first timed step runs,
         as a prefetching loader does at every step - otherwise each block would open with a capture on an idle GPU."""
+        _settle_heap()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -442,6 +456,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                                            "(graphs.GraphedStep); the next step's graphs are captured during the current step "
                                            "(next_batch=: prefetch depth 1; e2e: the next batch's H2D copy is enqueued one step ahead, "
                                            "inside the timed region)" if gstep is not None else "none"),
+                           "gc": "cyclic garbage collected and the heap frozen (gc.freeze) before each timed block, outside it; the collector stays on",
                            "pdl": _pdl_state(lib),
                            "grads": os.environ.get("BG_GRADS", "bucket"), "executor": os.environ.get("BG_EXECUTOR", "native"),
                            "gradient_exchange": sync_kind,
@@ -794,6 +809,7 @@ def _extra_workloads(cfg, dev, flush):
         gs = GraphedStep(G, D, og, od, cfg)
         for _ in range(8):  # one eager step, then the graph pools' steady state (see the conv-type block below)
             gs(lb1, vb1, sync_losses=False)
+        _settle_heap()
         torch.cuda.synchronize()
         k = 20
         e0.record()
@@ -824,6 +840,7 @@ def _extra_workloads(cfg, dev, flush):
             # meet cudaMalloc (readings of 3.8 .. 18 steps/s for the same model on different boxes)
             for _ in range(7):
                 gs2(lb32, vb32, sync_losses=False)
+            _settle_heap()
             torch.cuda.synchronize()
             k = 8
             e0.record()
